@@ -1,0 +1,476 @@
+"""CPU oracle for the quantise + multi-phase search hot path.  TEST INFRASTRUCTURE ONLY.
+
+This module restates, in NumPy, the arithmetic of aitrailblazer/VectorRAGQuantization for the path
+named in BASELINE.json.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import it; the product package (``vectorragquantization_b200``) never does
+and fails loudly when its CUDA library is missing.
+
+Pinning: every function here is checked in ``tests/test_oracle_golden.py`` against
+  * ``tests/golden/reference_static_methods.npz`` - outputs of the reference's OWN static methods
+    (imported from /root/reference with faiss / rocksdict stubbed) on seeded + adversarial inputs, and
+  * ``tests/golden/reference_dbs.npz`` - payloads decoded from the reference's committed 1000-document
+    databases (KAT-1..5).
+The Hamming top-k follows faiss ``IndexBinaryFlat.search`` semantics; faiss-cpu is an UNPINNED, un-vendored
+dependency (``dependencies.txt:2``) that is not installable here, so that one function is pinned only by
+KAT-4 (tie order in ``1.log:78-127``) and KAT-5 (file layout): "parity unpinned by tests" for the faiss
+boundary, restated from the published algorithm (max-heap of size k, strict ``<`` replacement, final
+``(distance, position)`` ascending reorder).
+
+All file:line citations are into /root/reference.  Batched forms are per-row equivalent to the reference's
+one-vector-at-a-time methods (verified in the tests, 0 mismatching elements).
+"""
+from __future__ import annotations
+
+import json
+import os
+import struct
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+INT32_MAX = np.int32(2147483647)
+
+# ----------------------------------------------------------------------------------------------
+# Quantisers / dequantisers
+# ----------------------------------------------------------------------------------------------
+
+
+def quantize_int8_perdoc(x: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """VectorDBInt8._quantize_to_int8 (VectorDBInt8.py:114-126), batched over rows.
+
+    scale = float32(127) / max(|min|, |max|)  (float32 IEEE division), q = trunc(x * scale) (astype(int8)
+    truncates toward zero - the reference does NOT round, SURVEY trap T1); rows with max == min -> zeros.
+    Returns (q int8[n,D], min f32[n], max f32[n]).
+    """
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if x.ndim == 1:
+        q, lo, hi = quantize_int8_perdoc(x[None])
+        return q[0], lo[0], hi[0]
+    lo = x.min(axis=1)
+    hi = x.max(axis=1)
+    m = np.maximum(np.abs(lo), np.abs(hi))
+    const = lo == hi
+    with np.errstate(divide="ignore", invalid="ignore"):
+        scale = np.float32(127) / m
+        q = (x * scale[:, None]).astype(np.int8)
+    q[const] = 0
+    return q, lo, hi
+
+
+def dequantize_int8_perdoc(q: np.ndarray, lo: np.ndarray, hi: np.ndarray) -> np.ndarray:
+    """VectorDBInt8._dequantize_int8 (VectorDBInt8.py:128-138): q.astype(f32) * (max(|min|,|max|)/127), f32."""
+    q = np.asarray(q, dtype=np.int8)
+    lo = np.asarray(lo, dtype=np.float32)
+    hi = np.asarray(hi, dtype=np.float32)
+    if q.ndim == 1:
+        return dequantize_int8_perdoc(q[None], lo[None], hi[None])[0]
+    scale = np.maximum(np.abs(lo), np.abs(hi)) / np.float32(127)
+    out = q.astype(np.float32) * scale[:, None]
+    out[lo == hi] = 0
+    return out
+
+
+def _global_quant(x: np.ndarray, limit: float, qmax: float, dtype) -> np.ndarray:
+    x = np.asarray(x, dtype=np.float32)
+    limit = float(limit)
+    # NumPy >= 2 (NEP 50): Python-float operands are "weak" -> cast to float32 before the ufunc.
+    clipped = np.clip(x, np.float32(-limit), np.float32(limit))
+    scale = np.float32(qmax / limit)  # float64 division, one rounding to float32
+    scaled = np.round(clipped * scale)  # float32 multiply, round-half-to-even
+    return np.clip(scaled, np.float32(-qmax), np.float32(qmax)).astype(dtype)
+
+
+def quantize_int8_global(x: np.ndarray, limit: float) -> np.ndarray:
+    """VectorDBInt8Global._quantize_to_int8 (VectorDBInt8Global.py:130-142)."""
+    return _global_quant(x, limit, 127.0, np.int8)
+
+
+def dequantize_int8_global(q: np.ndarray, limit: float) -> np.ndarray:
+    """VectorDBInt8Global._dequantize_int8 (VectorDBInt8Global.py:144-152)."""
+    return np.asarray(q, np.int8).astype(np.float32) * np.float32(float(limit) / 127.0)
+
+
+def quantize_int16_global(x: np.ndarray, limit: float) -> np.ndarray:
+    """VectorDBInt16Global._quantize_to_int16 (VectorDBInt16Global.py:130-142)."""
+    return _global_quant(x, limit, 32767.0, np.int16)
+
+
+def dequantize_int16_global(q: np.ndarray, limit: float) -> np.ndarray:
+    """VectorDBInt16Global._dequantize_int16 (VectorDBInt16Global.py:144-152)."""
+    return np.asarray(q, np.int16).astype(np.float32) * np.float32(float(limit) / 32767.0)
+
+
+def quantize_int4(x: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """VectorDBInt4._quantize_to_int4 (VectorDBInt4.py:116-154) == VectorDBInt4Global._quantize_to_int4
+    (VectorDBInt4Global.py:129-164; its ``limit`` argument is unused - SURVEY trap T2).
+
+    scale = float32(7.0 / float64(max(|min|,|max|))); s = clip(rint(x*scale), -8, 7); byte i =
+    ((s[2i]+8) << 4) | (s[2i+1]+8) stored as int8.  Odd D: the missing low nibble is 0.  max == min -> zeros.
+    Returns (packed int8[n,ceil(D/2)], min f64[n], max f64[n]).
+    """
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if x.ndim == 1:
+        p, lo, hi = quantize_int4(x[None])
+        return p[0], lo[0], hi[0]
+    n, d = x.shape
+    lo = x.min(axis=1).astype(np.float64)
+    hi = x.max(axis=1).astype(np.float64)
+    m = np.maximum(np.abs(lo), np.abs(hi))
+    const = lo == hi
+    with np.errstate(divide="ignore", invalid="ignore"):
+        scale = (7.0 / m).astype(np.float32)
+        s = np.clip(np.round(x * scale[:, None]), np.float32(-8), np.float32(7)).astype(np.int8)
+    u = (s.astype(np.int16) + 8).astype(np.uint8) & 0x0F
+    if d % 2:
+        u = np.concatenate([u, np.zeros((n, 1), np.uint8)], axis=1)
+    packed = ((u[:, 0::2] << 4) | u[:, 1::2]).astype(np.uint8).view(np.int8)
+    packed = packed.copy()
+    packed[const] = 0
+    return packed, lo, hi
+
+
+def _unpack_nibbles(packed: np.ndarray, length: int) -> np.ndarray:
+    u = np.asarray(packed, np.int8).view(np.uint8)
+    nib = np.empty(u.shape[:-1] + (u.shape[-1] * 2,), np.int64)
+    nib[..., 0::2] = u >> 4
+    nib[..., 1::2] = u & 0x0F
+    return nib[..., :length] - 8
+
+
+def dequantize_int4_perdoc(packed: np.ndarray, length: int, lo, hi) -> np.ndarray:
+    """VectorDBInt4._dequantize_int4 (VectorDBInt4.py:156-184), the NumPy-1.x intent (it raises
+    OverflowError under NumPy >= 2, SURVEY trap T8): out = float32( (nibble-8) * scale64 ),
+    scale64 = max(|min|,|max|)/7.0 in float64; zeros when max == min."""
+    packed = np.asarray(packed, np.int8)
+    if packed.ndim == 1:
+        return dequantize_int4_perdoc(packed[None], length, np.asarray([lo]), np.asarray([hi]))[0]
+    lo = np.asarray(lo, np.float64)
+    hi = np.asarray(hi, np.float64)
+    scale = np.maximum(np.abs(lo), np.abs(hi)) / 7.0
+    out = (_unpack_nibbles(packed, length).astype(np.float64) * scale[:, None]).astype(np.float32)
+    out[lo == hi] = 0
+    return out
+
+
+def dequantize_int4_global(packed: np.ndarray, length: int, limit: float) -> np.ndarray:
+    """VectorDBInt4Global._dequantize_int4 (VectorDBInt4Global.py:166-188): float32((nibble-8) * (limit/7.0));
+    no max==min short-circuit (an all-zero row dequantises to -8*limit/7 everywhere)."""
+    scale = float(limit) / 7.0
+    return (_unpack_nibbles(packed, length).astype(np.float64) * scale).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------
+# 1-bit codes
+# ----------------------------------------------------------------------------------------------
+
+
+def to_binary_f32(x: np.ndarray, ge: bool = False) -> np.ndarray:
+    """``_to_binary`` on float32 input (VectorDBInt8.py:140-146 and the four siblings):
+    packbits(x > mean(x)), np.mean = float32 pairwise sum / D; MSB-first bytes.
+    ge=True is CohereVectorDBBinary's ``>=`` (CohereVectorDBBinary.py:133-151, trap T10)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if x.ndim == 1:
+        return to_binary_f32(x[None], ge)[0]
+    mean = x.mean(axis=1, keepdims=True)  # C-contiguous rows: per-row pairwise tree == 1-D np.mean (tested)
+    bits = (x >= mean) if ge else (x > mean)
+    return np.packbits(bits, axis=1)
+
+
+def to_binary_int(x: np.ndarray, ge: bool = False) -> np.ndarray:
+    """``_to_binary`` on int8 / int16 input (CohereVectorDBInt8.py:130-135, VectorDBInt16.py:148-157,
+    CohereEnhancedVectorDB.py:130-134): np.mean of an integer vector is the float64 of an exact integer sum,
+    so x > mean  <=>  D*x > sum(x) in integers."""
+    x = np.ascontiguousarray(x)
+    assert x.dtype in (np.int8, np.int16)
+    if x.ndim == 1:
+        return to_binary_int(x[None], ge)[0]
+    mean = x.mean(axis=1, keepdims=True)
+    bits = (x >= mean) if ge else (x > mean)
+    return np.packbits(bits, axis=1)
+
+
+def pairwise_sum_f32(a: np.ndarray) -> np.float32:
+    """Explicit restatement of NumPy's float32 pairwise summation (numpy/_core/src/umath/loops_utils.h.src,
+    ``@TYPE@_pairwise_sum``) for a contiguous 1-D array - what ``np.mean`` / ``np.add.reduce`` run.
+    Used to pin the tree the CUDA kernel must reproduce."""
+    a = np.asarray(a, np.float32)
+    n = a.shape[0]
+    if n < 8:
+        r = np.float32(0.0) if n == 0 else np.float32(-0.0)
+        # numpy starts from -0.0 so that sum([-0.0]) == -0.0; for n == 0 reduce returns identity 0.0
+        for v in a:
+            r = np.float32(r + v)
+        return r
+    if n <= 128:
+        r = [np.float32(a[j]) for j in range(8)]
+        i = 8
+        while i < n - (n % 8):
+            for j in range(8):
+                r[j] = np.float32(r[j] + a[i + j])
+            i += 8
+        res = np.float32(np.float32(np.float32(r[0] + r[1]) + np.float32(r[2] + r[3]))
+                         + np.float32(np.float32(r[4] + r[5]) + np.float32(r[6] + r[7])))
+        while i < n:
+            res = np.float32(res + a[i])
+            i += 1
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return np.float32(pairwise_sum_f32(a[:n2]) + pairwise_sum_f32(a[n2:]))
+
+
+# ----------------------------------------------------------------------------------------------
+# Phase I: Hamming top-k (faiss IndexBinaryFlat.search semantics)
+# ----------------------------------------------------------------------------------------------
+
+
+def hamming_distances(codes: np.ndarray, q: np.ndarray) -> np.ndarray:
+    """int32[nq, N] popcount(q XOR code)."""
+    codes = np.ascontiguousarray(codes, np.uint8)
+    q = np.ascontiguousarray(q, np.uint8)
+    if q.ndim == 1:
+        q = q[None]
+    cb = codes.shape[1]
+    out = np.empty((q.shape[0], codes.shape[0]), np.int32)
+    if cb % 8 == 0:
+        c64 = codes.view(np.uint64)
+        q64 = q.view(np.uint64)
+        for i in range(q.shape[0]):
+            out[i] = np.bitwise_count(c64 ^ q64[i]).sum(axis=1, dtype=np.int32)
+    else:
+        for i in range(q.shape[0]):
+            out[i] = np.bitwise_count(codes ^ q[i]).sum(axis=1, dtype=np.int32)
+    return out
+
+
+def hamming_topk(codes: np.ndarray, q: np.ndarray, k: int, pos_base: int = 0,
+                 chunk: int = 1 << 20) -> Tuple[np.ndarray, np.ndarray]:
+    """faiss ``IndexBinaryFlat.search`` (called at CohereEnhancedVectorDB.py:268, VectorDBInt8.py:218 ...):
+    the k smallest codes under the key (distance, position), ascending; N < k pads with (INT32_MAX, -1).
+    Returns (dist int32[nq,k], pos int64[nq,k]) with pos = pos_base + row index."""
+    codes = np.ascontiguousarray(codes, np.uint8)
+    q = np.ascontiguousarray(q, np.uint8)
+    if q.ndim == 1:
+        q = q[None]
+    n = codes.shape[0]
+    nq = q.shape[0]
+    dist = np.full((nq, k), INT32_MAX, np.int32)
+    pos = np.full((nq, k), -1, np.int64)
+    best = [np.empty(0, np.int64) for _ in range(nq)]
+    for s in range(0, n, chunk):
+        d = hamming_distances(codes[s:s + chunk], q).astype(np.int64)
+        p = np.arange(s, s + d.shape[1], dtype=np.int64) + pos_base
+        for i in range(nq):
+            key = np.concatenate([best[i], (d[i] << 40) | p])
+            if key.shape[0] > k:
+                key = np.partition(key, k - 1)[:k]
+            best[i] = key
+    for i in range(nq):
+        key = np.sort(best[i])
+        m = key.shape[0]
+        dist[i, :m] = (key >> 40).astype(np.int32)
+        pos[i, :m] = key & ((1 << 40) - 1)
+    return dist, pos
+
+
+# ----------------------------------------------------------------------------------------------
+# Phase II / III rescoring and the 2-phase rescoring of the VectorDB* classes
+# ----------------------------------------------------------------------------------------------
+
+
+def rescore_binary(q_float: np.ndarray, cand_codes: np.ndarray, literal: bool = True) -> np.ndarray:
+    """Phase II (CohereEnhancedVectorDB.py:283-293): float(q.dot(2*unpackbits(code).astype(int32)-1)),
+    float32 . int32 promotes to a float64 dot.  q_float f32[D], cand_codes u8[m, D/8] -> f64[m]."""
+    q_float = np.asarray(q_float, np.float32)
+    cand_codes = np.asarray(cand_codes, np.uint8)
+    if literal:
+        out = np.empty(cand_codes.shape[0], np.float64)
+        for i, c in enumerate(cand_codes):
+            u = np.unpackbits(c, axis=-1).astype(np.int32)
+            u = 2 * u - 1
+            out[i] = float(q_float.dot(u))
+        return out
+    u = 2.0 * np.unpackbits(cand_codes, axis=1).astype(np.float64) - 1.0
+    return u @ q_float.astype(np.float64)
+
+
+def rescore_int8cos(q_float: np.ndarray, cand_int8: np.ndarray, literal: bool = True) -> np.ndarray:
+    """Phase III (CohereEnhancedVectorDB.py:302-318): float(q.dot(d_int8)) / np.linalg.norm(d_int8);
+    the dot is float32 (BLAS sdot), the norm float64, the divide float64; -inf when the norm is 0.
+    NOT a cosine: never divided by |q| (trap T5)."""
+    q_float = np.asarray(q_float, np.float32)
+    cand_int8 = np.asarray(cand_int8, np.int8)
+    out = np.empty(cand_int8.shape[0], np.float64)
+    if literal:
+        for i, d in enumerate(cand_int8):
+            nrm = np.linalg.norm(d)
+            out[i] = -np.inf if nrm == 0 else float(q_float.dot(d)) / nrm
+        return out
+    nrm = np.sqrt((cand_int8.astype(np.int64) ** 2).sum(axis=1).astype(np.float64))
+    dot = cand_int8.astype(np.float64) @ q_float.astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out = np.where(nrm == 0, -np.inf, dot / nrm)
+    return out
+
+
+def rescore_int8cos_absfloor(q_float: np.ndarray, cand_int8: np.ndarray) -> np.ndarray:
+    """Bound on the float32-accumulation error of the reference's sdot, 4 * 2^-24 * sum|q_i d_i| / |d|
+    (SURVEY H7): the absolute floor added to the 1e-5 relative gate in the parity tests."""
+    q = np.abs(np.asarray(q_float, np.float64))
+    d = np.abs(np.asarray(cand_int8, np.float64))
+    nrm = np.sqrt((d * d).sum(axis=1))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(nrm == 0, 0.0, 4.0 * 2.0 ** -24 * (d @ q) / nrm)
+
+
+def search3(codes: np.ndarray, ids: np.ndarray, int8_rows, q_float: np.ndarray, q_ubinary: np.ndarray,
+            k: int = 10, binary_oversample: int = 10, int8_oversample: int = 3,
+            literal: bool = True, pos_base: int = 0) -> List[dict]:
+    """CohereEnhancedVectorDB.search (CohereEnhancedVectorDB.py:247-322) for ONE query, on arrays.
+
+    ``int8_rows`` is either an int8[N, D] array indexed by position or a callable positions -> int8[m, D].
+    Returns the reference's list of dicts (doc_id, score_hamming, score_binary, score_cosine) plus 'pos'.
+    """
+    n = codes.shape[0]
+    if n == 0:
+        return []
+    binary_k = min(k * binary_oversample, n)
+    dist, pos = hamming_topk(codes, q_ubinary, binary_k, pos_base=0)
+    hits = [{"doc_id": int(ids[p]), "pos": int(p) + pos_base, "score_hamming": int(d)}
+            for d, p in zip(dist[0], pos[0]) if p != -1]
+    hits.sort(key=lambda h: h["score_hamming"])  # stable (:274)
+    cand = hits[:k * binary_oversample]
+    if not cand:
+        return []
+    p = np.array([h["pos"] - pos_base for h in cand], np.int64)
+    sb = rescore_binary(q_float, codes[p], literal)
+    for h, s in zip(cand, sb):
+        h["score_binary"] = float(s)
+    cand.sort(key=lambda h: h["score_binary"], reverse=True)  # stable (:296)
+    resc = cand[:k * int8_oversample]
+    p = np.array([h["pos"] - pos_base for h in resc], np.int64)
+    rows = int8_rows(p) if callable(int8_rows) else int8_rows[p]
+    sc = rescore_int8cos(q_float, rows, literal)
+    for h, s in zip(resc, sc):
+        h["score_cosine"] = float(s)
+    resc.sort(key=lambda h: h["score_cosine"], reverse=True)  # stable (:321)
+    return resc[:k]
+
+
+def search2(codes: np.ndarray, ids: np.ndarray, doc_emb_f32_rows, q_float: np.ndarray, q_ubinary: np.ndarray,
+            k: int = 10, binary_oversample: int = 10) -> List[dict]:
+    """The 2-phase search of the six VectorDB* classes (VectorDBInt8.py:203-242): Hamming top
+    min(k*oversample, ntotal), then float32 np.dot(q, doc_emb) for EVERY hit (no re-sort of phase-I hits),
+    stable sort descending, [:k].  ``doc_emb_f32_rows``: callable positions -> f32[m, D] (already dequantised
+    or the original float32 rows for compare_float32=True)."""
+    n = codes.shape[0]
+    if n == 0:
+        return []
+    binary_k = min(k * binary_oversample, n)
+    dist, pos = hamming_topk(codes, q_ubinary, binary_k)
+    keep = pos[0] != -1
+    p = pos[0][keep]
+    emb = doc_emb_f32_rows(p)
+    q_float = np.asarray(q_float, np.float32)
+    hits = [{"doc_id": int(ids[pp]), "pos": int(pp), "score": float(np.dot(q_float, e))} for pp, e in zip(p, emb)]
+    hits.sort(key=lambda h: h["score"], reverse=True)
+    return hits[:k]
+
+
+def merge_shard_results(shard_hits: Sequence[Sequence[dict]], k: int, binary_oversample: int,
+                        int8_oversample: int) -> List[dict]:
+    """Multi-GPU merge rule, restated on lists of per-shard candidate dicts that
+    already carry score_hamming / score_binary / score_cosine and a GLOBAL 'pos': global phase-I cut by
+    (hamming, pos), stable sort by score_binary desc, cut, stable sort by score_cosine desc, cut.
+    Equals ``search3`` run on the concatenated shards (scores are pure functions of (query, document))."""
+    allh = [dict(h) for hs in shard_hits for h in hs]
+    allh.sort(key=lambda h: (h["score_hamming"], h["pos"]))
+    cand = allh[:k * binary_oversample]
+    cand.sort(key=lambda h: h["score_binary"], reverse=True)
+    resc = cand[:k * int8_oversample]
+    resc.sort(key=lambda h: h["score_cosine"], reverse=True)
+    return resc[:k]
+
+
+# ----------------------------------------------------------------------------------------------
+# On-disk formats
+# ----------------------------------------------------------------------------------------------
+
+
+def write_index_binary_bytes(d: int, codes: np.ndarray, ids: np.ndarray) -> bytes:
+    """faiss.write_index_binary of IndexBinaryIDMap2(IndexBinaryFlat(d)) (CohereEnhancedVectorDB.py:346):
+    layout probed on the reference's eight committed index.bin files."""
+    codes = np.ascontiguousarray(codes, np.uint8)
+    ids = np.ascontiguousarray(ids, np.int64)
+    n = codes.shape[0]
+    cs = d // 8
+    hdr = struct.pack("<iiqBi", d, cs, n, 1, 1)
+    return (b"IBM2" + hdr + b"IBxF" + hdr + struct.pack("<Q", n * cs) + codes.tobytes()
+            + struct.pack("<Q", n) + ids.tobytes())
+
+
+def read_index_binary_bytes(b: bytes) -> Tuple[int, np.ndarray, np.ndarray]:
+    """faiss.read_index_binary (CohereEnhancedVectorDB.py:123) for the same layout."""
+    assert b[0:4] == b"IBM2" and b[25:29] == b"IBxF", "not an IndexBinaryIDMap2(IndexBinaryFlat) file"
+    d, cs, n = struct.unpack_from("<iiq", b, 4)
+    nbytes = struct.unpack_from("<Q", b, 50)[0]
+    codes = np.frombuffer(b, np.uint8, nbytes, 58).reshape(n, cs).copy()
+    nid = struct.unpack_from("<Q", b, 58 + nbytes)[0]
+    ids = np.frombuffer(b, np.int64, nid, 66 + nbytes).copy()
+    return d, codes, ids
+
+
+def config_json(model: str, embedding_dim: int, global_limit: Optional[float] = None) -> str:
+    """config.json as written by the reference (VectorDBInt8.py:54-56, VectorDBInt8Global.py:62-69)."""
+    cfg = {"version": "1.0", "model": model, "embedding_dim": embedding_dim}
+    if global_limit is not None:
+        cfg["global_limit"] = global_limit
+    return json.dumps(cfg)
+
+
+# ----------------------------------------------------------------------------------------------
+# Counter-based synthetic data (no network -> no Cohere / Ollama embeddings)
+# ----------------------------------------------------------------------------------------------
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _splitmix64(z: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        z = (z + np.uint64(0x9E3779B97F4A7C15))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def synth_f32(seed: int, row0: int, nrows: int, d: int = 1024, row_scale: bool = False) -> np.ndarray:
+    """x[r, c] = (S(h) - 131070 + m_c) * 2^-20 [* 2^((h_r & 3) - 1)],  h = splitmix64(seed*K + r*d + c),
+    S = sum of the four 16-bit fields of h (Irwin-Hall, sigma 0.0361), m_c = a fixed per-column offset in
+    [-16384, 16383] shared by every seed (real embeddings share a mean direction).  All integer arithmetic,
+    exactly representable in float32, identical on CPU and GPU."""
+    with np.errstate(over="ignore"):
+        r = np.arange(row0, row0 + nrows, dtype=np.uint64)[:, None]
+        c = np.arange(d, dtype=np.uint64)[None, :]
+        base = np.uint64(seed) * np.uint64(0xD1342543DE82EF95)
+        h = _splitmix64(base + r * np.uint64(d) + c)
+        s = ((h & np.uint64(0xFFFF)) + ((h >> np.uint64(16)) & np.uint64(0xFFFF))
+             + ((h >> np.uint64(32)) & np.uint64(0xFFFF)) + (h >> np.uint64(48))).astype(np.int64)
+        mc = (_splitmix64(c ^ np.uint64(0xC01DBEEFCAFEF00D)) & np.uint64(0x7FFF)).astype(np.int64) - 16384
+        v = (s - 131070 + mc).astype(np.float32) * np.float32(2.0 ** -20)
+        if row_scale:
+            hr = _splitmix64(base ^ (r + np.uint64(0x5851F42D4C957F2D)))
+            e = (hr & np.uint64(3)).astype(np.int64) - 1
+            v = v * np.exp2(e.astype(np.float32))
+    return v
+
+
+def synth_int8_from_f32(x: np.ndarray) -> np.ndarray:
+    """Cohere-like int8 of a synthetic float row: clip(rint(1259*x - 0.69), -128, 127) (SURVEY trap T4)."""
+    t = np.asarray(x, np.float32) * np.float32(1259.0)
+    t = t - np.float32(0.69)
+    return np.clip(np.rint(t), np.float32(-128), np.float32(127)).astype(np.int8)
+
+
+def synth_ubinary_from_f32(x: np.ndarray) -> np.ndarray:
+    """Cohere-like ubinary of a synthetic float row: packbits(x > 0) (SURVEY trap T4)."""
+    return np.packbits(np.asarray(x, np.float32) > 0, axis=-1)
