@@ -1,0 +1,11 @@
+"""B200-native quantise + multi-phase search path of aitrailblazer/VectorRAGQuantization.
+
+Host side (this package) mirrors the reference's Python class API; every array operation on the hot path runs in
+hand-written sm_100a CUDA kernels behind the C ABI in ``include/vrq.h`` (``libvrq.so``, bound with ctypes).
+There is no CPU fallback: without the built library or without a GPU the first kernel call raises ``VrqError``.
+"""
+from ._lib import Context, VrqError, default_context  # noqa: F401
+from .binary_index import (BinaryIndex, IndexBinaryFlat, IndexBinaryIDMap2, read_index_binary,  # noqa: F401
+                           write_index_binary)
+
+__version__ = "0.1.0"

@@ -1,0 +1,525 @@
+// Quantise / dequantise / 1-bit-code kernels (sm_100a).
+//
+// Every encoder is ONE pass over x: a warp owns a row, pulls it with 128-bit coalesced streaming loads, reduces
+// min/max/sum with warp shuffles, and writes the quantised row (+ the packbits code) with full-line stores.
+// HBM-bound: 4096 B read + {1024, 2048, 512} (+128) B written per 1024-d row.
+//
+// Bit-exactness contract: all float ops are single IEEE roundings (__fmul_rn / __fadd_rn /
+// __fdiv_rn, no FMA contraction, file compiled with --fmad=false as a second fence); np.mean's float32 pairwise
+// summation tree is reproduced add for add (A.2).
+#include <math.h>
+
+#include "vrq_internal.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+struct EncParams {
+    const float* x;
+    int64_t n;
+    int d;
+    float lim;    // np.float32(limit)
+    float scale;  // np.float32(qmax/limit)
+    void* q;
+    void* mn;
+    void* mx;
+    uint8_t* ubin;
+    int ge;
+};
+
+// ---- per-element quantisers --------------------------------------------------------------------------
+template <int CODEC>
+struct RowScale {
+    float scale;
+    bool constant;
+};
+
+__device__ __forceinline__ int q_perdoc8(float v, float scale) {
+    return __float2int_rz(__fmul_rn(v, scale));  // astype(int8) truncates (VectorDBInt8.py:126)
+}
+__device__ __forceinline__ int q_global(float v, float lim, float scale, float qmax) {
+    float c = fminf(fmaxf(v, -lim), lim);       // np.clip(x, -limit, limit)
+    float s = rintf(__fmul_rn(c, scale));       // np.round: half to even
+    s = fminf(fmaxf(s, -qmax), qmax);           // np.clip(., -qmax, qmax)
+    return __float2int_rz(s);
+}
+__device__ __forceinline__ int q_int4(float v, float scale) {
+    float s = rintf(__fmul_rn(v, scale));
+    s = fminf(fmaxf(s, -8.f), 7.f);
+    return (__float2int_rz(s) + 8) & 0xF;
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// =====================================================================================================
+// Fast path, d == 1024.  Lane l holds elements 128*j + 4*l .. +3 of the row for j = 0..7 (8 x LDG.128).
+// =====================================================================================================
+constexpr int ROW_PAD = 136;  // floats per 128-element block in shared memory (8 floats of padding)
+
+template <int CODEC, bool UBIN>
+__global__ void __launch_bounds__(256) encode1024_kernel(EncParams p) {
+    __shared__ __align__(16) float sbuf[UBIN ? 8 : 1][UBIN ? 8 * ROW_PAD : 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * 8;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < p.n; row += stride) {
+        const float4* src = reinterpret_cast<const float4*>(p.x + row * 1024);
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = ldg_stream_f4(src + j * 32 + lane);
+
+        // ---- np.mean(x) with NumPy's pairwise tree ----------------------------------
+        // 8 blocks of 128; inside a block 8 strided accumulators r[jj] += x[128b + 8s + jj], s = 0..15 in order;
+        // block = ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); total = ((B0+B1)+(B2+B3))+((B4+B5)+(B6+B7)).
+        // The row is transposed through padded shared memory so that lane (b = l/4, jp = l%4) owns the two
+        // sequential chains jj = 2jp, 2jp+1 of block b (conflict-free LDS.64), then combined with xor-shuffles.
+        float mean = 0.f;
+        if (UBIN) {
+            float* sb = sbuf[warp];
+#pragma unroll
+            for (int j = 0; j < 8; j++) *reinterpret_cast<float4*>(sb + ROW_PAD * j + 4 * lane) = v[j];
+            __syncwarp();
+            const int b = lane >> 2, jp = lane & 3;
+            const float2* cp = reinterpret_cast<const float2*>(sb + ROW_PAD * b + 2 * jp);
+            float2 e = cp[0];
+            float r0 = e.x, r1 = e.y;
+#pragma unroll
+            for (int s = 1; s < 16; s++) {
+                e = cp[4 * s];
+                r0 = __fadd_rn(r0, e.x);
+                r1 = __fadd_rn(r1, e.y);
+            }
+            float t = __fadd_rn(r0, r1);
+            t = __fadd_rn(t, __shfl_xor_sync(FULL, t, 1));
+            t = __fadd_rn(t, __shfl_xor_sync(FULL, t, 2));
+            t = __fadd_rn(t, __shfl_xor_sync(FULL, t, 4));
+            t = __fadd_rn(t, __shfl_xor_sync(FULL, t, 8));
+            t = __fadd_rn(t, __shfl_xor_sync(FULL, t, 16));
+            mean = __fdiv_rn(t, 1024.f);
+            __syncwarp();
+        }
+
+        // ---- per-row statistics ---------------------------------------------------------------------
+        float scale = p.scale;
+        bool constant = false;
+        if (CODEC == VRQ_CODEC_INT8_PERDOC || CODEC == VRQ_CODEC_INT4) {
+            float lo = v[0].x, hi = v[0].x;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                lo = fminf(fminf(fminf(lo, v[j].x), fminf(v[j].y, v[j].z)), v[j].w);
+                hi = fmaxf(fmaxf(fmaxf(hi, v[j].x), fmaxf(v[j].y, v[j].z)), v[j].w);
+            }
+            lo = warp_min(lo);
+            hi = warp_max(hi);
+            constant = (lo == hi);
+            const float m = fmaxf(fabsf(lo), fabsf(hi));
+            if (CODEC == VRQ_CODEC_INT8_PERDOC) {
+                scale = __fdiv_rn(127.f, m);  // np.float32 division (VectorDBInt8.py:125)
+                if (lane == 0) {
+                    if (p.mn) static_cast<float*>(p.mn)[row] = lo;
+                    if (p.mx) static_cast<float*>(p.mx)[row] = hi;
+                }
+            } else {
+                scale = (float)(7.0 / (double)m);  // Python float division, then cast (VectorDBInt4.py:136)
+                if (lane == 0) {
+                    if (p.mn) static_cast<double*>(p.mn)[row] = (double)lo;
+                    if (p.mx) static_cast<double*>(p.mx)[row] = (double)hi;
+                }
+            }
+        }
+
+        // ---- quantise + store -----------------------------------------------------------------------
+        if (CODEC == VRQ_CODEC_INT8_PERDOC || CODEC == VRQ_CODEC_INT8_GLOBAL) {
+            uint32_t* dst = static_cast<uint32_t*>(p.q) + row * 256;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                int a, b, c, d;
+                if (CODEC == VRQ_CODEC_INT8_PERDOC) {
+                    a = q_perdoc8(v[j].x, scale), b = q_perdoc8(v[j].y, scale);
+                    c = q_perdoc8(v[j].z, scale), d = q_perdoc8(v[j].w, scale);
+                } else {
+                    a = q_global(v[j].x, p.lim, scale, 127.f), b = q_global(v[j].y, p.lim, scale, 127.f);
+                    c = q_global(v[j].z, p.lim, scale, 127.f), d = q_global(v[j].w, p.lim, scale, 127.f);
+                }
+                uint32_t w = (a & 0xFF) | ((b & 0xFF) << 8) | ((c & 0xFF) << 16) | ((uint32_t)(d & 0xFF) << 24);
+                dst[j * 32 + lane] = constant ? 0u : w;
+            }
+        } else if (CODEC == VRQ_CODEC_INT16_GLOBAL) {
+            uint2* dst = static_cast<uint2*>(p.q) + row * 256;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                int a = q_global(v[j].x, p.lim, scale, 32767.f), b = q_global(v[j].y, p.lim, scale, 32767.f);
+                int c = q_global(v[j].z, p.lim, scale, 32767.f), d = q_global(v[j].w, p.lim, scale, 32767.f);
+                uint2 w;
+                w.x = (a & 0xFFFF) | ((uint32_t)(b & 0xFFFF) << 16);
+                w.y = (c & 0xFFFF) | ((uint32_t)(d & 0xFFFF) << 16);
+                dst[j * 32 + lane] = w;
+            }
+        } else if (CODEC == VRQ_CODEC_INT4) {
+            uint16_t* dst = static_cast<uint16_t*>(p.q) + row * 256;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t b0 = (q_int4(v[j].x, scale) << 4) | q_int4(v[j].y, scale);
+                uint32_t b1 = (q_int4(v[j].z, scale) << 4) | q_int4(v[j].w, scale);
+                dst[j * 32 + lane] = constant ? (uint16_t)0 : (uint16_t)(b0 | (b1 << 8));
+            }
+        }
+
+        // ---- np.packbits(x > mean): MSB-first; lane l owns nibble (l odd: low, l even: high) of byte 16j + l/2 ----
+        if (UBIN) {
+            uint32_t nibs = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                uint32_t nb;
+                if (p.ge)
+                    nb = ((v[j].x >= mean) << 3) | ((v[j].y >= mean) << 2) | ((v[j].z >= mean) << 1) | (v[j].w >= mean);
+                else
+                    nb = ((v[j].x > mean) << 3) | ((v[j].y > mean) << 2) | ((v[j].z > mean) << 1) | (v[j].w > mean);
+                nibs |= nb << (4 * j);
+            }
+            // lane (8m + j') assembles 32-bit word 4j' + m of the 128-byte code from the 8 lanes of its group
+            const int jsel = lane & 7, grp = lane & 24;
+            uint32_t word = 0;
+#pragma unroll
+            for (int s = 0; s < 8; s++) {
+                uint32_t ns = __shfl_sync(FULL, nibs, grp + s);
+                uint32_t nb = (ns >> (4 * jsel)) & 0xF;
+                word |= nb << (8 * (s >> 1) + ((s & 1) ? 0 : 4));
+            }
+            reinterpret_cast<uint32_t*>(p.ubin + row * 128)[4 * jsel + (lane >> 3)] = word;
+        }
+    }
+}
+
+// =====================================================================================================
+// Generic path: any d with d % 8 == 0, 8 <= d <= 8192.  One warp per row, the row staged in shared memory,
+// np.mean's recursion (split at n/2 rounded down to a multiple of 8 until n <= 128) evaluated leaf by leaf.
+// =====================================================================================================
+constexpr int GEN_WARPS = 4;
+constexpr int GEN_MAX_D = 8192;
+constexpr int GEN_MAX_LEAVES = GEN_MAX_D / 64;
+
+__device__ void enum_leaves(int off, int n, int* loff, int* llen, int& cnt) {
+    if (n <= 128) {
+        loff[cnt] = off;
+        llen[cnt] = n;
+        cnt++;
+        return;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    enum_leaves(off, n2, loff, llen, cnt);
+    enum_leaves(off + n2, n - n2, loff, llen, cnt);
+}
+__device__ float combine_leaves(const float* leaf, int& idx, int n) {
+    if (n <= 128) return leaf[idx++];
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    float a = combine_leaves(leaf, idx, n2);
+    float b = combine_leaves(leaf, idx, n - n2);
+    return __fadd_rn(a, b);
+}
+
+template <int CODEC, bool UBIN>
+__global__ void __launch_bounds__(GEN_WARPS * 32) encode_generic_kernel(EncParams p) {
+    extern __shared__ __align__(16) float dyn[];
+    __shared__ int loff[GEN_MAX_LEAVES], llen[GEN_MAX_LEAVES];
+    __shared__ int nleaves;
+    __shared__ float leafsum[GEN_WARPS][GEN_MAX_LEAVES];
+    const int d = p.d;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* row_s = dyn + (size_t)warp * d;
+    if (threadIdx.x == 0) {
+        int c = 0;
+        enum_leaves(0, d, loff, llen, c);
+        nleaves = c;
+    }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * GEN_WARPS;
+    for (int64_t row = (int64_t)blockIdx.x * GEN_WARPS + warp; row < p.n; row += stride) {
+        const float4* src = reinterpret_cast<const float4*>(p.x + row * d);
+        for (int c = lane; c < d / 4; c += 32) reinterpret_cast<float4*>(row_s)[c] = ldg_stream_f4(src + c);
+        __syncwarp();
+        float mean = 0.f;
+        if (UBIN) {
+            const int g = lane >> 3, j8 = lane & 7;
+            for (int l0 = 0; l0 < nleaves; l0 += 4) {
+                const int l = l0 + g;
+                const bool act = l < nleaves;
+                const int off = act ? loff[l] : 0, len = act ? llen[l] : 8;
+                float r = row_s[off + j8];
+                for (int i = 8; i < len; i += 8) r = __fadd_rn(r, row_s[off + i + j8]);
+                r = __fadd_rn(r, __shfl_xor_sync(FULL, r, 1));
+                r = __fadd_rn(r, __shfl_xor_sync(FULL, r, 2));
+                r = __fadd_rn(r, __shfl_xor_sync(FULL, r, 4));
+                if (act && j8 == 0) leafsum[warp][l] = r;
+            }
+            __syncwarp();
+            float s = 0.f;
+            if (lane == 0) {
+                int idx = 0;
+                s = combine_leaves(leafsum[warp], idx, d);
+            }
+            s = __shfl_sync(FULL, s, 0);
+            mean = __fdiv_rn(s, (float)d);
+        }
+        float scale = p.scale;
+        bool constant = false;
+        if (CODEC == VRQ_CODEC_INT8_PERDOC || CODEC == VRQ_CODEC_INT4) {
+            float lo = row_s[0], hi = row_s[0];
+            for (int c = lane; c < d; c += 32) {
+                lo = fminf(lo, row_s[c]);
+                hi = fmaxf(hi, row_s[c]);
+            }
+            lo = warp_min(lo);
+            hi = warp_max(hi);
+            constant = (lo == hi);
+            const float m = fmaxf(fabsf(lo), fabsf(hi));
+            if (CODEC == VRQ_CODEC_INT8_PERDOC) {
+                scale = __fdiv_rn(127.f, m);
+                if (lane == 0) {
+                    if (p.mn) static_cast<float*>(p.mn)[row] = lo;
+                    if (p.mx) static_cast<float*>(p.mx)[row] = hi;
+                }
+            } else {
+                scale = (float)(7.0 / (double)m);
+                if (lane == 0) {
+                    if (p.mn) static_cast<double*>(p.mn)[row] = (double)lo;
+                    if (p.mx) static_cast<double*>(p.mx)[row] = (double)hi;
+                }
+            }
+        }
+        if (CODEC == VRQ_CODEC_INT8_PERDOC || CODEC == VRQ_CODEC_INT8_GLOBAL) {
+            int8_t* dst = static_cast<int8_t*>(p.q) + row * d;
+            for (int c = lane; c < d; c += 32) {
+                int a = (CODEC == VRQ_CODEC_INT8_PERDOC) ? q_perdoc8(row_s[c], scale)
+                                                         : q_global(row_s[c], p.lim, scale, 127.f);
+                dst[c] = constant ? (int8_t)0 : (int8_t)a;
+            }
+        } else if (CODEC == VRQ_CODEC_INT16_GLOBAL) {
+            int16_t* dst = static_cast<int16_t*>(p.q) + row * d;
+            for (int c = lane; c < d; c += 32) dst[c] = (int16_t)q_global(row_s[c], p.lim, scale, 32767.f);
+        } else if (CODEC == VRQ_CODEC_INT4) {
+            uint8_t* dst = static_cast<uint8_t*>(p.q) + row * (d / 2);
+            for (int c = lane; c < d / 2; c += 32) {
+                uint32_t b = (q_int4(row_s[2 * c], scale) << 4) | q_int4(row_s[2 * c + 1], scale);
+                dst[c] = constant ? (uint8_t)0 : (uint8_t)b;
+            }
+        }
+        if (UBIN) {
+            uint8_t* dst = p.ubin + row * (d / 8);
+            for (int b = lane; b < d / 8; b += 32) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    float e = row_s[8 * b + j];
+                    v = (v << 1) | (uint32_t)(p.ge ? (e >= mean) : (e > mean));
+                }
+                dst[b] = (uint8_t)v;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- _to_binary on int8 / int16 rows: exact integer form d*x > sum(x) -----------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) to_binary_int_kernel(const T* __restrict__ x, int64_t n, int d, int ge,
+                                                            uint8_t* __restrict__ ubin) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * 8;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < n; row += stride) {
+        const T* src = x + row * d;
+        int s = 0;
+        for (int c = lane; c < d; c += 32) s += (int)src[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        uint8_t* dst = ubin + row * (d / 8);
+        for (int b = lane; b < d / 8; b += 32) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                int e = (int)src[8 * b + j] * d;
+                v = (v << 1) | (uint32_t)(ge ? (e >= s) : (e > s));
+            }
+            dst[b] = (uint8_t)v;
+        }
+    }
+}
+
+// ---- dequantisers (elementwise) ------------------------------------------------------------------------
+struct DeqParams {
+    int kind;
+    const void* q;
+    int64_t n;
+    int d;
+    const void* mn;
+    const void* mx;
+    float scale_f32;   // global kinds: np.float32(limit / qmax)
+    double scale_f64;  // INT4_GLOBAL: limit / 7.0
+    float* out;
+};
+
+__global__ void __launch_bounds__(256) dequant_kernel(DeqParams p) {
+    const int64_t total = p.n * (int64_t)p.d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = e / p.d;
+        const int col = (int)(e - row * p.d);
+        float r;
+        switch (p.kind) {
+            case VRQ_PAYLOAD_INT8_PERDOC: {
+                float lo = static_cast<const float*>(p.mn)[row], hi = static_cast<const float*>(p.mx)[row];
+                float sc = __fdiv_rn(fmaxf(fabsf(lo), fabsf(hi)), 127.f);
+                r = (lo == hi) ? 0.f : __fmul_rn((float)static_cast<const int8_t*>(p.q)[e], sc);
+                break;
+            }
+            case VRQ_PAYLOAD_INT8_GLOBAL:
+                r = __fmul_rn((float)static_cast<const int8_t*>(p.q)[e], p.scale_f32);
+                break;
+            case VRQ_PAYLOAD_INT16_GLOBAL:
+                r = __fmul_rn((float)static_cast<const int16_t*>(p.q)[e], p.scale_f32);
+                break;
+            case VRQ_PAYLOAD_INT4_PERDOC:
+            case VRQ_PAYLOAD_INT4_GLOBAL: {
+                uint8_t byte = static_cast<const uint8_t*>(p.q)[row * (p.d / 2) + (col >> 1)];
+                int nib = (col & 1) ? (byte & 0xF) : (byte >> 4);
+                double sc = p.scale_f64;
+                bool zero = false;
+                if (p.kind == VRQ_PAYLOAD_INT4_PERDOC) {
+                    double lo = static_cast<const double*>(p.mn)[row], hi = static_cast<const double*>(p.mx)[row];
+                    sc = fmax(fabs(lo), fabs(hi)) / 7.0;
+                    zero = (lo == hi);
+                }
+                r = zero ? 0.f : (float)__dmul_rn((double)(nib - 8), sc);
+                break;
+            }
+            default:
+                r = 0.f;
+        }
+        p.out[e] = r;
+    }
+}
+
+template <int CODEC>
+int launch_codec(vrq_ctx* ctx, const EncParams& p, cudaStream_t st) {
+    const bool ub = p.ubin != nullptr;
+    if (p.d == 1024) {
+        int64_t blocks = (p.n + 7) / 8;
+        int64_t cap = (int64_t)ctx->sm_count * 6;
+        int grid = (int)(blocks < cap ? blocks : cap);
+        if (ub)
+            encode1024_kernel<CODEC, true><<<grid, 256, 0, st>>>(p);
+        else
+            encode1024_kernel<CODEC, false><<<grid, 256, 0, st>>>(p);
+    } else {
+        size_t smem = (size_t)GEN_WARPS * p.d * sizeof(float);
+        auto kt = encode_generic_kernel<CODEC, true>;
+        auto kf = encode_generic_kernel<CODEC, false>;
+        if (smem > 40 * 1024) {
+            VRQ_CUDA(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            VRQ_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        int64_t blocks = (p.n + GEN_WARPS - 1) / GEN_WARPS;
+        int64_t cap = (int64_t)ctx->sm_count * 8;
+        int grid = (int)(blocks < cap ? blocks : cap);
+        if (ub)
+            kt<<<grid, GEN_WARPS * 32, smem, st>>>(p);
+        else
+            kf<<<grid, GEN_WARPS * 32, smem, st>>>(p);
+    }
+    vrq_count_launch(ctx);
+    VRQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int vrq_launch_encode(vrq_ctx* ctx, const vrq_encode_args& a, cudaStream_t st) {
+    if (a.n == 0) return 0;
+    if (a.d % 8 != 0 || a.d < 8) {
+        vrq_set_error("embedding_dim must be a positive multiple of 8 (got %d)", a.d);
+        return VRQ_ERR_ARG;
+    }
+    if (a.d != 1024 && a.d > GEN_MAX_D) {
+        vrq_set_error("embedding_dim %d > %d is not supported by the encode kernels", a.d, GEN_MAX_D);
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    EncParams p{a.x, a.n, a.d, a.limit_f32, a.scale_f32, a.q, a.mn, a.mx, a.ubin, a.ge};
+    vrq_timer_scope ts(ctx, VRQ_CAT_ENCODE, st);
+    switch (a.codec) {
+        case VRQ_CODEC_NONE:
+            return launch_codec<VRQ_CODEC_NONE>(ctx, p, st);
+        case VRQ_CODEC_INT8_PERDOC:
+            return launch_codec<VRQ_CODEC_INT8_PERDOC>(ctx, p, st);
+        case VRQ_CODEC_INT8_GLOBAL:
+            return launch_codec<VRQ_CODEC_INT8_GLOBAL>(ctx, p, st);
+        case VRQ_CODEC_INT16_GLOBAL:
+            return launch_codec<VRQ_CODEC_INT16_GLOBAL>(ctx, p, st);
+        case VRQ_CODEC_INT4:
+            return launch_codec<VRQ_CODEC_INT4>(ctx, p, st);
+    }
+    vrq_set_error("unknown codec %d", a.codec);
+    return VRQ_ERR_ARG;
+}
+
+int vrq_launch_to_binary_int(vrq_ctx* ctx, const void* x, int elem_bytes, int64_t n, int d, int ge, uint8_t* ubin,
+                             cudaStream_t st) {
+    if (n == 0) return 0;
+    if (d % 8 != 0 || d < 8) {
+        vrq_set_error("embedding_dim must be a positive multiple of 8 (got %d)", d);
+        return VRQ_ERR_ARG;
+    }
+    if ((int64_t)d * 32768 > 2147483647LL) {
+        vrq_set_error("embedding_dim %d too large for the integer threshold kernel", d);
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    int64_t blocks = (n + 7) / 8, cap = (int64_t)ctx->sm_count * 8;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    vrq_timer_scope ts(ctx, VRQ_CAT_ENCODE, st);
+    if (elem_bytes == 1)
+        to_binary_int_kernel<int8_t><<<grid, 256, 0, st>>>(static_cast<const int8_t*>(x), n, d, ge, ubin);
+    else
+        to_binary_int_kernel<int16_t><<<grid, 256, 0, st>>>(static_cast<const int16_t*>(x), n, d, ge, ubin);
+    vrq_count_launch(ctx);
+    VRQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int vrq_launch_dequant(vrq_ctx* ctx, const vrq_dequant_args& a, cudaStream_t st) {
+    if (a.n == 0) return 0;
+    DeqParams p{};
+    p.kind = a.kind;
+    p.q = a.q;
+    p.n = a.n;
+    p.d = a.d;
+    p.mn = a.mn;
+    p.mx = a.mx;
+    p.out = a.out;
+    if (a.kind == VRQ_PAYLOAD_INT8_GLOBAL) p.scale_f32 = (float)(a.limit / 127.0);
+    if (a.kind == VRQ_PAYLOAD_INT16_GLOBAL) p.scale_f32 = (float)(a.limit / 32767.0);
+    if (a.kind == VRQ_PAYLOAD_INT4_GLOBAL) p.scale_f64 = a.limit / 7.0;
+    int64_t total = a.n * (int64_t)a.d;
+    int64_t blocks = (total + 255) / 256, cap = (int64_t)ctx->sm_count * 16;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    dequant_kernel<<<grid, 256, 0, st>>>(p);
+    vrq_count_launch(ctx);
+    VRQ_CUDA(cudaGetLastError());
+    return 0;
+}

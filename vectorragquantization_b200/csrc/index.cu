@@ -1,0 +1,668 @@
+// Device-resident binary index: the faiss.IndexBinaryIDMap2(faiss.IndexBinaryFlat(d)) surface the reference
+// classes call, plus an optional per-position payload matrix that replaces the RocksDB
+// point-gets inside the reference's rescoring loops, and the fused multi-phase searches.
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "vrq_internal.cuh"
+
+struct vrq_index {
+    vrq_ctx* ctx = nullptr;
+    int d = 0;
+    int code_bytes = 0;
+    int64_t ntotal = 0, capacity = 0;
+    uint8_t* codes = nullptr;
+    int64_t* ids = nullptr;  // null while ids are implicit (id = id0 + position)
+    bool implicit_ids = true;
+    int64_t id0 = 0;
+    int payload_kind = VRQ_PAYLOAD_NONE;
+    double limit = 0.0;
+    size_t payload_row = 0, aux_row = 0;
+    uint8_t* payload = nullptr;
+    uint8_t* aux = nullptr;
+    std::vector<int64_t> host_ids;
+    bool host_ids_valid = false;
+    std::unordered_map<int64_t, int64_t> rev;  // id -> last position
+    bool rev_valid = false;
+};
+
+namespace {
+
+size_t payload_row_bytes(int kind, int d) {
+    switch (kind) {
+        case VRQ_PAYLOAD_INT8_RAW:
+        case VRQ_PAYLOAD_INT8_PERDOC:
+        case VRQ_PAYLOAD_INT8_GLOBAL:
+            return (size_t)d;
+        case VRQ_PAYLOAD_INT16_GLOBAL:
+            return (size_t)d * 2;
+        case VRQ_PAYLOAD_INT4_PERDOC:
+        case VRQ_PAYLOAD_INT4_GLOBAL:
+            return (size_t)d / 2;
+        case VRQ_PAYLOAD_F32:
+            return (size_t)d * 4;
+    }
+    return 0;
+}
+size_t aux_row_bytes(int kind) {
+    if (kind == VRQ_PAYLOAD_INT8_PERDOC) return 2 * sizeof(float);
+    if (kind == VRQ_PAYLOAD_INT4_PERDOC) return 2 * sizeof(double);
+    return 0;
+}
+
+int grow_one(vrq_index* ix, void** buf, size_t row_bytes, int64_t new_cap) {
+    if (row_bytes == 0) return 0;
+    void* nb = nullptr;
+    cudaError_t e = cudaMalloc(&nb, row_bytes * (size_t)new_cap);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        vrq_set_error("cudaMalloc of %zu bytes for the index failed: %s", row_bytes * (size_t)new_cap, cudaGetErrorString(e));
+        return VRQ_ERR_NOMEM;
+    }
+    if (*buf && ix->ntotal > 0)
+        VRQ_CUDA(cudaMemcpyAsync(nb, *buf, row_bytes * (size_t)ix->ntotal, cudaMemcpyDeviceToDevice, ix->ctx->stream));
+    if (*buf) {
+        VRQ_CUDA(cudaStreamSynchronize(ix->ctx->stream));
+        VRQ_CUDA(cudaFree(*buf));
+    }
+    *buf = nb;
+    return 0;
+}
+
+int ensure_capacity(vrq_index* ix, int64_t want) {
+    if (want <= ix->capacity) return 0;
+    int64_t nc = std::max<int64_t>(want, std::max<int64_t>(1024, ix->capacity + ix->capacity / 2));
+    VRQ_CUDA(cudaSetDevice(ix->ctx->device));
+    VRQ_TRY(grow_one(ix, (void**)&ix->codes, (size_t)ix->code_bytes, nc));
+    if (!ix->implicit_ids) VRQ_TRY(grow_one(ix, (void**)&ix->ids, sizeof(int64_t), nc));
+    VRQ_TRY(grow_one(ix, (void**)&ix->payload, ix->payload_row, nc));
+    VRQ_TRY(grow_one(ix, (void**)&ix->aux, ix->aux_row, nc));
+    ix->capacity = nc;
+    return 0;
+}
+
+int materialise_ids(vrq_index* ix) {
+    if (!ix->implicit_ids) return 0;
+    VRQ_CUDA(cudaSetDevice(ix->ctx->device));
+    if (ix->capacity > 0) {
+        VRQ_CUDA(cudaMalloc((void**)&ix->ids, sizeof(int64_t) * (size_t)ix->capacity));
+        VRQ_TRY(vrq_launch_iota_i64(ix->ctx, ix->ids, ix->ntotal, ix->id0, ix->ctx->stream));
+    }
+    ix->implicit_ids = false;
+    return 0;
+}
+
+int load_host_ids(vrq_index* ix) {
+    if (ix->host_ids_valid) return 0;
+    ix->host_ids.resize((size_t)ix->ntotal);
+    if (ix->implicit_ids) {
+        for (int64_t i = 0; i < ix->ntotal; i++) ix->host_ids[(size_t)i] = ix->id0 + i;
+    } else if (ix->ntotal > 0) {
+        VRQ_CUDA(cudaMemcpyAsync(ix->host_ids.data(), ix->ids, sizeof(int64_t) * (size_t)ix->ntotal, cudaMemcpyDeviceToHost,
+                                 ix->ctx->stream));
+        VRQ_CUDA(cudaStreamSynchronize(ix->ctx->stream));
+    }
+    ix->host_ids_valid = true;
+    return 0;
+}
+
+int build_rev(vrq_index* ix) {
+    if (ix->rev_valid) return 0;
+    VRQ_TRY(load_host_ids(ix));
+    ix->rev.clear();
+    ix->rev.reserve((size_t)ix->ntotal * 2);
+    for (int64_t i = 0; i < ix->ntotal; i++) ix->rev[ix->host_ids[(size_t)i]] = i;  // last added wins (IDMap2)
+    ix->rev_valid = true;
+    return 0;
+}
+
+__global__ void gather_rows_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__ positions, int64_t m,
+                                   int row_bytes, uint8_t* __restrict__ dst) {
+    // one warp per row, byte granularity in 4-byte words when possible
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < m; r += (int64_t)gridDim.x * 8) {
+        const int64_t p = positions[r];
+        const uint8_t* s = src + (size_t)p * row_bytes;
+        uint8_t* o = dst + (size_t)r * row_bytes;
+        if ((row_bytes & 3) == 0) {
+            for (int w = lane; w < row_bytes / 4; w += 32)
+                reinterpret_cast<uint32_t*>(o)[w] = reinterpret_cast<const uint32_t*>(s)[w];
+        } else {
+            for (int b = lane; b < row_bytes; b += 32) o[b] = s[b];
+        }
+    }
+}
+
+int gather_rows(vrq_ctx* ctx, const uint8_t* src, const int64_t* pos_dev, int64_t m, size_t row_bytes, uint8_t* dst,
+                cudaStream_t st) {
+    if (m == 0 || row_bytes == 0) return 0;
+    int64_t blocks = (m + 7) / 8, cap = (int64_t)ctx->sm_count * 16;
+    gather_rows_kernel<<<(unsigned)std::min(blocks, cap), 256, 0, st>>>(src, pos_dev, m, (int)row_bytes, dst);
+    vrq_count_launch(ctx);
+    VRQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+struct DevIO {
+    // Stages host arguments of one index call into scratch, remembers host outputs to copy back.
+    vrq_ctx* ctx;
+    bool host;
+    std::vector<std::pair<void*, std::pair<void*, size_t>>> outs;
+    int in(const void* p, size_t bytes, int slot, const void** dev) {
+        if (!host || !p) {
+            *dev = p;
+            return 0;
+        }
+        void* d;
+        VRQ_TRY(vrq_ws_get(ctx, slot, bytes, &d));
+        VRQ_CUDA(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        *dev = d;
+        return 0;
+    }
+    int out(void* p, size_t bytes, int slot, void** dev) {
+        if (!host || !p) {
+            *dev = p;
+            return 0;
+        }
+        void* d;
+        VRQ_TRY(vrq_ws_get(ctx, slot, bytes, &d));
+        outs.push_back({p, {d, bytes}});
+        *dev = d;
+        return 0;
+    }
+    int finish() {
+        if (!host) return 0;
+        for (auto& o : outs)
+            VRQ_CUDA(cudaMemcpyAsync(o.first, o.second.first, o.second.second, cudaMemcpyDeviceToHost, ctx->stream));
+        VRQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
+};
+
+}  // namespace
+
+extern "C" int vrq_index_create(vrq_ctx* ctx, int d, vrq_index** out) {
+    VRQ_CHECK_ARG(ctx != nullptr && out != nullptr, "null argument");
+    VRQ_CHECK_ARG(d > 0 && d % 8 == 0, "d must be a positive multiple of 8 (faiss binary indexes require it)");
+    if (d % 32 != 0) {
+        vrq_set_error("d=%d: the Hamming kernels need d %% 32 == 0", d);
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    vrq_index* ix = new vrq_index();
+    ix->ctx = ctx;
+    ix->d = d;
+    ix->code_bytes = d / 8;
+    *out = ix;
+    return 0;
+}
+
+extern "C" int vrq_index_free(vrq_index* ix) {
+    if (!ix) return 0;
+    cudaSetDevice(ix->ctx->device);
+    cudaStreamSynchronize(ix->ctx->stream);
+    if (ix->codes) cudaFree(ix->codes);
+    if (ix->ids) cudaFree(ix->ids);
+    if (ix->payload) cudaFree(ix->payload);
+    if (ix->aux) cudaFree(ix->aux);
+    delete ix;
+    return 0;
+}
+
+extern "C" int64_t vrq_index_ntotal(const vrq_index* ix) { return ix ? ix->ntotal : 0; }
+extern "C" int vrq_index_d(const vrq_index* ix) { return ix ? ix->d : 0; }
+extern "C" int vrq_index_payload_kind(const vrq_index* ix) { return ix ? ix->payload_kind : 0; }
+
+extern "C" int vrq_index_reserve(vrq_index* ix, int64_t cap) {
+    VRQ_CHECK_ARG(ix != nullptr && cap >= 0, "bad argument");
+    if (cap <= ix->capacity) return 0;
+    // exact reservation (no geometric slack): 100 M x (128 + 1024) B is most of the HBM
+    VRQ_CUDA(cudaSetDevice(ix->ctx->device));
+    VRQ_TRY(grow_one(ix, (void**)&ix->codes, (size_t)ix->code_bytes, cap));
+    if (!ix->implicit_ids) VRQ_TRY(grow_one(ix, (void**)&ix->ids, sizeof(int64_t), cap));
+    VRQ_TRY(grow_one(ix, (void**)&ix->payload, ix->payload_row, cap));
+    VRQ_TRY(grow_one(ix, (void**)&ix->aux, ix->aux_row, cap));
+    ix->capacity = cap;
+    return 0;
+}
+
+extern "C" int vrq_index_set_payload(vrq_index* ix, int kind, double global_limit) {
+    VRQ_CHECK_ARG(ix != nullptr, "index is null");
+    VRQ_CHECK_ARG(kind >= VRQ_PAYLOAD_NONE && kind <= VRQ_PAYLOAD_F32, "unknown payload kind");
+    if (ix->ntotal != 0 || ix->capacity != 0) {
+        vrq_set_error("payload kind can only be set on an empty, unreserved index");
+        return VRQ_ERR_STATE;
+    }
+    ix->payload_kind = kind;
+    ix->limit = global_limit;
+    ix->payload_row = payload_row_bytes(kind, ix->d);
+    ix->aux_row = aux_row_bytes(kind);
+    return 0;
+}
+
+extern "C" int vrq_index_add_with_ids(vrq_index* ix, int64_t n, const uint8_t* codes, const int64_t* ids, const void* payload,
+                                      const void* aux) {
+    VRQ_CHECK_ARG(ix != nullptr && n >= 0, "bad argument");
+    if (n == 0) return 0;
+    VRQ_CHECK_ARG(codes != nullptr && ids != nullptr, "codes / ids are null");
+    VRQ_CHECK_ARG((ix->payload_row == 0) == (payload == nullptr), "payload must be given exactly when a payload kind is set");
+    VRQ_CHECK_ARG((ix->aux_row == 0) == (aux == nullptr), "aux (min,max pairs) must be given exactly for the per-document kinds");
+    const void* all[4] = {codes, ids, payload, aux};
+    bool is_dev;
+    VRQ_TRY(vrq_space_of(all, 4, &is_dev));
+    VRQ_CUDA(cudaSetDevice(ix->ctx->device));
+    VRQ_TRY(materialise_ids(ix));
+    VRQ_TRY(ensure_capacity(ix, ix->ntotal + n));
+    if (!ix->ids) VRQ_CUDA(cudaMalloc((void**)&ix->ids, sizeof(int64_t) * (size_t)ix->capacity));
+    cudaStream_t st = ix->ctx->stream;
+    const cudaMemcpyKind kind = is_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    VRQ_CUDA(cudaMemcpyAsync(ix->codes + (size_t)ix->ntotal * ix->code_bytes, codes, (size_t)n * ix->code_bytes, kind, st));
+    VRQ_CUDA(cudaMemcpyAsync(ix->ids + ix->ntotal, ids, sizeof(int64_t) * (size_t)n, kind, st));
+    if (payload) VRQ_CUDA(cudaMemcpyAsync(ix->payload + (size_t)ix->ntotal * ix->payload_row, payload, (size_t)n * ix->payload_row, kind, st));
+    if (aux) VRQ_CUDA(cudaMemcpyAsync(ix->aux + (size_t)ix->ntotal * ix->aux_row, aux, (size_t)n * ix->aux_row, kind, st));
+    if (!is_dev) VRQ_CUDA(cudaStreamSynchronize(st));
+    ix->ntotal += n;
+    ix->host_ids_valid = false;
+    ix->rev_valid = false;
+    return 0;
+}
+
+extern "C" int vrq_index_add_synthetic(vrq_index* ix, uint64_t seed, int64_t row0, int64_t nrows, int64_t id0) {
+    VRQ_CHECK_ARG(ix != nullptr && nrows >= 0, "bad argument");
+    if (ix->payload_kind != VRQ_PAYLOAD_NONE && ix->payload_kind != VRQ_PAYLOAD_INT8_RAW) {
+        vrq_set_error("add_synthetic fills codes (+ INT8_RAW payload) only");
+        return VRQ_ERR_STATE;
+    }
+    if (nrows == 0) return 0;
+    VRQ_CUDA(cudaSetDevice(ix->ctx->device));
+    const bool contiguous = ix->implicit_ids && (ix->ntotal == 0 || ix->id0 + ix->ntotal == id0);
+    if (ix->ntotal == 0 && ix->implicit_ids) ix->id0 = id0;
+    if (!contiguous) VRQ_TRY(materialise_ids(ix));
+    VRQ_TRY(ensure_capacity(ix, ix->ntotal + nrows));
+    cudaStream_t st = ix->ctx->stream;
+    if (!ix->implicit_ids) {
+        if (!ix->ids) VRQ_CUDA(cudaMalloc((void**)&ix->ids, sizeof(int64_t) * (size_t)ix->capacity));
+        VRQ_TRY(vrq_launch_iota_i64(ix->ctx, ix->ids + ix->ntotal, nrows, id0, st));
+    }
+    VRQ_TRY(vrq_launch_synth_codes_int8(ix->ctx, seed, row0, nrows, ix->d, ix->codes + (size_t)ix->ntotal * ix->code_bytes,
+                                        ix->payload ? (int8_t*)(ix->payload + (size_t)ix->ntotal * ix->payload_row) : nullptr, st));
+    ix->ntotal += nrows;
+    ix->host_ids_valid = false;
+    ix->rev_valid = false;
+    return 0;
+}
+
+extern "C" int vrq_index_search(vrq_index* ix, int64_t nq, const uint8_t* q, int k, int32_t* dist, int64_t* labels) {
+    VRQ_CHECK_ARG(ix != nullptr && nq >= 0, "bad argument");
+    if (nq == 0) return 0;
+    VRQ_CHECK_ARG(q != nullptr && dist != nullptr && labels != nullptr, "null pointer");
+    VRQ_CHECK_ARG(k > 0, "k must be > 0");
+    const void* all[3] = {q, dist, labels};
+    bool is_dev;
+    VRQ_TRY(vrq_space_of(all, 3, &is_dev));
+    vrq_ctx* ctx = ix->ctx;
+    VRQ_CUDA(cudaSetDevice(ctx->device));
+    DevIO io{ctx, !is_dev, {}};
+    const void* dq;
+    void *dd, *dl, *keys;
+    VRQ_TRY(io.in(q, (size_t)nq * ix->code_bytes, VRQ_WS_QUERY_A, &dq));
+    VRQ_TRY(io.out(dist, sizeof(int32_t) * (size_t)nq * k, VRQ_WS_OUT_A, &dd));
+    VRQ_TRY(io.out(labels, sizeof(int64_t) * (size_t)nq * k, VRQ_WS_OUT_B, &dl));
+    VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_TOPK, sizeof(uint64_t) * (size_t)nq * k, &keys));
+    VRQ_TRY(vrq_hamming_topk_dev(ctx, ix->codes, ix->ntotal, ix->code_bytes, 0, (const uint8_t*)dq, nq, k, (uint64_t*)keys, ctx->stream));
+    VRQ_TRY(vrq_launch_keys_to_dist_labels(ctx, (const uint64_t*)keys, nq * (int64_t)k, 0, ix->implicit_ids ? nullptr : ix->ids,
+                                           ix->id0, (int32_t*)dd, (int64_t*)dl, ctx->stream));
+    return io.finish();
+}
+
+extern "C" int64_t vrq_index_position_of(vrq_index* ix, int64_t id) {
+    if (!ix) return -1;
+    if (ix->implicit_ids) return (id >= ix->id0 && id < ix->id0 + ix->ntotal) ? id - ix->id0 : -1;
+    if (build_rev(ix) != 0) return -1;
+    auto it = ix->rev.find(id);
+    return it == ix->rev.end() ? -1 : it->second;
+}
+
+extern "C" int vrq_index_reconstruct(vrq_index* ix, int64_t id, uint8_t* code_out) {
+    VRQ_CHECK_ARG(ix != nullptr && code_out != nullptr, "null argument");
+    const int64_t p = vrq_index_position_of(ix, id);
+    if (p < 0) {
+        vrq_set_error("reconstruct: id %lld not found", (long long)id);
+        return VRQ_ERR_ARG;
+    }
+    VRQ_CUDA(cudaSetDevice(ix->ctx->device));
+    VRQ_CUDA(cudaMemcpyAsync(code_out, ix->codes + (size_t)p * ix->code_bytes, ix->code_bytes, cudaMemcpyDefault, ix->ctx->stream));
+    VRQ_CUDA(cudaStreamSynchronize(ix->ctx->stream));
+    return 0;
+}
+
+extern "C" int vrq_index_get_payload(vrq_index* ix, int64_t m, const int64_t* positions, void* payload_out, void* aux_out) {
+    VRQ_CHECK_ARG(ix != nullptr && m >= 0, "bad argument");
+    if (m == 0) return 0;
+    VRQ_CHECK_ARG(positions != nullptr, "positions is null");
+    if (ix->payload_kind == VRQ_PAYLOAD_NONE) {
+        vrq_set_error("index has no payload");
+        return VRQ_ERR_STATE;
+    }
+    const void* all[3] = {positions, payload_out, aux_out};
+    bool is_dev;
+    VRQ_TRY(vrq_space_of(all, 3, &is_dev));
+    vrq_ctx* ctx = ix->ctx;
+    VRQ_CUDA(cudaSetDevice(ctx->device));
+    if (!is_dev)
+        for (int64_t i = 0; i < m; i++) VRQ_CHECK_ARG(positions[i] >= 0 && positions[i] < ix->ntotal, "position out of range");
+    DevIO io{ctx, !is_dev, {}};
+    const void* dp;
+    void *po, *ao;
+    VRQ_TRY(io.in(positions, sizeof(int64_t) * (size_t)m, VRQ_WS_SEARCH_B, &dp));
+    VRQ_TRY(io.out(payload_out, ix->payload_row * (size_t)m, VRQ_WS_OUT_A, &po));
+    VRQ_TRY(io.out(aux_out, ix->aux_row * (size_t)m, VRQ_WS_OUT_B, &ao));
+    if (po) VRQ_TRY(gather_rows(ctx, ix->payload, (const int64_t*)dp, m, ix->payload_row, (uint8_t*)po, ctx->stream));
+    if (ao && ix->aux_row) VRQ_TRY(gather_rows(ctx, ix->aux, (const int64_t*)dp, m, ix->aux_row, (uint8_t*)ao, ctx->stream));
+    return io.finish();
+}
+
+extern "C" int64_t vrq_index_remove_ids(vrq_index* ix, int64_t n, const int64_t* ids) {
+    if (!ix || n < 0 || (n > 0 && !ids)) {
+        vrq_set_error("remove_ids: bad argument");
+        return VRQ_ERR_ARG;
+    }
+    if (n == 0 || ix->ntotal == 0) return 0;
+    vrq_ctx* ctx = ix->ctx;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return VRQ_ERR_STATE;
+    bool is_dev;
+    vrq_is_device_ptr(ids, &is_dev);
+    std::vector<int64_t> hids((size_t)n);
+    if (is_dev) {
+        if (cudaMemcpy(hids.data(), ids, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) return VRQ_ERR_STATE;
+    } else {
+        memcpy(hids.data(), ids, sizeof(int64_t) * (size_t)n);
+    }
+    if (load_host_ids(ix) != 0) return VRQ_ERR_STATE;
+    std::unordered_set<int64_t> kill(hids.begin(), hids.end());
+    std::vector<int64_t> keep;
+    keep.reserve((size_t)ix->ntotal);
+    for (int64_t i = 0; i < ix->ntotal; i++)
+        if (!kill.count(ix->host_ids[(size_t)i])) keep.push_back(i);
+    const int64_t removed = ix->ntotal - (int64_t)keep.size();
+    if (removed == 0) return 0;
+    if (materialise_ids(ix) != 0) return VRQ_ERR_STATE;
+    const int64_t m = (int64_t)keep.size();
+    // order-preserving compaction (faiss shifts the tail down; ids keep their relative order)
+    void* kp = nullptr;
+    if (m > 0) {
+        if (vrq_ws_get(ctx, VRQ_WS_SEARCH_B, sizeof(int64_t) * (size_t)m, &kp) != 0) return VRQ_ERR_NOMEM;
+        if (cudaMemcpyAsync(kp, keep.data(), sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return VRQ_ERR_STATE;
+    }
+    auto compact = [&](uint8_t** buf, size_t row) -> int {
+        if (row == 0 || !*buf) return 0;
+        uint8_t* nb = nullptr;
+        if (cudaMalloc((void**)&nb, row * (size_t)std::max<int64_t>(ix->capacity, 1)) != cudaSuccess) return VRQ_ERR_NOMEM;
+        int r = gather_rows(ctx, *buf, (const int64_t*)kp, m, row, nb, ctx->stream);
+        if (r != 0) return r;
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(*buf);
+        *buf = nb;
+        return 0;
+    };
+    if (compact(&ix->codes, (size_t)ix->code_bytes) != 0) return VRQ_ERR_NOMEM;
+    if (compact((uint8_t**)&ix->ids, sizeof(int64_t)) != 0) return VRQ_ERR_NOMEM;
+    if (compact(&ix->payload, ix->payload_row) != 0) return VRQ_ERR_NOMEM;
+    if (compact(&ix->aux, ix->aux_row) != 0) return VRQ_ERR_NOMEM;
+    cudaStreamSynchronize(ctx->stream);
+    ix->ntotal = m;
+    ix->host_ids_valid = false;
+    ix->rev_valid = false;
+    return removed;
+}
+
+// ---- faiss file format ("IBM2" wrapping "IBxF"), SURVEY App. B.1 ----------------------------------------------------
+extern "C" int vrq_index_write(vrq_index* ix, const char* path) {
+    VRQ_CHECK_ARG(ix != nullptr && path != nullptr, "null argument");
+    VRQ_CUDA(cudaSetDevice(ix->ctx->device));
+    FILE* f = fopen(path, "wb");
+    if (!f) {
+        vrq_set_error("cannot open %s for writing", path);
+        return VRQ_ERR_IO;
+    }
+    auto hdr = [&](const char* fourcc) {
+        int32_t d = ix->d, cs = ix->code_bytes, metric = 1;
+        int64_t nt = ix->ntotal;
+        uint8_t trained = 1;
+        fwrite(fourcc, 1, 4, f);
+        fwrite(&d, 4, 1, f);
+        fwrite(&cs, 4, 1, f);
+        fwrite(&nt, 8, 1, f);
+        fwrite(&trained, 1, 1, f);
+        fwrite(&metric, 4, 1, f);
+    };
+    hdr("IBM2");
+    hdr("IBxF");
+    uint64_t nbytes = (uint64_t)ix->ntotal * ix->code_bytes;
+    fwrite(&nbytes, 8, 1, f);
+    const size_t CH = 64u << 20;
+    std::vector<uint8_t> tmp(std::min<size_t>(CH, std::max<size_t>(nbytes, 1)));
+    for (uint64_t off = 0; off < nbytes; off += CH) {
+        size_t len = (size_t)std::min<uint64_t>(CH, nbytes - off);
+        VRQ_CUDA(cudaMemcpyAsync(tmp.data(), ix->codes + off, len, cudaMemcpyDeviceToHost, ix->ctx->stream));
+        VRQ_CUDA(cudaStreamSynchronize(ix->ctx->stream));
+        if (fwrite(tmp.data(), 1, len, f) != len) {
+            fclose(f);
+            vrq_set_error("short write to %s", path);
+            return VRQ_ERR_IO;
+        }
+    }
+    uint64_t nids = (uint64_t)ix->ntotal;
+    fwrite(&nids, 8, 1, f);
+    int r = load_host_ids(ix);
+    if (r != 0) {
+        fclose(f);
+        return r;
+    }
+    if (nids && fwrite(ix->host_ids.data(), 8, nids, f) != nids) {
+        fclose(f);
+        vrq_set_error("short write to %s", path);
+        return VRQ_ERR_IO;
+    }
+    if (fclose(f) != 0) {
+        vrq_set_error("close of %s failed", path);
+        return VRQ_ERR_IO;
+    }
+    return 0;
+}
+
+extern "C" int vrq_index_read(vrq_ctx* ctx, const char* path, vrq_index** out) {
+    VRQ_CHECK_ARG(ctx != nullptr && path != nullptr && out != nullptr, "null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+        vrq_set_error("cannot open %s", path);
+        return VRQ_ERR_IO;
+    }
+    auto fail = [&](const char* why) {
+        fclose(f);
+        vrq_set_error("%s: %s", path, why);
+        return VRQ_ERR_IO;
+    };
+    struct H {
+        char cc[4];
+        int32_t d, cs;
+        int64_t nt;
+        uint8_t trained;
+        int32_t metric;
+    };
+    auto rd = [&](H* h) -> bool {
+        return fread(h->cc, 1, 4, f) == 4 && fread(&h->d, 4, 1, f) == 1 && fread(&h->cs, 4, 1, f) == 1 &&
+               fread(&h->nt, 8, 1, f) == 1 && fread(&h->trained, 1, 1, f) == 1 && fread(&h->metric, 4, 1, f) == 1;
+    };
+    H h1, h2;
+    if (!rd(&h1) || memcmp(h1.cc, "IBM2", 4) != 0) return fail("not an IndexBinaryIDMap2 file (fourcc IBM2 expected)");
+    if (!rd(&h2) || memcmp(h2.cc, "IBxF", 4) != 0) return fail("inner index is not IndexBinaryFlat (fourcc IBxF expected)");
+    if (h2.d <= 0 || h2.d % 8 != 0 || h2.cs != h2.d / 8 || h2.nt < 0) return fail("corrupt header");
+    uint64_t nbytes = 0;
+    if (fread(&nbytes, 8, 1, f) != 1 || nbytes != (uint64_t)h2.nt * h2.cs) return fail("code array size mismatch");
+    vrq_index* ix = nullptr;
+    int r = vrq_index_create(ctx, h2.d, &ix);
+    if (r != 0) {
+        fclose(f);
+        return r;
+    }
+    std::vector<uint8_t> codes((size_t)nbytes);
+    if (nbytes && fread(codes.data(), 1, (size_t)nbytes, f) != nbytes) {
+        vrq_index_free(ix);
+        return fail("truncated code array");
+    }
+    uint64_t nids = 0;
+    if (fread(&nids, 8, 1, f) != 1 || nids != (uint64_t)h2.nt) {
+        vrq_index_free(ix);
+        return fail("id map size mismatch");
+    }
+    std::vector<int64_t> ids((size_t)nids);
+    if (nids && fread(ids.data(), 8, (size_t)nids, f) != nids) {
+        vrq_index_free(ix);
+        return fail("truncated id map");
+    }
+    fclose(f);
+    if (h2.nt > 0) {
+        r = vrq_index_add_with_ids(ix, h2.nt, codes.data(), ids.data(), nullptr, nullptr);
+        if (r != 0) {
+            vrq_index_free(ix);
+            return r;
+        }
+    }
+    *out = ix;
+    return 0;
+}
+
+// ---- fused searches ---------------------------------------------------------------------------------------------------
+extern "C" int vrq_index_search3_local(vrq_index* ix, int64_t nq, const float* q_float, const uint8_t* q_ubin, int binary_k,
+                                       int64_t pos_base, uint64_t* keys, int64_t* labels, double* score_binary,
+                                       double* score_cosine) {
+    VRQ_CHECK_ARG(ix && q_float && q_ubin && keys && labels && score_binary && score_cosine, "null argument");
+    VRQ_CHECK_ARG(nq >= 0 && binary_k > 0, "bad sizes");
+    if (ix->payload_kind != VRQ_PAYLOAD_INT8_RAW) {
+        vrq_set_error("search3 needs an index with the INT8_RAW payload (CohereEnhancedVectorDB layout)");
+        return VRQ_ERR_STATE;
+    }
+    if (nq == 0) return 0;
+    vrq_ctx* ctx = ix->ctx;
+    cudaStream_t st = ctx->stream;
+    VRQ_CUDA(cudaSetDevice(ctx->device));
+    VRQ_TRY(vrq_hamming_topk_dev(ctx, ix->codes, ix->ntotal, ix->code_bytes, pos_base, q_ubin, nq, binary_k, keys, st));
+    VRQ_TRY(vrq_launch_keys_to_dist_labels(ctx, keys, nq * (int64_t)binary_k, pos_base, ix->implicit_ids ? nullptr : ix->ids,
+                                           ix->id0, nullptr, labels, st));
+    VRQ_TRY(vrq_launch_rescore_binary(ctx, ix->codes, ix->d, keys, nullptr, pos_base, nq, binary_k, q_float, score_binary, st));
+    VRQ_TRY(vrq_launch_rescore_int8cos(ctx, (const int8_t*)ix->payload, ix->d, keys, nullptr, pos_base, nq, binary_k, q_float,
+                                       score_cosine, st));
+    return 0;
+}
+
+extern "C" int vrq_index_search3(vrq_index* ix, int64_t nq, const float* q_float, const uint8_t* q_ubin, int k,
+                                 int binary_oversample, int int8_oversample, int64_t* labels, int32_t* hamming,
+                                 double* score_binary, double* score_cosine, int32_t* out_count) {
+    VRQ_CHECK_ARG(ix && q_float && q_ubin && labels && hamming && score_binary && score_cosine && out_count, "null argument");
+    VRQ_CHECK_ARG(nq >= 0 && k > 0 && binary_oversample > 0 && int8_oversample > 0, "bad sizes");
+    if (nq == 0) return 0;
+    const void* all[7] = {q_float, q_ubin, labels, hamming, score_binary, score_cosine, out_count};
+    bool is_dev;
+    VRQ_TRY(vrq_space_of(all, 7, &is_dev));
+    vrq_ctx* ctx = ix->ctx;
+    VRQ_CUDA(cudaSetDevice(ctx->device));
+    // binary_k = min(k * binary_oversample, ntotal)   (CohereEnhancedVectorDB.py:267)
+    int64_t bk64 = std::min<int64_t>((int64_t)k * binary_oversample, ix->ntotal);
+    if (bk64 > VRQ_MAX_K) {
+        vrq_set_error("k * binary_oversample = %lld exceeds the supported %d", (long long)bk64, VRQ_MAX_K);
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    DevIO io{ctx, !is_dev, {}};
+    const void *dqf, *dqb;
+    void *ol, *oh, *ob, *oc, *on;
+    VRQ_TRY(io.in(q_float, sizeof(float) * (size_t)nq * ix->d, VRQ_WS_QUERY_A, &dqf));
+    VRQ_TRY(io.in(q_ubin, (size_t)nq * ix->code_bytes, VRQ_WS_QUERY_B, &dqb));
+    VRQ_TRY(io.out(labels, 8 * (size_t)nq * k, VRQ_WS_OUT_A, &ol));
+    VRQ_TRY(io.out(hamming, 4 * (size_t)nq * k, VRQ_WS_OUT_B, &oh));
+    VRQ_TRY(io.out(score_binary, 8 * (size_t)nq * k, VRQ_WS_OUT_C, &ob));
+    VRQ_TRY(io.out(score_cosine, 8 * (size_t)nq * k, VRQ_WS_OUT_D, &oc));
+    VRQ_TRY(io.out(out_count, 4 * (size_t)nq, VRQ_WS_OUT_E, &on));
+    if (bk64 == 0) {
+        // empty index: the reference logs an error and returns [] (CohereEnhancedVectorDB.py:247-249)
+        VRQ_CUDA(cudaMemsetAsync(on, 0, 4 * (size_t)nq, ctx->stream));
+        VRQ_CUDA(cudaMemsetAsync(ol, 0xFF, 8 * (size_t)nq * k, ctx->stream));
+        return io.finish();
+    }
+    const int bk = (int)bk64;
+    void *keys, *lab, *sb, *sc;
+    const size_t cnt = (size_t)nq * bk;
+    VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_SEARCH_A, 8 * cnt, &keys));
+    VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_SEARCH_C, 8 * cnt, &lab));
+    VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_SEARCH_D, 8 * cnt, &sb));
+    VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_SEARCH_E, 8 * cnt, &sc));
+    VRQ_TRY(vrq_index_search3_local(ix, nq, (const float*)dqf, (const uint8_t*)dqb, bk, 0, (uint64_t*)keys, (int64_t*)lab,
+                                    (double*)sb, (double*)sc));
+    VRQ_TRY(vrq_launch_merge3(ctx, 1, nq, bk, (const uint64_t*)keys, (const int64_t*)lab, (const double*)sb, (const double*)sc, k,
+                              k * int8_oversample, (int64_t*)ol, (int32_t*)oh, (double*)ob, (double*)oc, (int32_t*)on, ctx->stream));
+    return io.finish();
+}
+
+extern "C" int vrq_index_search2(vrq_index* ix, int64_t nq, const float* q_float, const uint8_t* q_ubin, int k,
+                                 int binary_oversample, int64_t* labels, float* score, int32_t* out_count) {
+    VRQ_CHECK_ARG(ix && q_float && q_ubin && labels && score && out_count, "null argument");
+    VRQ_CHECK_ARG(nq >= 0 && k > 0 && binary_oversample > 0, "bad sizes");
+    if (ix->payload_kind == VRQ_PAYLOAD_NONE || ix->payload_kind == VRQ_PAYLOAD_INT8_RAW) {
+        vrq_set_error("search2 needs a quantised (or float32) payload");
+        return VRQ_ERR_STATE;
+    }
+    if (nq == 0) return 0;
+    const void* all[5] = {q_float, q_ubin, labels, score, out_count};
+    bool is_dev;
+    VRQ_TRY(vrq_space_of(all, 5, &is_dev));
+    vrq_ctx* ctx = ix->ctx;
+    VRQ_CUDA(cudaSetDevice(ctx->device));
+    int64_t bk64 = std::min<int64_t>((int64_t)k * binary_oversample, ix->ntotal);
+    if (bk64 > VRQ_MAX_K) {
+        vrq_set_error("k * binary_oversample = %lld exceeds the supported %d", (long long)bk64, VRQ_MAX_K);
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    DevIO io{ctx, !is_dev, {}};
+    const void *dqf, *dqb;
+    void *ol, *os, *on;
+    VRQ_TRY(io.in(q_float, sizeof(float) * (size_t)nq * ix->d, VRQ_WS_QUERY_A, &dqf));
+    VRQ_TRY(io.in(q_ubin, (size_t)nq * ix->code_bytes, VRQ_WS_QUERY_B, &dqb));
+    VRQ_TRY(io.out(labels, 8 * (size_t)nq * k, VRQ_WS_OUT_A, &ol));
+    VRQ_TRY(io.out(score, 4 * (size_t)nq * k, VRQ_WS_OUT_B, &os));
+    VRQ_TRY(io.out(out_count, 4 * (size_t)nq, VRQ_WS_OUT_E, &on));
+    if (bk64 == 0) {
+        VRQ_CUDA(cudaMemsetAsync(on, 0, 4 * (size_t)nq, ctx->stream));
+        VRQ_CUDA(cudaMemsetAsync(ol, 0xFF, 8 * (size_t)nq * k, ctx->stream));
+        return io.finish();
+    }
+    const int bk = (int)bk64;
+    const size_t cnt = (size_t)nq * bk;
+    void *keys, *lab, *sc;
+    VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_SEARCH_A, 8 * cnt, &keys));
+    VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_SEARCH_C, 8 * cnt, &lab));
+    VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_SEARCH_D, 4 * cnt, &sc));
+    cudaStream_t st = ctx->stream;
+    VRQ_TRY(vrq_hamming_topk_dev(ctx, ix->codes, ix->ntotal, ix->code_bytes, 0, (const uint8_t*)dqb, nq, bk, (uint64_t*)keys, st));
+    VRQ_TRY(vrq_launch_keys_to_dist_labels(ctx, (const uint64_t*)keys, (int64_t)cnt, 0, ix->implicit_ids ? nullptr : ix->ids, ix->id0,
+                                           nullptr, (int64_t*)lab, st));
+    vrq_rescore2_args a{};
+    a.kind = ix->payload_kind;
+    a.payload = ix->payload;
+    a.aux = ix->aux;
+    a.limit = ix->limit;
+    a.d = ix->d;
+    a.keys = (const uint64_t*)keys;
+    a.pos_base = 0;
+    a.nq = nq;
+    a.m = bk;
+    a.qf = (const float*)dqf;
+    a.score = (float*)sc;
+    VRQ_TRY(vrq_launch_rescore_payload_dot(ctx, a, st));
+    VRQ_TRY(vrq_launch_select2(ctx, nq, bk, (const uint64_t*)keys, (const int64_t*)lab, (const float*)sc, k, (int64_t*)ol, (float*)os,
+                               (int32_t*)on, st));
+    return io.finish();
+}

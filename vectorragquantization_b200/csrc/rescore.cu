@@ -1,0 +1,445 @@
+// Phase II / III rescoring, the 2-phase payload rescoring of the VectorDB* classes, and the per-query
+// select/sort kernels that replace the reference's Python list.sort calls.
+//
+// Reference lines: Phase II CohereEnhancedVectorDB.py:283-297, Phase III :302-322, 2-phase VectorDBInt8.py:226-242.
+// Every sort here reproduces a STABLE descending list.sort: the sort key is (score descending, previous rank
+// ascending), which is a total order, so the result is unique and equals the stable sort.
+#include <math.h>
+
+#include "topk_utils.cuh"
+#include "vrq_internal.cuh"
+
+namespace {
+
+using namespace vrq;
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int64_t cand_row(const uint64_t* keys, const int64_t* pos, size_t idx, int64_t pos_base) {
+    if (keys) {
+        uint64_t k = keys[idx];
+        return k == VRQ_KEY_NONE ? -1 : (int64_t)(k & VRQ_KEY_POS_MASK) - pos_base;
+    }
+    int64_t p = pos[idx];
+    return p < 0 ? -1 : p - pos_base;
+}
+
+// ---- Phase II: sum_i q[i] * (2*bit_i - 1), float64 accumulation ------------------------------------------------
+// One warp per (query, candidate).  Lane l owns dimensions {l, l+32, l+64, ...}: the query values it needs sit in
+// consecutive shared-memory words (conflict-free) and its bit of code word t is always bit 8*(l/8) + 7 - (l%8)
+// (np.packbits is MSB-first inside each byte).  The code is never unpacked to memory.
+__global__ void __launch_bounds__(256) rescore_binary_kernel(const uint8_t* __restrict__ codes, int d,
+                                                             const uint64_t* __restrict__ keys,
+                                                             const int64_t* __restrict__ pos, int64_t pos_base, int m,
+                                                             const float* __restrict__ qf, double* __restrict__ score) {
+    extern __shared__ float qs[];
+    const int q = blockIdx.y;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) qs[i] = qf[(size_t)q * d + i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int words = d >> 5;
+    const int bitpos = 8 * (lane >> 3) + 7 - (lane & 7);
+    for (int i = blockIdx.x * 8 + warp; i < m; i += gridDim.x * 8) {
+        const size_t idx = (size_t)q * m + i;
+        const int64_t row = cand_row(keys, pos, idx, pos_base);
+        if (row < 0) {
+            if (lane == 0) score[idx] = -INFINITY;
+            continue;
+        }
+        const uint32_t* code = reinterpret_cast<const uint32_t*>(codes + (size_t)row * (d >> 3));
+        double acc = 0.0;
+        for (int t = 0; t < words; t++) {
+            const uint32_t w = __ldg(code + t);  // same address on every lane: one broadcast transaction
+            const double v = (double)qs[32 * t + lane];
+            acc += ((w >> bitpos) & 1u) ? v : -v;
+        }
+        acc = warp_sum_f64(acc);
+        if (lane == 0) score[idx] = acc;
+    }
+}
+
+// ---- Phase III: dot(q, int8 row) / ||row||, -inf when the norm is 0 ----------------------------------------------
+// The reference does the dot in float32 (BLAS sdot, order unspecified); here it is accumulated in float64 (every
+// product q_i * d_i is exact in float64), which is within the 1e-5 parity tolerance and closer to the true value.
+__global__ void __launch_bounds__(256) rescore_int8cos_kernel(const int8_t* __restrict__ rows, int d,
+                                                              const uint64_t* __restrict__ keys,
+                                                              const int64_t* __restrict__ pos, int64_t pos_base, int m,
+                                                              const float* __restrict__ qf, double* __restrict__ score) {
+    extern __shared__ float qs[];
+    const int q = blockIdx.y;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) qs[i] = qf[(size_t)q * d + i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int words = d >> 2;
+    for (int i = blockIdx.x * 8 + warp; i < m; i += gridDim.x * 8) {
+        const size_t idx = (size_t)q * m + i;
+        const int64_t row = cand_row(keys, pos, idx, pos_base);
+        if (row < 0) {
+            if (lane == 0) score[idx] = -INFINITY;
+            continue;
+        }
+        const int* src = reinterpret_cast<const int*>(rows + (size_t)row * d);
+        double acc = 0.0;
+        int n2 = 0;
+        for (int w = lane; w < words; w += 32) {
+            const int v = __ldg(src + w);
+            const float4 qq = reinterpret_cast<const float4*>(qs)[w];
+            acc = fma((double)qq.x, (double)(int8_t)(v & 0xFF), acc);
+            acc = fma((double)qq.y, (double)(int8_t)((v >> 8) & 0xFF), acc);
+            acc = fma((double)qq.z, (double)(int8_t)((v >> 16) & 0xFF), acc);
+            acc = fma((double)qq.w, (double)(int8_t)((v >> 24) & 0xFF), acc);
+            n2 = __dp4a(v, v, n2);
+        }
+        acc = warp_sum_f64(acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(FULL, n2, o);
+        if (lane == 0) score[idx] = (n2 == 0) ? -INFINITY : acc / sqrt((double)n2);
+    }
+}
+
+// ---- 2-phase rescoring of the VectorDB* classes: float32 dot(q, dequantised payload row) -------------------------
+struct PayloadParams {
+    int kind;
+    const void* payload;
+    const void* aux;
+    float scale_f32;
+    double scale_f64;
+    int d;
+    const uint64_t* keys;
+    int64_t pos_base;
+    int m;
+    const float* qf;
+    float* score;
+};
+
+__global__ void __launch_bounds__(256) rescore_payload_kernel(PayloadParams p) {
+    extern __shared__ float qs[];
+    const int q = blockIdx.y, d = p.d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) qs[i] = p.qf[(size_t)q * d + i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = blockIdx.x * 8 + warp; i < p.m; i += gridDim.x * 8) {
+        const size_t idx = (size_t)q * p.m + i;
+        const int64_t row = cand_row(p.keys, nullptr, idx, p.pos_base);
+        if (row < 0) {
+            if (lane == 0) p.score[idx] = -INFINITY;
+            continue;
+        }
+        float sc32 = p.scale_f32;
+        double sc64 = p.scale_f64;
+        bool zero = false;
+        if (p.kind == VRQ_PAYLOAD_INT8_PERDOC) {
+            const float lo = static_cast<const float*>(p.aux)[2 * row], hi = static_cast<const float*>(p.aux)[2 * row + 1];
+            sc32 = __fdiv_rn(fmaxf(fabsf(lo), fabsf(hi)), 127.f);
+            zero = (lo == hi);
+        } else if (p.kind == VRQ_PAYLOAD_INT4_PERDOC) {
+            const double lo = static_cast<const double*>(p.aux)[2 * row], hi = static_cast<const double*>(p.aux)[2 * row + 1];
+            sc64 = fmax(fabs(lo), fabs(hi)) / 7.0;
+            zero = (lo == hi);
+        }
+        double acc = 0.0;
+        for (int e = lane; e < d; e += 32) {
+            float v;
+            switch (p.kind) {
+                case VRQ_PAYLOAD_INT8_PERDOC:
+                case VRQ_PAYLOAD_INT8_GLOBAL:
+                    v = __fmul_rn((float)static_cast<const int8_t*>(p.payload)[(size_t)row * d + e], sc32);
+                    break;
+                case VRQ_PAYLOAD_INT16_GLOBAL:
+                    v = __fmul_rn((float)static_cast<const int16_t*>(p.payload)[(size_t)row * d + e], sc32);
+                    break;
+                case VRQ_PAYLOAD_INT4_PERDOC:
+                case VRQ_PAYLOAD_INT4_GLOBAL: {
+                    const uint8_t b = static_cast<const uint8_t*>(p.payload)[(size_t)row * (d >> 1) + (e >> 1)];
+                    const int nib = (e & 1) ? (b & 0xF) : (b >> 4);
+                    v = (float)__dmul_rn((double)(nib - 8), sc64);
+                    break;
+                }
+                case VRQ_PAYLOAD_F32:
+                    v = static_cast<const float*>(p.payload)[(size_t)row * d + e];
+                    break;
+                default:
+                    v = 0.f;
+            }
+            if (zero) v = 0.f;
+            acc = fma((double)qs[e], (double)v, acc);
+        }
+        acc = warp_sum_f64(acc);
+        if (lane == 0) p.score[idx] = (float)acc;
+    }
+}
+
+// ---- keys -> (distance, label) -------------------------------------------------------------------------------------
+__global__ void keys_to_dist_labels_kernel(const uint64_t* __restrict__ keys, int64_t count, int64_t pos_base,
+                                           const int64_t* __restrict__ id_map, int64_t id0, int32_t* __restrict__ dist,
+                                           int64_t* __restrict__ labels) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint64_t k = keys[i];
+    if (k == VRQ_KEY_NONE) {
+        if (dist) dist[i] = 0x7fffffff;
+        if (labels) labels[i] = -1;
+        return;
+    }
+    if (dist) dist[i] = (int32_t)(k >> VRQ_KEY_POS_BITS);
+    if (labels) {
+        const int64_t lp = (int64_t)(k & VRQ_KEY_POS_MASK) - pos_base;
+        labels[i] = id_map ? id_map[lp] : id0 + lp;
+    }
+}
+
+// ---- the three list.sort calls of CohereEnhancedVectorDB.search, per query, + the multi-GPU merge ----------------
+constexpr int M3_THREADS = 256;
+
+__global__ void __launch_bounds__(M3_THREADS) merge3_kernel(int world, int nq, int bk, const uint64_t* __restrict__ keys,
+                                                            const int64_t* __restrict__ labels,
+                                                            const double* __restrict__ sbin,
+                                                            const double* __restrict__ scos, int k, int k2,
+                                                            int64_t* __restrict__ out_labels, int32_t* __restrict__ out_ham,
+                                                            double* __restrict__ out_sbin, double* __restrict__ out_scos,
+                                                            int32_t* __restrict__ out_count) {
+    extern __shared__ unsigned long long sm3[];
+    const int P = next_pow2(bk);
+    unsigned long long* skey = sm3;                   // P
+    uint32_t* sval = (uint32_t*)(skey + P);           // P
+    uint32_t* src1 = sval + P;                        // P: phase-I rank -> flat source index (w * bk + j)
+    uint32_t* r2 = src1 + P;                          // P: phase-II rank -> phase-I rank
+    __shared__ SelectScratch sc;
+    __shared__ int total_s;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    auto gidx = [&](uint32_t flat) -> size_t { return ((size_t)(flat / bk) * nq + q) * bk + (flat % bk); };
+
+    // (A) global phase-I cut: the bk smallest (hamming, position) keys over all ranks
+    if (tid == 0) total_s = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int f = tid; f < world * bk; f += M3_THREADS) mine += (keys[gidx(f)] != VRQ_KEY_NONE);
+    if (mine) atomicAdd(&total_s, mine);
+    for (int i = tid; i < P; i += M3_THREADS) {
+        skey[i] = VRQ_KEY_NONE;
+        sval[i] = 0xffffffffu;
+    }
+    __syncthreads();
+    const int total = total_s;
+    const int c1 = total < bk ? total : bk;
+    unsigned long long kth = VRQ_KEY_NONE - 1;
+    if (total > bk) {
+        auto fe = [&](int t, auto f) {
+            for (int x = t; x < world * bk; x += M3_THREADS) f((unsigned long long)keys[gidx(x)]);
+        };
+        kth = radix_select_kth<M3_THREADS>(fe, bk, tid, &sc, 0);
+    }
+    if (tid == 0) sc.counter = 0;
+    __syncthreads();
+    for (int f = tid; f < world * bk; f += M3_THREADS) {
+        const unsigned long long key = keys[gidx(f)];
+        if (key <= kth) {
+            const int s = atomicAdd(&sc.counter, 1);
+            skey[s] = key;
+            sval[s] = (uint32_t)f;
+        }
+    }
+    bitonic_sort<M3_THREADS, true>(skey, sval, P, tid, 0);
+    // keep phase-I order; (B) sort by score_binary descending, stable w.r.t. phase-I rank
+    for (int i = tid; i < P; i += M3_THREADS) src1[i] = sval[i];
+    __syncthreads();
+    for (int i = tid; i < P; i += M3_THREADS) {
+        if (i < c1) {
+            skey[i] = ~ordered_from_double(sbin[gidx(src1[i])]);
+            sval[i] = (uint32_t)i;
+        } else {
+            skey[i] = VRQ_KEY_NONE;
+            sval[i] = 0xffffffffu;
+        }
+    }
+    bitonic_sort<M3_THREADS, true>(skey, sval, P, tid, 0);
+    const int c2 = c1 < k2 ? c1 : k2;
+    for (int i = tid; i < P; i += M3_THREADS) r2[i] = sval[i];
+    __syncthreads();
+    // (C) sort the first c2 by score_cosine descending, stable w.r.t. phase-II rank
+    for (int i = tid; i < P; i += M3_THREADS) {
+        if (i < c2) {
+            skey[i] = ~ordered_from_double(scos[gidx(src1[r2[i]])]);
+            sval[i] = (uint32_t)i;
+        } else {
+            skey[i] = VRQ_KEY_NONE;
+            sval[i] = 0xffffffffu;
+        }
+    }
+    bitonic_sort<M3_THREADS, true>(skey, sval, P, tid, 0);
+    const int c3 = c2 < k ? c2 : k;
+    for (int i = tid; i < k; i += M3_THREADS) {
+        const size_t o = (size_t)q * k + i;
+        if (i < c3) {
+            const size_t g = gidx(src1[r2[sval[i]]]);
+            out_labels[o] = labels[g];
+            out_ham[o] = (int32_t)(keys[g] >> VRQ_KEY_POS_BITS);
+            out_sbin[o] = sbin[g];
+            out_scos[o] = scos[g];
+        } else {
+            out_labels[o] = -1;
+            out_ham[o] = 0x7fffffff;
+            out_sbin[o] = -INFINITY;
+            out_scos[o] = -INFINITY;
+        }
+    }
+    if (tid == 0) out_count[q] = c3;
+}
+
+// ---- 2-phase classes: stable sort of all phase-I hits by float32 score descending, first k --------------------------
+__global__ void __launch_bounds__(M3_THREADS) select2_kernel(int m, const uint64_t* __restrict__ keys,
+                                                             const int64_t* __restrict__ labels,
+                                                             const float* __restrict__ score, int k,
+                                                             int64_t* __restrict__ out_labels, float* __restrict__ out_score,
+                                                             int32_t* __restrict__ out_count) {
+    extern __shared__ unsigned long long sm2[];
+    const int P = next_pow2(m);
+    unsigned long long* skey = sm2;
+    uint32_t* sval = (uint32_t*)(skey + P);
+    __shared__ int valid_s;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) valid_s = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int i = tid; i < P; i += M3_THREADS) {
+        const bool ok = i < m && keys[(size_t)q * m + i] != VRQ_KEY_NONE;
+        mine += ok;
+        skey[i] = ok ? (0xFFFFFFFFull - ordered_from_float(score[(size_t)q * m + i])) : VRQ_KEY_NONE;
+        sval[i] = ok ? (uint32_t)i : 0xffffffffu;
+    }
+    if (mine) atomicAdd(&valid_s, mine);
+    bitonic_sort<M3_THREADS, true>(skey, sval, P, tid, 0);
+    const int c = valid_s < k ? valid_s : k;
+    for (int i = tid; i < k; i += M3_THREADS) {
+        const size_t o = (size_t)q * k + i;
+        if (i < c) {
+            const size_t g = (size_t)q * m + sval[i];
+            out_labels[o] = labels[g];
+            out_score[o] = score[g];
+        } else {
+            out_labels[o] = -1;
+            out_score[o] = -INFINITY;
+        }
+    }
+    if (tid == 0) out_count[q] = c;
+}
+
+int grid_x_for(vrq_ctx* ctx, int64_t nq, int m) {
+    int64_t want = (m + 7) / 8;
+    int64_t cap = ((int64_t)ctx->sm_count * 8 + nq - 1) / nq;
+    if (cap < 1) cap = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+}  // namespace
+
+int vrq_launch_rescore_binary(vrq_ctx* ctx, const uint8_t* codes, int d, const uint64_t* keys, const int64_t* pos,
+                              int64_t pos_base, int64_t nq, int m, const float* qf, double* score, cudaStream_t st) {
+    if (nq == 0 || m == 0) return 0;
+    if (d % 32 != 0 || d > 12288) {
+        vrq_set_error("rescore_binary needs d %% 32 == 0 and d <= 12288 (got %d)", d);
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    vrq_timer_scope ts(ctx, VRQ_CAT_RESCORE, st);
+    dim3 grid(grid_x_for(ctx, nq, m), (unsigned)nq);
+    rescore_binary_kernel<<<grid, 256, sizeof(float) * d, st>>>(codes, d, keys, pos, pos_base, m, qf, score);
+    vrq_count_launch(ctx);
+    VRQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int vrq_launch_rescore_int8cos(vrq_ctx* ctx, const int8_t* rows, int d, const uint64_t* keys, const int64_t* pos,
+                               int64_t pos_base, int64_t nq, int m, const float* qf, double* score, cudaStream_t st) {
+    if (nq == 0 || m == 0) return 0;
+    if (d % 32 != 0 || d > 12288) {
+        vrq_set_error("rescore_int8cos needs d %% 32 == 0 and d <= 12288 (got %d)", d);
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    vrq_timer_scope ts(ctx, VRQ_CAT_RESCORE, st);
+    dim3 grid(grid_x_for(ctx, nq, m), (unsigned)nq);
+    rescore_int8cos_kernel<<<grid, 256, sizeof(float) * d, st>>>(rows, d, keys, pos, pos_base, m, qf, score);
+    vrq_count_launch(ctx);
+    VRQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int vrq_launch_rescore_payload_dot(vrq_ctx* ctx, const vrq_rescore2_args& a, cudaStream_t st) {
+    if (a.nq == 0 || a.m == 0) return 0;
+    if (a.d % 32 != 0 || a.d > 12288) {
+        vrq_set_error("payload rescoring needs d %% 32 == 0 and d <= 12288 (got %d)", a.d);
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    PayloadParams p{};
+    p.kind = a.kind;
+    p.payload = a.payload;
+    p.aux = a.aux;
+    p.d = a.d;
+    p.keys = a.keys;
+    p.pos_base = a.pos_base;
+    p.m = a.m;
+    p.qf = a.qf;
+    p.score = a.score;
+    if (a.kind == VRQ_PAYLOAD_INT8_GLOBAL) p.scale_f32 = (float)(a.limit / 127.0);
+    if (a.kind == VRQ_PAYLOAD_INT16_GLOBAL) p.scale_f32 = (float)(a.limit / 32767.0);
+    if (a.kind == VRQ_PAYLOAD_INT4_GLOBAL) p.scale_f64 = a.limit / 7.0;
+    vrq_timer_scope ts(ctx, VRQ_CAT_RESCORE, st);
+    dim3 grid(grid_x_for(ctx, a.nq, a.m), (unsigned)a.nq);
+    rescore_payload_kernel<<<grid, 256, sizeof(float) * a.d, st>>>(p);
+    vrq_count_launch(ctx);
+    VRQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int vrq_launch_keys_to_dist_labels(vrq_ctx* ctx, const uint64_t* keys, int64_t count, int64_t pos_base,
+                                   const int64_t* id_map, int64_t id0, int32_t* dist, int64_t* labels, cudaStream_t st) {
+    if (count == 0) return 0;
+    keys_to_dist_labels_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(keys, count, pos_base, id_map, id0, dist, labels);
+    vrq_count_launch(ctx);
+    VRQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int vrq_launch_merge3(vrq_ctx* ctx, int world, int64_t nq, int bk, const uint64_t* keys, const int64_t* labels,
+                      const double* sbin, const double* scos, int k, int k2, int64_t* out_labels, int32_t* out_ham,
+                      double* out_sbin, double* out_scos, int32_t* out_count, cudaStream_t st) {
+    if (nq == 0) return 0;
+    if (bk <= 0 || bk > VRQ_MAX_K || k <= 0 || k2 <= 0 || world <= 0) {
+        vrq_set_error("merge3: need 1 <= binary_k <= %d, k > 0, k2 > 0, world > 0", VRQ_MAX_K);
+        return VRQ_ERR_ARG;
+    }
+    int P = 1;
+    while (P < bk) P <<= 1;
+    size_t smem = (size_t)P * (8 + 4 + 4 + 4);
+    if (smem > 40 * 1024)
+        VRQ_CUDA(cudaFuncSetAttribute(merge3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vrq_timer_scope ts(ctx, VRQ_CAT_MERGE, st);
+    merge3_kernel<<<(unsigned)nq, M3_THREADS, smem, st>>>(world, (int)nq, bk, keys, labels, sbin, scos, k, k2, out_labels,
+                                                          out_ham, out_sbin, out_scos, out_count);
+    vrq_count_launch(ctx);
+    VRQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int vrq_launch_select2(vrq_ctx* ctx, int64_t nq, int m, const uint64_t* keys, const int64_t* labels, const float* score,
+                       int k, int64_t* out_labels, float* out_score, int32_t* out_count, cudaStream_t st) {
+    if (nq == 0) return 0;
+    if (m <= 0 || m > VRQ_MAX_K || k <= 0) {
+        vrq_set_error("select2: need 1 <= m <= %d and k > 0", VRQ_MAX_K);
+        return VRQ_ERR_ARG;
+    }
+    int P = 1;
+    while (P < m) P <<= 1;
+    size_t smem = (size_t)P * 12;
+    if (smem > 40 * 1024)
+        VRQ_CUDA(cudaFuncSetAttribute(select2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vrq_timer_scope ts(ctx, VRQ_CAT_MERGE, st);
+    select2_kernel<<<(unsigned)nq, M3_THREADS, smem, st>>>(m, keys, labels, score, k, out_labels, out_score, out_count);
+    vrq_count_launch(ctx);
+    VRQ_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,542 @@
+// Phase I: exact Hamming top-k over a flat array of binary codes (replacement for faiss
+// IndexBinaryFlat::search as called at CohereEnhancedVectorDB.py:268 / VectorDBInt8.py:218).
+//
+// Result contract: for every query the k codes with the smallest key (hamming << 40 | position), ascending -
+// i.e. ties broken by ascending position, exactly what faiss's (distance, id)-ordered heap + reorder returns.
+//
+// Kernel design (B200):
+//   * grid = (query tiles) x (row strips); one persistent CTA walks its strip in ascending row order.
+//   * A producer warp streams 256-row x 128-byte tiles of codes with TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B)
+//     into a ring of shared-memory stages guarded by full/empty mbarriers.
+//   * 8 consumer warps: thread = one code.  The 128-byte code is pulled from the swizzled stage with 8
+//     conflict-free LDS.128 into registers, the stage is released immediately, and the thread then walks the
+//     query tile held in shared memory (broadcast LDS.128) doing XOR + POPC + ADD.
+//   * Top-k: a per-(strip, query) threshold tau (the k-th best distance seen so far in rows with LOWER positions)
+//     filters candidates with a strict '<' - exact under the (distance, position) key because the strip is walked
+//     in ascending position.  Survivors are appended to a per-(strip, query) list in global memory; when a list
+//     could overflow, the consumer warps radix-select the k smallest keys in shared memory and tighten tau.
+//   * A prefix pass over the first rows of the database seeds tau for the main pass, so lists rarely compact.
+//   * A per-query merge kernel radix-selects the k smallest keys over all strips' lists and bitonic-sorts them.
+// Bounds: <= ~3 queries per pass the kernel is HBM-bound (128 B per code per pass); for query batches it is bound by
+// the integer pipes (32 x (LOP3 + POPC + IADD) per (query, code) pair).  See DESIGN.md section 3.
+#include <cuda.h>
+
+#include "topk_utils.cuh"
+#include "vrq_internal.cuh"
+
+namespace {
+
+using namespace vrq;
+
+constexpr int TILE_ROWS = 256;
+constexpr int CODE_BYTES = 128;
+constexpr int STAGE_BYTES = TILE_ROWS * CODE_BYTES;  // 32 KiB
+constexpr int CONSUMER_WARPS = 8;
+constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
+constexpr int SCAN_THREADS = CONSUMER_THREADS + 32;
+constexpr int BAR_CONSUMERS = 1;
+
+struct ScanParams {
+    const uint8_t* codes;  // local row 0
+    int code_bytes;
+    int64_t row_begin, row_end;  // local rows scanned by this launch
+    int64_t pos_base;            // global position of local row 0
+    const uint8_t* queries;      // [nq][code_bytes]
+    int nq, k;
+    int num_strips;
+    int64_t rows_per_strip;  // multiple of TILE_ROWS
+    int qtile;               // queries per CTA
+    int cap;                 // capacity of one list
+    int group_tiles;         // tiles between overflow checks
+    int stages;
+    uint64_t* lists;  // [list_strips][nq][cap]
+    int* counts;      // [list_strips][nq]
+    const int* tau0;  // [nq] or null
+};
+
+// ---- PTX helpers ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+
+// ---- list compaction: keep the k smallest keys of one (strip, query) list --------------------------------
+__device__ void compact_list(uint64_t* glist, int n, int k, unsigned long long* scratch, SelectScratch* sc, int tid,
+                             int* cnt_q, int* tau_q) {
+    for (int i = tid; i < n; i += CONSUMER_THREADS) scratch[i] = glist[i];
+    group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
+    auto fe = [&](int t, auto f) {
+        for (int i = t; i < n; i += CONSUMER_THREADS) f(scratch[i]);
+    };
+    const unsigned long long kth = radix_select_kth<CONSUMER_THREADS>(fe, k, tid, sc, BAR_CONSUMERS);
+    if (tid == 0) sc->counter = 0;
+    group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
+    for (int i = tid; i < n; i += CONSUMER_THREADS) {
+        unsigned long long key = scratch[i];
+        if (key <= kth) glist[atomicAdd(&sc->counter, 1)] = key;
+    }
+    group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
+    if (tid == 0) {
+        *cnt_q = k;
+        *tau_q = (int)(kth >> VRQ_KEY_POS_BITS);
+    }
+}
+
+// ---- the scan kernel ---------------------------------------------------------------------------------------
+// TMA128 = true : code_bytes == 128, TMA + swizzled shared-memory pipeline (the fast path)
+// TMA128 = false: any code_bytes % 4 == 0, codes read straight from global memory (correct, not tuned)
+template <bool TMA128>
+__global__ void __launch_bounds__(SCAN_THREADS, 1)
+hamming_scan_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // carve shared memory: [stages | query codes | tau | cnt | scratch | select scratch | barriers]
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* stage_mem = base;
+    uint8_t* ptr = base + (TMA128 ? (size_t)p.stages * STAGE_BYTES : 0);
+    uint8_t* qsm = ptr;
+    ptr += (size_t)p.qtile * p.code_bytes;
+    ptr = (uint8_t*)(((uintptr_t)ptr + 15) & ~(uintptr_t)15);
+    int* tau_s = (int*)ptr;
+    ptr += sizeof(int) * p.qtile;
+    int* cnt_s = (int*)ptr;
+    ptr += sizeof(int) * p.qtile;
+    ptr = (uint8_t*)(((uintptr_t)ptr + 15) & ~(uintptr_t)15);
+    unsigned long long* scratch = (unsigned long long*)ptr;
+    ptr += sizeof(unsigned long long) * p.cap;
+    SelectScratch* sc = (SelectScratch*)ptr;
+    ptr += sizeof(SelectScratch);
+    ptr = (uint8_t*)(((uintptr_t)ptr + 7) & ~(uintptr_t)7);
+    unsigned long long* bars = (unsigned long long*)ptr;  // full[stages], empty[stages]
+    int* flag = (int*)(bars + 2 * 8);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * p.qtile;
+    const int qt = min(p.qtile, p.nq - q0);
+    const int strip = blockIdx.y;
+    const int64_t s_begin = p.row_begin + (int64_t)strip * p.rows_per_strip;
+    const int64_t s_end = min(p.row_end, s_begin + p.rows_per_strip);
+    const int64_t nrows = s_end > s_begin ? s_end - s_begin : 0;
+    const int ntiles = (int)((nrows + TILE_ROWS - 1) / TILE_ROWS);
+
+    if (TMA128 && tid == 0) {
+        for (int s = 0; s < p.stages; s++) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[8 + s]), CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // query tile -> shared memory; thresholds and counters
+    for (int i = tid; i < p.qtile * p.code_bytes / 4; i += SCAN_THREADS) {
+        const int q = i / (p.code_bytes / 4);
+        uint32_t v = 0;
+        if (q < qt) v = reinterpret_cast<const uint32_t*>(p.queries + (size_t)q0 * p.code_bytes)[i];
+        reinterpret_cast<uint32_t*>(qsm)[i] = v;
+    }
+    for (int q = tid; q < p.qtile; q += SCAN_THREADS) {
+        tau_s[q] = (q < qt) ? (p.tau0 ? p.tau0[q0 + q] : 0x7fffffff) : 0;
+        cnt_s[q] = 0;
+    }
+    if (tid == 0) *flag = 0;
+    __syncthreads();
+
+    uint64_t* my_lists = p.lists + ((size_t)strip * p.nq + q0) * p.cap;
+
+    if (warp == CONSUMER_WARPS) {
+        // ===================== TMA producer warp =====================
+        if (TMA128 && lane == 0) {
+            for (int t = 0; t < ntiles; t++) {
+                const int s = t % p.stages;
+                const uint32_t ph = (uint32_t)(t / p.stages) & 1u;
+                mbar_wait(smem_u32(&bars[8 + s]), ph ^ 1u);
+                mbar_expect_tx(smem_u32(&bars[s]), STAGE_BYTES);
+                tma_load_2d(smem_u32(stage_mem + (size_t)s * STAGE_BYTES), &tmap, 0,
+                            (int)(s_begin + (int64_t)t * TILE_ROWS), smem_u32(&bars[s]));
+            }
+        }
+    } else {
+        // ===================== consumer warps: thread = one code =====================
+        const int r = warp * 32 + lane;
+        const int w_words = p.code_bytes / 4;
+        for (int t = 0; t < ntiles; t++) {
+            const int64_t lrow = s_begin + (int64_t)t * TILE_ROWS + r;
+            const bool valid = lrow < s_end;
+            const unsigned long long pos = (unsigned long long)(p.pos_base + lrow);
+            if (TMA128) {
+                const int s = t % p.stages;
+                mbar_wait(smem_u32(&bars[s]), (uint32_t)(t / p.stages) & 1u);
+                const uint32_t rowaddr = smem_u32(stage_mem + (size_t)s * STAGE_BYTES) + r * CODE_BYTES;
+                uint4 c[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) c[j] = lds128(rowaddr + ((j ^ (r & 7)) << 4));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars[8 + s]));  // stage is free again: registers hold the tile
+                const uint32_t qbase = smem_u32(qsm);
+#pragma unroll 2
+                for (int q = 0; q < qt; q++) {
+                    int d = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const uint4 qq = lds128(qbase + q * CODE_BYTES + j * 16);
+                        d += __popc(c[j].x ^ qq.x) + __popc(c[j].y ^ qq.y) + __popc(c[j].z ^ qq.z) + __popc(c[j].w ^ qq.w);
+                    }
+                    if (d < tau_s[q] && valid) {
+                        const int slot = atomicAdd(&cnt_s[q], 1);
+                        my_lists[(size_t)q * p.cap + slot] = ((unsigned long long)d << VRQ_KEY_POS_BITS) | pos;
+                    }
+                }
+            } else {
+                const uint32_t* crow = reinterpret_cast<const uint32_t*>(p.codes + (size_t)(valid ? lrow : 0) * p.code_bytes);
+                for (int q = 0; q < qt; q++) {
+                    const uint32_t* qrow = reinterpret_cast<const uint32_t*>(qsm + (size_t)q * p.code_bytes);
+                    int d = 0;
+                    for (int w = 0; w < w_words; w++) d += __popc(__ldg(crow + w) ^ qrow[w]);
+                    if (d < tau_s[q] && valid) {
+                        const int slot = atomicAdd(&cnt_s[q], 1);
+                        my_lists[(size_t)q * p.cap + slot] = ((unsigned long long)d << VRQ_KEY_POS_BITS) | pos;
+                    }
+                }
+            }
+            // ---- overflow check every group_tiles tiles: no list may exceed cap during the next group ----
+            if ((t + 1) % p.group_tiles == 0 && t + 1 < ntiles) {
+                group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
+                const int limit = p.cap - p.group_tiles * TILE_ROWS;
+                for (int q = tid; q < qt; q += CONSUMER_THREADS)
+                    if (cnt_s[q] > limit) atomicOr(flag, 1);
+                group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
+                if (*flag) {
+                    for (int q = 0; q < qt; q++) {
+                        const int n = cnt_s[q];
+                        if (n > limit) compact_list(my_lists + (size_t)q * p.cap, n, p.k, scratch, sc, tid, &cnt_s[q], &tau_s[q]);
+                    }
+                    group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
+                    if (tid == 0) *flag = 0;
+                    group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
+                }
+            }
+        }
+        group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
+        for (int q = tid; q < qt; q += CONSUMER_THREADS) p.counts[(size_t)strip * p.nq + q0 + q] = cnt_s[q];
+    }
+}
+
+// ---- per-query merge of all strips' lists: k smallest keys, sorted ---------------------------------------
+constexpr int MERGE_THREADS = 512;
+
+__global__ void __launch_bounds__(MERGE_THREADS) merge_lists_kernel(const uint64_t* __restrict__ lists,
+                                                                    const int* __restrict__ counts, int list_strips,
+                                                                    int nq, int cap, int k, uint64_t* __restrict__ out,
+                                                                    int* __restrict__ tau_out) {
+    extern __shared__ unsigned long long msm[];  // next_pow2(k) keys
+    __shared__ SelectScratch sc;
+    __shared__ int total_s;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) total_s = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int s = tid; s < list_strips; s += MERGE_THREADS) mine += counts[(size_t)s * nq + q];
+    if (mine) atomicAdd(&total_s, mine);
+    __syncthreads();
+    const int total = total_s;
+    const int n2 = next_pow2(k);
+    for (int i = tid; i < n2; i += MERGE_THREADS) msm[i] = VRQ_KEY_NONE;
+    auto fe = [&](int t, auto f) {
+        for (int s = 0; s < list_strips; s++) {
+            const int c = counts[(size_t)s * nq + q];
+            const uint64_t* l = lists + ((size_t)s * nq + q) * cap;
+            for (int i = t; i < c; i += MERGE_THREADS) f((unsigned long long)l[i]);
+        }
+    };
+    unsigned long long kth = VRQ_KEY_NONE;
+    if (total > k) kth = radix_select_kth<MERGE_THREADS>(fe, k, tid, &sc, 0);
+    if (tid == 0) sc.counter = 0;
+    __syncthreads();
+    fe(tid, [&](unsigned long long key) {
+        if (key <= kth) msm[atomicAdd(&sc.counter, 1)] = key;
+    });
+    bitonic_sort<MERGE_THREADS, false>(msm, nullptr, n2, tid, 0);
+    for (int i = tid; i < k; i += MERGE_THREADS) out[(size_t)q * k + i] = msm[i];
+    if (tau_out && tid == 0) {
+        // threshold for a following pass over rows with HIGHER positions: strict '<' against the k-th best distance
+        const unsigned long long last = msm[k - 1];
+        tau_out[q] = (last == VRQ_KEY_NONE) ? 0x7fffffff : (int)(last >> VRQ_KEY_POS_BITS);
+    }
+}
+
+__global__ void fill_int_kernel(int* p, int n, int v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_codes_tmap(const uint8_t* codes, int64_t nrows, CUtensorMap* out) {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !f) {
+            vrq_set_error("cuTensorMapEncodeTiled is not available from the driver");
+            return VRQ_ERR_UNSUPPORTED;
+        }
+        fn = (PFN_tmapEncodeTiled)f;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)CODE_BYTES, (cuuint64_t)nrows};
+    cuuint64_t gstride[1] = {(cuuint64_t)CODE_BYTES};
+    cuuint32_t box[2] = {(cuuint32_t)CODE_BYTES, (cuuint32_t)TILE_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)codes, gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        vrq_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    return 0;
+}
+
+struct ScanPlan {
+    int qtile, qtiles, strips, group_tiles, cap, stages;
+    int64_t rows_per_strip;
+    size_t smem;
+};
+
+size_t scan_smem_bytes(bool tma, int stages, int qtile, int code_bytes, int cap) {
+    size_t b = 1024;  // alignment slack
+    if (tma) b += (size_t)stages * STAGE_BYTES;
+    b += (size_t)qtile * code_bytes + 16;
+    b += sizeof(int) * 2 * (size_t)qtile + 16;
+    b += sizeof(unsigned long long) * (size_t)cap;
+    b += sizeof(SelectScratch) + 8;
+    b += sizeof(unsigned long long) * 16 + 16;
+    return b;
+}
+
+int plan_scan(vrq_ctx* ctx, bool tma, int code_bytes, int64_t rows, int nq, int k, ScanPlan* pl) {
+    const int sms = ctx->sm_count;
+    const bool stream_regime = nq <= 8;
+    int max_qtile = 256;
+    if ((size_t)max_qtile * code_bytes > 32 * 1024) max_qtile = (int)(32 * 1024 / code_bytes);
+    if (max_qtile < 1) max_qtile = 1;
+    pl->qtiles = (nq + max_qtile - 1) / max_qtile;
+    pl->qtile = (nq + pl->qtiles - 1) / pl->qtiles;  // balanced tiles
+    if (!stream_regime && pl->qtile < max_qtile) pl->qtile = ((pl->qtile + 7) / 8) * 8 < max_qtile ? ((pl->qtile + 7) / 8) * 8 : max_qtile;
+    pl->qtiles = (nq + pl->qtile - 1) / pl->qtile;
+    pl->group_tiles = stream_regime ? 8 : 1;
+    const int slack = k < 256 ? 256 : (k > 2048 ? 2048 : k);
+    pl->cap = k + slack + pl->group_tiles * TILE_ROWS;
+    int strips = sms / pl->qtiles;
+    if (strips < 1) strips = 1;
+    int64_t tiles = (rows + TILE_ROWS - 1) / TILE_ROWS;
+    if (tiles < 1) tiles = 1;
+    if (strips > tiles) strips = (int)tiles;
+    int64_t tps = (tiles + strips - 1) / strips;
+    pl->rows_per_strip = tps * TILE_ROWS;
+    pl->strips = (int)((tiles + tps - 1) / tps);
+    const size_t limit = ctx->smem_optin ? ctx->smem_optin : 227 * 1024;
+    pl->stages = 0;
+    if (tma) {
+        for (int s = 6; s >= 2; s--) {
+            if (scan_smem_bytes(true, s, pl->qtile, code_bytes, pl->cap) <= limit) {
+                pl->stages = s;
+                break;
+            }
+        }
+        if (pl->stages == 0) {
+            vrq_set_error("Hamming top-k with k=%d does not fit the shared-memory plan", k);
+            return VRQ_ERR_UNSUPPORTED;
+        }
+    }
+    pl->smem = scan_smem_bytes(tma, pl->stages, pl->qtile, code_bytes, pl->cap);
+    if (pl->smem > limit) {
+        vrq_set_error("Hamming top-k with k=%d does not fit the shared-memory plan", k);
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    return 0;
+}
+
+int launch_scan(vrq_ctx* ctx, bool tma, const CUtensorMap& tmap, const ScanParams& sp, const ScanPlan& pl, cudaStream_t st) {
+    dim3 grid(pl.qtiles, pl.strips);
+    if (tma) {
+        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        hamming_scan_kernel<true><<<grid, SCAN_THREADS, pl.smem, st>>>(tmap, sp);
+    } else {
+        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        hamming_scan_kernel<false><<<grid, SCAN_THREADS, pl.smem, st>>>(tmap, sp);
+    }
+    vrq_count_launch(ctx);
+    VRQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_merge(vrq_ctx* ctx, const uint64_t* lists, const int* counts, int list_strips, int nq, int cap, int k,
+                 uint64_t* out, int* tau_out, cudaStream_t st) {
+    int n2 = 1;
+    while (n2 < k) n2 <<= 1;
+    size_t smem = sizeof(unsigned long long) * (size_t)n2;
+    if (smem > 40 * 1024)
+        VRQ_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_lists_kernel<<<nq, MERGE_THREADS, smem, st>>>(lists, counts, list_strips, nq, cap, k, out, tau_out);
+    vrq_count_launch(ctx);
+    VRQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// One batch of queries (nq <= 1024): optional prefix pass, main pass, merge.
+static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_bytes, int64_t pos_base,
+                      const uint8_t* q_dev, int nq, int k, uint64_t* keys_out, cudaStream_t st) {
+    const bool tma = (code_bytes == CODE_BYTES) && ((uintptr_t)codes % 16 == 0) && n > 0;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (tma) VRQ_TRY(make_codes_tmap(codes, n, &tmap));
+
+    // prefix pass: an exact top-k of the first m rows seeds the thresholds of the main pass
+    ScanPlan main_pl;
+    VRQ_TRY(plan_scan(ctx, tma, code_bytes, n, nq, k, &main_pl));
+    int64_t m = 0;
+    if (n >= (int64_t)64 * TILE_ROWS * main_pl.strips && n >= (int64_t)16 * k) {
+        m = main_pl.rows_per_strip;  // about one strip's worth of rows
+        if (m < 4 * (int64_t)k) m = ((4 * (int64_t)k + TILE_ROWS - 1) / TILE_ROWS) * TILE_ROWS;
+        if (m > n / 2) m = 0;
+    }
+    ScanPlan pre_pl;
+    if (m > 0) {
+        VRQ_TRY(plan_scan(ctx, tma, code_bytes, m, nq, k, &pre_pl));
+        VRQ_TRY(plan_scan(ctx, tma, code_bytes, n - m, nq, k, &main_pl));
+    }
+    const int cap = main_pl.cap > (m > 0 ? pre_pl.cap : 0) ? main_pl.cap : pre_pl.cap;
+    main_pl.cap = cap;
+    main_pl.smem = scan_smem_bytes(tma, main_pl.stages, main_pl.qtile, code_bytes, cap);
+    if (m > 0) {
+        pre_pl.cap = cap;
+        pre_pl.smem = scan_smem_bytes(tma, pre_pl.stages, pre_pl.qtile, code_bytes, cap);
+    }
+    const int max_strips = (m > 0 && pre_pl.strips > main_pl.strips + 1) ? pre_pl.strips : main_pl.strips + 1;
+
+    void *lists_v, *counts_v, *tau_v;
+    VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_LISTS, sizeof(uint64_t) * (size_t)max_strips * nq * cap, &lists_v));
+    VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_COUNTS, sizeof(int) * (size_t)max_strips * nq, &counts_v));
+    VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_TAU, sizeof(int) * (size_t)nq, &tau_v));
+    uint64_t* lists = (uint64_t*)lists_v;
+    int* counts = (int*)counts_v;
+    int* tau = (int*)tau_v;
+
+    ScanParams sp{};
+    sp.codes = codes;
+    sp.code_bytes = code_bytes;
+    sp.pos_base = pos_base;
+    sp.queries = q_dev;
+    sp.nq = nq;
+    sp.k = k;
+    sp.lists = lists;
+    sp.counts = counts;
+
+    vrq_timer_scope ts(ctx, VRQ_CAT_SCAN, st);
+    int extra = 0;
+    if (m > 0) {
+        sp.row_begin = 0;
+        sp.row_end = m;
+        sp.num_strips = pre_pl.strips;
+        sp.rows_per_strip = pre_pl.rows_per_strip;
+        sp.qtile = pre_pl.qtile;
+        sp.cap = cap;
+        sp.group_tiles = pre_pl.group_tiles;
+        sp.stages = pre_pl.stages;
+        sp.tau0 = nullptr;
+        VRQ_TRY(launch_scan(ctx, tma, tmap, sp, pre_pl, st));
+        // prefix top-k -> slot [main_pl.strips] of the list array (written after the main scan reuses slots 0..)
+        // so park it in keys_out first, then copy.
+        VRQ_TRY(launch_merge(ctx, lists, counts, pre_pl.strips, nq, cap, k, keys_out, tau, st));
+        extra = 1;
+    }
+    sp.row_begin = m;
+    sp.row_end = n;
+    sp.num_strips = main_pl.strips;
+    sp.rows_per_strip = main_pl.rows_per_strip;
+    sp.qtile = main_pl.qtile;
+    sp.cap = cap;
+    sp.group_tiles = main_pl.group_tiles;
+    sp.stages = main_pl.stages;
+    sp.tau0 = m > 0 ? tau : nullptr;
+    if (n - m > 0) {
+        VRQ_TRY(launch_scan(ctx, tma, tmap, sp, main_pl, st));
+    } else {
+        VRQ_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)main_pl.strips * nq, st));
+    }
+    if (extra) {
+        // append the prefix result as one more "strip": keys (k per query, padded with NONE which sorts last)
+        uint64_t* slot = lists + (size_t)main_pl.strips * nq * cap;
+        VRQ_CUDA(cudaMemcpy2DAsync(slot, sizeof(uint64_t) * cap, keys_out, sizeof(uint64_t) * k, sizeof(uint64_t) * k, nq,
+                                   cudaMemcpyDeviceToDevice, st));
+        // count = number of real keys = min(k, m) == k here (m >= 4k)
+        fill_int_kernel<<<(nq + 255) / 256, 256, 0, st>>>(counts + (size_t)main_pl.strips * nq, nq, k);
+        vrq_count_launch(ctx);
+    }
+    VRQ_TRY(launch_merge(ctx, lists, counts, main_pl.strips + extra, nq, cap, k, keys_out, nullptr, st));
+    return 0;
+}
+
+int vrq_hamming_topk_dev(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_bytes, int64_t pos_base,
+                         const uint8_t* q_dev, int64_t nq, int k, uint64_t* keys_out, cudaStream_t st) {
+    if (nq == 0) return 0;
+    if (k <= 0 || k > VRQ_MAX_K) {
+        vrq_set_error("Hamming top-k supports 1 <= k <= %d (got %d)", VRQ_MAX_K, k);
+        return k <= 0 ? VRQ_ERR_ARG : VRQ_ERR_UNSUPPORTED;
+    }
+    if (code_bytes % 4 != 0 || code_bytes <= 0) {
+        vrq_set_error("code size must be a positive multiple of 4 bytes (got %d)", code_bytes);
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    if (n >= (1ll << 31)) {
+        vrq_set_error("one shard holds at most 2^31 - 1 codes (TMA row coordinate); shard the database across GPUs");
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    if (pos_base < 0 || pos_base + n >= (1ll << VRQ_KEY_POS_BITS)) {
+        vrq_set_error("positions beyond 2^40 are not supported");
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    VRQ_CUDA(cudaSetDevice(ctx->device));
+    const int64_t QB = 1024;
+    for (int64_t q0 = 0; q0 < nq; q0 += QB) {
+        const int nb = (int)(nq - q0 < QB ? nq - q0 : QB);
+        VRQ_TRY(topk_batch(ctx, codes, n, code_bytes, pos_base, q_dev + q0 * code_bytes, nb, k, keys_out + q0 * k, st));
+    }
+    return 0;
+}

@@ -1,0 +1,136 @@
+// Block-level exact selection and sorting primitives on 64-bit keys (shared + global memory).
+// Keys are unique by construction ((hamming << 40) | position, or (score, rank)), so "the k smallest keys" is a
+// well-defined set and every selection here is exact and deterministic.
+#pragma once
+#include <stdint.h>
+
+namespace vrq {
+
+template <int NT>
+__device__ __forceinline__ void group_sync(int bar_id) {
+    // named barrier over NT threads (bar 0 == __syncthreads when NT == blockDim)
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NT) : "memory");
+}
+
+struct SelectScratch {
+    uint32_t hist[256];
+    unsigned long long prefix;
+    unsigned long long mask;
+    int kk;
+    int counter;
+};
+
+// k-th smallest (1-based, 1 <= k <= number of keys visited) of the keys enumerated by `for_each`.
+// `for_each(tid, f)` must call f(key) for a disjoint share of the keys on every thread of the group, and
+// enumerate the same multiset on every call.  All NT threads of the group must call this function.
+template <int NT, class ForEach>
+__device__ unsigned long long radix_select_kth(ForEach for_each, int k, int tid, SelectScratch* sc, int bar_id) {
+    if (tid == 0) {
+        sc->prefix = 0ull;
+        sc->mask = 0ull;
+        sc->kk = k;
+    }
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int i = tid; i < 256; i += NT) sc->hist[i] = 0;
+        group_sync<NT>(bar_id);
+        const unsigned long long prefix = sc->prefix, mask = sc->mask;
+        for_each(tid, [&](unsigned long long key) {
+            if ((key & mask) == prefix) atomicAdd(&sc->hist[(unsigned)(key >> shift) & 255u], 1u);
+        });
+        group_sync<NT>(bar_id);
+        if (tid < 32) {
+            // 8 bins per lane, inclusive scan over lanes, locate the bin holding rank kk
+            uint32_t c[8], s = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                c[i] = sc->hist[tid * 8 + i];
+                s += c[i];
+            }
+            uint32_t inc = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (tid >= o) inc += v;
+            }
+            const uint32_t kk = (uint32_t)sc->kk;
+            const uint32_t before = inc - s;
+            const bool mine = (before < kk) && (kk <= inc);
+            __syncwarp();
+            if (mine) {
+                uint32_t acc = before;
+                int bin = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (acc + c[i] < kk) {
+                        acc += c[i];
+                        bin = i + 1;
+                    } else {
+                        break;
+                    }
+                }
+                sc->kk = (int)(kk - acc);
+                sc->prefix = prefix | ((unsigned long long)(tid * 8 + bin) << shift);
+                sc->mask = mask | (0xFFull << shift);
+            }
+        }
+        group_sync<NT>(bar_id);
+    }
+    return sc->prefix;
+}
+
+// In-place ascending bitonic sort of n2 (power of two) keys in shared memory, optional 32-bit payload.
+template <int NT, bool HAS_VAL>
+__device__ void bitonic_sort(unsigned long long* keys, uint32_t* vals, int n2, int tid, int bar_id) {
+    for (int size = 2; size <= n2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            group_sync<NT>(bar_id);
+            for (int i = tid; i < (n2 >> 1); i += NT) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool asc = ((lo & size) == 0);
+                unsigned long long a = keys[lo], b = keys[hi];
+                bool sw;
+                if (HAS_VAL) {
+                    uint32_t va = vals[lo], vb = vals[hi];
+                    const bool gt = (a > b) || (a == b && va > vb);
+                    sw = (gt == asc);
+                    if (sw && (a != b || va != vb)) {
+                        keys[lo] = b;
+                        keys[hi] = a;
+                        vals[lo] = vb;
+                        vals[hi] = va;
+                    }
+                } else {
+                    sw = ((a > b) == asc);
+                    if (sw && a != b) {
+                        keys[lo] = b;
+                        keys[hi] = a;
+                    }
+                }
+            }
+        }
+    }
+    group_sync<NT>(bar_id);
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// Monotone map double -> u64 (ascending); -0.0 is folded onto +0.0 first so that it ties with +0.0 the way
+// Python's float comparison does in list.sort.
+__device__ __forceinline__ unsigned long long ordered_from_double(double v) {
+    v = v + 0.0;
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ unsigned long long ordered_from_float(float v) {
+    v = v + 0.0f;
+    uint32_t b = __float_as_uint(v);
+    b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return (unsigned long long)b;
+}
+
+}  // namespace vrq
