@@ -150,7 +150,9 @@ int vrq_index_search2(vrq_index*, int64_t nq, const float* q_float, const uint8_
 int vrq_index_search3_local(vrq_index*, int64_t nq, const float* q_float, const uint8_t* q_ubin, int binary_k,
                             int64_t pos_base, uint64_t* keys /*[nq,binary_k] (hamming<<40 | global pos), ~0 = none*/,
                             int64_t* labels /*[nq,binary_k]*/, double* score_binary, double* score_cosine);
-int vrq_merge3(vrq_ctx*, int world, int64_t nq, int binary_k, const uint64_t* keys /*[world,nq,binary_k]*/,
+/* rank_stride: elements between consecutive ranks' [nq,binary_k] blocks inside each of the four input arrays
+ * (0 = nq*binary_k, i.e. dense [world,nq,binary_k]); lets one packed all-gather buffer feed the merge directly. */
+int vrq_merge3(vrq_ctx*, int world, int64_t nq, int binary_k, int64_t rank_stride, const uint64_t* keys,
                const int64_t* labels, const double* score_binary, const double* score_cosine, int k, int k2,
                int64_t* out_labels, int32_t* out_hamming, double* out_score_binary, double* out_score_cosine,
                int32_t* out_count);

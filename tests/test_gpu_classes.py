@@ -1,0 +1,180 @@
+"""GPU tests of the reference-shaped classes: same calls the reference's drivers make (main.py:401-428,
+maisnowflake.py:288-381), results checked against the oracle's literal restatement of each class's search."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle_c as oc  # noqa: E402
+from oracle import vrq_oracle as o  # noqa: E402
+
+DOCS = [f"AI topic number {i} is transforming field {i % 37}." for i in range(600)]
+IDS = list(range(len(DOCS)))
+QUERY = "Artificial intelligence is transforming industries."
+
+
+def synth_rows(texts, seed=1, row_scale=False):
+    from vectorragquantization_b200.embedder import text_row
+    return np.stack([oc.synth_f32(seed, text_row(t), 1, 1024, row_scale)[0] for t in texts])
+
+
+def close(a, b, floor):
+    return abs(a - b) <= 1e-5 * abs(b) + floor
+
+
+def check_search2(res, ref, floor=1e-7):
+    assert len(res) == len(ref)
+    rs = np.array([h["score"] for h in ref])
+    for i, (r, h) in enumerate(zip(res, ref)):
+        assert close(r["score"], h["score"], floor)
+        sep = (i == 0 or rs[i - 1] - rs[i] > 4e-5 * abs(rs[i]) + 4 * floor) and (
+            i == len(ref) - 1 or rs[i] - rs[i + 1] > 4e-5 * abs(rs[i]) + 4 * floor)
+        if sep:
+            assert r["doc_id"] == h["doc_id"]
+
+
+@pytest.mark.parametrize("cls,kw,deq", [
+    ("VectorDBInt8", {}, lambda x: o.dequantize_int8_perdoc(*o.quantize_int8_perdoc(x))),
+    ("VectorDBInt8Global", {"global_limit": 0.3}, lambda x: o.dequantize_int8_global(o.quantize_int8_global(x, 0.3), 0.3)),
+    ("VectorDBInt16Global", {"global_limit": 1.0}, lambda x: o.dequantize_int16_global(o.quantize_int16_global(x, 1.0), 1.0)),
+    ("VectorDBInt4", {}, lambda x: o.dequantize_int4_perdoc(*((lambda p, lo, hi: (p, 1024, lo, hi))(*o.quantize_int4(x))))),
+    ("VectorDBInt4Global", {"global_limit": 0.18}, lambda x: o.dequantize_int4_global(o.quantize_int4(x)[0], 1024, 0.18)),
+])
+def test_vectordb_classes(tmp_path, cls, kw, deq):
+    import vectorragquantization_b200 as V
+    C = getattr(V, cls)
+    folder = os.path.join(tmp_path, "db")
+    db = C(folder, **kw)
+    db.add_documents(IDS, DOCS, batch_size=64)
+    assert len(db) == len(DOCS) and db.index.ntotal == len(DOCS)
+    cfg = json.load(open(os.path.join(folder, "config.json")))
+    assert cfg["model"] == "snowflake-arctic-embed2" and cfg["embedding_dim"] == 1024
+    if kw:
+        assert cfg["global_limit"] == kw["global_limit"] and db.global_limit == kw["global_limit"]
+    x = synth_rows(DOCS)
+    ub = o.to_binary_f32(x)
+    assert open(os.path.join(folder, "index.bin"), "rb").read() == o.write_index_binary_bytes(1024, ub, np.array(IDS))
+    qf = synth_rows([QUERY])[0]
+    qb = o.to_binary_f32(qf)
+    emb = deq(x)
+    for k, bo in ((10, 10), (5, 3), (100, 10)):
+        ref = o.search2(ub, np.array(IDS), lambda p: emb[p], qf, qb, k, bo)
+        res = db.search(QUERY, k=k, binary_oversample=bo)
+        check_search2(res, ref)
+        assert all(r["doc"] == DOCS[r["doc_id"]] for r in res)
+        ref32 = o.search2(ub, np.array(IDS), lambda p: x[p], qf, qb, k, bo)
+        check_search2(db.search(QUERY, k=k, binary_oversample=bo, compare_float32=True), ref32)
+    with pytest.raises(ValueError):
+        db.add_documents([1, 2], ["only one"])
+    # re-adding an id replaces it (remove + add), order-preserving like faiss
+    db.add_documents([3], ["a replaced document"], save=False)
+    assert len(db) == len(DOCS)
+    assert db.index.position_of(3) == len(DOCS) - 1
+    db.remove_document(7)
+    assert len(db) == len(DOCS) - 1 and "7" not in db.doc_db
+    db.save()
+    # reopen: config + index + quantised vectors come back; float_embeddings do not (reference: RAM only)
+    db2 = C(folder, **({"global_limit": 9.9} if kw else {}))
+    if kw:
+        assert db2.global_limit == kw["global_limit"]  # stored limit wins (VectorDBInt8Global.py:73)
+    assert len(db2) == len(DOCS) - 1
+    r1, r2 = db.search(QUERY, k=10), db2.search(QUERY, k=10)
+    assert [h["doc_id"] for h in r1] == [h["doc_id"] for h in r2] and [h["score"] for h in r1] == [h["score"] for h in r2]
+    with pytest.raises(KeyError):
+        db2.search(QUERY, k=10, compare_float32=True)
+
+
+def test_static_methods_like_reference():
+    import vectorragquantization_b200 as V
+    x = oc.synth_f32(3, 0, 4, row_scale=True)
+    q, lo, hi = V.VectorDBInt8._quantize_to_int8(x[0])
+    rq, rlo, rhi = o.quantize_int8_perdoc(x[0])
+    assert np.array_equal(q, rq) and lo == rlo and hi == rhi
+    assert np.array_equal(V.VectorDBInt8._dequantize_int8(q, (lo, hi)), o.dequantize_int8_perdoc(rq, rlo, rhi))
+    assert np.array_equal(V.VectorDBInt8._to_binary(x[1]), o.to_binary_f32(x[1]))
+    assert np.array_equal(V.VectorDBInt8Global._quantize_to_int8(x[2], 0.3), o.quantize_int8_global(x[2], 0.3))
+    assert np.array_equal(V.VectorDBInt16Global._quantize_to_int16(x[2], 1.0), o.quantize_int16_global(x[2], 1.0))
+    p, a, b = V.VectorDBInt4._quantize_to_int4(x[3])
+    rp, ra, rb = o.quantize_int4(x[3])
+    assert np.array_equal(p, rp) and a == ra and b == rb and isinstance(a, float)
+    assert np.array_equal(V.VectorDBInt4Global._quantize_to_int4(x[3], 0.18), rp)  # limit ignored (trap T2)
+    assert np.array_equal(V.VectorDBInt4._dequantize_int4(p, 1024, (a, b)), o.dequantize_int4_perdoc(rp, 1024, ra, rb))
+    assert np.array_equal(V.VectorDBInt4Global._dequantize_int4(p, 1024, 0.18), o.dequantize_int4_global(rp, 1024, 0.18))
+
+
+def test_vectordb_int16_hamming_only(tmp_path):
+    import vectorragquantization_b200 as V
+    db = V.VectorDBInt16(os.path.join(tmp_path, "db16"))
+    db.add_documents(IDS, DOCS)
+    x = synth_rows(DOCS)
+    i16 = o.quantize_int16_global(x, 1.0)
+    codes = o.to_binary_int(i16)
+    q16 = o.quantize_int16_global(synth_rows([QUERY]), 1.0)
+    d, p = oc.hamming_topk(codes, o.to_binary_int(q16), 100)
+    res = db.search(QUERY, k=10)
+    assert [r["doc_id"] for r in res] == p[0][:10].tolist() and [r["score"] for r in res] == d[0][:10].tolist()
+    assert db.search(QUERY, k=1000, binary_oversample=10)[-1]["doc_id"] == oc.hamming_topk(codes, o.to_binary_int(q16), 600)[1][0][-1]
+
+
+def test_cohere_enhanced_class(tmp_path):
+    import vectorragquantization_b200 as V
+    from vectorragquantization_b200.embedder import text_row
+    folder = os.path.join(tmp_path, "enh")
+    db = V.CohereEnhancedVectorDB(folder)
+    db.add_documents(IDS, DOCS, batch_size=64)
+    assert len(db) == len(DOCS)
+    assert open(os.path.join(folder, "config.json")).read() == o.config_json("embed-english-v3.0", 1024)
+    rows = [text_row(t) for t in DOCS]
+    pairs = [oc.synth_codes_int8(1, r, 1) for r in rows]
+    codes = np.stack([p[0][0] for p in pairs])
+    i8 = np.stack([p[1][0] for p in pairs])
+    assert open(os.path.join(folder, "index.bin"), "rb").read() == o.write_index_binary_bytes(1024, codes, np.array(IDS))
+    qr = text_row(QUERY)
+    qf = oc.synth_f32(1, qr, 1)[0]
+    qb = oc.synth_codes_int8(1, qr, 1)[0][0]
+    for k, bo, io in ((10, 10, 3), (50, 10, 3), (3, 2, 2)):
+        ref = o.search3(codes, np.array(IDS), i8, qf, qb, k, bo, io)
+        res = db.search(QUERY, k=k, binary_oversample=bo, int8_oversample=io)
+        assert [r["doc_id"] for r in res] == [h["doc_id"] for h in ref]
+        assert [r["score_hamming"] for r in res] == [h["score_hamming"] for h in ref]
+        for r, h in zip(res, ref):
+            assert isinstance(r["doc_id"], int) and r["doc"] == DOCS[r["doc_id"]]
+            assert close(r["score_binary"], h["score_binary"], 1e-12)
+            assert close(r["score_cosine"], h["score_cosine"], float(o.rescore_int8cos_absfloor(qf, i8[[h["doc_id"]]])[0]))
+    db.remove_document(ref[0]["doc_id"])
+    assert db.search(QUERY, k=3, binary_oversample=2, int8_oversample=2)[0]["doc_id"] != ref[0]["doc_id"]
+    db2 = V.CohereEnhancedVectorDB(folder)
+    assert len(db2) == len(DOCS) - 1
+    a, b = db.search(QUERY, k=10), db2.search(QUERY, k=10)
+    assert a == b
+    assert V.CohereEnhancedVectorDB(os.path.join(tmp_path, "empty")).search(QUERY) == []
+    with pytest.raises(Exception):
+        os.makedirs(os.path.join(tmp_path, "junk"))
+        open(os.path.join(tmp_path, "junk", "x"), "w").write("x")
+        V.CohereEnhancedVectorDB(os.path.join(tmp_path, "junk"))
+
+
+def test_sharded_world1_cuda_engine():
+    """ShardedSearch3 with the CUDA engine and no process group == BinaryIndex.search3."""
+    import torch
+    import vectorragquantization_b200 as V
+    from vectorragquantization_b200 import _lib as L
+    from vectorragquantization_b200.sharded import CudaEngine, ShardedSearch3
+    n, nq = 50000, 16
+    ix = V.BinaryIndex(1024, payload_kind=L.PAYLOAD_INT8_RAW)
+    ix.add_synthetic(5, 0, n, 100)
+    x = oc.synth_f32(5, 0, nq) + oc.synth_f32(6, 0, nq) * np.float32(0.5)
+    qf, qb = x.astype(np.float32), o.synth_ubinary_from_f32(x.astype(np.float32))
+    want = ix.search3(qf, qb, 10, 10, 3)
+    s = ShardedSearch3(CudaEngine(ix), pos_base=0)
+    out = s.search(qf, qb, 10, 10, 3)
+    torch.cuda.synchronize()
+    got = [out[k].cpu().numpy() for k in ("labels", "hamming", "score_binary", "score_cosine", "count")]
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
+    codes, i8 = oc.synth_codes_int8(5, 0, n)
+    ref = o.search3(codes, np.arange(n) + 100, i8, qf[0], qb[0], 10, 10, 3)
+    assert [h["doc_id"] for h in ref] == got[0][0].tolist()

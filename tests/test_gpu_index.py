@@ -246,14 +246,14 @@ def test_merge3_equals_single_index(V):
            np.empty((nq, k), np.float64), np.empty(nq, np.int32)]
     lib = L.load()
     hk, hl, hb, hc = keys.cpu().numpy(), labels.cpu().numpy(), sbin.cpu().numpy(), scos.cpu().numpy()
-    L.check(lib.vrq_merge3(ctx.handle, W, nq, bk, L.ptr(hk), L.ptr(hl), L.ptr(hb), L.ptr(hc), k, k * io,
+    L.check(lib.vrq_merge3(ctx.handle, W, nq, bk, 0, L.ptr(hk), L.ptr(hl), L.ptr(hb), L.ptr(hc), k, k * io,
                            *[L.ptr(a) for a in out]))
     # and once more entirely on device pointers (the path sharded.py uses)
     dout = [torch.empty((nq, k), dtype=torch.int64, device=dev), torch.empty((nq, k), dtype=torch.int32, device=dev),
             torch.empty((nq, k), dtype=torch.float64, device=dev), torch.empty((nq, k), dtype=torch.float64, device=dev),
             torch.empty(nq, dtype=torch.int32, device=dev)]
     torch.cuda.synchronize()
-    L.check(lib.vrq_merge3(ctx.handle, W, nq, bk, L.ptr(keys), L.ptr(labels), L.ptr(sbin), L.ptr(scos), k, k * io,
+    L.check(lib.vrq_merge3(ctx.handle, W, nq, bk, 0, L.ptr(keys), L.ptr(labels), L.ptr(sbin), L.ptr(scos), k, k * io,
                            *[L.ptr(a) for a in dout]))
     ctx.sync()
     for a, b in zip(want, dout):

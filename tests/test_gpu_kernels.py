@@ -59,8 +59,11 @@ def test_encoders_bit_exact(K, d):
     q, lo, hi, ub = K.quantize_int8_perdoc(x, want_binary=True)
     rq, rlo, rhi = o.quantize_int8_perdoc(x)
     rub = o.to_binary_f32(x)
-    assert np.array_equal(q, rq) and np.array_equal(lo, rlo) and np.array_equal(hi, rhi)
-    assert np.array_equal(ub, rub)
+    assert np.array_equal(lo, rlo) and np.array_equal(hi, rhi)
+    bad = np.nonzero((q != rq).any(axis=1))[0]
+    assert bad.size == 0, (bad[:10], [(int(c), int(q[r, c]), int(rq[r, c])) for r in bad[:3] for c in np.nonzero(q[r] != rq[r])[0][:4]])
+    bad = np.nonzero((ub != rub).any(axis=1))[0]
+    assert bad.size == 0, bad[:10]
     for lim in (0.18, 0.3, 1.0):
         q8, ub8 = K.quantize_int8_global(x, lim, want_binary=True)
         assert np.array_equal(q8, o.quantize_int8_global(x, lim)) and np.array_equal(ub8, rub)
@@ -68,7 +71,9 @@ def test_encoders_bit_exact(K, d):
         assert np.array_equal(q16, o.quantize_int16_global(x, lim))
     p4, l4, h4, ub4 = K.quantize_int4(x, want_binary=True)
     r4, rl4, rh4 = o.quantize_int4(x)
-    assert np.array_equal(p4, r4) and np.array_equal(l4, rl4) and np.array_equal(h4, rh4) and np.array_equal(ub4, rub)
+    bad = np.nonzero((p4 != r4).any(axis=1))[0]
+    assert bad.size == 0, (bad[:10], [(int(c), int(p4[r, c]), int(r4[r, c])) for r in bad[:3] for c in np.nonzero(p4[r] != r4[r])[0][:4]])
+    assert np.array_equal(l4, rl4) and np.array_equal(h4, rh4) and np.array_equal(ub4, rub)
     assert np.array_equal(K.to_binary(x), rub)
     assert np.array_equal(K.to_binary(x, ge=True), o.to_binary_f32(x, ge=True))
     # single-vector call shape, like the reference's static methods

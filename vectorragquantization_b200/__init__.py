@@ -9,3 +9,8 @@ from .binary_index import (BinaryIndex, IndexBinaryFlat, IndexBinaryIDMap2, read
                            write_index_binary)
 
 __version__ = "0.1.0"
+from .cohere_enhanced import CohereEnhancedVectorDB  # noqa: F401,E402
+from .docstore import DocStore, Rdict  # noqa: F401,E402
+from .embedder import SyntheticCohereEmbedder, SyntheticEmbedder  # noqa: F401,E402
+from .vectordb import (VectorDBInt4, VectorDBInt4Global, VectorDBInt8, VectorDBInt8Global, VectorDBInt16,  # noqa: F401,E402
+                       VectorDBInt16Global)

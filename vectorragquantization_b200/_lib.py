@@ -79,7 +79,7 @@ SIGNATURES = {
     "vrq_index_search3": (_i32, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vrq_index_search2": (_i32, [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "vrq_index_search3_local": (_i32, [_vp, _i64, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
-    "vrq_merge3": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "vrq_merge3": (_i32, [_vp, _i32, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vrq_rescore_binary": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp]),
     "vrq_rescore_int8cos": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp]),
     "vrq_synth_f32": (_i32, [_vp, _u64, _i64, _i64, _i32, _i32, _vp]),

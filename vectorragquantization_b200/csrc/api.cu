@@ -304,7 +304,8 @@ extern "C" int vrq_synth_codes_int8(vrq_ctx* ctx, uint64_t seed, int64_t row0, i
     return s.finish();
 }
 
-extern "C" int vrq_merge3(vrq_ctx* ctx, int world, int64_t nq, int binary_k, const uint64_t* keys, const int64_t* labels,
+extern "C" int vrq_merge3(vrq_ctx* ctx, int world, int64_t nq, int binary_k, int64_t rank_stride, const uint64_t* keys,
+                          const int64_t* labels,
                           const double* score_binary, const double* score_cosine, int k, int k2, int64_t* out_labels,
                           int32_t* out_hamming, double* out_score_binary, double* out_score_cosine, int32_t* out_count) {
     VRQ_CHECK_ARG(ctx && keys && labels && score_binary && score_cosine, "null input");
@@ -314,7 +315,9 @@ extern "C" int vrq_merge3(vrq_ctx* ctx, int world, int64_t nq, int binary_k, con
     VRQ_TRY(vrq_space_of(all, 9, &is_dev));
     VRQ_CUDA(cudaSetDevice(ctx->device));
     Staged s{ctx, !is_dev, {}};
-    const size_t cnt = (size_t)world * nq * binary_k;
+    if (rank_stride <= 0) rank_stride = nq * (int64_t)binary_k;
+    VRQ_CHECK_ARG(rank_stride >= nq * (int64_t)binary_k, "rank_stride smaller than one rank's block");
+    const size_t cnt = (size_t)(world - 1) * (size_t)rank_stride + (size_t)nq * binary_k;
     const void *dk, *dl, *db, *dc;
     void *ol, *oh, *ob, *oc, *on;
     VRQ_TRY(s.in(keys, 8 * cnt, VRQ_WS_SEARCH_A, &dk));
@@ -326,7 +329,7 @@ extern "C" int vrq_merge3(vrq_ctx* ctx, int world, int64_t nq, int binary_k, con
     VRQ_TRY(s.out(out_score_binary, 8 * (size_t)nq * k, VRQ_WS_OUT_C, &ob));
     VRQ_TRY(s.out(out_score_cosine, 8 * (size_t)nq * k, VRQ_WS_OUT_D, &oc));
     VRQ_TRY(s.out(out_count, 4 * (size_t)nq, VRQ_WS_OUT_E, &on));
-    VRQ_TRY(vrq_launch_merge3(ctx, world, nq, binary_k, (const uint64_t*)dk, (const int64_t*)dl, (const double*)db,
+    VRQ_TRY(vrq_launch_merge3(ctx, world, nq, binary_k, rank_stride, (const uint64_t*)dk, (const int64_t*)dl, (const double*)db,
                               (const double*)dc, k, k2, (int64_t*)ol, (int32_t*)oh, (double*)ob, (double*)oc, (int32_t*)on,
                               ctx->stream));
     return s.finish();

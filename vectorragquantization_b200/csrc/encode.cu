@@ -43,8 +43,13 @@ struct RowScale {
     bool constant;
 };
 
+// float -> int conversion with x86 cvttss2si semantics (what NumPy's astype compiles to on the reference's hosts):
+// NaN and out-of-range values give the "integer indefinite" 0x80000000, whose low byte is 0.  Only reachable when a
+// row's max|x| is so small (< ~4e-37) that the per-document scale overflows to inf.
+__device__ __forceinline__ int cvt_x86(float t) { return (fabsf(t) < 2147483648.f) ? __float2int_rz(t) : (int)0x80000000; }
+
 __device__ __forceinline__ int q_perdoc8(float v, float scale) {
-    return __float2int_rz(__fmul_rn(v, scale));  // astype(int8) truncates (VectorDBInt8.py:126)
+    return cvt_x86(__fmul_rn(v, scale));  // astype(int8) truncates (VectorDBInt8.py:126)
 }
 __device__ __forceinline__ int q_global(float v, float lim, float scale, float qmax) {
     float c = fminf(fmaxf(v, -lim), lim);       // np.clip(x, -limit, limit)
@@ -54,8 +59,8 @@ __device__ __forceinline__ int q_global(float v, float lim, float scale, float q
 }
 __device__ __forceinline__ int q_int4(float v, float scale) {
     float s = rintf(__fmul_rn(v, scale));
-    s = fminf(fmaxf(s, -8.f), 7.f);
-    return (__float2int_rz(s) + 8) & 0xF;
+    s = (s != s) ? s : fminf(fmaxf(s, -8.f), 7.f);  // np.clip propagates NaN (0 * inf when the scale overflowed)
+    return (cvt_x86(s) + 8) & 0xF;
 }
 
 __device__ __forceinline__ float warp_min(float v) {

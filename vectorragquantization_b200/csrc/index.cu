@@ -602,7 +602,7 @@ extern "C" int vrq_index_search3(vrq_index* ix, int64_t nq, const float* q_float
     VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_SEARCH_E, 8 * cnt, &sc));
     VRQ_TRY(vrq_index_search3_local(ix, nq, (const float*)dqf, (const uint8_t*)dqb, bk, 0, (uint64_t*)keys, (int64_t*)lab,
                                     (double*)sb, (double*)sc));
-    VRQ_TRY(vrq_launch_merge3(ctx, 1, nq, bk, (const uint64_t*)keys, (const int64_t*)lab, (const double*)sb, (const double*)sc, k,
+    VRQ_TRY(vrq_launch_merge3(ctx, 1, nq, bk, 0, (const uint64_t*)keys, (const int64_t*)lab, (const double*)sb, (const double*)sc, k,
                               k * int8_oversample, (int64_t*)ol, (int32_t*)oh, (double*)ob, (double*)oc, (int32_t*)on, ctx->stream));
     return io.finish();
 }

@@ -196,7 +196,8 @@ __global__ void keys_to_dist_labels_kernel(const uint64_t* __restrict__ keys, in
 // ---- the three list.sort calls of CohereEnhancedVectorDB.search, per query, + the multi-GPU merge ----------------
 constexpr int M3_THREADS = 256;
 
-__global__ void __launch_bounds__(M3_THREADS) merge3_kernel(int world, int nq, int bk, const uint64_t* __restrict__ keys,
+__global__ void __launch_bounds__(M3_THREADS) merge3_kernel(int world, int nq, int bk, int64_t rank_stride,
+                                                            const uint64_t* __restrict__ keys,
                                                             const int64_t* __restrict__ labels,
                                                             const double* __restrict__ sbin,
                                                             const double* __restrict__ scos, int k, int k2,
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(M3_THREADS) merge3_kernel(int world, int nq, i
     __shared__ SelectScratch sc;
     __shared__ int total_s;
     const int q = blockIdx.x, tid = threadIdx.x;
-    auto gidx = [&](uint32_t flat) -> size_t { return ((size_t)(flat / bk) * nq + q) * bk + (flat % bk); };
+    auto gidx = [&](uint32_t flat) -> size_t { return (size_t)(flat / bk) * (size_t)rank_stride + (size_t)q * bk + (flat % bk); };
 
     // (A) global phase-I cut: the bk smallest (hamming, position) keys over all ranks
     if (tid == 0) total_s = 0;
@@ -404,7 +405,7 @@ int vrq_launch_keys_to_dist_labels(vrq_ctx* ctx, const uint64_t* keys, int64_t c
     return 0;
 }
 
-int vrq_launch_merge3(vrq_ctx* ctx, int world, int64_t nq, int bk, const uint64_t* keys, const int64_t* labels,
+int vrq_launch_merge3(vrq_ctx* ctx, int world, int64_t nq, int bk, int64_t rank_stride, const uint64_t* keys, const int64_t* labels,
                       const double* sbin, const double* scos, int k, int k2, int64_t* out_labels, int32_t* out_ham,
                       double* out_sbin, double* out_scos, int32_t* out_count, cudaStream_t st) {
     if (nq == 0) return 0;
@@ -418,7 +419,8 @@ int vrq_launch_merge3(vrq_ctx* ctx, int world, int64_t nq, int bk, const uint64_
     if (smem > 40 * 1024)
         VRQ_CUDA(cudaFuncSetAttribute(merge3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     vrq_timer_scope ts(ctx, VRQ_CAT_MERGE, st);
-    merge3_kernel<<<(unsigned)nq, M3_THREADS, smem, st>>>(world, (int)nq, bk, keys, labels, sbin, scos, k, k2, out_labels,
+    if (rank_stride <= 0) rank_stride = nq * (int64_t)bk;
+    merge3_kernel<<<(unsigned)nq, M3_THREADS, smem, st>>>(world, (int)nq, bk, rank_stride, keys, labels, sbin, scos, k, k2, out_labels,
                                                           out_ham, out_sbin, out_scos, out_count);
     vrq_count_launch(ctx);
     VRQ_CUDA(cudaGetLastError());

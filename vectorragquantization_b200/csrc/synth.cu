@@ -1,5 +1,5 @@
 // Counter-based synthetic embeddings (there is no network, so no Cohere / Ollama vectors).  Integer-exact and
-// identical to oracle/vrq_oracle.py:synth_f32 / oracle_c.c:vrqo_synth_*: every element is a pure function of
+// identical to the test oracle's generator (oracle/): every element is a pure function of
 // (seed, row, column), so any shard on any GPU - and the CPU oracle - regenerates the same database.
 #include "vrq_internal.cuh"
 

@@ -142,7 +142,7 @@ struct vrq_rescore2_args {
     float* score;  // [nq, m] float32
 };
 int vrq_launch_rescore_payload_dot(vrq_ctx* ctx, const vrq_rescore2_args& a, cudaStream_t st);
-int vrq_launch_merge3(vrq_ctx* ctx, int world, int64_t nq, int bk, const uint64_t* keys, const int64_t* labels,
+int vrq_launch_merge3(vrq_ctx* ctx, int world, int64_t nq, int bk, int64_t rank_stride, const uint64_t* keys, const int64_t* labels,
                       const double* sbin, const double* scos, int k, int k2, int64_t* out_labels, int32_t* out_ham,
                       double* out_sbin, double* out_scos, int32_t* out_count, cudaStream_t st);
 int vrq_launch_select2(vrq_ctx* ctx, int64_t nq, int m, const uint64_t* keys, const int64_t* labels, const float* score,
