@@ -45,8 +45,11 @@ const char* vrq_last_error(void);
 /* ---------------------------------------------------------------- context ------------------------- */
 int vrq_ctx_create(int device, vrq_ctx** out);
 int vrq_ctx_destroy(vrq_ctx* ctx);
-/* Run device-pointer calls on this cudaStream_t (e.g. torch's current stream).  NULL = the ctx's own stream. */
+/* Run all subsequent work of this ctx on the given cudaStream_t (e.g. torch's current stream; NULL = CUDA's legacy
+ * default stream, which is torch's default stream).  A new ctx runs on its own non-blocking stream;
+ * vrq_ctx_reset_stream goes back to it. */
 int vrq_ctx_set_stream(vrq_ctx* ctx, void* cuda_stream);
+int vrq_ctx_reset_stream(vrq_ctx* ctx);
 int vrq_ctx_sync(vrq_ctx* ctx);
 /* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 int64_t vrq_ctx_launch_count(const vrq_ctx* ctx);

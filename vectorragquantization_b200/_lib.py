@@ -44,6 +44,7 @@ SIGNATURES = {
     "vrq_ctx_create": (_i32, [_i32, C.POINTER(_vp)]),
     "vrq_ctx_destroy": (_i32, [_vp]),
     "vrq_ctx_set_stream": (_i32, [_vp, _vp]),
+    "vrq_ctx_reset_stream": (_i32, [_vp]),
     "vrq_ctx_sync": (_i32, [_vp]),
     "vrq_ctx_launch_count": (_i64, [_vp]),
     "vrq_ctx_device": (_i32, [_vp]),
@@ -148,7 +149,11 @@ class Context:
         return self._h
 
     def set_stream(self, cuda_stream: Optional[int]):
+        """Enqueue on this cudaStream_t (0 / None = the legacy default stream, i.e. torch's default stream)."""
         check(load().vrq_ctx_set_stream(self.handle, _vp(cuda_stream or 0)))
+
+    def reset_stream(self):
+        check(load().vrq_ctx_reset_stream(self.handle))
 
     def sync(self):
         check(load().vrq_ctx_sync(self.handle))

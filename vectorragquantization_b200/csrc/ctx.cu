@@ -69,7 +69,13 @@ extern "C" int vrq_ctx_destroy(vrq_ctx* c) {
 
 extern "C" int vrq_ctx_set_stream(vrq_ctx* c, void* s) {
     VRQ_CHECK_ARG(c != nullptr, "ctx is null");
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    c->stream = (cudaStream_t)s;  // NULL is CUDA's legacy default stream - which is what torch's default stream is
+    return 0;
+}
+
+extern "C" int vrq_ctx_reset_stream(vrq_ctx* c) {
+    VRQ_CHECK_ARG(c != nullptr, "ctx is null");
+    c->stream = c->own_stream;
     return 0;
 }
 
