@@ -20,6 +20,8 @@
 // Bounds: <= ~3 queries per pass the kernel is HBM-bound (128 B per code per pass); for query batches it is bound by
 // the integer pipes (32 x (LOP3 + POPC + IADD) per (query, code) pair).  See DESIGN.md section 3.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "topk_utils.cuh"
 #include "vrq_internal.cuh"
@@ -28,13 +30,18 @@ namespace {
 
 using namespace vrq;
 
-constexpr int TILE_ROWS = 256;
 constexpr int CODE_BYTES = 128;
-constexpr int STAGE_BYTES = TILE_ROWS * CODE_BYTES;  // 32 KiB
-constexpr int CONSUMER_WARPS = 8;
-constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
-constexpr int SCAN_THREADS = CONSUMER_THREADS + 32;
+constexpr int TMA_BOX_ROWS = 256;  // rows per TMA box (hardware limit per box dimension)
 constexpr int BAR_CONSUMERS = 1;
+// CW = consumer warps per CTA: 8 for query batches (long inner loops keep the POPC pipe busy), 16 for <= 8 queries
+// per pass (short per-tile work: the second warp group hides the first one's shared-memory / barrier latency).
+template <int CW>
+struct ScanCfg {
+    static constexpr int CONSUMER_THREADS = CW * 32;
+    static constexpr int THREADS = CONSUMER_THREADS + 32;
+    static constexpr int TILE_ROWS = CW * 32;
+    static constexpr int STAGE_BYTES = TILE_ROWS * CODE_BYTES;
+};
 
 struct ScanParams {
     const uint8_t* codes;  // local row 0
@@ -91,6 +98,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 
 // ---- list compaction: keep the k smallest keys of one (strip, query) list --------------------------------
+template <int CONSUMER_THREADS>
 __device__ void compact_list(uint64_t* glist, int n, int k, unsigned long long* scratch, SelectScratch* sc, int tid,
                              int* cnt_q, int* tau_q) {
     for (int i = tid; i < n; i += CONSUMER_THREADS) scratch[i] = glist[i];
@@ -115,9 +123,14 @@ __device__ void compact_list(uint64_t* glist, int n, int k, unsigned long long* 
 // ---- the scan kernel ---------------------------------------------------------------------------------------
 // TMA128 = true : code_bytes == 128, TMA + swizzled shared-memory pipeline (the fast path)
 // TMA128 = false: any code_bytes % 4 == 0, codes read straight from global memory (correct, not tuned)
-template <bool TMA128>
-__global__ void __launch_bounds__(SCAN_THREADS, 1)
+template <bool TMA128, int CW>
+__global__ void __launch_bounds__(ScanCfg<CW>::THREADS, 1)
 hamming_scan_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p) {
+    constexpr int CONSUMER_WARPS = CW;
+    constexpr int CONSUMER_THREADS = ScanCfg<CW>::CONSUMER_THREADS;
+    constexpr int SCAN_THREADS = ScanCfg<CW>::THREADS;
+    constexpr int TILE_ROWS = ScanCfg<CW>::TILE_ROWS;
+    constexpr int STAGE_BYTES = ScanCfg<CW>::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     // carve shared memory: [stages | query codes | tau | cnt | scratch | select scratch | barriers]
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -181,8 +194,10 @@ hamming_scan_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p) {
                 const uint32_t ph = (uint32_t)(t / p.stages) & 1u;
                 mbar_wait(smem_u32(&bars[8 + s]), ph ^ 1u);
                 mbar_expect_tx(smem_u32(&bars[s]), STAGE_BYTES);
-                tma_load_2d(smem_u32(stage_mem + (size_t)s * STAGE_BYTES), &tmap, 0,
-                            (int)(s_begin + (int64_t)t * TILE_ROWS), smem_u32(&bars[s]));
+#pragma unroll
+                for (int b = 0; b < TILE_ROWS / TMA_BOX_ROWS; b++)
+                    tma_load_2d(smem_u32(stage_mem + (size_t)s * STAGE_BYTES + (size_t)b * TMA_BOX_ROWS * CODE_BYTES), &tmap, 0,
+                                (int)(s_begin + (int64_t)t * TILE_ROWS + b * TMA_BOX_ROWS), smem_u32(&bars[s]));
             }
         }
     } else {
@@ -238,7 +253,7 @@ hamming_scan_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p) {
                 if (*flag) {
                     for (int q = 0; q < qt; q++) {
                         const int n = cnt_s[q];
-                        if (n > limit) compact_list(my_lists + (size_t)q * p.cap, n, p.k, scratch, sc, tid, &cnt_s[q], &tau_s[q]);
+                        if (n > limit) compact_list<CONSUMER_THREADS>(my_lists + (size_t)q * p.cap, n, p.k, scratch, sc, tid, &cnt_s[q], &tau_s[q]);
                     }
                     group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
                     if (tid == 0) *flag = 0;
@@ -247,50 +262,82 @@ hamming_scan_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p) {
             }
         }
         group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
+        // final compaction: every list leaves the kernel with at most k keys (bounds the merge's working set)
+        for (int q = 0; q < qt; q++) {
+            const int n = cnt_s[q];
+            if (n > p.k) compact_list<CONSUMER_THREADS>(my_lists + (size_t)q * p.cap, n, p.k, scratch, sc, tid, &cnt_s[q], &tau_s[q]);
+        }
+        group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
         for (int q = tid; q < qt; q += CONSUMER_THREADS) p.counts[(size_t)strip * p.nq + q0 + q] = cnt_s[q];
     }
 }
 
-// ---- per-query merge of all strips' lists: k smallest keys, sorted ---------------------------------------
+// ---- per-query merge of the strips' lists: k smallest keys, sorted ------------------------------------------
+// Tree of shared-memory merges: CTA (g, q) copies the lists of strips [g*gs, (g+1)*gs) of query q into shared memory
+// (every list holds <= k keys when the scan kernel exits), radix-selects the k smallest there, and either writes them
+// as one list of the next level or - at the last level - bitonic-sorts them into the final result.
 constexpr int MERGE_THREADS = 512;
 
-__global__ void __launch_bounds__(MERGE_THREADS) merge_lists_kernel(const uint64_t* __restrict__ lists,
-                                                                    const int* __restrict__ counts, int list_strips,
-                                                                    int nq, int cap, int k, uint64_t* __restrict__ out,
-                                                                    int* __restrict__ tau_out) {
-    extern __shared__ unsigned long long msm[];  // next_pow2(k) keys
+__global__ void __launch_bounds__(MERGE_THREADS) merge_group_kernel(const uint64_t* __restrict__ lists,
+                                                                    const int* __restrict__ counts, int nq, int cap_in,
+                                                                    int s_total, int gs, int k, int buf_cap,
+                                                                    uint64_t* __restrict__ out_lists, int* __restrict__ out_counts,
+                                                                    uint64_t* __restrict__ final_out, int* __restrict__ tau_out) {
+    extern __shared__ unsigned long long msm[];  // buf[buf_cap] | sel[next_pow2(k)] (final level only)
     __shared__ SelectScratch sc;
-    __shared__ int total_s;
-    const int q = blockIdx.x, tid = threadIdx.x;
-    if (tid == 0) total_s = 0;
-    __syncthreads();
-    int mine = 0;
-    for (int s = tid; s < list_strips; s += MERGE_THREADS) mine += counts[(size_t)s * nq + q];
-    if (mine) atomicAdd(&total_s, mine);
-    __syncthreads();
-    const int total = total_s;
-    const int n2 = next_pow2(k);
-    for (int i = tid; i < n2; i += MERGE_THREADS) msm[i] = VRQ_KEY_NONE;
-    auto fe = [&](int t, auto f) {
-        for (int s = 0; s < list_strips; s++) {
-            const int c = counts[(size_t)s * nq + q];
-            const uint64_t* l = lists + ((size_t)s * nq + q) * cap;
-            for (int i = t; i < c; i += MERGE_THREADS) f((unsigned long long)l[i]);
+    __shared__ int offs[65];
+    const int g = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
+    const int s0 = g * gs, s1 = min(s_total, s0 + gs), ns = s1 - s0;
+    unsigned long long* buf = msm;
+    unsigned long long* sel = msm + buf_cap;
+    if (tid == 0) {
+        int acc = 0;
+        for (int i = 0; i < ns; i++) {
+            offs[i] = acc;
+            acc += counts[(size_t)(s0 + i) * nq + q];
         }
-    };
-    unsigned long long kth = VRQ_KEY_NONE;
-    if (total > k) kth = radix_select_kth<MERGE_THREADS>(fe, k, tid, &sc, 0);
-    if (tid == 0) sc.counter = 0;
+        offs[ns] = acc;
+    }
     __syncthreads();
-    fe(tid, [&](unsigned long long key) {
-        if (key <= kth) msm[atomicAdd(&sc.counter, 1)] = key;
-    });
-    bitonic_sort<MERGE_THREADS, false>(msm, nullptr, n2, tid, 0);
-    for (int i = tid; i < k; i += MERGE_THREADS) out[(size_t)q * k + i] = msm[i];
-    if (tau_out && tid == 0) {
-        // threshold for a following pass over rows with HIGHER positions: strict '<' against the k-th best distance
-        const unsigned long long last = msm[k - 1];
-        tau_out[q] = (last == VRQ_KEY_NONE) ? 0x7fffffff : (int)(last >> VRQ_KEY_POS_BITS);
+    const int total = offs[ns];
+    if (total > buf_cap) __trap();  // cannot happen: lists are compacted to <= k keys by the scan kernel
+    for (int i = 0; i < ns; i++) {
+        const uint64_t* l = lists + ((size_t)(s0 + i) * nq + q) * cap_in;
+        const int c = offs[i + 1] - offs[i];
+        for (int j = tid; j < c; j += MERGE_THREADS) buf[offs[i] + j] = l[j];
+    }
+    __syncthreads();
+    unsigned long long kth = VRQ_KEY_NONE;
+    if (total > k) {
+        auto fe = [&](int t, auto f) {
+            for (int i = t; i < total; i += MERGE_THREADS) f(buf[i]);
+        };
+        kth = radix_select_kth<MERGE_THREADS>(fe, k, tid, &sc, 0);
+    }
+    if (tid == 0) sc.counter = 0;
+    if (final_out) {
+        const int n2 = next_pow2(k);
+        for (int i = tid; i < n2; i += MERGE_THREADS) sel[i] = VRQ_KEY_NONE;
+        __syncthreads();
+        for (int i = tid; i < total; i += MERGE_THREADS) {
+            const unsigned long long key = buf[i];
+            if (key <= kth) sel[atomicAdd(&sc.counter, 1)] = key;
+        }
+        bitonic_sort<MERGE_THREADS, false>(sel, nullptr, n2, tid, 0);
+        for (int i = tid; i < k; i += MERGE_THREADS) final_out[(size_t)q * k + i] = sel[i];
+        if (tau_out && tid == 0) {
+            // threshold for a following pass over rows with HIGHER positions: strict '<' against the k-th best distance
+            const unsigned long long last = sel[k - 1];
+            tau_out[q] = (last == VRQ_KEY_NONE) ? 0x7fffffff : (int)(last >> VRQ_KEY_POS_BITS);
+        }
+    } else {
+        __syncthreads();
+        uint64_t* o = out_lists + ((size_t)g * nq + q) * k;
+        for (int i = tid; i < total; i += MERGE_THREADS) {
+            const unsigned long long key = buf[i];
+            if (key <= kth) o[atomicAdd(&sc.counter, 1)] = key;
+        }
+        if (tid == 0) out_counts[(size_t)g * nq + q] = total < k ? total : k;
     }
 }
 
@@ -318,7 +365,7 @@ int make_codes_tmap(const uint8_t* codes, int64_t nrows, CUtensorMap* out) {
     }
     cuuint64_t gdim[2] = {(cuuint64_t)CODE_BYTES, (cuuint64_t)nrows};
     cuuint64_t gstride[1] = {(cuuint64_t)CODE_BYTES};
-    cuuint32_t box[2] = {(cuuint32_t)CODE_BYTES, (cuuint32_t)TILE_ROWS};
+    cuuint32_t box[2] = {(cuuint32_t)CODE_BYTES, (cuuint32_t)TMA_BOX_ROWS};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)codes, gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -331,14 +378,16 @@ int make_codes_tmap(const uint8_t* codes, int64_t nrows, CUtensorMap* out) {
 }
 
 struct ScanPlan {
+    int cw;  // consumer warps (8 or 16)
     int qtile, qtiles, strips, group_tiles, cap, stages;
     int64_t rows_per_strip;
     size_t smem;
+    int tile_rows() const { return cw * 32; }
 };
 
-size_t scan_smem_bytes(bool tma, int stages, int qtile, int code_bytes, int cap) {
+size_t scan_smem_bytes(bool tma, int cw, int stages, int qtile, int code_bytes, int cap) {
     size_t b = 1024;  // alignment slack
-    if (tma) b += (size_t)stages * STAGE_BYTES;
+    if (tma) b += (size_t)stages * cw * 32 * CODE_BYTES;
     b += (size_t)qtile * code_bytes + 16;
     b += sizeof(int) * 2 * (size_t)qtile + 16;
     b += sizeof(unsigned long long) * (size_t)cap;
@@ -347,9 +396,18 @@ size_t scan_smem_bytes(bool tma, int stages, int qtile, int code_bytes, int cap)
     return b;
 }
 
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 int plan_scan(vrq_ctx* ctx, bool tma, int code_bytes, int64_t rows, int nq, int k, ScanPlan* pl) {
     const int sms = ctx->sm_count;
     const bool stream_regime = nq <= 8;
+    // tuning knobs (defaults chosen from the measurements in profiles/): VRQ_SCAN_CW_STREAM / VRQ_SCAN_CW_BATCH
+    pl->cw = tma ? (stream_regime ? env_int("VRQ_SCAN_CW_STREAM", 16) : env_int("VRQ_SCAN_CW_BATCH", 8)) : 8;
+    if (pl->cw != 16) pl->cw = 8;
+    const int tile_rows = pl->tile_rows();
     int max_qtile = 256;
     if ((size_t)max_qtile * code_bytes > 32 * 1024) max_qtile = (int)(32 * 1024 / code_bytes);
     if (max_qtile < 1) max_qtile = 1;
@@ -357,22 +415,23 @@ int plan_scan(vrq_ctx* ctx, bool tma, int code_bytes, int64_t rows, int nq, int 
     pl->qtile = (nq + pl->qtiles - 1) / pl->qtiles;  // balanced tiles
     if (!stream_regime && pl->qtile < max_qtile) pl->qtile = ((pl->qtile + 7) / 8) * 8 < max_qtile ? ((pl->qtile + 7) / 8) * 8 : max_qtile;
     pl->qtiles = (nq + pl->qtile - 1) / pl->qtile;
-    pl->group_tiles = stream_regime ? 8 : 1;
+    pl->group_tiles = stream_regime ? env_int("VRQ_SCAN_GROUP_TILES", 4) : 1;
     const int slack = k < 256 ? 256 : (k > 2048 ? 2048 : k);
-    pl->cap = k + slack + pl->group_tiles * TILE_ROWS;
+    pl->cap = k + slack + pl->group_tiles * tile_rows;
     int strips = sms / pl->qtiles;
     if (strips < 1) strips = 1;
-    int64_t tiles = (rows + TILE_ROWS - 1) / TILE_ROWS;
+    int64_t tiles = (rows + tile_rows - 1) / tile_rows;
     if (tiles < 1) tiles = 1;
     if (strips > tiles) strips = (int)tiles;
     int64_t tps = (tiles + strips - 1) / strips;
-    pl->rows_per_strip = tps * TILE_ROWS;
+    pl->rows_per_strip = tps * tile_rows;
     pl->strips = (int)((tiles + tps - 1) / tps);
     const size_t limit = ctx->smem_optin ? ctx->smem_optin : 227 * 1024;
     pl->stages = 0;
     if (tma) {
-        for (int s = 6; s >= 2; s--) {
-            if (scan_smem_bytes(true, s, pl->qtile, code_bytes, pl->cap) <= limit) {
+        const int max_stages = env_int("VRQ_SCAN_STAGES", 8);
+        for (int s = max_stages > 8 ? 8 : max_stages; s >= 2; s--) {
+            if (scan_smem_bytes(true, pl->cw, s, pl->qtile, code_bytes, pl->cap) <= limit) {
                 pl->stages = s;
                 break;
             }
@@ -382,7 +441,7 @@ int plan_scan(vrq_ctx* ctx, bool tma, int code_bytes, int64_t rows, int nq, int 
             return VRQ_ERR_UNSUPPORTED;
         }
     }
-    pl->smem = scan_smem_bytes(tma, pl->stages, pl->qtile, code_bytes, pl->cap);
+    pl->smem = scan_smem_bytes(tma, pl->cw, pl->stages, pl->qtile, code_bytes, pl->cap);
     if (pl->smem > limit) {
         vrq_set_error("Hamming top-k with k=%d does not fit the shared-memory plan", k);
         return VRQ_ERR_UNSUPPORTED;
@@ -390,30 +449,69 @@ int plan_scan(vrq_ctx* ctx, bool tma, int code_bytes, int64_t rows, int nq, int 
     return 0;
 }
 
-int launch_scan(vrq_ctx* ctx, bool tma, const CUtensorMap& tmap, const ScanParams& sp, const ScanPlan& pl, cudaStream_t st) {
+template <bool TMA, int CW>
+int launch_scan_t(const CUtensorMap& tmap, const ScanParams& sp, const ScanPlan& pl, cudaStream_t st) {
     dim3 grid(pl.qtiles, pl.strips);
-    if (tma) {
-        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        hamming_scan_kernel<true><<<grid, SCAN_THREADS, pl.smem, st>>>(tmap, sp);
-    } else {
-        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        hamming_scan_kernel<false><<<grid, SCAN_THREADS, pl.smem, st>>>(tmap, sp);
-    }
+    VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_kernel<TMA, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    hamming_scan_kernel<TMA, CW><<<grid, ScanCfg<CW>::THREADS, pl.smem, st>>>(tmap, sp);
+    return 0;
+}
+
+int launch_scan(vrq_ctx* ctx, bool tma, const CUtensorMap& tmap, const ScanParams& sp, const ScanPlan& pl, cudaStream_t st) {
+    if (!tma)
+        VRQ_TRY((launch_scan_t<false, 8>(tmap, sp, pl, st)));
+    else if (pl.cw == 16)
+        VRQ_TRY((launch_scan_t<true, 16>(tmap, sp, pl, st)));
+    else
+        VRQ_TRY((launch_scan_t<true, 8>(tmap, sp, pl, st)));
     vrq_count_launch(ctx);
     VRQ_CUDA(cudaGetLastError());
     return 0;
 }
 
-int launch_merge(vrq_ctx* ctx, const uint64_t* lists, const int* counts, int list_strips, int nq, int cap, int k,
-                 uint64_t* out, int* tau_out, cudaStream_t st) {
+// Merge tree over `strips` lists per query (each holding <= k keys, row stride cap): returns sorted keys in out.
+int launch_merge(vrq_ctx* ctx, const uint64_t* lists, const int* counts, int strips, int nq, int cap, int k, uint64_t* out,
+                 int* tau_out, cudaStream_t st) {
     int n2 = 1;
     while (n2 < k) n2 <<= 1;
-    size_t smem = sizeof(unsigned long long) * (size_t)n2;
-    if (smem > 40 * 1024)
-        VRQ_CUDA(cudaFuncSetAttribute(merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    merge_lists_kernel<<<nq, MERGE_THREADS, smem, st>>>(lists, counts, list_strips, nq, cap, k, out, tau_out);
-    vrq_count_launch(ctx);
-    VRQ_CUDA(cudaGetLastError());
+    const size_t budget = 200 * 1024;
+    int gs = (int)((budget - sizeof(unsigned long long) * (size_t)n2) / (sizeof(unsigned long long) * (size_t)k));
+    if (gs > 64) gs = 64;
+    if (gs < 2) {
+        vrq_set_error("merge: k=%d too large for the shared-memory merge", k);
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    const uint64_t* cur_lists = lists;
+    const int* cur_counts = counts;
+    int cur_strips = strips, cur_cap = cap, level = 0;
+    while (true) {
+        const bool final_level = cur_strips <= gs;
+        const int g = final_level ? 1 : (cur_strips + gs - 1) / gs;
+        const int ns = final_level ? cur_strips : gs;
+        const int buf_cap = ns * k;
+        const size_t smem = sizeof(unsigned long long) * ((size_t)buf_cap + (final_level ? (size_t)n2 : 0));
+        VRQ_CUDA(cudaFuncSetAttribute(merge_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget + 8192)));
+        uint64_t* nxt_lists = nullptr;
+        int* nxt_counts = nullptr;
+        if (!final_level) {
+            void *a, *b;
+            VRQ_TRY(vrq_ws_get(ctx, (level & 1) ? VRQ_WS_MERGE_B : VRQ_WS_MERGE_A, sizeof(uint64_t) * (size_t)g * nq * k, &a));
+            VRQ_TRY(vrq_ws_get(ctx, (level & 1) ? VRQ_WS_MERGE_CB : VRQ_WS_MERGE_CA, sizeof(int) * (size_t)g * nq, &b));
+            nxt_lists = (uint64_t*)a;
+            nxt_counts = (int*)b;
+        }
+        merge_group_kernel<<<dim3(g, nq), MERGE_THREADS, smem, st>>>(cur_lists, cur_counts, nq, cur_cap, cur_strips, ns, k, buf_cap,
+                                                                     nxt_lists, nxt_counts, final_level ? out : nullptr,
+                                                                     final_level ? tau_out : nullptr);
+        vrq_count_launch(ctx);
+        VRQ_CUDA(cudaGetLastError());
+        if (final_level) break;
+        cur_lists = nxt_lists;
+        cur_counts = nxt_counts;
+        cur_strips = g;
+        cur_cap = k;
+        level++;
+    }
     return 0;
 }
 
@@ -431,9 +529,9 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
     ScanPlan main_pl;
     VRQ_TRY(plan_scan(ctx, tma, code_bytes, n, nq, k, &main_pl));
     int64_t m = 0;
-    if (n >= (int64_t)64 * TILE_ROWS * main_pl.strips && n >= (int64_t)16 * k) {
+    if (n >= (int64_t)64 * main_pl.tile_rows() * main_pl.strips && n >= (int64_t)16 * k) {
         m = main_pl.rows_per_strip;  // about one strip's worth of rows
-        if (m < 4 * (int64_t)k) m = ((4 * (int64_t)k + TILE_ROWS - 1) / TILE_ROWS) * TILE_ROWS;
+        if (m < 4 * (int64_t)k) m = ((4 * (int64_t)k + main_pl.tile_rows() - 1) / main_pl.tile_rows()) * main_pl.tile_rows();
         if (m > n / 2) m = 0;
     }
     ScanPlan pre_pl;
@@ -443,10 +541,10 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
     }
     const int cap = main_pl.cap > (m > 0 ? pre_pl.cap : 0) ? main_pl.cap : pre_pl.cap;
     main_pl.cap = cap;
-    main_pl.smem = scan_smem_bytes(tma, main_pl.stages, main_pl.qtile, code_bytes, cap);
+    main_pl.smem = scan_smem_bytes(tma, main_pl.cw, main_pl.stages, main_pl.qtile, code_bytes, cap);
     if (m > 0) {
         pre_pl.cap = cap;
-        pre_pl.smem = scan_smem_bytes(tma, pre_pl.stages, pre_pl.qtile, code_bytes, cap);
+        pre_pl.smem = scan_smem_bytes(tma, pre_pl.cw, pre_pl.stages, pre_pl.qtile, code_bytes, cap);
     }
     const int max_strips = (m > 0 && pre_pl.strips > main_pl.strips + 1) ? pre_pl.strips : main_pl.strips + 1;
 
@@ -481,8 +579,7 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
         sp.stages = pre_pl.stages;
         sp.tau0 = nullptr;
         VRQ_TRY(launch_scan(ctx, tma, tmap, sp, pre_pl, st));
-        // prefix top-k -> slot [main_pl.strips] of the list array (written after the main scan reuses slots 0..)
-        // so park it in keys_out first, then copy.
+        // the prefix top-k is parked in keys_out, then appended to the main pass's lists as one more "strip"
         VRQ_TRY(launch_merge(ctx, lists, counts, pre_pl.strips, nq, cap, k, keys_out, tau, st));
         extra = 1;
     }
@@ -501,7 +598,6 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
         VRQ_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)main_pl.strips * nq, st));
     }
     if (extra) {
-        // append the prefix result as one more "strip": keys (k per query, padded with NONE which sorts last)
         uint64_t* slot = lists + (size_t)main_pl.strips * nq * cap;
         VRQ_CUDA(cudaMemcpy2DAsync(slot, sizeof(uint64_t) * cap, keys_out, sizeof(uint64_t) * k, sizeof(uint64_t) * k, nq,
                                    cudaMemcpyDeviceToDevice, st));
