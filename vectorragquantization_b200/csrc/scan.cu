@@ -33,6 +33,8 @@ using namespace vrq;
 constexpr int CODE_BYTES = 128;
 constexpr int TMA_BOX_ROWS = 256;  // rows per TMA box (hardware limit per box dimension)
 constexpr int BAR_CONSUMERS = 1;
+constexpr int TAU_INF = 1 << 28;   // "no threshold yet": above any distance
+constexpr int ROW_INVALID_BIAS = 1 << 29;  // added to the distance of rows past the end of a strip: never < tau
 // CW = consumer warps per CTA: 8 for query batches (long inner loops keep the POPC pipe busy), 16 for <= 8 queries
 // per pass (short per-tile work: the second warp group hides the first one's shared-memory / barrier latency).
 template <int CW>
@@ -59,6 +61,7 @@ struct ScanParams {
     uint64_t* lists;  // [list_strips][nq][cap]
     int* counts;      // [list_strips][nq]
     const int* tau0;  // [nq] or null
+    int one;          // == 1, opaque to the compiler: multiplier that keeps the popcount accumulation on the FMA pipe (IMAD)
 };
 
 // ---- PTX helpers ----------------------------------------------------------------------------------------
@@ -91,10 +94,140 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tma
         "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ int lds32(uint32_t addr) {
+    int r;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
     return r;
+}
+
+// ---- Hamming distance of one 1024-bit code held in registers against one query in shared memory ---------------
+// Plain form: 32 x (XOR, POPC, ADD) - bound by the POPC pipe (16 lanes/clk/SM measured, profiles/microbench).
+__device__ __forceinline__ int hamming128_popc(const uint4 (&c)[8], uint32_t qaddr) {
+    int d = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint4 qq = lds128(qaddr + j * 16);
+        d += __popc(c[j].x ^ qq.x) + __popc(c[j].y ^ qq.y) + __popc(c[j].z ^ qq.z) + __popc(c[j].w ^ qq.w);
+    }
+    return d;
+}
+
+__device__ __forceinline__ void csa(uint32_t& s, uint32_t& cy, uint32_t a, uint32_t b, uint32_t d) {
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s) : "r"(a), "r"(b), "r"(d));   // a ^ b ^ d
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(cy) : "r"(a), "r"(b), "r"(d));  // majority(a, b, d)
+}
+
+// Carry-save form: 16 carry-save adders (2 LOP3 each, ALU pipe at 64 lanes/clk/SM) fold the 32 XOR words into
+// 4 words of weight 1, 10 of weight 2 and 2 of weight 4, so only 16 POPC remain: 64 LOP3 + 16 POPC per pair keeps
+// the ALU pipe and the POPC pipe equally busy (~1 clk per pair per SM instead of 2).  Exact: a CSA preserves
+// popc(a) + popc(b) + popc(d) = popc(sum) + 2 popc(carry).
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// Same carry-save tree, but the 16 population counts are accumulated with integer multiply-adds whose multiplier
+// (1, 2 or 4, derived from a kernel argument so ptxas cannot turn them back into IADD3/LEA) sits in a register: the
+// adds leave the saturated ALU pipe for the idle FMA pipe.
+__device__ __forceinline__ int hamming128_csa_imad(const uint4 (&c)[8], uint32_t qaddr, uint32_t one, uint32_t two, uint32_t four) {
+    uint32_t x[32];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint4 qq = lds128(qaddr + j * 16);
+        x[4 * j + 0] = c[j].x ^ qq.x;
+        x[4 * j + 1] = c[j].y ^ qq.y;
+        x[4 * j + 2] = c[j].z ^ qq.z;
+        x[4 * j + 3] = c[j].w ^ qq.w;
+    }
+    uint32_t s1[10], c1[10];
+#pragma unroll
+    for (int t = 0; t < 10; t++) csa(s1[t], c1[t], x[3 * t], x[3 * t + 1], x[3 * t + 2]);
+    uint32_t s2[4], c2[4];
+    csa(s2[0], c2[0], s1[0], s1[1], s1[2]);
+    csa(s2[1], c2[1], s1[3], s1[4], s1[5]);
+    csa(s2[2], c2[2], s1[6], s1[7], s1[8]);
+    csa(s2[3], c2[3], s1[9], x[30], x[31]);
+    uint32_t s3[2], c3[2];
+    csa(s3[0], c3[0], c1[0], c1[1], c1[2]);
+    csa(s3[1], c3[1], c1[3], c1[4], c1[5]);
+    uint32_t a0 = imad(__popc(s2[0]), one, __popc(s2[1]));
+    uint32_t a1 = imad(__popc(s2[2]), one, __popc(s2[3]));
+    uint32_t a2 = imad(__popc(c3[0]), four, 0u);
+    uint32_t a3 = imad(__popc(c3[1]), four, 0u);
+    a0 = imad(__popc(c1[6]), two, a0);
+    a1 = imad(__popc(c1[7]), two, a1);
+    a2 = imad(__popc(c1[8]), two, a2);
+    a3 = imad(__popc(c1[9]), two, a3);
+    a0 = imad(__popc(c2[0]), two, a0);
+    a1 = imad(__popc(c2[1]), two, a1);
+    a2 = imad(__popc(c2[2]), two, a2);
+    a3 = imad(__popc(c2[3]), two, a3);
+    a0 = imad(__popc(s3[0]), two, a0);
+    a1 = imad(__popc(s3[1]), two, a1);
+    a0 = imad(a1, one, a0);
+    a2 = imad(a3, one, a2);
+    return (int)imad(a2, one, a0);
+}
+
+__device__ __forceinline__ int hamming128_csa(const uint4 (&c)[8], uint32_t qaddr) {
+    uint32_t x[32];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint4 qq = lds128(qaddr + j * 16);
+        x[4 * j + 0] = c[j].x ^ qq.x;
+        x[4 * j + 1] = c[j].y ^ qq.y;
+        x[4 * j + 2] = c[j].z ^ qq.z;
+        x[4 * j + 3] = c[j].w ^ qq.w;
+    }
+    uint32_t s1[10], c1[10];
+#pragma unroll
+    for (int t = 0; t < 10; t++) csa(s1[t], c1[t], x[3 * t], x[3 * t + 1], x[3 * t + 2]);
+    uint32_t s2[4], c2[4];
+    csa(s2[0], c2[0], s1[0], s1[1], s1[2]);
+    csa(s2[1], c2[1], s1[3], s1[4], s1[5]);
+    csa(s2[2], c2[2], s1[6], s1[7], s1[8]);
+    csa(s2[3], c2[3], s1[9], x[30], x[31]);
+    uint32_t s3[2], c3[2];
+    csa(s3[0], c3[0], c1[0], c1[1], c1[2]);
+    csa(s3[1], c3[1], c1[3], c1[4], c1[5]);
+    const int w1 = __popc(s2[0]) + __popc(s2[1]) + __popc(s2[2]) + __popc(s2[3]);
+    const int w2 = __popc(c1[6]) + __popc(c1[7]) + __popc(c1[8]) + __popc(c1[9]) + __popc(c2[0]) + __popc(c2[1]) +
+                   __popc(c2[2]) + __popc(c2[3]) + __popc(s3[0]) + __popc(s3[1]);
+    const int w4 = __popc(c3[0]) + __popc(c3[1]);
+    return w1 + 2 * w2 + 4 * w4;
+}
+
+// 14-CSA variant: 4 words of weight 1 + 14 of weight 2 -> 18 POPC, 60 LOP3: balances the two pipes when the final
+// adds also sit on the ALU pipe.
+__device__ __forceinline__ int hamming128_csa14(const uint4 (&c)[8], uint32_t qaddr) {
+    uint32_t x[32];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint4 qq = lds128(qaddr + j * 16);
+        x[4 * j + 0] = c[j].x ^ qq.x;
+        x[4 * j + 1] = c[j].y ^ qq.y;
+        x[4 * j + 2] = c[j].z ^ qq.z;
+        x[4 * j + 3] = c[j].w ^ qq.w;
+    }
+    uint32_t s1[10], c1[10];
+#pragma unroll
+    for (int t = 0; t < 10; t++) csa(s1[t], c1[t], x[3 * t], x[3 * t + 1], x[3 * t + 2]);
+    uint32_t s2[4], c2[4];
+    csa(s2[0], c2[0], s1[0], s1[1], s1[2]);
+    csa(s2[1], c2[1], s1[3], s1[4], s1[5]);
+    csa(s2[2], c2[2], s1[6], s1[7], s1[8]);
+    csa(s2[3], c2[3], s1[9], x[30], x[31]);
+    const int w1 = __popc(s2[0]) + __popc(s2[1]) + __popc(s2[2]) + __popc(s2[3]);
+    int w2 = __popc(c2[0]) + __popc(c2[1]) + __popc(c2[2]) + __popc(c2[3]);
+#pragma unroll
+    for (int t = 0; t < 10; t++) w2 += __popc(c1[t]);
+    return w1 + 2 * w2;
 }
 
 // ---- list compaction: keep the k smallest keys of one (strip, query) list --------------------------------
@@ -123,7 +256,7 @@ __device__ void compact_list(uint64_t* glist, int n, int k, unsigned long long* 
 // ---- the scan kernel ---------------------------------------------------------------------------------------
 // TMA128 = true : code_bytes == 128, TMA + swizzled shared-memory pipeline (the fast path)
 // TMA128 = false: any code_bytes % 4 == 0, codes read straight from global memory (correct, not tuned)
-template <bool TMA128, int CW>
+template <bool TMA128, int CW, int CSA>
 __global__ void __launch_bounds__(ScanCfg<CW>::THREADS, 1)
 hamming_scan_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p) {
     constexpr int CONSUMER_WARPS = CW;
@@ -178,7 +311,7 @@ hamming_scan_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p) {
         reinterpret_cast<uint32_t*>(qsm)[i] = v;
     }
     for (int q = tid; q < p.qtile; q += SCAN_THREADS) {
-        tau_s[q] = (q < qt) ? (p.tau0 ? p.tau0[q0 + q] : 0x7fffffff) : 0;
+        tau_s[q] = (q < qt) ? (p.tau0 ? min(p.tau0[q0 + q], TAU_INF) : TAU_INF) : 0;
         cnt_s[q] = 0;
     }
     if (tid == 0) *flag = 0;
@@ -217,16 +350,17 @@ hamming_scan_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p) {
                 for (int j = 0; j < 8; j++) c[j] = lds128(rowaddr + ((j ^ (r & 7)) << 4));
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars[8 + s]));  // stage is free again: registers hold the tile
-                const uint32_t qbase = smem_u32(qsm);
-#pragma unroll 2
-                for (int q = 0; q < qt; q++) {
-                    int d = 0;
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const uint4 qq = lds128(qbase + q * CODE_BYTES + j * 16);
-                        d += __popc(c[j].x ^ qq.x) + __popc(c[j].y ^ qq.y) + __popc(c[j].z ^ qq.z) + __popc(c[j].w ^ qq.w);
-                    }
-                    if (d < tau_s[q] && valid) {
+                const uint32_t qbase = smem_u32(qsm), taubase = smem_u32(tau_s);
+                const int bias = valid ? 0 : ROW_INVALID_BIAS;  // rows past the end of the strip never pass the filter
+                uint32_t qaddr = qbase, taddr = taubase;
+                const uint32_t one = (uint32_t)p.one, two = one + one, four = two + two;
+#pragma unroll 4
+                for (int q = 0; q < qt; q++, qaddr += CODE_BYTES, taddr += 4) {
+                    const int d = (CSA == 17   ? hamming128_csa_imad(c, qaddr, one, two, four)
+                                   : CSA == 16 ? hamming128_csa(c, qaddr)
+                                   : CSA == 14 ? hamming128_csa14(c, qaddr)
+                                               : hamming128_popc(c, qaddr)) + bias;
+                    if (d < lds32(taddr)) {
                         const int slot = atomicAdd(&cnt_s[q], 1);
                         my_lists[(size_t)q * p.cap + slot] = ((unsigned long long)d << VRQ_KEY_POS_BITS) | pos;
                     }
@@ -379,6 +513,7 @@ int make_codes_tmap(const uint8_t* codes, int64_t nrows, CUtensorMap* out) {
 
 struct ScanPlan {
     int cw;  // consumer warps (8 or 16)
+    int csa;  // carry-save popcount (1) or plain XOR+POPC (0)
     int qtile, qtiles, strips, group_tiles, cap, stages;
     int64_t rows_per_strip;
     size_t smem;
@@ -405,8 +540,10 @@ int plan_scan(vrq_ctx* ctx, bool tma, int code_bytes, int64_t rows, int nq, int 
     const int sms = ctx->sm_count;
     const bool stream_regime = nq <= 8;
     // tuning knobs (defaults chosen from the measurements in profiles/): VRQ_SCAN_CW_STREAM / VRQ_SCAN_CW_BATCH
-    pl->cw = tma ? (stream_regime ? env_int("VRQ_SCAN_CW_STREAM", 16) : env_int("VRQ_SCAN_CW_BATCH", 8)) : 8;
+    pl->cw = tma ? (stream_regime ? env_int("VRQ_SCAN_CW_STREAM", 16) : env_int("VRQ_SCAN_CW_BATCH", 16)) : 8;
     if (pl->cw != 16) pl->cw = 8;
+    pl->csa = env_int("VRQ_SCAN_CSA", 16);  // 0 = plain XOR+POPC, 14 / 16 = number of carry-save adders per pair
+    if (pl->csa != 14 && pl->csa != 16 && pl->csa != 17) pl->csa = 0;  // 17 = 16 CSAs + IMAD accumulation
     const int tile_rows = pl->tile_rows();
     int max_qtile = 256;
     if ((size_t)max_qtile * code_bytes > 32 * 1024) max_qtile = (int)(32 * 1024 / code_bytes);
@@ -449,21 +586,33 @@ int plan_scan(vrq_ctx* ctx, bool tma, int code_bytes, int64_t rows, int nq, int 
     return 0;
 }
 
-template <bool TMA, int CW>
+template <bool TMA, int CW, int CSA>
 int launch_scan_t(const CUtensorMap& tmap, const ScanParams& sp, const ScanPlan& pl, cudaStream_t st) {
     dim3 grid(pl.qtiles, pl.strips);
-    VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_kernel<TMA, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    hamming_scan_kernel<TMA, CW><<<grid, ScanCfg<CW>::THREADS, pl.smem, st>>>(tmap, sp);
+    VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_kernel<TMA, CW, CSA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    hamming_scan_kernel<TMA, CW, CSA><<<grid, ScanCfg<CW>::THREADS, pl.smem, st>>>(tmap, sp);
     return 0;
 }
 
 int launch_scan(vrq_ctx* ctx, bool tma, const CUtensorMap& tmap, const ScanParams& sp, const ScanPlan& pl, cudaStream_t st) {
     if (!tma)
-        VRQ_TRY((launch_scan_t<false, 8>(tmap, sp, pl, st)));
+        VRQ_TRY((launch_scan_t<false, 8, 0>(tmap, sp, pl, st)));
+    else if (pl.cw == 16 && pl.csa == 17)
+        VRQ_TRY((launch_scan_t<true, 16, 17>(tmap, sp, pl, st)));
+    else if (pl.cw == 8 && pl.csa == 17)
+        VRQ_TRY((launch_scan_t<true, 8, 17>(tmap, sp, pl, st)));
+    else if (pl.cw == 16 && pl.csa == 16)
+        VRQ_TRY((launch_scan_t<true, 16, 16>(tmap, sp, pl, st)));
+    else if (pl.cw == 16 && pl.csa == 14)
+        VRQ_TRY((launch_scan_t<true, 16, 14>(tmap, sp, pl, st)));
     else if (pl.cw == 16)
-        VRQ_TRY((launch_scan_t<true, 16>(tmap, sp, pl, st)));
+        VRQ_TRY((launch_scan_t<true, 16, 0>(tmap, sp, pl, st)));
+    else if (pl.csa == 16)
+        VRQ_TRY((launch_scan_t<true, 8, 16>(tmap, sp, pl, st)));
+    else if (pl.csa == 14)
+        VRQ_TRY((launch_scan_t<true, 8, 14>(tmap, sp, pl, st)));
     else
-        VRQ_TRY((launch_scan_t<true, 8>(tmap, sp, pl, st)));
+        VRQ_TRY((launch_scan_t<true, 8, 0>(tmap, sp, pl, st)));
     vrq_count_launch(ctx);
     VRQ_CUDA(cudaGetLastError());
     return 0;
@@ -565,6 +714,7 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
     sp.k = k;
     sp.lists = lists;
     sp.counts = counts;
+    sp.one = 1;
 
     vrq_timer_scope ts(ctx, VRQ_CAT_SCAN, st);
     int extra = 0;
