@@ -230,10 +230,7 @@ __global__ void __launch_bounds__(M3_THREADS) merge3_kernel(int world, int nq, i
     const int c1 = total < bk ? total : bk;
     unsigned long long kth = VRQ_KEY_NONE - 1;
     if (total > bk) {
-        auto fe = [&](int t, auto f) {
-            for (int x = t; x < world * bk; x += M3_THREADS) f((unsigned long long)keys[gidx(x)]);
-        };
-        kth = radix_select_kth<M3_THREADS>(fe, bk, tid, &sc, 0);
+        kth = radix_select_kth<M3_THREADS>([&](int x) { return (unsigned long long)keys[gidx((uint32_t)x)]; }, world * bk, bk, tid, &sc, 0);
     }
     if (tid == 0) sc.counter = 0;
     __syncthreads();

@@ -236,10 +236,8 @@ __device__ void compact_list(uint64_t* glist, int n, int k, unsigned long long* 
                              int* cnt_q, int* tau_q) {
     for (int i = tid; i < n; i += CONSUMER_THREADS) scratch[i] = glist[i];
     group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
-    auto fe = [&](int t, auto f) {
-        for (int i = t; i < n; i += CONSUMER_THREADS) f(scratch[i]);
-    };
-    const unsigned long long kth = radix_select_kth<CONSUMER_THREADS>(fe, k, tid, sc, BAR_CONSUMERS);
+    const unsigned long long kth =
+        radix_select_kth<CONSUMER_THREADS>([&](int i) { return scratch[i]; }, n, k, tid, sc, BAR_CONSUMERS);
     if (tid == 0) sc->counter = 0;
     group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
     for (int i = tid; i < n; i += CONSUMER_THREADS) {
@@ -435,18 +433,28 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_group_kernel(const uint64
     __syncthreads();
     const int total = offs[ns];
     if (total > buf_cap) __trap();  // cannot happen: lists are compacted to <= k keys by the scan kernel
-    for (int i = 0; i < ns; i++) {
-        const uint64_t* l = lists + ((size_t)(s0 + i) * nq + q) * cap_in;
-        const int c = offs[i + 1] - offs[i];
-        for (int j = tid; j < c; j += MERGE_THREADS) buf[offs[i] + j] = l[j];
+    {
+        // warp w copies lists w, w + 16, ...; 4 independent 8-byte loads in flight per lane (the copy is latency-bound)
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int i = warp; i < ns; i += MERGE_THREADS / 32) {
+            const uint64_t* l = lists + ((size_t)(s0 + i) * nq + q) * cap_in;
+            unsigned long long* dst = buf + offs[i];
+            const int c = offs[i + 1] - offs[i];
+            int j = lane;
+            for (; j + 96 < c; j += 128) {
+                const unsigned long long a0 = l[j], a1 = l[j + 32], a2 = l[j + 64], a3 = l[j + 96];
+                dst[j] = a0;
+                dst[j + 32] = a1;
+                dst[j + 64] = a2;
+                dst[j + 96] = a3;
+            }
+            for (; j < c; j += 32) dst[j] = l[j];
+        }
     }
     __syncthreads();
     unsigned long long kth = VRQ_KEY_NONE;
     if (total > k) {
-        auto fe = [&](int t, auto f) {
-            for (int i = t; i < total; i += MERGE_THREADS) f(buf[i]);
-        };
-        kth = radix_select_kth<MERGE_THREADS>(fe, k, tid, &sc, 0);
+        kth = radix_select_kth<MERGE_THREADS>([&](int i) { return buf[i]; }, total, k, tid, &sc, 0);
     }
     if (tid == 0) sc.counter = 0;
     if (final_out) {

@@ -16,27 +16,71 @@ struct SelectScratch {
     uint32_t hist[256];
     unsigned long long prefix;
     unsigned long long mask;
+    unsigned long long kmin, kmax;
     int kk;
     int counter;
 };
 
-// k-th smallest (1-based, 1 <= k <= number of keys visited) of the keys enumerated by `for_each`.
-// `for_each(tid, f)` must call f(key) for a disjoint share of the keys on every thread of the group, and
-// enumerate the same multiset on every call.  All NT threads of the group must call this function.
-template <int NT, class ForEach>
-__device__ unsigned long long radix_select_kth(ForEach for_each, int k, int tid, SelectScratch* sc, int bar_id) {
+// k-th smallest (1-based, 1 <= k <= n) of the n keys load(0) .. load(n-1).  All NT threads of the group must call.
+// MSB-first radix select, 8 bits per pass, with two refinements that matter for (distance << 40 | position) keys:
+//   * the passes start at the first byte in which the keys actually differ (min ^ max), so the all-equal top bytes
+//     cost nothing;
+//   * lanes that hold the same digit are merged with match.any before the shared-memory atomic, so a digit on which
+//     most keys agree (the distance byte near the threshold) does not serialise the whole block on one address.
+template <int NT, class Load>
+__device__ unsigned long long radix_select_kth(Load load, int n, int k, int tid, SelectScratch* sc, int bar_id) {
+    const int lane = tid & 31;
+    group_sync<NT>(bar_id);  // nobody is still reading the scratch of a previous call
     if (tid == 0) {
-        sc->prefix = 0ull;
-        sc->mask = 0ull;
+        sc->kmin = ~0ull;
+        sc->kmax = 0ull;
         sc->kk = k;
     }
-    for (int shift = 56; shift >= 0; shift -= 8) {
+    group_sync<NT>(bar_id);
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (int i = tid; i < n; i += NT) {
+        const unsigned long long key = load(i);
+        lo = key < lo ? key : lo;
+        hi = key > hi ? key : hi;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = l2 < lo ? l2 : lo;
+        hi = h2 > hi ? h2 : hi;
+    }
+    if (lane == 0) {
+        atomicMin(&sc->kmin, lo);
+        atomicMax(&sc->kmax, hi);
+    }
+    group_sync<NT>(bar_id);
+    const unsigned long long diff = sc->kmin ^ sc->kmax;
+    if (diff == 0ull) return sc->kmin;  // every key identical
+    const int top_shift = ((63 - __clzll((long long)diff)) >> 3) << 3;
+    if (tid == 0) {
+        sc->mask = (top_shift >= 56) ? 0ull : (~0ull << (top_shift + 8));
+        sc->prefix = sc->kmin & sc->mask;
+    }
+    const int n_round = ((n + 31) >> 5) << 5;  // whole warps stay converged for match.any
+    for (int shift = top_shift; shift >= 0; shift -= 8) {
         for (int i = tid; i < 256; i += NT) sc->hist[i] = 0;
         group_sync<NT>(bar_id);
         const unsigned long long prefix = sc->prefix, mask = sc->mask;
-        for_each(tid, [&](unsigned long long key) {
-            if ((key & mask) == prefix) atomicAdd(&sc->hist[(unsigned)(key >> shift) & 255u], 1u);
-        });
+        for (int i = tid; i < n_round; i += NT) {
+            unsigned long long key = 0ull;
+            bool ok = false;
+            if (i < n) {
+                key = load(i);
+                ok = (key & mask) == prefix;
+            }
+#ifdef VRQ_SELECT_MATCH_ANY
+            const unsigned digit = ok ? ((unsigned)(key >> shift) & 255u) : (256u + (unsigned)lane);
+            const unsigned peers = __match_any_sync(0xffffffffu, digit);
+            if (ok && lane == (__ffs(peers) - 1)) atomicAdd(&sc->hist[digit], (uint32_t)__popc(peers));
+#else
+            if (ok) atomicAdd(&sc->hist[(unsigned)(key >> shift) & 255u], 1u);
+#endif
+        }
         group_sync<NT>(bar_id);
         if (tid < 32) {
             // 8 bins per lane, inclusive scan over lanes, locate the bin holding rank kk
