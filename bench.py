@@ -87,7 +87,7 @@ def cpu_search3_sample(n_s: int, nq_s: int, step: int = 0):
 
 def cpu_baseline(target_s: float = 12.0):
     from oracle import oracle_c as oc
-    cores = oc.num_threads()
+    cores = oc.use_all_cores()
     n_s, nq_s = 2_000_000, max(cores, 8)
     t = cpu_search3_sample(n_s, nq_s)
     while t < target_s / 3 and nq_s < 512:
@@ -104,7 +104,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle_c as oc
-    cores = oc.num_threads()
+    cores = oc.use_all_cores()
     cb, (n_s, nq_s) = cpu_baseline(6.0)
     for w in range(args.warmup):
         cpu_search3_sample(n_s, nq_s, w)

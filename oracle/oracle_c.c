@@ -323,6 +323,14 @@ void vrqo_synth_codes_int8(uint64_t seed, int64_t row0, int64_t nrows, int d, ui
     }
 }
 
+void vrqo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int vrqo_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

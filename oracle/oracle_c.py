@@ -40,6 +40,13 @@ def num_threads() -> int:
     return int(lib().vrqo_num_threads())
 
 
+def use_all_cores() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline legs want every core this process may run on."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().vrqo_set_num_threads(C.c_int(n))
+    return num_threads()
+
+
 def pairwise_sum_f32(a: np.ndarray) -> np.float32:
     a = np.ascontiguousarray(a, np.float32)
     return np.float32(lib().vrqo_pairwise_sum_f32(_p(a), C.c_int64(a.shape[0])))
