@@ -339,6 +339,7 @@ def run_gpu(args):
 
 
 def hbm_bound_kernels(torch, ctx, lib, L, index, qb_d, dev, stream, hbm_peak, peak_src, n_local):
+    h = ctx.handle
     """The two HBM-bound kernels BASELINE.json's metric names, measured with CUDA events on the launching stream:
     Hamming scan with <= 2 queries per pass (128 B per code) and the fused encoders (4096 B in + codes out per row)."""
     out = {}
@@ -385,6 +386,27 @@ def hbm_bound_kernels(torch, ctx, lib, L, index, qb_d, dev, stream, hbm_peak, pe
         s = timed(fn, 5)
         gbs = n_enc * bpr / s / 1e9
         enc[name] = {"GB/s": gbs, "frac": gbs / hbm_peak, "ms": s * 1e3, "bytes_per_row": bpr}
+    # BASELINE config 5: Phase III micro - 4096 queries x 1000 gathered int8 candidates each (HBM-gather-bound)
+    codes_p, _, pay_p, _ = index.device_ptrs()
+    if pay_p:
+        nq5, m5 = 4096, 1000
+        g = torch.Generator(device=dev)
+        g.manual_seed(5)
+        pos5 = torch.randint(0, n_local, (nq5, m5), dtype=torch.int64, device=dev, generator=g)
+        qf5 = torch.empty((nq5, D), dtype=torch.float32, device=dev)
+        L.check(lib.vrq_synth_f32(ctx.handle, 9, 0, nq5, D, 0, L.ptr(qf5)))
+        sc5 = torch.empty((nq5, m5), dtype=torch.float64, device=dev)
+        s3 = timed(lambda: L.check(lib.vrq_rescore_int8cos(h, pay_p, n_local, D, L.ptr(pos5), nq5, m5, L.ptr(qf5), L.ptr(sc5))), 5)
+        s2 = timed(lambda: L.check(lib.vrq_rescore_binary(h, codes_p, n_local, D, L.ptr(pos5), nq5, m5, L.ptr(qf5), L.ptr(sc5))), 5)
+        gb3 = nq5 * m5 * 1024 / s3 / 1e9
+        out["roofline_rescore_int8cos"] = {"kernel": "rescore_int8cos_kernel<d=1024> (CUDA-core path, float64 accumulation)",
+                                           "workload": "cfg5: 4096 queries x 1000 gathered int8 candidates, random positions over the resident rows",
+                                           "bound": "hbm", "unit": "GB/s", "achieved": gb3, "peak": hbm_peak, "frac": gb3 / hbm_peak,
+                                           "peak_source": peak_src, "ms": s3 * 1e3, "traffic": None,
+                                           "pairs_per_s": nq5 * m5 / s3,
+                                           "imma_path": "not built: 1 KB gathered per (query, candidate) with no operand reuse, so the kernel is "
+                                                        "bound by the gather; tensor cores have nothing to amortise (DESIGN.md 3.3)"}
+        out["rescore_binary_cfg5"] = {"ms": s2 * 1e3, "pairs_per_s": nq5 * m5 / s2, "GB/s": nq5 * m5 * 128 / s2 / 1e9}
     out["roofline_encode"] = {"kernel": "encode1024_kernel<INT8_GLOBAL, ubinary fused>", "bound": "hbm", "unit": "GB/s",
                               "achieved": enc["int8_global+ubinary"]["GB/s"], "peak": hbm_peak,
                               "frac": enc["int8_global+ubinary"]["frac"], "peak_source": peak_src, "rows": n_enc, "traffic": None,

@@ -103,6 +103,9 @@ int vrq_index_free(vrq_index*);
 int64_t vrq_index_ntotal(const vrq_index*); /* .ntotal  (CohereEnhancedVectorDB.py:247,267) */
 int vrq_index_d(const vrq_index*);
 int vrq_index_reserve(vrq_index*, int64_t capacity_rows);
+/* Device addresses of the resident arrays (codes u8[ntotal,d/8], ids i64[ntotal] or NULL while ids are implicit,
+ * payload rows, aux pairs) for callers that launch the stand-alone kernels on them; invalidated by add / remove. */
+int vrq_index_device_ptrs(vrq_index*, void** codes, void** ids, void** payload, void** aux);
 
 /* Optional per-position payload stored beside the codes (what the reference keeps in RocksDB and fetches one
  * pickle at a time inside its rescoring loops: CohereEnhancedVectorDB.py:303, VectorDBInt8.py:228). */

@@ -67,6 +67,7 @@ SIGNATURES = {
     "vrq_index_ntotal": (_i64, [_vp]),
     "vrq_index_d": (_i32, [_vp]),
     "vrq_index_reserve": (_i32, [_vp, _i64]),
+    "vrq_index_device_ptrs": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "vrq_index_set_payload": (_i32, [_vp, _i32, _dbl]),
     "vrq_index_payload_kind": (_i32, [_vp]),
     "vrq_index_add_with_ids": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp]),

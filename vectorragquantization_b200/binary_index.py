@@ -98,6 +98,12 @@ class BinaryIndex:
     def reserve(self, n: int) -> None:
         L.check(self._lib.vrq_index_reserve(self._h, int(n)))
 
+    def device_ptrs(self):
+        """(codes, ids, payload, aux) device addresses (ints; 0 where absent) - for the stand-alone kernels."""
+        ptrs = [C.c_void_p() for _ in range(4)]
+        L.check(self._lib.vrq_index_device_ptrs(self._h, *[C.byref(p) for p in ptrs]))
+        return tuple(p.value or 0 for p in ptrs)
+
     def position_of(self, doc_id: int) -> int:
         return int(self._lib.vrq_index_position_of(self._h, int(doc_id)))
 

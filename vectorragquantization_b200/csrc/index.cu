@@ -217,6 +217,15 @@ extern "C" int64_t vrq_index_ntotal(const vrq_index* ix) { return ix ? ix->ntota
 extern "C" int vrq_index_d(const vrq_index* ix) { return ix ? ix->d : 0; }
 extern "C" int vrq_index_payload_kind(const vrq_index* ix) { return ix ? ix->payload_kind : 0; }
 
+extern "C" int vrq_index_device_ptrs(vrq_index* ix, void** codes, void** ids, void** payload, void** aux) {
+    VRQ_CHECK_ARG(ix != nullptr, "index is null");
+    if (codes) *codes = ix->codes;
+    if (ids) *ids = ix->ids;
+    if (payload) *payload = ix->payload;
+    if (aux) *aux = ix->aux;
+    return 0;
+}
+
 extern "C" int vrq_index_reserve(vrq_index* ix, int64_t cap) {
     VRQ_CHECK_ARG(ix != nullptr && cap >= 0, "bad argument");
     if (cap <= ix->capacity) return 0;

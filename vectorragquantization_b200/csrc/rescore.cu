@@ -31,15 +31,16 @@ __device__ __forceinline__ int64_t cand_row(const uint64_t* keys, const int64_t*
 
 // ---- Phase II: sum_i q[i] * (2*bit_i - 1), float64 accumulation ------------------------------------------------
 // One warp per (query, candidate).  Lane l owns dimensions {l, l+32, l+64, ...}: the query values it needs sit in
-// consecutive shared-memory words (conflict-free) and its bit of code word t is always bit 8*(l/8) + 7 - (l%8)
-// (np.packbits is MSB-first inside each byte).  The code is never unpacked to memory.
+// consecutive shared-memory words (conflict-free, already widened to float64 once per CTA) and its bit of code word t
+// is always bit 8*(l/8) + 7 - (l%8) (np.packbits is MSB-first inside each byte).  The code is never unpacked to
+// memory: the bit only flips the sign bit of the float64 addend.
 __global__ void __launch_bounds__(256) rescore_binary_kernel(const uint8_t* __restrict__ codes, int d,
                                                              const uint64_t* __restrict__ keys,
                                                              const int64_t* __restrict__ pos, int64_t pos_base, int m,
                                                              const float* __restrict__ qf, double* __restrict__ score) {
-    extern __shared__ float qs[];
+    extern __shared__ double qd[];
     const int q = blockIdx.y;
-    for (int i = threadIdx.x; i < d; i += blockDim.x) qs[i] = qf[(size_t)q * d + i];
+    for (int i = threadIdx.x; i < d; i += blockDim.x) qd[i] = (double)qf[(size_t)q * d + i];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int words = d >> 5;
@@ -52,11 +53,17 @@ __global__ void __launch_bounds__(256) rescore_binary_kernel(const uint8_t* __re
             continue;
         }
         const uint32_t* code = reinterpret_cast<const uint32_t*>(codes + (size_t)row * (d >> 3));
+        // lane l fetches word l (+32, ...) once, coalesced; every lane then needs every word -> shuffle broadcast
         double acc = 0.0;
-        for (int t = 0; t < words; t++) {
-            const uint32_t w = __ldg(code + t);  // same address on every lane: one broadcast transaction
-            const double v = (double)qs[32 * t + lane];
-            acc += ((w >> bitpos) & 1u) ? v : -v;
+        for (int t0 = 0; t0 < words; t0 += 32) {
+            const uint32_t mine = (t0 + lane < words) ? __ldg(code + t0 + lane) : 0u;
+            const int nt = min(32, words - t0);
+            for (int t = 0; t < nt; t++) {
+                const uint32_t w = __shfl_sync(FULL, mine, t);
+                const double v = qd[32 * (t0 + t) + lane];
+                const int hi = __double2hiint(v) ^ (int)((~(w >> bitpos) & 1u) << 31);  // bit 0 -> negate
+                acc += __hiloint2double(hi, __double2loint(v));
+            }
         }
         acc = warp_sum_f64(acc);
         if (lane == 0) score[idx] = acc;
@@ -65,40 +72,140 @@ __global__ void __launch_bounds__(256) rescore_binary_kernel(const uint8_t* __re
 
 // ---- Phase III: dot(q, int8 row) / ||row||, -inf when the norm is 0 ----------------------------------------------
 // The reference does the dot in float32 (BLAS sdot, order unspecified); here it is accumulated in float64 (every
-// product q_i * d_i is exact in float64), which is within the 1e-5 parity tolerance and closer to the true value.
-__global__ void __launch_bounds__(256) rescore_int8cos_kernel(const int8_t* __restrict__ rows, int d,
+// product is exact in float64), which is within the 1e-5 parity tolerance and closer to the true value.
+// HBM-gather-bound: 1 KB per (query, candidate), no operand reuse.  To stay under the gather time the inner loop has
+// no int->float conversion: byte b (offset by 128) is dropped into the mantissa of the double 4096 + (b + 128) with
+// one PRMT, so each element costs one PRMT + one DFMA; the offset is removed once per candidate with sum(q).
+template <bool D1024>
+__global__ void __launch_bounds__(256, 2) rescore_int8cos_kernel(const int8_t* __restrict__ rows, int d,
                                                               const uint64_t* __restrict__ keys,
                                                               const int64_t* __restrict__ pos, int64_t pos_base, int m,
                                                               const float* __restrict__ qf, double* __restrict__ score) {
-    extern __shared__ float qs[];
+    extern __shared__ double qd[];  // generic path only
+    __shared__ double qsum_s[8];
     const int q = blockIdx.y;
-    for (int i = threadIdx.x; i < d; i += blockDim.x) qs[i] = qf[(size_t)q * d + i];
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int words = d >> 2;
-    for (int i = blockIdx.x * 8 + warp; i < m; i += gridDim.x * 8) {
-        const size_t idx = (size_t)q * m + i;
-        const int64_t row = cand_row(keys, pos, idx, pos_base);
-        if (row < 0) {
-            if (lane == 0) score[idx] = -INFINITY;
-            continue;
-        }
-        const int* src = reinterpret_cast<const int*>(rows + (size_t)row * d);
-        double acc = 0.0;
-        int n2 = 0;
-        for (int w = lane; w < words; w += 32) {
-            const int v = __ldg(src + w);
-            const float4 qq = reinterpret_cast<const float4*>(qs)[w];
-            acc = fma((double)qq.x, (double)(int8_t)(v & 0xFF), acc);
-            acc = fma((double)qq.y, (double)(int8_t)((v >> 8) & 0xFF), acc);
-            acc = fma((double)qq.z, (double)(int8_t)((v >> 16) & 0xFF), acc);
-            acc = fma((double)qq.w, (double)(int8_t)((v >> 24) & 0xFF), acc);
-            n2 = __dp4a(v, v, n2);
-        }
-        acc = warp_sum_f64(acc);
+    // lane-private query slice, float64: for d == 1024 the 32 elements of the two 16-byte chunks this lane loads
+    double qr[D1024 ? 32 : 1];
+    double qsum = 0.0;
+    if (D1024) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(FULL, n2, o);
-        if (lane == 0) score[idx] = (n2 == 0) ? -INFINITY : acc / sqrt((double)n2);
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                // opaque conversion: keeps the 32 float64 values resident in registers (otherwise the compiler
+                // re-converts the float32 inside the loop and the kernel becomes bound by the conversion unit)
+                const float f = qf[(size_t)q * 1024 + 512 * h + 16 * lane + e];
+                asm volatile("cvt.f64.f32 %0, %1;" : "=d"(qr[16 * h + e]) : "f"(f));
+                qsum += qr[16 * h + e];
+            }
+    } else {
+        for (int i = threadIdx.x; i < d; i += blockDim.x) qd[i] = (double)qf[(size_t)q * d + i];
+        __syncthreads();
+        for (int i = lane; i < d; i += 32) qsum += qd[i];
+    }
+    qsum = warp_sum_f64(qsum);
+    (void)qsum_s;
+    const double offset = 4224.0 * qsum;  // sum_i q_i * (4096 + 128)
+    if (D1024) {
+        // Per candidate the dependent chain is position -> row address -> 1 KB row -> 8-deep DFMA chain -> shuffle tree
+        // -> sqrt -> divide.  Candidates are processed in chunks of 32: lane j fetches the position of candidate j
+        // (one coalesced load per chunk), rows are double-buffered in registers, and lane j keeps the reduced
+        // (dot, sum of squares) of candidate j so that the 32 sqrt + divide + store run once per chunk, in parallel.
+        const int step = gridDim.x * 8, first = blockIdx.x * 8 + warp;
+        const int ncand = first < m ? (m - first + step - 1) / step : 0;
+        for (int c0 = 0; c0 < ncand; c0 += 32) {
+            const int nchunk = min(32, ncand - c0);
+            const size_t myidx = (size_t)q * m + first + (size_t)(c0 + lane) * step;
+            const int64_t myrow = (lane < nchunk) ? cand_row(keys, pos, myidx, pos_base) : -1;
+            double my_acc = 0.0;
+            int my_n2 = 0;
+            // register ring: the rows of candidates j .. j+3 are in flight (4 KB per warp, ~64 KB per SM)
+            uint4 ra[4], rb[4];
+            int64_t rr[4];
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                ra[p] = make_uint4(0, 0, 0, 0);
+                rb[p] = ra[p];
+                rr[p] = __shfl_sync(FULL, myrow, p);
+                if (p < nchunk && rr[p] >= 0) {
+                    const uint4* src = reinterpret_cast<const uint4*>(rows + (size_t)rr[p] * 1024);
+                    ra[p] = __ldg(src + lane);
+                    rb[p] = __ldg(src + 32 + lane);
+                }
+            }
+#pragma unroll 1
+            for (int j = 0; j < nchunk; j++) {
+                const uint4 v0 = ra[0], v1 = rb[0];
+                const int64_t row = rr[0];
+#pragma unroll
+                for (int p = 0; p < 3; p++) {
+                    ra[p] = ra[p + 1];
+                    rb[p] = rb[p + 1];
+                    rr[p] = rr[p + 1];
+                }
+                rr[3] = __shfl_sync(FULL, myrow, (j + 4) & 31);
+                if (j + 4 < nchunk && rr[3] >= 0) {
+                    const uint4* src = reinterpret_cast<const uint4*>(rows + (size_t)rr[3] * 1024);
+                    ra[3] = __ldg(src + lane);
+                    rb[3] = __ldg(src + 32 + lane);
+                }
+                if (row >= 0) {
+                    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+                    int n2 = 0;
+                    const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w}, w1[4] = {v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        n2 = __dp4a((int)w0[c], (int)w0[c], n2);
+                        n2 = __dp4a((int)w1[c], (int)w1[c], n2);
+                        const uint32_t u0 = w0[c] ^ 0x80808080u, u1 = w1[c] ^ 0x80808080u;  // bytes + 128, unsigned
+#pragma unroll
+                        for (int b = 0; b < 4; b += 2) {
+                            // hi word 0x40B0_uu00: the double 4096 + u
+                            acc0 = fma(qr[4 * c + b], __hiloint2double((int)__byte_perm(0x40B00000u, u0, 0x3200 | ((4 + b) << 4)), 0), acc0);
+                            acc1 = fma(qr[16 + 4 * c + b], __hiloint2double((int)__byte_perm(0x40B00000u, u1, 0x3200 | ((4 + b) << 4)), 0), acc1);
+                            acc2 = fma(qr[4 * c + b + 1], __hiloint2double((int)__byte_perm(0x40B00000u, u0, 0x3200 | ((5 + b) << 4)), 0), acc2);
+                            acc3 = fma(qr[16 + 4 * c + b + 1], __hiloint2double((int)__byte_perm(0x40B00000u, u1, 0x3200 | ((5 + b) << 4)), 0), acc3);
+                        }
+                    }
+                    const double acc = warp_sum_f64((acc0 + acc1) + (acc2 + acc3));
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(FULL, n2, o);
+                    if (lane == j) {
+                        my_acc = acc;
+                        my_n2 = n2;
+                    }
+                }
+            }
+            if (lane < nchunk)
+                score[myidx] = (myrow < 0 || my_n2 == 0) ? -INFINITY : (my_acc - offset) / sqrt((double)my_n2);
+        }
+    } else {
+        for (int i = blockIdx.x * 8 + warp; i < m; i += gridDim.x * 8) {
+            const size_t idx = (size_t)q * m + i;
+            const int64_t row = cand_row(keys, pos, idx, pos_base);
+            if (row < 0) {
+                if (lane == 0) score[idx] = -INFINITY;
+                continue;
+            }
+            double acc = 0.0;
+            int n2 = 0;
+            const int* src = reinterpret_cast<const int*>(rows + (size_t)row * d);
+            for (int w = lane; w < (d >> 2); w += 32) {
+                const uint32_t x = (uint32_t)__ldg(src + w);
+                n2 = __dp4a((int)x, (int)x, n2);
+                const uint32_t u = x ^ 0x80808080u;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int hi = (int)(0x40B00000u | (((u >> (8 * b)) & 0xFFu) << 8));
+                    acc = fma(qd[4 * w + b], __hiloint2double(hi, 0), acc);
+                }
+            }
+            acc = warp_sum_f64(acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(FULL, n2, o);
+            if (lane == 0) score[idx] = (n2 == 0) ? -INFINITY : (acc - offset) / sqrt((double)n2);
+        }
     }
 }
 
@@ -345,7 +452,7 @@ int vrq_launch_rescore_binary(vrq_ctx* ctx, const uint8_t* codes, int d, const u
     }
     vrq_timer_scope ts(ctx, VRQ_CAT_RESCORE, st);
     dim3 grid(grid_x_for(ctx, nq, m), (unsigned)nq);
-    rescore_binary_kernel<<<grid, 256, sizeof(float) * d, st>>>(codes, d, keys, pos, pos_base, m, qf, score);
+    rescore_binary_kernel<<<grid, 256, sizeof(double) * d, st>>>(codes, d, keys, pos, pos_base, m, qf, score);
     vrq_count_launch(ctx);
     VRQ_CUDA(cudaGetLastError());
     return 0;
@@ -360,7 +467,10 @@ int vrq_launch_rescore_int8cos(vrq_ctx* ctx, const int8_t* rows, int d, const ui
     }
     vrq_timer_scope ts(ctx, VRQ_CAT_RESCORE, st);
     dim3 grid(grid_x_for(ctx, nq, m), (unsigned)nq);
-    rescore_int8cos_kernel<<<grid, 256, sizeof(float) * d, st>>>(rows, d, keys, pos, pos_base, m, qf, score);
+    if (d == 1024)
+        rescore_int8cos_kernel<true><<<grid, 256, 0, st>>>(rows, d, keys, pos, pos_base, m, qf, score);
+    else
+        rescore_int8cos_kernel<false><<<grid, 256, sizeof(double) * d, st>>>(rows, d, keys, pos, pos_base, m, qf, score);
     vrq_count_launch(ctx);
     VRQ_CUDA(cudaGetLastError());
     return 0;
