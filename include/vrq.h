@@ -117,6 +117,7 @@ int vrq_index_device_ptrs(vrq_index*, void** codes, void** ids, void** payload, 
 #define VRQ_PAYLOAD_INT4_PERDOC 5  /* int8[d/2] + f64 min,max VectorDBInt4                          */
 #define VRQ_PAYLOAD_INT4_GLOBAL 6  /* int8[d/2], limit       VectorDBInt4Global                     */
 #define VRQ_PAYLOAD_F32 7          /* float32[d]             the float_embeddings dict (compare_float32=True) */
+#define VRQ_PAYLOAD_CODES_PM1 8    /* no extra rows: the 1-bit code itself unpacked to +-1.0f (CohereVectorDBBinary.py:153-159, :227) */
 int vrq_index_set_payload(vrq_index*, int kind, double global_limit); /* only while ntotal == 0 */
 int vrq_index_payload_kind(const vrq_index*);
 

@@ -178,3 +178,43 @@ def test_sharded_world1_cuda_engine():
     codes, i8 = oc.synth_codes_int8(5, 0, n)
     ref = o.search3(codes, np.arange(n) + 100, i8, qf[0], qb[0], 10, 10, 3)
     assert [h["doc_id"] for h in ref] == got[0][0].tolist()
+
+
+def test_cohere_binary_class(tmp_path):
+    """CohereVectorDBBinary: '>=' mean threshold, rescoring = float32 dot(query, +-1 unpacked code)."""
+    import vectorragquantization_b200 as V
+    db = V.CohereVectorDBBinary(os.path.join(tmp_path, "bin"))
+    db.add_documents(IDS, DOCS)
+    x = synth_rows(DOCS)
+    codes = o.to_binary_f32(x, ge=True)
+    assert open(os.path.join(tmp_path, "bin", "index.bin"), "rb").read() == o.write_index_binary_bytes(1024, codes, np.array(IDS))
+    qf = synth_rows([QUERY])[0]
+    qb = o.to_binary_f32(qf, ge=True)
+    pm1 = np.where(np.unpackbits(codes, axis=1) == 0, -1, 1).astype(np.float32)
+    for k, bo in ((10, 10), (7, 3)):
+        check_search2(db.search(QUERY, k=k, binary_oversample=bo), o.search2(codes, np.array(IDS), lambda p: pm1[p], qf, qb, k, bo), 1e-5)
+        check_search2(db.search(QUERY, k=k, binary_oversample=bo, compare_float32=True),
+                      o.search2(codes, np.array(IDS), lambda p: x[p], qf, qb, k, bo))
+    sb = V.CohereVectorDBBinary._to_signed_binary(x[5])
+    assert np.array_equal(sb, np.where(x[5] >= x[5].mean(), 1, -1)) and sb.dtype == np.int8
+    assert np.array_equal(V.CohereVectorDBBinary._pack_signed_binary(sb), codes[5])
+    assert np.array_equal(V.CohereVectorDBBinary._unpack_signed_binary(codes[5], 1024), pm1[5])
+    db2 = V.CohereVectorDBBinary(os.path.join(tmp_path, "bin"))
+    assert [h["doc_id"] for h in db2.search(QUERY, k=10)] == [h["doc_id"] for h in db.search(QUERY, k=10)]
+
+
+def test_cohere_int8_class(tmp_path):
+    """CohereVectorDBInt8: packbits(int8 > mean(int8)) codes, Hamming-only search."""
+    import vectorragquantization_b200 as V
+    from vectorragquantization_b200.embedder import text_row
+    db = V.CohereVectorDBInt8(os.path.join(tmp_path, "ci8"))
+    db.add_documents(IDS, DOCS)
+    i8 = np.stack([oc.synth_codes_int8(1, text_row(t), 1, want_codes=False)[1][0] for t in DOCS])
+    codes = o.to_binary_int(i8)
+    assert open(os.path.join(tmp_path, "ci8", "index.bin"), "rb").read() == o.write_index_binary_bytes(1024, codes, np.array(IDS))
+    q8 = oc.synth_codes_int8(1, text_row(QUERY), 1, want_codes=False)[1]
+    d, p = oc.hamming_topk(codes, o.to_binary_int(q8), 100)
+    res = db.search(QUERY, k=10)
+    assert [r["doc_id"] for r in res] == p[0][:10].tolist() and [r["score"] for r in res] == d[0][:10].tolist()
+    with pytest.raises(NotImplementedError):
+        db.search_rerank_cohere(QUERY)

@@ -14,3 +14,4 @@ from .docstore import DocStore, Rdict  # noqa: F401,E402
 from .embedder import SyntheticCohereEmbedder, SyntheticEmbedder  # noqa: F401,E402
 from .vectordb import (VectorDBInt4, VectorDBInt4Global, VectorDBInt8, VectorDBInt8Global, VectorDBInt16,  # noqa: F401,E402
                        VectorDBInt16Global)
+from .cohere_variants import CohereVectorDBBinary, CohereVectorDBInt8  # noqa: F401,E402

@@ -20,6 +20,7 @@ ERR_ARG, ERR_UNSUPPORTED, ERR_IO, ERR_STATE, ERR_NOMEM = -1, -2, -3, -4, -5
 
 PAYLOAD_NONE, PAYLOAD_INT8_RAW, PAYLOAD_INT8_PERDOC, PAYLOAD_INT8_GLOBAL = 0, 1, 2, 3
 PAYLOAD_INT16_GLOBAL, PAYLOAD_INT4_PERDOC, PAYLOAD_INT4_GLOBAL, PAYLOAD_F32 = 4, 5, 6, 7
+PAYLOAD_CODES_PM1 = 8
 
 KEY_POS_BITS = 40
 KEY_NONE = 0xFFFFFFFFFFFFFFFF

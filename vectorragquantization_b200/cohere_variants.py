@@ -1,0 +1,151 @@
+"""``CohereVectorDBInt8`` (CohereVectorDBInt8.py) and ``CohereVectorDBBinary`` (CohereVectorDBBinary.py) on the B200
+path - the two remaining binary-index classes of the reference.  Both reuse the kernels of the
+main path: the integer ``_to_binary`` threshold, the Hamming top-k scan, and the fused gather + dot rescoring with the
+1-bit code itself as the payload (unpacked to +-1.0 in registers, never in memory).
+
+The Cohere / Azure embedding services are out of scope (no network): embeddings come from an injectable ``embedder``.
+``search_rerank_cohere`` (CohereVectorDBInt8.py:237-339) calls Cohere's rerank web service and is not provided.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+
+from . import _lib as L
+from . import kernels as K
+from .vectordb import _Progress, _VectorDBBase
+
+logger = logging.getLogger(__name__)
+
+
+class CohereVectorDBInt8(_VectorDBBase):
+    """Cohere int8 embeddings -> packbits(int8 > mean) -> Hamming-only search (CohereVectorDBInt8.py:130-235)."""
+
+    _payload_kind = L.PAYLOAD_NONE
+    _desc = "Indexing docs (Int8)"
+
+    def __init__(self, folder: str, model: str = "embed-english-v3.0", embedding_dim: int = 1024, rdict_options=None,
+                 embedder: Optional[Callable] = None, ctx=None):
+        if embedder is None:
+            from .embedder import SyntheticCohereEmbedder
+            coh = SyntheticCohereEmbedder(embedding_dim, ctx=ctx)
+            embedder = lambda texts, input_type="search_document": coh(texts, input_type, ["int8"])["int8"]  # noqa: E731
+        super().__init__(folder, model, embedding_dim, rdict_options, "", embedder, ctx)
+        self._int8_store: Dict[str, np.ndarray] = {}
+
+    @staticmethod
+    def _to_binary(embedding: np.ndarray) -> np.ndarray:
+        """CohereVectorDBInt8.py:130-135."""
+        return K.to_binary(np.asarray(embedding, np.int8))
+
+    def _generate_int8_embeddings(self, texts: List[str], input_type: str = "search_document") -> Dict[str, np.ndarray]:
+        """CohereVectorDBInt8.py:82-128: {text: int8[D]}; {} on failure."""
+        try:
+            try:
+                e = np.asarray(self._embedder(list(texts), input_type))
+            except TypeError:
+                e = np.asarray(self._embedder(list(texts)))
+        except Exception as ex:
+            logger.error(f"Int8 embedding generation failed: {ex}")
+            return {}
+        if e.dtype != np.int8 or e.shape != (len(texts), self.embedding_dim):
+            logger.error(f"Unexpected int8 embeddings: dtype {e.dtype}, shape {e.shape}")
+            return {}
+        return {t: e[i] for i, t in enumerate(texts)}
+
+    def add_documents(self, doc_ids: List[int], docs: List[str], batch_size: int = 64, save: bool = True):
+        if len(doc_ids) != len(docs):
+            raise ValueError("doc_ids and docs must have the same length.")
+        for doc_id in doc_ids:
+            if str(doc_id) in self.doc_db:
+                self.remove_document(doc_id, save=False)
+        with _Progress(len(docs), self._desc) as pbar:
+            for start in range(0, len(docs), batch_size):
+                batch_ids = doc_ids[start:start + batch_size]
+                batch_texts = docs[start:start + batch_size]
+                emb_map = self._generate_int8_embeddings(batch_texts, input_type="search_document")
+                if not emb_map:
+                    logger.error(f"Int8 embedding generation failed for batch: {batch_texts}")
+                    pbar.update(len(batch_texts))
+                    continue
+                rows = np.stack([emb_map[t] for t in batch_texts])
+                self.index.add_with_ids(K.to_binary(rows, ctx=self._ctx), np.array(batch_ids, dtype=np.int64))
+                for d_id, text in zip(batch_ids, batch_texts):
+                    self.doc_db[str(d_id)] = {"doc": text}
+                    self._int8_store[str(d_id)] = emb_map[text]
+                pbar.update(len(batch_texts))
+        if save:
+            self.save()
+
+    def search(self, query: str, k: int = 10, binary_oversample: int = 10) -> List[Dict]:
+        """CohereVectorDBInt8.py:192-235: Hamming top min(k*oversample, ntotal), stable sort by distance, first k."""
+        if self.index.ntotal == 0:
+            logger.error("No documents indexed. Please add documents before searching.")
+            return []
+        emb_map = self._generate_int8_embeddings([query], input_type="search_query")
+        if not emb_map or query not in emb_map:
+            logger.error("Query embedding generation failed. Returning empty results.")
+            return []
+        query_bin = self._to_binary(emb_map[query])
+        binary_k = min(k * binary_oversample, self.index.ntotal)
+        distances, ids = self.index.search(query_bin.reshape(1, -1), binary_k)
+        initial_hits = [(doc_id, dist) for doc_id, dist in zip(ids[0], distances[0]) if doc_id != -1]
+        initial_hits.sort(key=lambda x: x[1])
+        results = []
+        for doc_id, dist in initial_hits[:k]:
+            doc_data = self.doc_db.get(str(doc_id), {})
+            results.append({"doc_id": doc_id, "score": dist, "doc": doc_data.get("doc", "N/A")})
+        return results
+
+    def search_rerank_cohere(self, *a, **kw):
+        raise NotImplementedError("Cohere's rerank web service is out of scope (no network); see DESIGN.md section 0")
+
+    def remove_document(self, doc_id: int, save: bool = True):
+        doc_id_str = str(doc_id)
+        if doc_id_str in self.doc_db:
+            self.index.remove_ids(np.array([doc_id], dtype=np.int64))
+            del self.doc_db[doc_id_str]
+            self._int8_store.pop(doc_id_str, None)
+            logger.info(f"Document {doc_id} removed.")
+        else:
+            logger.warning(f"Document {doc_id} not found in the database.")
+        if save:
+            self.save()
+
+
+class CohereVectorDBBinary(_VectorDBBase):
+    """float32 embeddings -> signed binary (x >= mean -> +1) packed into the index; 2-phase search whose rescoring is
+    float32 dot(query, +-1 vector) or, with compare_float32=True, dot(query, float32 row)  (CohereVectorDBBinary.py)."""
+
+    _payload_kind = L.PAYLOAD_CODES_PM1
+    _desc = "Indexing docs (signed binary)"
+    _ge = True
+
+    def __init__(self, folder: str, model: str = "embed-english-v3.0", embedding_dim: int = 1024, rdict_options=None,
+                 embedder: Optional[Callable] = None, ctx=None):
+        super().__init__(folder, model, embedding_dim, rdict_options, "", embedder, ctx)
+
+    @staticmethod
+    def _to_signed_binary(embedding: np.ndarray) -> np.ndarray:
+        """CohereVectorDBBinary.py:133-141: +1 where x >= mean(x), else -1 (int8)."""
+        bits = np.unpackbits(K.to_binary(np.asarray(embedding, np.float32), ge=True))[: np.asarray(embedding).shape[-1]]
+        return np.where(bits == 1, 1, -1).astype(np.int8)
+
+    @staticmethod
+    def _pack_signed_binary(signed_binary: np.ndarray) -> np.ndarray:
+        """CohereVectorDBBinary.py:143-150."""
+        return np.packbits(((np.asarray(signed_binary) + 1) // 2).astype(np.uint8))
+
+    @staticmethod
+    def _unpack_signed_binary(packed: np.ndarray, length: int) -> np.ndarray:
+        """CohereVectorDBBinary.py:152-159."""
+        bits = np.unpackbits(np.asarray(packed, np.uint8))[:length]
+        return np.where(bits == 0, -1, 1).astype(np.float32)
+
+    def _encode(self, x):
+        return None, None, K.to_binary(x, ge=True, ctx=self._ctx)
+
+    def _result_entry(self, x, payload, aux, ub):
+        return {"float": x, "packed_binary": ub}

@@ -241,7 +241,7 @@ extern "C" int vrq_index_reserve(vrq_index* ix, int64_t cap) {
 
 extern "C" int vrq_index_set_payload(vrq_index* ix, int kind, double global_limit) {
     VRQ_CHECK_ARG(ix != nullptr, "index is null");
-    VRQ_CHECK_ARG(kind >= VRQ_PAYLOAD_NONE && kind <= VRQ_PAYLOAD_F32, "unknown payload kind");
+    VRQ_CHECK_ARG(kind >= VRQ_PAYLOAD_NONE && kind <= VRQ_PAYLOAD_CODES_PM1, "unknown payload kind");
     if (ix->ntotal != 0 || ix->capacity != 0) {
         vrq_set_error("payload kind can only be set on an empty, unreserved index");
         return VRQ_ERR_STATE;
@@ -660,7 +660,7 @@ extern "C" int vrq_index_search2(vrq_index* ix, int64_t nq, const float* q_float
                                            nullptr, (int64_t*)lab, st));
     vrq_rescore2_args a{};
     a.kind = ix->payload_kind;
-    a.payload = ix->payload;
+    a.payload = ix->payload_kind == VRQ_PAYLOAD_CODES_PM1 ? (const void*)ix->codes : (const void*)ix->payload;
     a.aux = ix->aux;
     a.limit = ix->limit;
     a.d = ix->d;

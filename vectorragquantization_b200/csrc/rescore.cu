@@ -270,6 +270,11 @@ __global__ void __launch_bounds__(256) rescore_payload_kernel(PayloadParams p) {
                 case VRQ_PAYLOAD_F32:
                     v = static_cast<const float*>(p.payload)[(size_t)row * d + e];
                     break;
+                case VRQ_PAYLOAD_CODES_PM1: {  // np.unpackbits -> where(bits == 0, -1, 1).astype(float32)
+                    const uint8_t b = static_cast<const uint8_t*>(p.payload)[(size_t)row * (d >> 3) + (e >> 3)];
+                    v = ((b >> (7 - (e & 7))) & 1) ? 1.f : -1.f;
+                    break;
+                }
                 default:
                     v = 0.f;
             }

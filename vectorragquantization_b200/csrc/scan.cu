@@ -230,6 +230,13 @@ __device__ __forceinline__ int hamming128_csa14(const uint4 (&c)[8], uint32_t qa
     return w1 + 2 * w2;
 }
 
+// The append is the cold path (a few candidates per million pairs once tau has converged): keep it out of line so
+// the hot loop carries no address arithmetic for it.
+__device__ __noinline__ void append_candidate(int* cnt_s, uint64_t* lists, int q, int cap, int d, unsigned long long pos) {
+    const int slot = atomicAdd(&cnt_s[q], 1);
+    lists[(size_t)q * cap + slot] = ((unsigned long long)d << VRQ_KEY_POS_BITS) | pos;
+}
+
 // ---- list compaction: keep the k smallest keys of one (strip, query) list --------------------------------
 template <int CONSUMER_THREADS>
 __device__ void compact_list(uint64_t* glist, int n, int k, unsigned long long* scratch, SelectScratch* sc, int tid,
@@ -358,10 +365,7 @@ hamming_scan_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p) {
                                    : CSA == 16 ? hamming128_csa(c, qaddr)
                                    : CSA == 14 ? hamming128_csa14(c, qaddr)
                                                : hamming128_popc(c, qaddr)) + bias;
-                    if (d < lds32(taddr)) {
-                        const int slot = atomicAdd(&cnt_s[q], 1);
-                        my_lists[(size_t)q * p.cap + slot] = ((unsigned long long)d << VRQ_KEY_POS_BITS) | pos;
-                    }
+                    if (d < lds32(taddr)) append_candidate(cnt_s, my_lists, q, p.cap, d, pos);
                 }
             } else {
                 const uint32_t* crow = reinterpret_cast<const uint32_t*>(p.codes + (size_t)(valid ? lrow : 0) * p.code_bytes);

@@ -60,6 +60,7 @@ class _VectorDBBase:
     _payload_kind = L.PAYLOAD_NONE
     _desc = "Indexing docs"
     _has_global_limit = False
+    _ge = False  # '>=' mean threshold (CohereVectorDBBinary) instead of '>'
 
     def __init__(self, folder: str, model: str = "snowflake-arctic-embed2", embedding_dim: int = 1024, rdict_options=None,
                  embed_url: str = "http://localhost:11434/api/embed", embedder: Optional[Callable] = None, ctx=None):
@@ -119,6 +120,18 @@ class _VectorDBBase:
         """index.bin holds codes + ids only (faiss layout); the quantised rows the reference keeps in RocksDB pickles
         are persisted as payload.npz next to it and re-attached to the device index on open."""
         if self._loaded is None or self._payload_kind == L.PAYLOAD_NONE:
+            return
+        if self._payload_kind == L.PAYLOAD_CODES_PM1:
+            # no side file: the rescoring payload is the code itself; rebuild the index with that kind set
+            import struct
+            raw = open(os.path.join(self.folder, "index.bin"), "rb").read()
+            n = self._loaded.ntotal
+            new = BinaryIndex(self.embedding_dim, ctx=self._ctx, payload_kind=self._payload_kind)
+            if n:
+                cs = self.embedding_dim // 8
+                new.add_with_ids(np.frombuffer(raw, np.uint8, n * cs, 58).reshape(n, cs), np.frombuffer(raw, np.int64, n, 66 + n * cs))
+            self._loaded.close()
+            self.index, self._loaded = new, None
             return
         src = self._loaded
         n = src.ntotal
@@ -241,7 +254,7 @@ class _VectorDBBase:
     def search_batch(self, q_float: np.ndarray, k: int = 10, binary_oversample: int = 10, compare_float32: bool = False):
         """Batched ``search`` on precomputed query embeddings: (doc_ids i64[nq,k], scores f32[nq,k], count i32[nq])."""
         qf = np.ascontiguousarray(q_float, np.float32)
-        qb = K.to_binary(qf, ctx=self._ctx)  # query_bin = self._to_binary(query float)  (VectorDBInt8.py:213)
+        qb = K.to_binary(qf, ge=self._ge, ctx=self._ctx)  # query_bin = self._to_binary(query float)  (VectorDBInt8.py:213)
         if compare_float32:
             if self._findex is None or self._findex.ntotal != self.index.ntotal:
                 # the reference's float_embeddings dict is RAM-only and gone after a reopen: KeyError (VectorDBInt8.py:232)
@@ -267,7 +280,7 @@ class _VectorDBBase:
 
     def save(self):
         write_index_binary(self.index, os.path.join(self.folder, "index.bin"))
-        if self._payload_kind != L.PAYLOAD_NONE:
+        if self._payload_kind not in (L.PAYLOAD_NONE, L.PAYLOAD_CODES_PM1):
             self._save_payload()
         logger.info("FAISS index saved to disk.")
 
