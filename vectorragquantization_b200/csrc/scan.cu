@@ -34,7 +34,6 @@ constexpr int CODE_BYTES = 128;
 constexpr int TMA_BOX_ROWS = 256;  // rows per TMA box (hardware limit per box dimension)
 constexpr int BAR_CONSUMERS = 1;
 constexpr int TAU_INF = 1 << 28;   // "no threshold yet": above any distance
-constexpr int ROW_INVALID_BIAS = 1 << 29;  // added to the distance of rows past the end of a strip: never < tau
 // CW = consumer warps per CTA: 8 for query batches (long inner loops keep the POPC pipe busy), 16 for <= 8 queries
 // per pass (short per-tile work: the second warp group hides the first one's shared-memory / barrier latency).
 template <int CW>
@@ -356,16 +355,18 @@ hamming_scan_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars[8 + s]));  // stage is free again: registers hold the tile
                 const uint32_t qbase = smem_u32(qsm), taubase = smem_u32(tau_s);
-                const int bias = valid ? 0 : ROW_INVALID_BIAS;  // rows past the end of the strip never pass the filter
                 uint32_t qaddr = qbase, taddr = taubase;
                 const uint32_t one = (uint32_t)p.one, two = one + one, four = two + two;
+                // rows past the end of the strip (last tile only) sit the loop out: no per-query validity arithmetic
+                if (valid) {
 #pragma unroll 4
                 for (int q = 0; q < qt; q++, qaddr += CODE_BYTES, taddr += 4) {
                     const int d = (CSA == 17   ? hamming128_csa_imad(c, qaddr, one, two, four)
                                    : CSA == 16 ? hamming128_csa(c, qaddr)
                                    : CSA == 14 ? hamming128_csa14(c, qaddr)
-                                               : hamming128_popc(c, qaddr)) + bias;
+                                               : hamming128_popc(c, qaddr));
                     if (d < lds32(taddr)) append_candidate(cnt_s, my_lists, q, p.cap, d, pos);
+                }
                 }
             } else {
                 const uint32_t* crow = reinterpret_cast<const uint32_t*>(p.codes + (size_t)(valid ? lrow : 0) * p.code_bytes);
