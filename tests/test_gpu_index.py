@@ -260,3 +260,62 @@ def test_merge3_equals_single_index(V):
         assert np.array_equal(a, b.cpu().numpy())
     for a, b in zip(want, out):
         assert np.array_equal(a, b)
+
+
+def test_limits_and_errors(V):
+    """Argument checking at the C ABI: errors are loud VrqErrors with the documented codes, never silent fallbacks."""
+    from vectorragquantization_b200 import _lib as L
+    from vectorragquantization_b200 import kernels as K
+    with pytest.raises(V.VrqError) as e:
+        V.BinaryIndex(1000)  # d % 32 != 0
+    assert e.value.code == L.ERR_UNSUPPORTED
+    with pytest.raises(V.VrqError) as e:
+        V.BinaryIndex(1027)
+    assert e.value.code == L.ERR_ARG
+    ix = V.BinaryIndex(1024)
+    rng = np.random.default_rng(0)
+    codes = rng.integers(0, 256, (5000, 128), dtype=np.uint8)
+    ix.add_with_ids(codes, np.arange(5000))
+    with pytest.raises(V.VrqError) as e:
+        ix.search(codes[:1], 5000)  # k > 4096
+    assert e.value.code == L.ERR_UNSUPPORTED
+    with pytest.raises(V.VrqError):
+        ix.search(codes[:1], 0)
+    with pytest.raises(V.VrqError) as e:
+        ix.search3(np.zeros((1, 1024), np.float32), codes[:1], 10)  # no int8 payload
+    assert e.value.code == L.ERR_STATE
+    with pytest.raises(V.VrqError):
+        K.quantize_int8_global(np.zeros((2, 1020), np.float32), 0.3)  # d % 8 != 0
+    with pytest.raises(V.VrqError):
+        K.quantize_int8_global(np.zeros((2, 1024), np.float32), 0.0)  # limit must be > 0
+    with pytest.raises(V.VrqError):
+        ix.add_with_ids(codes[:2], np.arange(2), payload=np.zeros((2, 1024), np.int8))  # payload without a payload kind
+    # maximum supported k, and a query count that spans several internal batches
+    d, l = ix.search(codes[:3], 4096)
+    rd, rp = oc.hamming_topk(codes, codes[:3], 4096)
+    assert np.array_equal(d, rd) and np.array_equal(l, rp)
+    q = rng.integers(0, 256, (1100, 128), dtype=np.uint8)
+    d, l = ix.search(q, 7)
+    rd, rp = oc.hamming_topk(codes, q, 7)
+    assert np.array_equal(d, rd) and np.array_equal(l, rp)
+
+
+def test_search3_other_dim(V):
+    """d = 2048: generic (non-TMA) scan and the generic rescoring paths."""
+    from vectorragquantization_b200 import _lib as L
+    n, nq, d = 6000, 5, 2048
+    x = o.synth_f32(91, 0, n, d)
+    codes, i8 = o.synth_ubinary_from_f32(x), o.synth_int8_from_f32(x)
+    ids = np.arange(n, dtype=np.int64)
+    qf = (x[:nq] * np.float32(0.8) + o.synth_f32(92, 0, nq, d) * np.float32(0.4)).astype(np.float32)
+    qb = o.synth_ubinary_from_f32(qf)
+    ix = V.BinaryIndex(d, payload_kind=L.PAYLOAD_INT8_RAW)
+    ix.add_with_ids(codes, ids, payload=i8)
+    labels, ham, sb, sc, cnt = ix.search3(qf, qb, 10, 10, 3)
+    for qi in range(nq):
+        ref = o.search3(codes, ids, i8, qf[qi], qb[qi], 10, 10, 3)
+        assert [h["doc_id"] for h in ref] == labels[qi].tolist()
+        assert [h["score_hamming"] for h in ref] == ham[qi].tolist()
+        rc = np.array([h["score_cosine"] for h in ref])
+        fl = o.rescore_int8cos_absfloor(qf[qi], i8[labels[qi]])
+        assert np.all(np.abs(sc[qi] - rc) <= 1e-5 * np.abs(rc) + fl)

@@ -565,7 +565,9 @@ int plan_scan(vrq_ctx* ctx, bool tma, int code_bytes, int64_t rows, int nq, int 
     pl->qtile = (nq + pl->qtiles - 1) / pl->qtiles;  // balanced tiles
     if (!stream_regime && pl->qtile < max_qtile) pl->qtile = ((pl->qtile + 7) / 8) * 8 < max_qtile ? ((pl->qtile + 7) / 8) * 8 : max_qtile;
     pl->qtiles = (nq + pl->qtile - 1) / pl->qtile;
-    pl->group_tiles = stream_regime ? env_int("VRQ_SCAN_GROUP_TILES", 4) : 1;
+    // tiles between overflow checks (one named barrier each): few queries per tile -> amortise over more tiles
+    pl->group_tiles = env_int("VRQ_SCAN_GROUP_TILES", pl->qtile <= 8 ? 4 : (pl->qtile <= 16 ? 2 : 1));
+    if (pl->group_tiles < 1) pl->group_tiles = 1;
     const int slack = k < 256 ? 256 : (k > 2048 ? 2048 : k);
     pl->cap = k + slack + pl->group_tiles * tile_rows;
     int strips = sms / pl->qtiles;
