@@ -365,27 +365,6 @@ def hbm_bound_kernels(torch, ctx, lib, L, index, qb_d, dev, stream, hbm_peak, pe
         out[f"roofline_scan_stream_nq{nq}"] = {"kernel": f"hamming_scan_kernel<true> + merge, {nq} query/pass, top-{kk}", "bound": "hbm",
                                                 "unit": "GB/s", "achieved": gbs, "peak": hbm_peak, "frac": gbs / hbm_peak,
                                                 "peak_source": peak_src, "ms": s * 1e3, "traffic": None}
-    n_enc = 2_000_000
-    x = torch.empty((n_enc, D), dtype=torch.float32, device=dev)
-    L.check(lib.vrq_synth_f32(ctx.handle, 7, 0, n_enc, D, 1, L.ptr(x)))
-    ub = torch.empty((n_enc, D // 8), dtype=torch.uint8, device=dev)
-    q8 = torch.empty((n_enc, D), dtype=torch.int8, device=dev)
-    q16 = torch.empty((n_enc, D), dtype=torch.int16, device=dev)
-    lo = torch.empty((n_enc,), dtype=torch.float64, device=dev)
-    hi = torch.empty((n_enc,), dtype=torch.float64, device=dev)
-    h = ctx.handle
-    cases = {
-        "int8_global+ubinary": (lambda: L.check(lib.vrq_quantize_int8_global(h, L.ptr(x), n_enc, D, 0.3, L.ptr(q8), L.ptr(ub))), 4096 + 1024 + 128),
-        "int16_global+ubinary": (lambda: L.check(lib.vrq_quantize_int16_global(h, L.ptr(x), n_enc, D, 1.0, L.ptr(q16), L.ptr(ub))), 4096 + 2048 + 128),
-        "int4+ubinary": (lambda: L.check(lib.vrq_quantize_int4(h, L.ptr(x), n_enc, D, L.ptr(q8), L.ptr(lo), L.ptr(hi), L.ptr(ub))), 4096 + 512 + 16 + 128),
-        "int8_perdoc+ubinary": (lambda: L.check(lib.vrq_quantize_int8_perdoc(h, L.ptr(x), n_enc, D, L.ptr(q8), L.ptr(lo), L.ptr(hi), L.ptr(ub))), 4096 + 1024 + 8 + 128),
-        "ubinary_only": (lambda: L.check(lib.vrq_to_binary_f32(h, L.ptr(x), n_enc, D, 0, L.ptr(ub))), 4096 + 128),
-    }
-    enc = {}
-    for name, (fn, bpr) in cases.items():
-        s = timed(fn, 5)
-        gbs = n_enc * bpr / s / 1e9
-        enc[name] = {"GB/s": gbs, "frac": gbs / hbm_peak, "ms": s * 1e3, "bytes_per_row": bpr}
     # BASELINE config 5: Phase III micro - 4096 queries x 1000 gathered int8 candidates each (HBM-gather-bound)
     codes_p, _, pay_p, _ = index.device_ptrs()
     if pay_p:
@@ -407,10 +386,47 @@ def hbm_bound_kernels(torch, ctx, lib, L, index, qb_d, dev, stream, hbm_peak, pe
                                            "imma_path": "not built: 1 KB gathered per (query, candidate) with no operand reuse, so the kernel is "
                                                         "bound by the gather; tensor cores have nothing to amortise (DESIGN.md 3.3)"}
         out["rescore_binary_cfg5"] = {"ms": s2 * 1e3, "pairs_per_s": nq5 * m5 / s2, "GB/s": nq5 * m5 * 128 / s2 / 1e9}
+    # BASELINE config 2: global-limit encode of 10 M x 1024 float32 rows resident in HBM (41 GB in); the search index is
+    # released first so that input + every output fit
+    index.close()
+    torch.cuda.empty_cache()
+    n_enc = 10_000_000
+    x = torch.empty((n_enc, D), dtype=torch.float32, device=dev)
+    L.check(lib.vrq_synth_f32(ctx.handle, 7, 0, n_enc, D, 1, L.ptr(x)))
+    ub = torch.empty((n_enc, D // 8), dtype=torch.uint8, device=dev)
+    q8 = torch.empty((n_enc, D), dtype=torch.int8, device=dev)
+    q16 = torch.empty((n_enc, D), dtype=torch.int16, device=dev)
+    lo = torch.empty((n_enc,), dtype=torch.float64, device=dev)
+    hi = torch.empty((n_enc,), dtype=torch.float64, device=dev)
+    h = ctx.handle
+    cases = {
+        "int8_global+ubinary": (lambda: L.check(lib.vrq_quantize_int8_global(h, L.ptr(x), n_enc, D, 0.3, L.ptr(q8), L.ptr(ub))), 4096 + 1024 + 128),
+        "int16_global+ubinary": (lambda: L.check(lib.vrq_quantize_int16_global(h, L.ptr(x), n_enc, D, 1.0, L.ptr(q16), L.ptr(ub))), 4096 + 2048 + 128),
+        "int4+ubinary": (lambda: L.check(lib.vrq_quantize_int4(h, L.ptr(x), n_enc, D, L.ptr(q8), L.ptr(lo), L.ptr(hi), L.ptr(ub))), 4096 + 512 + 16 + 128),
+        "int8_perdoc+ubinary": (lambda: L.check(lib.vrq_quantize_int8_perdoc(h, L.ptr(x), n_enc, D, L.ptr(q8), L.ptr(lo), L.ptr(hi), L.ptr(ub))), 4096 + 1024 + 8 + 128),
+        "ubinary_only": (lambda: L.check(lib.vrq_to_binary_f32(h, L.ptr(x), n_enc, D, 0, L.ptr(ub))), 4096 + 128),
+    }
+    enc = {}
+    for name, (fn, bpr) in cases.items():
+        s = timed(fn, 5)
+        gbs = n_enc * bpr / s / 1e9
+        enc[name] = {"GB/s": gbs, "frac": gbs / hbm_peak, "ms": s * 1e3, "bytes_per_row": bpr, "rows": n_enc}
+    # the same encoder through the C ABI with HOST buffers (pinned): H2D of x and D2H of codes inside the call
+    n_h = 1_000_000
+    xh = torch.empty((n_h, D), dtype=torch.float32).pin_memory()
+    xh.copy_(x[:n_h])
+    q8h = torch.empty((n_h, D), dtype=torch.int8).pin_memory()
+    ubh = torch.empty((n_h, D // 8), dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    L.check(lib.vrq_quantize_int8_global(h, L.ptr(xh), n_h, D, 0.3, L.ptr(q8h), L.ptr(ubh)))
+    th = time.perf_counter() - t0
+    enc["int8_global+ubinary_host_buffers"] = {"GB/s": n_h * 5248 / th / 1e9, "ms": th * 1e3, "rows": n_h,
+                                               "note": "end to end with pinned host input/output: PCIe-bound (4096 B in + 1152 B out per row)"}
     out["roofline_encode"] = {"kernel": "encode1024_kernel<INT8_GLOBAL, ubinary fused>", "bound": "hbm", "unit": "GB/s",
                               "achieved": enc["int8_global+ubinary"]["GB/s"], "peak": hbm_peak,
                               "frac": enc["int8_global+ubinary"]["frac"], "peak_source": peak_src, "rows": n_enc, "traffic": None,
-                              "all_codecs": enc}
+                              "workload": "cfg2: 10M x 1024 float32 rows resident in HBM", "all_codecs": enc}
     return out
 
 
