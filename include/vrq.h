@@ -129,6 +129,10 @@ int vrq_index_add_with_ids(vrq_index*, int64_t n, const uint8_t* codes, const in
 /* .search (CohereEnhancedVectorDB.py:268, VectorDBInt8.py:218): the k codes with smallest (hamming, position),
  * ascending; dist int32[nq,k], labels int64[nq,k]; ntotal < k pads with (INT32_MAX, -1). */
 int vrq_index_search(vrq_index*, int64_t nq, const uint8_t* q, int k, int32_t* dist, int64_t* labels);
+/* Every Hamming distance, dist int32[nq, ntotal] (what IndexBinaryFlat computes internally before its heap), straight
+ * from the tensor-core scan's accumulators.  d must be 1024; VRQ_ERR_UNSUPPORTED otherwise.  Used by the parity tests to
+ * check the int8 MMA contraction element by element; small ntotal only (the output is nq * ntotal * 4 bytes). */
+int vrq_index_distances(vrq_index*, int64_t nq, const uint8_t* q, int32_t* dist);
 /* .reconstruct(id) (CohereEnhancedVectorDB.py:286); last added wins on duplicate ids; host output. */
 int vrq_index_reconstruct(vrq_index*, int64_t id, uint8_t* code_out);
 /* .remove_ids (CohereEnhancedVectorDB.py:334): order-preserving compaction; returns the number removed (>= 0). */

@@ -73,6 +73,7 @@ SIGNATURES = {
     "vrq_index_payload_kind": (_i32, [_vp]),
     "vrq_index_add_with_ids": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "vrq_index_search": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
+    "vrq_index_distances": (_i32, [_vp, _i64, _vp, _vp]),
     "vrq_index_reconstruct": (_i32, [_vp, _i64, _vp]),
     "vrq_index_remove_ids": (_i64, [_vp, _i64, _vp]),
     "vrq_index_write": (_i32, [_vp, C.c_char_p]),

@@ -82,6 +82,17 @@ class BinaryIndex:
         L.check(self._lib.vrq_index_search(self._h, nq, L.ptr(q), int(k), L.ptr(dist), L.ptr(labels)))
         return dist, labels
 
+    def distances(self, q) -> np.ndarray:
+        """Every Hamming distance int32[nq, ntotal] from the tensor-core scan's accumulators (d == 1024 only)."""
+        q = np.ascontiguousarray(q, np.uint8)
+        if q.ndim == 1:
+            q = q[None]
+        if q.shape[1] != self.code_size:
+            raise ValueError("query codes must be uint8[nq, d/8]")
+        dist = np.empty((q.shape[0], self.ntotal), np.int32)
+        L.check(self._lib.vrq_index_distances(self._h, q.shape[0], L.ptr(q), L.ptr(dist)))
+        return dist
+
     def reconstruct(self, doc_id: int) -> np.ndarray:
         out = np.empty(self.code_size, np.uint8)
         L.check(self._lib.vrq_index_reconstruct(self._h, int(doc_id), L.ptr(out)))

@@ -328,6 +328,26 @@ extern "C" int vrq_index_search(vrq_index* ix, int64_t nq, const uint8_t* q, int
     return io.finish();
 }
 
+extern "C" int vrq_index_distances(vrq_index* ix, int64_t nq, const uint8_t* q, int32_t* dist) {
+    VRQ_CHECK_ARG(ix != nullptr && nq >= 0, "bad argument");
+    if (nq == 0 || ix->ntotal == 0) return 0;
+    VRQ_CHECK_ARG(q != nullptr && dist != nullptr, "null pointer");
+    const void* all[2] = {q, dist};
+    bool is_dev;
+    VRQ_TRY(vrq_space_of(all, 2, &is_dev));
+    vrq_ctx* ctx = ix->ctx;
+    VRQ_CUDA(cudaSetDevice(ctx->device));
+    DevIO io{ctx, !is_dev, {}};
+    const void* dq;
+    void *dd, *keys;
+    VRQ_TRY(io.in(q, (size_t)nq * ix->code_bytes, VRQ_WS_QUERY_A, &dq));
+    VRQ_TRY(io.out(dist, sizeof(int32_t) * (size_t)nq * ix->ntotal, VRQ_WS_OUT_A, &dd));
+    VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_TOPK, sizeof(uint64_t) * (size_t)nq, &keys));
+    VRQ_TRY(vrq_hamming_topk_dev(ctx, ix->codes, ix->ntotal, ix->code_bytes, 0, (const uint8_t*)dq, nq, 1, (uint64_t*)keys, ctx->stream,
+                                 (int32_t*)dd));
+    return io.finish();
+}
+
 extern "C" int64_t vrq_index_position_of(vrq_index* ix, int64_t id) {
     if (!ix) return -1;
     if (ix->implicit_ids) return (id >= ix->id0 && id < ix->id0 + ix->ntotal) ? id - ix->id0 : -1;

@@ -19,90 +19,11 @@
 //   * A per-query merge kernel radix-selects the k smallest keys over all strips' lists and bitonic-sorts them.
 // Bounds: <= ~3 queries per pass the kernel is HBM-bound (128 B per code per pass); for query batches it is bound by
 // the integer pipes (32 x (LOP3 + POPC + IADD) per (query, code) pair).  See DESIGN.md section 3.
-#include <cuda.h>
-#include <stdlib.h>
-#include <string.h>
-
-#include "topk_utils.cuh"
-#include "vrq_internal.cuh"
+#include "scan_common.cuh"
 
 namespace {
 
 using namespace vrq;
-
-constexpr int CODE_BYTES = 128;
-constexpr int TMA_BOX_ROWS = 256;  // rows per TMA box (hardware limit per box dimension)
-constexpr int BAR_CONSUMERS = 1;
-constexpr int TAU_INF = 1 << 28;   // "no threshold yet": above any distance
-// CW = consumer warps per CTA: 8 for query batches (long inner loops keep the POPC pipe busy), 16 for <= 8 queries
-// per pass (short per-tile work: the second warp group hides the first one's shared-memory / barrier latency).
-template <int CW>
-struct ScanCfg {
-    static constexpr int CONSUMER_THREADS = CW * 32;
-    static constexpr int THREADS = CONSUMER_THREADS + 32;
-    static constexpr int TILE_ROWS = CW * 32;
-    static constexpr int STAGE_BYTES = TILE_ROWS * CODE_BYTES;
-};
-
-struct ScanParams {
-    const uint8_t* codes;  // local row 0
-    int code_bytes;
-    int64_t row_begin, row_end;  // local rows scanned by this launch
-    int64_t pos_base;            // global position of local row 0
-    const uint8_t* queries;      // [nq][code_bytes]
-    int nq, k;
-    int num_strips;
-    int64_t rows_per_strip;  // multiple of TILE_ROWS
-    int qtile;               // queries per CTA
-    int cap;                 // capacity of one list
-    int group_tiles;         // tiles between overflow checks
-    int stages;
-    uint64_t* lists;  // [list_strips][nq][cap]
-    int* counts;      // [list_strips][nq]
-    const int* tau0;  // [nq] or null
-    int one;          // == 1, opaque to the compiler: multiplier that keeps the popcount accumulation on the FMA pipe (IMAD)
-};
-
-// ---- PTX helpers ----------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-        "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ int lds32(uint32_t addr) {
-    int r;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-    return r;
-}
 
 // ---- Hamming distance of one 1024-bit code held in registers against one query in shared memory ---------------
 // Plain form: 32 x (XOR, POPC, ADD) - bound by the POPC pipe (16 lanes/clk/SM measured, profiles/microbench).
@@ -236,27 +157,6 @@ __device__ __noinline__ void append_candidate(int* cnt_s, uint64_t* lists, int q
     lists[(size_t)q * cap + slot] = ((unsigned long long)d << VRQ_KEY_POS_BITS) | pos;
 }
 
-// ---- list compaction: keep the k smallest keys of one (strip, query) list --------------------------------
-template <int CONSUMER_THREADS>
-__device__ void compact_list(uint64_t* glist, int n, int k, unsigned long long* scratch, SelectScratch* sc, int tid,
-                             int* cnt_q, int* tau_q) {
-    for (int i = tid; i < n; i += CONSUMER_THREADS) scratch[i] = glist[i];
-    group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
-    const unsigned long long kth =
-        radix_select_kth<CONSUMER_THREADS>([&](int i) { return scratch[i]; }, n, k, tid, sc, BAR_CONSUMERS);
-    if (tid == 0) sc->counter = 0;
-    group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
-    for (int i = tid; i < n; i += CONSUMER_THREADS) {
-        unsigned long long key = scratch[i];
-        if (key <= kth) glist[atomicAdd(&sc->counter, 1)] = key;
-    }
-    group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
-    if (tid == 0) {
-        *cnt_q = k;
-        *tau_q = (int)(kth >> VRQ_KEY_POS_BITS);
-    }
-}
-
 // ---- the scan kernel ---------------------------------------------------------------------------------------
 // TMA128 = true : code_bytes == 128, TMA + swizzled shared-memory pipeline (the fast path)
 // TMA128 = false: any code_bytes % 4 == 0, codes read straight from global memory (correct, not tuned)
@@ -352,8 +252,6 @@ hamming_scan_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p) {
                 uint4 c[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) c[j] = lds128(rowaddr + ((j ^ (r & 7)) << 4));
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bars[8 + s]));  // stage is free again: registers hold the tile
                 const uint32_t qbase = smem_u32(qsm), taubase = smem_u32(tau_s);
                 uint32_t qaddr = qbase, taddr = taubase;
                 const uint32_t one = (uint32_t)p.one, two = one + one, four = two + two;
@@ -368,6 +266,13 @@ hamming_scan_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p) {
                     if (d < lds32(taddr)) append_candidate(cnt_s, my_lists, q, p.cap, d, pos);
                 }
                 }
+                // The stage goes back to the producer only here: ld.shared merely ISSUES the read, and an mbarrier
+                // arrive placed right behind it can overtake the outstanding loads (observed on B200 in scan_mma.cu:
+                // TMA refilled the stage before the reads returned).  After the query loop every c[j] has been an
+                // operand of real instructions, so the reads have completed.  (Rows past the end of the strip never
+                // use their registers.)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars[8 + s]));
             } else {
                 const uint32_t* crow = reinterpret_cast<const uint32_t*>(p.codes + (size_t)(valid ? lrow : 0) * p.code_bytes);
                 for (int q = 0; q < qt; q++) {
@@ -494,36 +399,6 @@ __global__ void fill_int_kernel(int* p, int n, int v) {
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int make_codes_tmap(const uint8_t* codes, int64_t nrows, CUtensorMap* out) {
-    static PFN_tmapEncodeTiled fn = nullptr;
-    if (!fn) {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres);
-        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !f) {
-            vrq_set_error("cuTensorMapEncodeTiled is not available from the driver");
-            return VRQ_ERR_UNSUPPORTED;
-        }
-        fn = (PFN_tmapEncodeTiled)f;
-    }
-    cuuint64_t gdim[2] = {(cuuint64_t)CODE_BYTES, (cuuint64_t)nrows};
-    cuuint64_t gstride[1] = {(cuuint64_t)CODE_BYTES};
-    cuuint32_t box[2] = {(cuuint32_t)CODE_BYTES, (cuuint32_t)TMA_BOX_ROWS};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)codes, gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        vrq_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-        return VRQ_ERR_UNSUPPORTED;
-    }
-    return 0;
-}
-
 struct ScanPlan {
     int cw;  // consumer warps (8 or 16)
     int csa;  // carry-save popcount (1) or plain XOR+POPC (0)
@@ -542,11 +417,6 @@ size_t scan_smem_bytes(bool tma, int cw, int stages, int qtile, int code_bytes, 
     b += sizeof(SelectScratch) + 8;
     b += sizeof(unsigned long long) * 16 + 16;
     return b;
-}
-
-int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
 }
 
 int plan_scan(vrq_ctx* ctx, bool tma, int code_bytes, int64_t rows, int nq, int k, ScanPlan* pl) {
@@ -681,36 +551,82 @@ int launch_merge(vrq_ctx* ctx, const uint64_t* lists, const int* counts, int str
 
 }  // namespace
 
+// Plan of one scan launch on either kernel: the integer-pipe kernel above or the tensor-core kernel of scan_mma.cu.
+struct PassPlan {
+    bool mma = false;
+    ScanPlan sp{};
+    MmaPlan mp{};
+    int strips() const { return mma ? mp.strips : sp.strips; }
+    int cap() const { return mma ? mp.cap : sp.cap; }
+    int tile_rows() const { return mma ? MMA_TILE_ROWS : sp.tile_rows(); }
+    int64_t rows_per_strip() const { return mma ? mp.rows_per_strip : sp.rows_per_strip; }
+    void set_cap(bool tma, int code_bytes, int cap) {
+        if (mma) {
+            mma_plan_set_cap(&mp, cap);
+        } else {
+            sp.cap = cap;
+            sp.smem = scan_smem_bytes(tma, sp.cw, sp.stages, sp.qtile, code_bytes, cap);
+        }
+    }
+};
+
+static int plan_pass(vrq_ctx* ctx, bool tma, bool mma, int code_bytes, int64_t rows, int nq, int k, PassPlan* pl) {
+    pl->mma = mma;
+    if (mma) return plan_scan_mma(ctx, rows, nq, k, &pl->mp);
+    return plan_scan(ctx, tma, code_bytes, rows, nq, k, &pl->sp);
+}
+
+static int launch_pass(vrq_ctx* ctx, bool tma, const CUtensorMap& tmap, const CUtensorMap& tmap_mma, ScanParams sp, const PassPlan& pl,
+                       cudaStream_t st) {
+    sp.num_strips = pl.strips();
+    sp.rows_per_strip = pl.rows_per_strip();
+    sp.cap = pl.cap();
+    if (pl.mma) {
+        sp.qtile = 128;
+        sp.group_tiles = pl.mp.group_tiles;
+        return launch_scan_mma(ctx, tmap_mma, sp, pl.mp, st);
+    }
+    sp.qtile = pl.sp.qtile;
+    sp.group_tiles = pl.sp.group_tiles;
+    sp.stages = pl.sp.stages;
+    return launch_scan(ctx, tma, tmap, sp, pl.sp, st);
+}
+
 // One batch of queries (nq <= 1024): optional prefix pass, main pass, merge.
 static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_bytes, int64_t pos_base,
-                      const uint8_t* q_dev, int nq, int k, uint64_t* keys_out, cudaStream_t st) {
+                      const uint8_t* q_dev, int nq, int k, uint64_t* keys_out, int32_t* dbg, cudaStream_t st) {
     const bool tma = (code_bytes == CODE_BYTES) && ((uintptr_t)codes % 16 == 0) && n > 0;
-    CUtensorMap tmap;
+    // query batches go to the tensor cores (scan_mma.cu); a few queries per pass are HBM-bound on the integer pipes
+    const int mma_mode = env_int("VRQ_SCAN_MMA", 1);
+    const bool mma = tma && mma_mode != 0 && (nq >= env_int("VRQ_SCAN_MMA_MIN_NQ", 32) || mma_mode == 2) && k + 2048 + 256 <= 8192;
+    if (dbg && !mma) {
+        vrq_set_error("the distance dump is only available on the tensor-core scan path");
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    CUtensorMap tmap, tmap_mma;
     memset(&tmap, 0, sizeof(tmap));
-    if (tma) VRQ_TRY(make_codes_tmap(codes, n, &tmap));
+    memset(&tmap_mma, 0, sizeof(tmap_mma));
+    if (tma) VRQ_TRY(make_codes_tmap(codes, n, TMA_BOX_ROWS, &tmap));
+    if (mma) VRQ_TRY(make_codes_tmap(codes, n, MMA_TILE_ROWS, &tmap_mma));
 
     // prefix pass: an exact top-k of the first m rows seeds the thresholds of the main pass
-    ScanPlan main_pl;
-    VRQ_TRY(plan_scan(ctx, tma, code_bytes, n, nq, k, &main_pl));
+    PassPlan main_pl;
+    VRQ_TRY(plan_pass(ctx, tma, mma, code_bytes, n, nq, k, &main_pl));
     int64_t m = 0;
-    if (n >= (int64_t)64 * main_pl.tile_rows() * main_pl.strips && n >= (int64_t)16 * k) {
-        m = main_pl.rows_per_strip;  // about one strip's worth of rows
+    if (n >= (int64_t)64 * main_pl.tile_rows() * main_pl.strips() && n >= (int64_t)16 * k) {
+        m = main_pl.rows_per_strip();  // about one strip's worth of rows
         if (m < 4 * (int64_t)k) m = ((4 * (int64_t)k + main_pl.tile_rows() - 1) / main_pl.tile_rows()) * main_pl.tile_rows();
         if (m > n / 2) m = 0;
     }
-    ScanPlan pre_pl;
+    PassPlan pre_pl;
     if (m > 0) {
-        VRQ_TRY(plan_scan(ctx, tma, code_bytes, m, nq, k, &pre_pl));
-        VRQ_TRY(plan_scan(ctx, tma, code_bytes, n - m, nq, k, &main_pl));
+        VRQ_TRY(plan_pass(ctx, tma, mma, code_bytes, m, nq, k, &pre_pl));
+        VRQ_TRY(plan_pass(ctx, tma, mma, code_bytes, n - m, nq, k, &main_pl));
     }
-    const int cap = main_pl.cap > (m > 0 ? pre_pl.cap : 0) ? main_pl.cap : pre_pl.cap;
-    main_pl.cap = cap;
-    main_pl.smem = scan_smem_bytes(tma, main_pl.cw, main_pl.stages, main_pl.qtile, code_bytes, cap);
-    if (m > 0) {
-        pre_pl.cap = cap;
-        pre_pl.smem = scan_smem_bytes(tma, pre_pl.cw, pre_pl.stages, pre_pl.qtile, code_bytes, cap);
-    }
-    const int max_strips = (m > 0 && pre_pl.strips > main_pl.strips + 1) ? pre_pl.strips : main_pl.strips + 1;
+    const int cap = main_pl.cap() > (m > 0 ? pre_pl.cap() : 0) ? main_pl.cap() : pre_pl.cap();
+    main_pl.set_cap(tma, code_bytes, cap);
+    if (m > 0) pre_pl.set_cap(tma, code_bytes, cap);
+    const int max_strips = (m > 0 && pre_pl.strips() > main_pl.strips() + 1) ? pre_pl.strips() : main_pl.strips() + 1;
 
     void *lists_v, *counts_v, *tau_v;
     VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_LISTS, sizeof(uint64_t) * (size_t)max_strips * nq * cap, &lists_v));
@@ -729,6 +645,8 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
     sp.k = k;
     sp.lists = lists;
     sp.counts = counts;
+    sp.dbg = dbg;
+    sp.dbg_stride = n;
     sp.one = 1;
 
     vrq_timer_scope ts(ctx, VRQ_CAT_SCAN, st);
@@ -736,46 +654,34 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
     if (m > 0) {
         sp.row_begin = 0;
         sp.row_end = m;
-        sp.num_strips = pre_pl.strips;
-        sp.rows_per_strip = pre_pl.rows_per_strip;
-        sp.qtile = pre_pl.qtile;
-        sp.cap = cap;
-        sp.group_tiles = pre_pl.group_tiles;
-        sp.stages = pre_pl.stages;
         sp.tau0 = nullptr;
-        VRQ_TRY(launch_scan(ctx, tma, tmap, sp, pre_pl, st));
+        VRQ_TRY(launch_pass(ctx, tma, tmap, tmap_mma, sp, pre_pl, st));
         // the prefix top-k is parked in keys_out, then appended to the main pass's lists as one more "strip"
-        VRQ_TRY(launch_merge(ctx, lists, counts, pre_pl.strips, nq, cap, k, keys_out, tau, st));
+        VRQ_TRY(launch_merge(ctx, lists, counts, pre_pl.strips(), nq, cap, k, keys_out, tau, st));
         extra = 1;
     }
     sp.row_begin = m;
     sp.row_end = n;
-    sp.num_strips = main_pl.strips;
-    sp.rows_per_strip = main_pl.rows_per_strip;
-    sp.qtile = main_pl.qtile;
-    sp.cap = cap;
-    sp.group_tiles = main_pl.group_tiles;
-    sp.stages = main_pl.stages;
     sp.tau0 = m > 0 ? tau : nullptr;
     if (n - m > 0) {
-        VRQ_TRY(launch_scan(ctx, tma, tmap, sp, main_pl, st));
+        VRQ_TRY(launch_pass(ctx, tma, tmap, tmap_mma, sp, main_pl, st));
     } else {
-        VRQ_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)main_pl.strips * nq, st));
+        VRQ_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)main_pl.strips() * nq, st));
     }
     if (extra) {
-        uint64_t* slot = lists + (size_t)main_pl.strips * nq * cap;
+        uint64_t* slot = lists + (size_t)main_pl.strips() * nq * cap;
         VRQ_CUDA(cudaMemcpy2DAsync(slot, sizeof(uint64_t) * cap, keys_out, sizeof(uint64_t) * k, sizeof(uint64_t) * k, nq,
                                    cudaMemcpyDeviceToDevice, st));
         // count = number of real keys = min(k, m) == k here (m >= 4k)
-        fill_int_kernel<<<(nq + 255) / 256, 256, 0, st>>>(counts + (size_t)main_pl.strips * nq, nq, k);
+        fill_int_kernel<<<(nq + 255) / 256, 256, 0, st>>>(counts + (size_t)main_pl.strips() * nq, nq, k);
         vrq_count_launch(ctx);
     }
-    VRQ_TRY(launch_merge(ctx, lists, counts, main_pl.strips + extra, nq, cap, k, keys_out, nullptr, st));
+    VRQ_TRY(launch_merge(ctx, lists, counts, main_pl.strips() + extra, nq, cap, k, keys_out, nullptr, st));
     return 0;
 }
 
 int vrq_hamming_topk_dev(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_bytes, int64_t pos_base,
-                         const uint8_t* q_dev, int64_t nq, int k, uint64_t* keys_out, cudaStream_t st) {
+                         const uint8_t* q_dev, int64_t nq, int k, uint64_t* keys_out, cudaStream_t st, int32_t* dbg) {
     if (nq == 0) return 0;
     if (k <= 0 || k > VRQ_MAX_K) {
         vrq_set_error("Hamming top-k supports 1 <= k <= %d (got %d)", VRQ_MAX_K, k);
@@ -797,7 +703,8 @@ int vrq_hamming_topk_dev(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code
     const int64_t QB = 1024;
     for (int64_t q0 = 0; q0 < nq; q0 += QB) {
         const int nb = (int)(nq - q0 < QB ? nq - q0 : QB);
-        VRQ_TRY(topk_batch(ctx, codes, n, code_bytes, pos_base, q_dev + q0 * code_bytes, nb, k, keys_out + q0 * k, st));
+        VRQ_TRY(topk_batch(ctx, codes, n, code_bytes, pos_base, q_dev + q0 * code_bytes, nb, k, keys_out + q0 * k,
+                           dbg ? dbg + q0 * n : nullptr, st));
     }
     return 0;
 }

@@ -1,0 +1,157 @@
+// Pieces shared by the two Phase-I scan kernels (scan.cu: XOR + POPC on the integer pipes; scan_mma.cu: tcgen05 int8
+// tensor-core contraction): launch parameters, PTX wrappers, list compaction and the TMA descriptor of the code array.
+#pragma once
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "topk_utils.cuh"
+#include "vrq_internal.cuh"
+
+namespace vrq {
+
+constexpr int CODE_BYTES = 128;
+constexpr int TMA_BOX_ROWS = 256;  // rows per TMA box (hardware limit per box dimension)
+constexpr int BAR_CONSUMERS = 1;
+constexpr int TAU_INF = 1 << 28;   // "no threshold yet": above any distance
+// CW = consumer warps per CTA: 8 for query batches (long inner loops keep the POPC pipe busy), 16 for <= 8 queries
+// per pass (short per-tile work: the second warp group hides the first one's shared-memory / barrier latency).
+template <int CW>
+struct ScanCfg {
+    static constexpr int CONSUMER_THREADS = CW * 32;
+    static constexpr int THREADS = CONSUMER_THREADS + 32;
+    static constexpr int TILE_ROWS = CW * 32;
+    static constexpr int STAGE_BYTES = TILE_ROWS * CODE_BYTES;
+};
+
+struct ScanParams {
+    const uint8_t* codes;  // local row 0
+    int code_bytes;
+    int64_t row_begin, row_end;  // local rows scanned by this launch
+    int64_t pos_base;            // global position of local row 0
+    const uint8_t* queries;      // [nq][code_bytes]
+    int nq, k;
+    int num_strips;
+    int64_t rows_per_strip;  // multiple of TILE_ROWS
+    int qtile;               // queries per CTA
+    int cap;                 // capacity of one list
+    int group_tiles;         // tiles between overflow checks
+    int stages;
+    uint64_t* lists;  // [list_strips][nq][cap]
+    int* counts;      // [list_strips][nq]
+    const int* tau0;  // [nq] or null
+    int32_t* dbg;     // tests only: every (query, row) Hamming distance of the launch, [nq][dbg_stride] (tensor-core kernel)
+    int64_t dbg_stride;
+    int one;          // == 1, opaque to the compiler: multiplier that keeps the popcount accumulation on the FMA pipe (IMAD)
+};
+
+// ---- PTX helpers ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ int lds32(uint32_t addr) {
+    int r;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+
+// ---- list compaction: keep the k smallest keys of one (strip, query) list --------------------------------
+template <int CONSUMER_THREADS>
+__device__ void compact_list(uint64_t* glist, int n, int k, unsigned long long* scratch, SelectScratch* sc, int tid,
+                             int* cnt_q, int* tau_q) {
+    for (int i = tid; i < n; i += CONSUMER_THREADS) scratch[i] = glist[i];
+    group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
+    const unsigned long long kth =
+        radix_select_kth<CONSUMER_THREADS>([&](int i) { return scratch[i]; }, n, k, tid, sc, BAR_CONSUMERS);
+    if (tid == 0) sc->counter = 0;
+    group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
+    for (int i = tid; i < n; i += CONSUMER_THREADS) {
+        unsigned long long key = scratch[i];
+        if (key <= kth) glist[atomicAdd(&sc->counter, 1)] = key;
+    }
+    group_sync<CONSUMER_THREADS>(BAR_CONSUMERS);
+    if (tid == 0) {
+        *cnt_q = k;
+        *tau_q = (int)(kth >> VRQ_KEY_POS_BITS);
+    }
+}
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline int make_codes_tmap(const uint8_t* codes, int64_t nrows, int box_rows, CUtensorMap* out) {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !f) {
+            vrq_set_error("cuTensorMapEncodeTiled is not available from the driver");
+            return VRQ_ERR_UNSUPPORTED;
+        }
+        fn = (PFN_tmapEncodeTiled)f;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)CODE_BYTES, (cuuint64_t)nrows};
+    cuuint64_t gstride[1] = {(cuuint64_t)CODE_BYTES};
+    cuuint32_t box[2] = {(cuuint32_t)CODE_BYTES, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)codes, gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        vrq_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    return 0;
+}
+
+// ---- scan_mma.cu: tensor-core variant of the scan kernel (same lists / counts / thresholds contract) ----------
+struct MmaPlan {
+    int qtiles, strips, group_tiles, cap, raw_stages, b_stages;
+    int64_t rows_per_strip;
+    size_t smem;
+};
+constexpr int MMA_TILE_ROWS = 128;
+int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl);
+void mma_plan_set_cap(MmaPlan* pl, int cap);
+int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const ScanParams& sp, const MmaPlan& pl, cudaStream_t st);
+
+inline int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+
+}  // namespace vrq

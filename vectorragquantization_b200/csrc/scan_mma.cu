@@ -1,0 +1,400 @@
+// Phase I for query batches on the 5th-generation tensor cores (tcgen05, sm_100a): the same exact Hamming top-k as
+// scan.cu (faiss IndexBinaryFlat::search, CohereEnhancedVectorDB.py:268 / VectorDBInt8.py:218), with the
+// (query, code) bit contraction done by tcgen05.mma.kind::i8 instead of XOR + POPC on the integer pipes.
+//
+// Arithmetic (exact, int32 accumulation):  with database bits c_k in {0, 1} and query bits mapped to s_k in {+1, -1}
+//     dot(q, c) = sum_k s_k c_k = #(c=1, q=1) - #(c=1, q=0)      and      hamming(q, c) = popc(q) - dot(q, c)
+// so "hamming < tau" is "dot > popc(q) - tau", one integer compare per accumulator element.
+//
+// Kernel (one CTA per SM, grid = query tiles x row strips; a CTA walks its strip in ascending row order):
+//   * A operand = 128 queries x 1024 (+-1 int8), written ONCE into tensor memory (256 TMEM columns) with tcgen05.st
+//     and read from there by every MMA (the ".ts" form): shared-memory bandwidth is left to the B operand.
+//   * B operand = 128 database rows x 1024 {0,1} int8, never materialised in HBM: a producer warp TMA-loads the raw
+//     128-byte codes (16 KB per tile), eight expander warps blow each 16 code bytes up to one 128-byte K-block row
+//     ((w >> t) & 0x01010101 - the bit -> byte permutation inside a K-block is arbitrary as long as the query side
+//     uses the same one) and store it with the 128-byte swizzle the UMMA shared-memory descriptor expects.
+//   * One thread issues 32 MMAs (M=128, N=128, K=32) per tile into one of two 128-column TMEM accumulators.
+//   * Four epilogue warps read the accumulator with tcgen05.ld (lane = query, 32 columns = 32 database rows per
+//     load), take the maximum of the 32 dots and compare it with the query's threshold held in a register; only
+//     when a group holds a survivor are the 32 values looked at individually and appended to the (strip, query)
+//     list.  Lists, thresholds, compaction and the merge tree are exactly those of scan.cu.
+#include "scan_common.cuh"
+
+namespace vrq {
+namespace {
+
+constexpr int MQ = 128;      // queries per CTA  (MMA M)
+constexpr int MROWS = 128;   // database rows per tile (MMA N)
+constexpr int KBLOCKS = 8;   // K-blocks of 128 int8 (= 16 code bytes) per row
+constexpr int STAGE_BYTES_B = MROWS * 128;
+constexpr int STAGE_BYTES_RAW = MROWS * CODE_BYTES;
+constexpr int EPI_WARPS = 4;
+constexpr int EXP_WARPS = 8;
+constexpr int WARP_MMA = 4, WARP_TMA = 5, WARP_EXP0 = 6;
+constexpr int MMA_KERNEL_THREADS = (WARP_EXP0 + EXP_WARPS) * 32;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr uint32_t TMEM_COLS = 512, TMEM_A_COL = 0, TMEM_D_COL = 256;
+constexpr int MAX_B_STAGES = 12, MAX_RAW_STAGES = 4;
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = signed 8 bit, both K-major, N = 128, M = 128
+constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MROWS >> 3) << 17) | ((uint32_t)(MQ >> 4) << 24);
+
+// ---- tcgen05 wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major operand tile, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// named barrier over the epilogue threads that also ORs a predicate
+__device__ __forceinline__ int epi_sync_or(int pred) {
+    int out;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.s32 q, %1, 0;\n"
+        "bar.red.or.pred p, %2, %3, q;\n"
+        "selp.s32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(out)
+        : "r"(pred), "n"(BAR_CONSUMERS), "n"(EPI_THREADS)
+        : "memory");
+    return out;
+}
+
+struct MmaSmem {
+    unsigned long long raw_full[MAX_RAW_STAGES], raw_empty[MAX_RAW_STAGES];
+    unsigned long long b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
+    unsigned long long acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    int tau_s[MQ];
+    int cnt_s[MQ];
+    SelectScratch sc;
+};
+
+__global__ void __launch_bounds__(MMA_KERNEL_THREADS, 1)
+hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, int raw_stages, int b_stages) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* raw_mem = base;
+    uint8_t* b_mem = raw_mem + (size_t)raw_stages * STAGE_BYTES_RAW;
+    unsigned long long* scratch = (unsigned long long*)(b_mem + (size_t)b_stages * STAGE_BYTES_B);
+    MmaSmem* sm = (MmaSmem*)(scratch + p.cap);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * MQ;
+    const int qt = min(MQ, p.nq - q0);
+    const int strip = blockIdx.y;
+    const int64_t s_begin = p.row_begin + (int64_t)strip * p.rows_per_strip;
+    const int64_t s_end = min(p.row_end, s_begin + p.rows_per_strip);
+    const int64_t nrows = s_end > s_begin ? s_end - s_begin : 0;
+    const int ntiles = (int)((nrows + MROWS - 1) / MROWS);
+
+    if (tid == 0) {
+        for (int s = 0; s < raw_stages; s++) {
+            mbar_init(smem_u32(&sm->raw_full[s]), 1);
+            mbar_init(smem_u32(&sm->raw_empty[s]), EXP_WARPS);
+        }
+        for (int s = 0; s < b_stages; s++) {
+            mbar_init(smem_u32(&sm->b_full[s]), EXP_WARPS / 2);
+            mbar_init(smem_u32(&sm->b_empty[s]), 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(smem_u32(&sm->acc_full[s]), 1);
+            mbar_init(smem_u32(&sm->acc_empty[s]), EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm->tmem_base;
+
+    // ---- the query tile becomes the A operand in tensor memory: lane = query, column 8 W + t = plane t of code word W
+    int pcq = 0;
+    if (warp < EPI_WARPS) {
+        const int q = tid;
+        const bool qvalid = q < qt;
+        const uint32_t* qrow = reinterpret_cast<const uint32_t*>(p.queries + (size_t)(q0 + (qvalid ? q : 0)) * CODE_BYTES);
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16) + TMEM_A_COL;
+#pragma unroll 4
+        for (int W = 0; W < 32; W++) {
+            const uint32_t w = qvalid ? __ldg(qrow + W) : 0u;
+            pcq += __popc(w);
+            uint32_t v[8];
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                const uint32_t m = (w >> t) & 0x01010101u;           // bit set   -> +1
+                v[t] = qvalid ? (m | ((m ^ 0x01010101u) * 0xFFu)) : 0u;  // bit clear -> -1 (0xFF)
+            }
+            tmem_st8(lane_base + 8 * W, v);
+        }
+        tmem_wait_st();
+        sm->tau_s[q] = qvalid ? (p.tau0 ? min(p.tau0[q0 + q], TAU_INF) : TAU_INF) : 0;
+        sm->cnt_s[q] = 0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == WARP_TMA) {
+        // ===================== raw-code producer =====================
+        if (lane == 0) {
+            for (int t = 0; t < ntiles; t++) {
+                const int s = t % raw_stages;
+                const uint32_t u = (uint32_t)(t / raw_stages);
+                mbar_wait(smem_u32(&sm->raw_empty[s]), (u & 1u) ^ 1u);
+                mbar_expect_tx(smem_u32(&sm->raw_full[s]), STAGE_BYTES_RAW);
+                tma_load_2d(smem_u32(raw_mem + (size_t)s * STAGE_BYTES_RAW), &tmap, 0, (int)(s_begin + (int64_t)t * MROWS),
+                            smem_u32(&sm->raw_full[s]));
+            }
+        }
+    } else if (warp == WARP_MMA) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int t = 0; t < ntiles; t++) {
+                const int as = t & 1;
+                mbar_wait(smem_u32(&sm->acc_empty[as]), (((uint32_t)t >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + TMEM_D_COL + (uint32_t)as * MROWS;
+                for (int kb = 0; kb < KBLOCKS; kb++, g++) {
+                    const int s = (int)(g % (uint32_t)b_stages);
+                    mbar_wait(smem_u32(&sm->b_full[s]), (g / (uint32_t)b_stages) & 1u);
+                    tc_fence_after();
+                    const uint32_t baddr = smem_u32(b_mem + (size_t)s * STAGE_BYTES_B);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; k4++)
+                        umma_i8_ts(d_tmem, tmem + TMEM_A_COL + (uint32_t)(kb * 4 + k4) * 8, umma_desc_sw128(baddr + k4 * 32), IDESC_I8,
+                                   (kb | k4) != 0);
+                    tc_commit(smem_u32(&sm->b_empty[s]));
+                }
+                tc_commit(smem_u32(&sm->acc_full[as]));
+            }
+        }
+    } else if (warp >= WARP_EXP0) {
+        // ===================== expanders: 16 code bytes -> one 128-byte K-block row of {0,1} int8 =====================
+        const int et = tid - WARP_EXP0 * 32;
+        const int row = et & (MROWS - 1);
+        const int par = et >> 7;  // this thread expands K-blocks par, par + 2, par + 4, par + 6
+        const uint32_t sw = (uint32_t)(row & 7);
+        const uint32_t row_off = (uint32_t)row * 128u;
+        for (int t = 0; t < ntiles; t++) {
+            const int rs = t % raw_stages;
+            mbar_wait(smem_u32(&sm->raw_full[rs]), (uint32_t)(t / raw_stages) & 1u);
+            const uint32_t raddr = smem_u32(raw_mem + (size_t)rs * STAGE_BYTES_RAW) + row_off;
+            uint4 c[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) c[j] = lds128(raddr + ((((uint32_t)(2 * j + par)) ^ sw) << 4));
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t g = (uint32_t)t * KBLOCKS + (uint32_t)(2 * j + par);
+                const int s = (int)(g % (uint32_t)b_stages);
+                mbar_wait(smem_u32(&sm->b_empty[s]), ((g / (uint32_t)b_stages) & 1u) ^ 1u);
+                const uint32_t baddr = smem_u32(b_mem + (size_t)s * STAGE_BYTES_B) + row_off;
+                const uint32_t w[4] = {c[j].x, c[j].y, c[j].z, c[j].w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const uint32_t ch = (uint32_t)(2 * i + h);
+                        sts128(baddr + ((ch ^ sw) << 4), (w[i] >> (4 * h)) & 0x01010101u, (w[i] >> (4 * h + 1)) & 0x01010101u,
+                               (w[i] >> (4 * h + 2)) & 0x01010101u, (w[i] >> (4 * h + 3)) & 0x01010101u);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sm->b_full[s]));
+            }
+            // the raw tile goes back to the producer only now: every c[j] has been consumed by real instructions, so the
+            // shared-memory reads above are known to have completed (an arrive right after the ld.shared can overtake them)
+            if (lane == 0) mbar_arrive(smem_u32(&sm->raw_empty[rs]));
+        }
+    } else {
+        // ===================== epilogue: lane = query, columns = database rows =====================
+        const int q = tid;
+        const bool qvalid = q < qt;
+        uint64_t* my_list = p.lists + ((size_t)strip * p.nq + q0 + (qvalid ? q : 0)) * p.cap;
+        int cnt = 0;
+        int thr = qvalid ? pcq - sm->tau_s[q] : 0x7fffffff;  // survivor <=> dot > thr <=> hamming < tau
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16) + TMEM_D_COL;
+        const int limit = p.cap - p.group_tiles * MROWS;
+        for (int t = 0; t < ntiles; t++) {
+            const int as = t & 1;
+            mbar_wait(smem_u32(&sm->acc_full[as]), ((uint32_t)t >> 1) & 1u);
+            tc_fence_after();
+            const int64_t lrow0 = s_begin + (int64_t)t * MROWS;
+            const int nvalid = (int)min((int64_t)MROWS, s_end - lrow0);
+#pragma unroll 1
+            for (int cc = 0; cc < MROWS / 32; cc++) {
+                int v[32];
+                __syncwarp();
+                tmem_ld32(lane_base + (uint32_t)as * MROWS + 32 * cc, v);
+                tmem_wait_ld();
+                if (cc == MROWS / 32 - 1) {
+                    // the accumulator is in registers: hand the TMEM stage back to the MMA issuer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[as]));
+                }
+                const int nv = nvalid - 32 * cc;  // valid columns in this group (>= 32: all)
+                if (p.dbg) {
+                    if (qvalid)
+                        for (int j = 0; j < 32; j++)
+                            if (j < nv) p.dbg[(size_t)(q0 + q) * p.dbg_stride + (lrow0 + 32 * cc + j)] = pcq - v[j];
+                }
+                int m = v[0];
+#pragma unroll
+                for (int j = 1; j < 32; j++) m = max(m, v[j]);
+                if (m > thr) {
+                    const unsigned long long pos0 = (unsigned long long)(p.pos_base + lrow0 + 32 * cc);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        if (v[j] > thr && j < nv) {
+                            my_list[cnt] = ((unsigned long long)(pcq - v[j]) << VRQ_KEY_POS_BITS) | (pos0 + j);
+                            cnt++;
+                        }
+                    }
+                }
+            }
+            // ---- overflow check every group_tiles tiles: no list may exceed cap during the next group ----
+            if ((t + 1) % p.group_tiles == 0 && t + 1 < ntiles) {
+                sm->cnt_s[q] = cnt;
+                if (epi_sync_or(cnt > limit)) {
+                    for (int qq = 0; qq < qt; qq++) {
+                        const int n = sm->cnt_s[qq];
+                        if (n > limit)
+                            compact_list<EPI_THREADS>(p.lists + ((size_t)strip * p.nq + q0 + qq) * p.cap, n, p.k, scratch, &sm->sc, tid,
+                                                      &sm->cnt_s[qq], &sm->tau_s[qq]);
+                    }
+                    group_sync<EPI_THREADS>(BAR_CONSUMERS);
+                    cnt = sm->cnt_s[q];
+                    if (qvalid) thr = pcq - sm->tau_s[q];
+                }
+            }
+        }
+        sm->cnt_s[q] = cnt;
+        group_sync<EPI_THREADS>(BAR_CONSUMERS);
+        // final compaction: every list leaves the kernel with at most k keys (bounds the merge's working set)
+        for (int qq = 0; qq < qt; qq++) {
+            const int n = sm->cnt_s[qq];
+            if (n > p.k)
+                compact_list<EPI_THREADS>(p.lists + ((size_t)strip * p.nq + q0 + qq) * p.cap, n, p.k, scratch, &sm->sc, tid, &sm->cnt_s[qq],
+                                          &sm->tau_s[qq]);
+        }
+        group_sync<EPI_THREADS>(BAR_CONSUMERS);
+        if (qvalid) p.counts[(size_t)strip * p.nq + q0 + q] = sm->cnt_s[q];
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+size_t mma_smem_bytes(int raw_stages, int b_stages, int cap) {
+    return 1024 + (size_t)raw_stages * STAGE_BYTES_RAW + (size_t)b_stages * STAGE_BYTES_B + sizeof(unsigned long long) * (size_t)cap +
+           sizeof(MmaSmem) + 16;
+}
+
+}  // namespace
+
+int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
+    const int sms = ctx->sm_count;
+    pl->qtiles = (nq + MQ - 1) / MQ;
+    pl->group_tiles = env_int("VRQ_MMA_GROUP_TILES", 2);
+    if (pl->group_tiles < 1) pl->group_tiles = 1;
+    const int slack = k < 256 ? 256 : (k > 2048 ? 2048 : k);
+    pl->cap = k + slack + pl->group_tiles * MROWS;
+    int strips = sms / pl->qtiles;
+    if (strips < 1) strips = 1;
+    int64_t tiles = (rows + MROWS - 1) / MROWS;
+    if (tiles < 1) tiles = 1;
+    if (strips > tiles) strips = (int)tiles;
+    const int64_t tps = (tiles + strips - 1) / strips;
+    pl->rows_per_strip = tps * MROWS;
+    pl->strips = (int)((tiles + tps - 1) / tps);
+    pl->raw_stages = env_int("VRQ_MMA_RAW_STAGES", 3);
+    if (pl->raw_stages < 1) pl->raw_stages = 1;
+    if (pl->raw_stages > MAX_RAW_STAGES) pl->raw_stages = MAX_RAW_STAGES;
+    const size_t limit = ctx->smem_optin ? ctx->smem_optin : 227 * 1024;
+    int max_b = env_int("VRQ_MMA_B_STAGES", MAX_B_STAGES);
+    if (max_b > MAX_B_STAGES) max_b = MAX_B_STAGES;
+    pl->b_stages = 0;
+    for (int s = max_b; s >= 4; s--) {
+        if (mma_smem_bytes(pl->raw_stages, s, pl->cap) <= limit) {
+            pl->b_stages = s;
+            break;
+        }
+    }
+    if (pl->b_stages == 0) {
+        vrq_set_error("tensor-core Hamming top-k with k=%d does not fit the shared-memory plan", k);
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    pl->smem = mma_smem_bytes(pl->raw_stages, pl->b_stages, pl->cap);
+    return 0;
+}
+
+void mma_plan_set_cap(MmaPlan* pl, int cap) {
+    pl->cap = cap;
+    pl->smem = mma_smem_bytes(pl->raw_stages, pl->b_stages, cap);
+}
+
+int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const ScanParams& sp, const MmaPlan& pl, cudaStream_t st) {
+    const size_t limit = ctx->smem_optin ? ctx->smem_optin : 227 * 1024;
+    if (pl.smem > limit) {
+        vrq_set_error("tensor-core Hamming top-k: shared-memory plan of %zu bytes exceeds %zu", pl.smem, limit);
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    dim3 grid(pl.qtiles, pl.strips);
+    VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    hamming_scan_mma_kernel<<<grid, MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, pl.b_stages);
+    vrq_count_launch(ctx);
+    VRQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace vrq

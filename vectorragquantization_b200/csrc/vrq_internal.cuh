@@ -117,7 +117,8 @@ int vrq_launch_dequant(vrq_ctx* ctx, const vrq_dequant_args& a, cudaStream_t st)
 // ---- scan.cu ----------------------------------------------------------------------------------------
 // keys out: [nq, k] sorted ascending, key = (hamming << 40) | (pos_base + row); missing = ~0ull.
 int vrq_hamming_topk_dev(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_bytes, int64_t pos_base,
-                         const uint8_t* q_dev, int64_t nq, int k, uint64_t* keys_out, cudaStream_t st);
+                         const uint8_t* q_dev, int64_t nq, int k, uint64_t* keys_out, cudaStream_t st,
+                         int32_t* dbg_dist = nullptr);  // dbg_dist: tests only, [nq][n] every distance (tensor-core path)
 #define VRQ_KEY_POS_BITS 40
 #define VRQ_KEY_POS_MASK ((1ull << VRQ_KEY_POS_BITS) - 1ull)
 #define VRQ_KEY_NONE (~0ull)
