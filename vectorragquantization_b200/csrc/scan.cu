@@ -189,6 +189,7 @@ hamming_scan_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p) {
     unsigned long long* bars = (unsigned long long*)ptr;  // full[stages], empty[stages]
     int* flag = (int*)(bars + 2 * 8);
 
+    if (p.guard && *p.guard == 0) return;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * p.qtile;
@@ -324,7 +325,9 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_group_kernel(const uint64
                                                                     const int* __restrict__ counts, int nq, int cap_in,
                                                                     int s_total, int gs, int k, int buf_cap,
                                                                     uint64_t* __restrict__ out_lists, int* __restrict__ out_counts,
-                                                                    uint64_t* __restrict__ final_out, int* __restrict__ tau_out) {
+                                                                    uint64_t* __restrict__ final_out, int* __restrict__ tau_out,
+                                                                    const int* __restrict__ guard) {
+    if (guard && *guard == 0) return;
     extern __shared__ unsigned long long msm[];  // buf[buf_cap] | sel[next_pow2(k)] (final level only)
     __shared__ SelectScratch sc;
     __shared__ int offs[65];
@@ -391,6 +394,16 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_group_kernel(const uint64
         }
         if (tid == 0) out_counts[(size_t)g * nq + q] = total < k ? total : k;
     }
+}
+
+// After a pass whose thresholds came from a sample: does every query hold at least `need` candidates over all strips?
+// (A list that was compacted holds k >= need keys on its own.)  Sets *flag otherwise - the exact fallback pass runs.
+__global__ void verify_counts_kernel(const int* __restrict__ counts, int strips, int nq, int need, int* flag) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    long long total = 0;
+    for (int s = 0; s < strips; s++) total += counts[(size_t)s * nq + q];
+    if (total < need) atomicOr(flag, 1);
 }
 
 __global__ void fill_int_kernel(int* p, int n, int v) {
@@ -505,7 +518,7 @@ int launch_scan(vrq_ctx* ctx, bool tma, const CUtensorMap& tmap, const ScanParam
 
 // Merge tree over `strips` lists per query (each holding <= k keys, row stride cap): returns sorted keys in out.
 int launch_merge(vrq_ctx* ctx, const uint64_t* lists, const int* counts, int strips, int nq, int cap, int k, uint64_t* out,
-                 int* tau_out, cudaStream_t st) {
+                 int* tau_out, cudaStream_t st, const int* guard = nullptr) {
     int n2 = 1;
     while (n2 < k) n2 <<= 1;
     const size_t budget = 200 * 1024;
@@ -536,7 +549,7 @@ int launch_merge(vrq_ctx* ctx, const uint64_t* lists, const int* counts, int str
         }
         merge_group_kernel<<<dim3(g, nq), MERGE_THREADS, smem, st>>>(cur_lists, cur_counts, nq, cur_cap, cur_strips, ns, k, buf_cap,
                                                                      nxt_lists, nxt_counts, final_level ? out : nullptr,
-                                                                     final_level ? tau_out : nullptr);
+                                                                     final_level ? tau_out : nullptr, guard);
         vrq_count_launch(ctx);
         VRQ_CUDA(cudaGetLastError());
         if (final_level) break;
@@ -584,6 +597,7 @@ static int launch_pass(vrq_ctx* ctx, bool tma, const CUtensorMap& tmap, const CU
     if (pl.mma) {
         sp.qtile = 128;
         sp.group_tiles = pl.mp.group_tiles;
+        if (sp.tile_step == 0) sp.tile_step = MMA_TILE_ROWS;
         return launch_scan_mma(ctx, tmap_mma, sp, pl.mp, st);
     }
     sp.qtile = pl.sp.qtile;
@@ -608,6 +622,83 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
     memset(&tmap_mma, 0, sizeof(tmap_mma));
     if (tma) VRQ_TRY(make_codes_tmap(codes, n, TMA_BOX_ROWS, &tmap));
     if (mma) VRQ_TRY(make_codes_tmap(codes, n, MMA_TILE_ROWS, &tmap_mma));
+
+    if (mma) {
+        // ---- thresholds from a strided sample (tensor-core path) ------------------------------------------------
+        // The k'-th best distance T over a sample of m rows bounds the number of rows with d <= T in the whole database
+        // at about k' n / m; m is chosen so that this is `safety` x k.  One dense pass with tau = T + 1 then collects a
+        // few thousand candidates per query instead of k per strip, with no list compaction.  The result stays exact:
+        // a verification kernel checks that every query collected >= min(k, n) candidates and otherwise raises a flag
+        // that un-gates an exact fallback pass (tau starts at infinity) enqueued right behind.
+        const int kp = env_int("VRQ_MMA_SAMPLE_K", 32);
+        const int safety = env_int("VRQ_MMA_SAFETY", 8);
+        const int64_t total_tiles = (n + MMA_TILE_ROWS - 1) / MMA_TILE_ROWS;
+        int64_t sample_tiles = 0;
+        if (safety > 0 && kp > 0 && kp <= k * safety) {
+            const int64_t want_rows = (int64_t)(((double)kp * (double)n) / ((double)safety * (double)k)) + 1;
+            sample_tiles = (want_rows + MMA_TILE_ROWS - 1) / MMA_TILE_ROWS;
+            if (sample_tiles * 16 > total_tiles || sample_tiles * MMA_TILE_ROWS < (int64_t)64 * kp) sample_tiles = 0;
+        }
+        if (sample_tiles > 0) {
+            const int64_t step_tiles = total_tiles / sample_tiles;
+            const int64_t tile_step = step_tiles * MMA_TILE_ROWS;
+            const int64_t actual_tiles = (n + tile_step - 1) / tile_step;
+            PassPlan s_pl, m_pl;
+            VRQ_TRY(plan_pass(ctx, tma, true, code_bytes, actual_tiles * MMA_TILE_ROWS, nq, kp, &s_pl));
+            VRQ_TRY(plan_pass(ctx, tma, true, code_bytes, n, nq, k, &m_pl));
+            const int cap = s_pl.cap() > m_pl.cap() ? s_pl.cap() : m_pl.cap();
+            s_pl.set_cap(tma, code_bytes, cap);
+            m_pl.set_cap(tma, code_bytes, cap);
+            const int max_strips = s_pl.strips() > m_pl.strips() ? s_pl.strips() : m_pl.strips();
+            void *lists_v, *counts_v, *tau_v, *skeys_v, *flag_v;
+            VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_LISTS, sizeof(uint64_t) * (size_t)max_strips * nq * cap, &lists_v));
+            VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_COUNTS, sizeof(int) * (size_t)max_strips * nq, &counts_v));
+            VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_TAU, sizeof(int) * (size_t)nq, &tau_v));
+            VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_SAMPLE_KEYS, sizeof(uint64_t) * (size_t)nq * kp, &skeys_v));
+            VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_FLAG, sizeof(int) * 4, &flag_v));
+            uint64_t* lists = (uint64_t*)lists_v;
+            int* counts = (int*)counts_v;
+            int* tau = (int*)tau_v;
+            int* flag = (int*)flag_v;
+            ScanParams sp{};
+            sp.codes = codes;
+            sp.code_bytes = code_bytes;
+            sp.pos_base = pos_base;
+            sp.queries = q_dev;
+            sp.nq = nq;
+            sp.lists = lists;
+            sp.counts = counts;
+            sp.dbg_stride = n;
+            sp.one = 1;
+            sp.row_begin = 0;
+            sp.row_end = n;
+            vrq_timer_scope ts(ctx, VRQ_CAT_SCAN, st);
+            // 1. sample pass: exact top-k' of the sampled tiles -> tau[q] = k'-th best distance
+            sp.k = kp;
+            sp.tile_step = tile_step;
+            VRQ_TRY(launch_pass(ctx, tma, tmap, tmap_mma, sp, s_pl, st));
+            VRQ_TRY(launch_merge(ctx, lists, counts, s_pl.strips(), nq, cap, kp, (uint64_t*)skeys_v, tau, st));
+            // 2. dense pass with the inclusive threshold d <= T
+            sp.k = k;
+            sp.tile_step = MMA_TILE_ROWS;
+            sp.tau0 = tau;
+            sp.tau_bias = 1;
+            sp.dbg = dbg;
+            VRQ_TRY(launch_pass(ctx, tma, tmap, tmap_mma, sp, m_pl, st));
+            VRQ_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+            const int need = (int)((int64_t)k < n ? (int64_t)k : n);
+            verify_counts_kernel<<<(nq + 127) / 128, 128, 0, st>>>(counts, m_pl.strips(), nq, need, flag);
+            vrq_count_launch(ctx);
+            VRQ_TRY(launch_merge(ctx, lists, counts, m_pl.strips(), nq, cap, k, keys_out, nullptr, st));
+            // 3. exact fallback, a no-op unless the verification raised the flag
+            sp.tau0 = nullptr;
+            sp.tau_bias = 0;
+            sp.guard = flag;
+            VRQ_TRY(launch_pass(ctx, tma, tmap, tmap_mma, sp, m_pl, st));
+            VRQ_TRY(launch_merge(ctx, lists, counts, m_pl.strips(), nq, cap, k, keys_out, nullptr, st, flag));
+            return 0;
+        }
+    }
 
     // prefix pass: an exact top-k of the first m rows seeds the thresholds of the main pass
     PassPlan main_pl;

@@ -40,6 +40,9 @@ struct ScanParams {
     uint64_t* lists;  // [list_strips][nq][cap]
     int* counts;      // [list_strips][nq]
     const int* tau0;  // [nq] or null
+    const int* guard;  // nullable: the launch does nothing when *guard == 0 (fallback passes enqueued ahead of knowing they are needed)
+    int tau_bias;      // added to tau0 (1 turns a k'-th distance T of a sample into the inclusive bound "d <= T")
+    int64_t tile_step; // tensor-core kernel: rows between the starts of consecutive tiles (128 = dense scan; larger = strided sample)
     int32_t* dbg;     // tests only: every (query, row) Hamming distance of the launch, [nq][dbg_stride] (tensor-core kernel)
     int64_t dbg_stride;
     int one;          // == 1, opaque to the compiler: multiplier that keeps the popcount accumulation on the FMA pipe (IMAD)
@@ -141,7 +144,7 @@ inline int make_codes_tmap(const uint8_t* codes, int64_t nrows, int box_rows, CU
 struct MmaPlan {
     int qtiles, strips, group_tiles, cap, raw_stages, b_stages;
     int64_t rows_per_strip;
-    size_t smem;
+    size_t smem, smem_limit;
 };
 constexpr int MMA_TILE_ROWS = 128;
 int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl);

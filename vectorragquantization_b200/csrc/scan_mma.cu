@@ -120,10 +120,15 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
     const int q0 = blockIdx.x * MQ;
     const int qt = min(MQ, p.nq - q0);
     const int strip = blockIdx.y;
-    const int64_t s_begin = p.row_begin + (int64_t)strip * p.rows_per_strip;
-    const int64_t s_end = min(p.row_end, s_begin + p.rows_per_strip);
-    const int64_t nrows = s_end > s_begin ? s_end - s_begin : 0;
-    const int ntiles = (int)((nrows + MROWS - 1) / MROWS);
+    // tiles of this launch start at row_begin + i * tile_step (tile_step == MROWS: a dense scan; larger: a strided sample
+    // of the database); a strip owns tiles_per_strip consecutive tiles
+    const int tiles_per_strip = (int)(p.rows_per_strip / MROWS);
+    const int64_t total_tiles = p.row_end > p.row_begin ? (p.row_end - p.row_begin + p.tile_step - 1) / p.tile_step : 0;
+    const int64_t tile0 = (int64_t)strip * tiles_per_strip;
+    const int ntiles = (int)max((int64_t)0, min((int64_t)tiles_per_strip, total_tiles - tile0));
+    const int64_t s_begin = p.row_begin + tile0 * p.tile_step;
+    const int64_t s_end = p.row_end;
+    if (p.guard && *p.guard == 0) return;
 
     if (tid == 0) {
         for (int s = 0; s < raw_stages; s++) {
@@ -171,7 +176,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
             tmem_st8(lane_base + 8 * W, v);
         }
         tmem_wait_st();
-        sm->tau_s[q] = qvalid ? (p.tau0 ? min(p.tau0[q0 + q], TAU_INF) : TAU_INF) : 0;
+        sm->tau_s[q] = qvalid ? (p.tau0 ? min(p.tau0[q0 + q], TAU_INF - 1) + p.tau_bias : TAU_INF) : 0;
         sm->cnt_s[q] = 0;
     }
     tc_fence_before();
@@ -186,7 +191,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                 const uint32_t u = (uint32_t)(t / raw_stages);
                 mbar_wait(smem_u32(&sm->raw_empty[s]), (u & 1u) ^ 1u);
                 mbar_expect_tx(smem_u32(&sm->raw_full[s]), STAGE_BYTES_RAW);
-                tma_load_2d(smem_u32(raw_mem + (size_t)s * STAGE_BYTES_RAW), &tmap, 0, (int)(s_begin + (int64_t)t * MROWS),
+                tma_load_2d(smem_u32(raw_mem + (size_t)s * STAGE_BYTES_RAW), &tmap, 0, (int)(s_begin + (int64_t)t * p.tile_step),
                             smem_u32(&sm->raw_full[s]));
             }
         }
@@ -264,7 +269,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
             const int as = t & 1;
             mbar_wait(smem_u32(&sm->acc_full[as]), ((uint32_t)t >> 1) & 1u);
             tc_fence_after();
-            const int64_t lrow0 = s_begin + (int64_t)t * MROWS;
+            const int64_t lrow0 = s_begin + (int64_t)t * p.tile_step;
             const int nvalid = (int)min((int64_t)MROWS, s_end - lrow0);
 #pragma unroll 1
             for (int cc = 0; cc < MROWS / 32; cc++) {
@@ -288,12 +293,24 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
 #pragma unroll
                 for (int j = 1; j < 32; j++) m = max(m, v[j]);
                 if (m > thr) {
+                    // Some column of this lane survives.  bit (31 - j) of mask <=> v[j] > thr: the sign of thr - v[j] is
+                    // shifted in with one funnel shift per column (2 instructions per column, no branches).
                     const unsigned long long pos0 = (unsigned long long)(p.pos_base + lrow0 + 32 * cc);
+                    uint32_t mask = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        if (v[j] > thr && j < nv) {
-                            my_list[cnt] = ((unsigned long long)(pcq - v[j]) << VRQ_KEY_POS_BITS) | (pos0 + j);
-                            cnt++;
+                    for (int j = 0; j < 32; j++) mask = __funnelshift_l((uint32_t)(thr - v[j]), mask, 1);
+                    if (nv < 32) mask = nv <= 0 ? 0u : (mask & ~(0xFFFFFFFFu >> nv));
+                    if (__popc(mask) == 1 && nv >= 32) {
+                        // the usual case once tau has converged: the single survivor is the maximum itself
+                        my_list[cnt] = ((unsigned long long)(pcq - m) << VRQ_KEY_POS_BITS) | (pos0 + __clz((int)mask));
+                        cnt++;
+                    } else if (mask) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            if ((mask >> (31 - j)) & 1u) {
+                                my_list[cnt] = ((unsigned long long)(pcq - v[j]) << VRQ_KEY_POS_BITS) | (pos0 + j);
+                                cnt++;
+                            }
                         }
                     }
                 }
@@ -361,6 +378,7 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
     if (pl->raw_stages < 1) pl->raw_stages = 1;
     if (pl->raw_stages > MAX_RAW_STAGES) pl->raw_stages = MAX_RAW_STAGES;
     const size_t limit = ctx->smem_optin ? ctx->smem_optin : 227 * 1024;
+    pl->smem_limit = limit;
     int max_b = env_int("VRQ_MMA_B_STAGES", MAX_B_STAGES);
     if (max_b > MAX_B_STAGES) max_b = MAX_B_STAGES;
     pl->b_stages = 0;
@@ -380,6 +398,7 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
 
 void mma_plan_set_cap(MmaPlan* pl, int cap) {
     pl->cap = cap;
+    while (pl->b_stages > 4 && mma_smem_bytes(pl->raw_stages, pl->b_stages, cap) > pl->smem_limit) pl->b_stages--;
     pl->smem = mma_smem_bytes(pl->raw_stages, pl->b_stages, cap);
 }
 

@@ -50,7 +50,7 @@ struct vrq_buf {
 enum { VRQ_WS_STAGE_IN0 = 0, VRQ_WS_STAGE_IN1, VRQ_WS_STAGE_OUT0, VRQ_WS_STAGE_OUT1, VRQ_WS_LISTS, VRQ_WS_COUNTS,
        VRQ_WS_TOPK, VRQ_WS_SEARCH_A, VRQ_WS_SEARCH_B, VRQ_WS_SEARCH_C, VRQ_WS_SEARCH_D, VRQ_WS_SEARCH_E,
        VRQ_WS_QUERY_A, VRQ_WS_QUERY_B, VRQ_WS_OUT_A, VRQ_WS_OUT_B, VRQ_WS_OUT_C, VRQ_WS_OUT_D, VRQ_WS_OUT_E,
-       VRQ_WS_MISC, VRQ_WS_TAU, VRQ_WS_MERGE_A, VRQ_WS_MERGE_B, VRQ_WS_MERGE_CA, VRQ_WS_MERGE_CB, VRQ_WS_SLOTS };
+       VRQ_WS_MISC, VRQ_WS_TAU, VRQ_WS_MERGE_A, VRQ_WS_MERGE_B, VRQ_WS_MERGE_CA, VRQ_WS_MERGE_CB, VRQ_WS_SAMPLE_KEYS, VRQ_WS_FLAG, VRQ_WS_SLOTS };
 
 struct vrq_ctx {
     int device = 0;
