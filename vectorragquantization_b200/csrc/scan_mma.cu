@@ -59,6 +59,17 @@ __device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uin
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
                  "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
@@ -186,10 +197,9 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
     if (warp == WARP_TMA) {
         // ===================== raw-code producer =====================
         if (lane == 0) {
-            for (int t = 0; t < ntiles; t++) {
-                const int s = t % raw_stages;
-                const uint32_t u = (uint32_t)(t / raw_stages);
-                mbar_wait(smem_u32(&sm->raw_empty[s]), (u & 1u) ^ 1u);
+            uint32_t s = 0, ph = 0;
+            for (int t = 0; t < ntiles; t++, s = (s + 1 == (uint32_t)raw_stages) ? 0 : s + 1, ph ^= (s == 0)) {
+                mbar_wait(smem_u32(&sm->raw_empty[s]), ph ^ 1u);
                 mbar_expect_tx(smem_u32(&sm->raw_full[s]), STAGE_BYTES_RAW);
                 tma_load_2d(smem_u32(raw_mem + (size_t)s * STAGE_BYTES_RAW), &tmap, 0, (int)(s_begin + (int64_t)t * p.tile_step),
                             smem_u32(&sm->raw_full[s]));
@@ -197,25 +207,33 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         }
     } else if (warp == WARP_MMA) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            uint32_t g = 0;
-            for (int t = 0; t < ntiles; t++) {
-                const int as = t & 1;
-                mbar_wait(smem_u32(&sm->acc_empty[as]), (((uint32_t)t >> 1) & 1u) ^ 1u);
+        // The whole warp walks the loop (ring positions stay warp-uniform, i.e. in uniform registers); one elected lane
+        // issues.  Per K-block: 4 MMAs (K = 32 each) whose B descriptors differ by 32 bytes, one commit.
+        uint32_t s = 0, ph = 0;  // B-ring stage and the parity of its current use
+        const uint64_t desc0 = umma_desc_sw128(smem_u32(b_mem));
+        for (int t = 0; t < ntiles; t++) {
+            const int as = t & 1;
+            mbar_wait(smem_u32(&sm->acc_empty[as]), (((uint32_t)t >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem + TMEM_D_COL + (uint32_t)as * MROWS;
+#pragma unroll
+            for (int kb = 0; kb < KBLOCKS; kb++) {
+                mbar_wait(smem_u32(&sm->b_full[s]), ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem + TMEM_D_COL + (uint32_t)as * MROWS;
-                for (int kb = 0; kb < KBLOCKS; kb++, g++) {
-                    const int s = (int)(g % (uint32_t)b_stages);
-                    mbar_wait(smem_u32(&sm->b_full[s]), (g / (uint32_t)b_stages) & 1u);
-                    tc_fence_after();
-                    const uint32_t baddr = smem_u32(b_mem + (size_t)s * STAGE_BYTES_B);
+                if (elect_one()) {
+                    const uint64_t desc = desc0 + (uint64_t)(s * (uint32_t)(STAGE_BYTES_B >> 4));
 #pragma unroll
                     for (int k4 = 0; k4 < 4; k4++)
-                        umma_i8_ts(d_tmem, tmem + TMEM_A_COL + (uint32_t)(kb * 4 + k4) * 8, umma_desc_sw128(baddr + k4 * 32), IDESC_I8,
+                        umma_i8_ts(d_tmem, tmem + TMEM_A_COL + (uint32_t)(kb * 4 + k4) * 8, desc + (uint64_t)(k4 * 2), IDESC_I8,
                                    (kb | k4) != 0);
                     tc_commit(smem_u32(&sm->b_empty[s]));
+                    if (kb == KBLOCKS - 1) tc_commit(smem_u32(&sm->acc_full[as]));
                 }
-                tc_commit(smem_u32(&sm->acc_full[as]));
+                __syncwarp();
+                if (++s == (uint32_t)b_stages) {
+                    s = 0;
+                    ph ^= 1u;
+                }
             }
         }
     } else if (warp >= WARP_EXP0) {
@@ -225,19 +243,18 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         const int par = et >> 7;  // this thread expands K-blocks par, par + 2, par + 4, par + 6
         const uint32_t sw = (uint32_t)(row & 7);
         const uint32_t row_off = (uint32_t)row * 128u;
+        uint32_t rs = 0, rph = 0;                 // raw ring
+        uint32_t s = (uint32_t)par, ph = 0;       // B ring: this thread's stages advance by 2 (b_stages >= 4 > par)
         for (int t = 0; t < ntiles; t++) {
-            const int rs = t % raw_stages;
-            mbar_wait(smem_u32(&sm->raw_full[rs]), (uint32_t)(t / raw_stages) & 1u);
-            const uint32_t raddr = smem_u32(raw_mem + (size_t)rs * STAGE_BYTES_RAW) + row_off;
+            mbar_wait(smem_u32(&sm->raw_full[rs]), rph);
+            const uint32_t raddr = smem_u32(raw_mem) + rs * (uint32_t)STAGE_BYTES_RAW + row_off;
             uint4 c[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) c[j] = lds128(raddr + ((((uint32_t)(2 * j + par)) ^ sw) << 4));
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const uint32_t g = (uint32_t)t * KBLOCKS + (uint32_t)(2 * j + par);
-                const int s = (int)(g % (uint32_t)b_stages);
-                mbar_wait(smem_u32(&sm->b_empty[s]), ((g / (uint32_t)b_stages) & 1u) ^ 1u);
-                const uint32_t baddr = smem_u32(b_mem + (size_t)s * STAGE_BYTES_B) + row_off;
+                mbar_wait(smem_u32(&sm->b_empty[s]), ph ^ 1u);
+                const uint32_t baddr = smem_u32(b_mem) + s * (uint32_t)STAGE_BYTES_B + row_off;
                 const uint32_t w[4] = {c[j].x, c[j].y, c[j].z, c[j].w};
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
@@ -251,10 +268,19 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&sm->b_full[s]));
+                s += 2;
+                if (s >= (uint32_t)b_stages) {
+                    s -= (uint32_t)b_stages;
+                    ph ^= 1u;
+                }
             }
             // the raw tile goes back to the producer only now: every c[j] has been consumed by real instructions, so the
             // shared-memory reads above are known to have completed (an arrive right after the ld.shared can overtake them)
             if (lane == 0) mbar_arrive(smem_u32(&sm->raw_empty[rs]));
+            if (++rs == (uint32_t)raw_stages) {
+                rs = 0;
+                rph ^= 1u;
+            }
         }
     } else {
         // ===================== epilogue: lane = query, columns = database rows =====================
