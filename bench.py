@@ -12,9 +12,10 @@ shard (weak scaling: the database is N x 100 M rows), each query is answered exa
 (per-shard candidates -> one NCCL all-gather -> device merge), and `value` counts queries x (database rows / 100 M)
 per second, i.e. it is plain QPS@100M at N=1 and total pair throughput in the same unit for N>1.
 
-The JSON line carries, besides the base contract: `roofline` (dominant kernel = batched Hamming scan, bound by the
-POPC pipe, with its HBM figures alongside), `roofline_scan_stream` / `roofline_encode` (the two HBM-bound kernels the
-metric names: scan at <=2 queries per pass, fused int8 encode), `cpu_baseline`, `e2e`, `clocks`, `gpu_launches`.
+The JSON line carries, besides the base contract: `roofline` (dominant kernel = the dense pass of the batched Hamming
+scan, a tcgen05 int8 contraction bound by the tensor pipe, with its HBM figures alongside), `roofline_scan_stream` /
+`roofline_encode` (the two HBM-bound kernels the metric names: scan at <=2 queries per pass, fused int8 encode),
+`cpu_baseline`, `e2e`, `clocks`, `gpu_launches`.
 """
 from __future__ import annotations
 
@@ -44,11 +45,22 @@ METRIC = "3-phase search QPS @100Mx1024-d"
 UNIT = "queries/s per 100M codes"
 
 
+INT8_DENSE_NOMINAL_TOPS = 4500.0  # B200 dense int8 / fp8 tensor rate (B200_PROFILING.md, nominal table)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def bf16_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["bf16_tflops"]), float(j.get("bf16_tflops_sustained", j["bf16_tflops"])), "measured (MEASURED_PEAKS.json)"
+    return 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -227,6 +239,7 @@ def run_gpu(args):
     barrier()
     ctx.enable_timing(True)
     ctx.timing_ms("scan")
+    ctx.timing_ms("scan_dense")
     ctx.timing_ms("rescore")
     ctx.timing_ms("merge")
     launches0 = ctx.launch_count()
@@ -243,6 +256,7 @@ def run_gpu(args):
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - launches0
     scan_ms, scan_n = ctx.timing_ms("scan")
+    dense_ms, dense_n = ctx.timing_ms("scan_dense")
     resc_ms, _ = ctx.timing_ms("rescore")
     merge_ms, _ = ctx.timing_ms("merge")
     ctx.enable_timing(False)
@@ -291,22 +305,46 @@ def run_gpu(args):
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     alu_peak = LOP3_PER_CLK_PER_SM * 148 * sm_mhz * 1e6 / LOP3_PER_PAIR  # (query, code) pairs per second at the measured clock
     popc_ceiling = POPC_PER_CLK_PER_SM * 148 * sm_mhz * 1e6 / 32.0
-    roofline = {
-        "kernel": "hamming_scan_kernel<TMA, 16 consumer warps, 16-CSA> (batched: 1024 queries per pass)",
-        "bound": "alu", "unit": "Gpair/s",
-        "achieved": pairs_per_step / scan_s / 1e9, "peak": alu_peak / 1e9, "frac": pairs_per_step / scan_s / alu_peak,
-        "peak_source": f"ALU-pipe (LOP3) issue rate measured at 64 lanes/clk/SM (profiles/microbench) x 148 SMs x {sm_mhz:.0f} MHz "
-                       "sampled during the run / 64 LOP3 per 1024-bit pair (32 XOR + 16 carry-save adders); ncu shows the ALU pipe "
-                       "as the busiest unit (profiles/r01). The plain XOR+POPC form is capped by the POPC pipe instead "
-                       f"(16 lanes/clk/SM -> {popc_ceiling / 1e9:.1f} Gpair/s)",
-        "plain_popc_ceiling": popc_ceiling / 1e9,
-        "traffic": None,
-        "hbm": {"bound": "hbm", "unit": "GB/s", "achieved": n_local * 128 / scan_s / 1e9, "peak": hbm_peak,
-                "frac": n_local * 128 / scan_s / 1e9 / hbm_peak, "peak_source": peak_src,
-                "note": "algorithmic bytes = 128 B per code per 1024-query pass; not the binding resource for a query batch"},
-        "scan_ms_per_step": scan_ms / args.steps, "rescore_ms_per_step": resc_ms / args.steps,
-        "merge_ms_per_step": merge_ms / args.steps,
-    }
+    mma_path = os.environ.get("VRQ_SCAN_MMA", "1") != "0"
+    if mma_path and dense_n > 0:
+        dense_s = dense_ms / 1e3 / dense_n
+        ops = 2.0 * D * pairs_per_step  # one int8 multiply-add per (query bit, code bit) = 2 ops
+        bf16_burst, bf16_sust, bf16_src = bf16_peaks()
+        roofline = {
+            "kernel": "hamming_scan_mma_kernel, dense pass (tcgen05.mma.cta_group::1.kind::i8, M=128 queries in TMEM x N=128 codes "
+                      "expanded to {0,1} int8 in shared memory, K=1024; 1024-query batch)",
+            "bound": "tensor", "unit": "TFLOP/s", "ops": "int8 multiply-add = 2 ops",
+            "achieved": ops / dense_s / 1e12, "peak": INT8_DENSE_NOMINAL_TOPS, "frac": ops / dense_s / 1e12 / INT8_DENSE_NOMINAL_TOPS,
+            "peak_source": "nominal dense int8 tensor rate (B200_PROFILING.md table; MEASURED_PEAKS.json holds no int8 figure). "
+                           f"For reference 2 x the {bf16_src} cuBLAS bf16 numbers = {2 * bf16_burst:.0f} (burst) / {2 * bf16_sust:.0f} "
+                           "(sustained) TFLOP/s: the +-1 / {0,1} operands of a Hamming contraction toggle few datapath bits, so "
+                           "this kernel holds a higher SM clock under the power cap than a dense bf16 GEMM does (see clocks)",
+            "frac_of_2x_measured_bf16_sustained": ops / dense_s / 1e12 / (2 * bf16_sust),
+            "kernel_ms": dense_s * 1e3, "pairs_per_s": pairs_per_step / dense_s,
+            "traffic": None,
+            "hbm": {"bound": "hbm", "unit": "GB/s", "achieved": n_local * 128 * 8 / dense_s / 1e9, "peak": hbm_peak,
+                    "frac": n_local * 128 * 8 / dense_s / 1e9 / hbm_peak, "peak_source": peak_src,
+                    "note": "algorithmic bytes = 128 B per code per 128-query tile (8 tiles per 1024-query batch, mostly served by "
+                            "L2); not the binding resource for a query batch"},
+            "integer_pipe_kernel": {"note": "scan.cu (XOR + carry-save POPC) handles <= 31 queries per pass and VRQ_SCAN_MMA=0; "
+                                            "its 1024-query rate measured in round 1 was 216 Gpair/s (profiles/r01)",
+                                    "alu_peak_Gpair_s": alu_peak / 1e9},
+            "scan_ms_per_step": scan_ms / args.steps, "rescore_ms_per_step": resc_ms / args.steps,
+            "merge_ms_per_step": merge_ms / args.steps,
+        }
+    else:
+        roofline = {
+            "kernel": "hamming_scan_kernel<TMA, 16 consumer warps, 16-CSA> (batched: 1024 queries per pass)",
+            "bound": "alu", "unit": "Gpair/s",
+            "achieved": pairs_per_step / scan_s / 1e9, "peak": alu_peak / 1e9, "frac": pairs_per_step / scan_s / alu_peak,
+            "peak_source": f"ALU-pipe (LOP3) issue rate measured at 64 lanes/clk/SM (profiles/microbench) x 148 SMs x {sm_mhz:.0f} MHz "
+                           "sampled during the run / 64 LOP3 per 1024-bit pair (32 XOR + 16 carry-save adders)",
+            "plain_popc_ceiling": popc_ceiling / 1e9, "traffic": None,
+            "hbm": {"bound": "hbm", "unit": "GB/s", "achieved": n_local * 128 / scan_s / 1e9, "peak": hbm_peak,
+                    "frac": n_local * 128 / scan_s / 1e9 / hbm_peak, "peak_source": peak_src},
+            "scan_ms_per_step": scan_ms / args.steps, "rescore_ms_per_step": resc_ms / args.steps,
+            "merge_ms_per_step": merge_ms / args.steps,
+        }
 
     extras = {}
     if world == 1 and not args.no_extras:
@@ -316,7 +354,7 @@ def run_gpu(args):
         cb, _ = cpu_baseline()
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8 tensor-core contraction of u8 bit codes (Phase I) / f64 (Phases II-III)",
             "data": "synthetic",
             "config": {"workload": "cfg3: CohereEnhancedVectorDB 3-phase search, Hamming top-1000 over 100M x 1024-bit codes per GPU, "
                                    "1024-query batch, k=100, binary_oversample=10, int8_oversample=3",

@@ -17,6 +17,7 @@ for k in (100, 1000):
 for name, env in [("default", {}), ("forced fallback", {"VRQ_MMA_SAMPLE_K": "1", "VRQ_MMA_SAFETY": "1"}), ("no sampling", {"VRQ_MMA_SAFETY": "0"}), ("integer pipes", {"VRQ_SCAN_MMA": "0"})]:
     for a, b in env.items(): os.environ[a] = b
     for k in (100, 1000):
+        ix.search(q, k)
         t0 = time.time()
         dist, labels = ix.search(q, k)
         dt = time.time() - t0

@@ -1,0 +1,152 @@
+"""GPU parity tests for the tensor-core Phase-I scan (csrc/scan_mma.cu) through the C ABI.
+
+The contraction runs on tcgen05.mma.kind::i8; every test here checks it bit for bit against the oracle (or NumPy's
+bitwise_count), and against the integer-pipe kernel of csrc/scan.cu, on the paths a query batch can take: thresholds from
+a strided sample, the gated exact fallback, no sampling (small databases), ragged tails, ties."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle_c as oc  # noqa: E402
+from oracle import vrq_oracle as o  # noqa: E402
+
+ENVS = {
+    "default": {},
+    "forced_fallback": {"VRQ_MMA_SAMPLE_K": "1", "VRQ_MMA_SAFETY": "1"},  # a threshold far too tight -> verification fails
+    "no_sampling": {"VRQ_MMA_SAFETY": "0"},
+    "force_mma_small_batch": {"VRQ_SCAN_MMA": "2"},
+    "integer_pipes": {"VRQ_SCAN_MMA": "0"},
+}
+
+
+@pytest.fixture(scope="module")
+def V():
+    import vectorragquantization_b200 as v
+    return v
+
+
+def set_env(monkeypatch, name):
+    for k in ("VRQ_MMA_SAMPLE_K", "VRQ_MMA_SAFETY", "VRQ_SCAN_MMA", "VRQ_MMA_B_STAGES", "VRQ_MMA_RAW_STAGES"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in ENVS[name].items():
+        monkeypatch.setenv(k, v)
+
+
+def ref_distances(q, codes):
+    return np.stack([np.bitwise_count(qq[None, :] ^ codes).sum(-1).astype(np.int32) for qq in q])
+
+
+@pytest.mark.parametrize("n,nq", [(1, 33), (127, 40), (128, 128), (129, 64), (5000, 200), (40000, 5), (300001, 130)])
+def test_mma_distance_matrix_exact(V, monkeypatch, n, nq):
+    """Every accumulator element: popc(q) - dot(+-1 query, {0,1} code) == Hamming distance."""
+    set_env(monkeypatch, "force_mma_small_batch")
+    rng = np.random.default_rng(n * 1000 + nq)
+    codes = rng.integers(0, 256, (n, 128), dtype=np.uint8)
+    q = rng.integers(0, 256, (nq, 128), dtype=np.uint8)
+    if n > 2:
+        codes[0] = 0
+        codes[1] = 255
+        q[0] = 0
+        q[-1] = 255
+    ix = V.BinaryIndex(1024)
+    ix.add_with_ids(codes, np.arange(n))
+    d = ix.distances(q)
+    assert d.shape == (nq, n)
+    assert np.array_equal(d, ref_distances(q, codes))
+
+
+@pytest.mark.parametrize("stages", [("4", "1"), ("7", "2"), ("12", "4")])
+def test_mma_pipeline_depths(V, monkeypatch, stages):
+    """Ring depths (B stages, raw stages) must not change a single distance: the hazards are in the hand-offs."""
+    set_env(monkeypatch, "force_mma_small_batch")
+    monkeypatch.setenv("VRQ_MMA_B_STAGES", stages[0])
+    monkeypatch.setenv("VRQ_MMA_RAW_STAGES", stages[1])
+    rng = np.random.default_rng(7)
+    n, nq = 200000, 128
+    codes = rng.integers(0, 256, (n, 128), dtype=np.uint8)
+    q = rng.integers(0, 256, (nq, 128), dtype=np.uint8)
+    ix = V.BinaryIndex(1024)
+    ix.add_with_ids(codes, np.arange(n))
+    d = ix.distances(q)
+    sel = [0, 1, 63, 64, 127]
+    assert np.array_equal(d[sel], ref_distances(q[sel], codes))
+
+
+@pytest.mark.parametrize("env", ["default", "forced_fallback", "no_sampling", "integer_pipes"])
+def test_mma_topk_matches_oracle_all_paths(V, monkeypatch, env):
+    set_env(monkeypatch, env)
+    n, nq = 2_000_000, 300
+    codes, _ = oc.synth_codes_int8(61, 0, n, want_int8=False)
+    qx = oc.synth_f32(62, 0, nq)
+    q = o.synth_ubinary_from_f32(qx)
+    q[0] = codes[n - 5]  # an exact hit near the end of the last strip
+    ix = V.BinaryIndex(1024)
+    ix.add_with_ids(codes, np.arange(n))
+    for k in (10, 100, 1000):
+        dist, labels = ix.search(q, k)
+        rd, rp = oc.hamming_topk(codes, q, k)
+        assert np.array_equal(dist, rd)
+        assert np.array_equal(labels, rp)
+
+
+@pytest.mark.parametrize("env", ["default", "no_sampling"])
+def test_mma_massive_ties(V, monkeypatch, env):
+    """Thousands of codes at the k-th distance: ties resolve by ascending position across strips and query tiles."""
+    set_env(monkeypatch, env)
+    rng = np.random.default_rng(42)
+    n = 700000
+    base = rng.integers(0, 256, (16, 128), dtype=np.uint8)
+    codes = base[rng.integers(0, 16, n)]
+    q = np.concatenate([base[:3], rng.integers(0, 256, (37, 128), dtype=np.uint8)])
+    ix = V.BinaryIndex(1024)
+    ix.add_with_ids(codes, np.arange(n))
+    for k in (1, 100, 1000, 4096):
+        dist, labels = ix.search(q, k)
+        rd, rp = oc.hamming_topk(codes, q, k)
+        assert np.array_equal(dist, rd) and np.array_equal(labels, rp)
+    codes[:] = base[0]  # all-equal database: every candidate ties
+    ix2 = V.BinaryIndex(1024)
+    ix2.add_with_ids(codes, np.arange(n))
+    dist, labels = ix2.search(q[:40], 1000)
+    rd, rp = oc.hamming_topk(codes, q[:40], 1000)
+    assert np.array_equal(dist, rd) and np.array_equal(labels, rp)
+
+
+def test_mma_sorted_database_worst_case(V, monkeypatch):
+    """Database sorted by DEcreasing distance to the queries' common ancestor: a strided sample is still representative,
+    but every strip ends with its best rows (stress for list compaction under the sampled threshold)."""
+    set_env(monkeypatch, "default")
+    rng = np.random.default_rng(4)
+    n = 600000
+    q0 = rng.integers(0, 256, (1, 128), dtype=np.uint8)
+    flips = np.sort(rng.integers(0, 1024, n))[::-1]
+    bits = np.unpackbits(np.repeat(q0, n, 0), axis=1)
+    mask = np.arange(1024)[None, :] < flips[:, None]
+    codes = np.packbits(bits ^ mask, axis=1)
+    q = np.repeat(q0, 48, 0)
+    q[1:] ^= rng.integers(0, 256, (47, 128), dtype=np.uint8) & rng.integers(0, 256, (47, 128), dtype=np.uint8) & 1
+    ix = V.BinaryIndex(1024)
+    ix.add_with_ids(codes, np.arange(n))
+    for k in (77, 1000):
+        dist, labels = ix.search(q, k)
+        rd, rp = oc.hamming_topk(codes, q, k)
+        assert np.array_equal(dist, rd) and np.array_equal(labels, rp)
+
+
+def test_mma_and_integer_kernels_agree_with_ids(V, monkeypatch):
+    """Same index, same queries, both kernels: identical (distance, label) lists, explicit (non-contiguous) ids."""
+    rng = np.random.default_rng(99)
+    n, nq, k = 1_000_000, 256, 500
+    codes = rng.integers(0, 256, (n, 128), dtype=np.uint8)
+    q = rng.integers(0, 256, (nq, 128), dtype=np.uint8)
+    ids = rng.permutation(n).astype(np.int64) * 3 + 11
+    ix = V.BinaryIndex(1024)
+    ix.add_with_ids(codes, ids)
+    set_env(monkeypatch, "default")
+    a = ix.search(q, k)
+    set_env(monkeypatch, "integer_pipes")
+    b = ix.search(q, k)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    rd, rp = oc.hamming_topk(codes, q[:8], k)
+    assert np.array_equal(a[0][:8], rd) and np.array_equal(a[1][:8], ids[rp])

@@ -183,6 +183,7 @@ static int cat_of(const char* which) {
     if (!strcmp(which, "encode")) return VRQ_CAT_ENCODE;
     if (!strcmp(which, "rescore")) return VRQ_CAT_RESCORE;
     if (!strcmp(which, "merge")) return VRQ_CAT_MERGE;
+    if (!strcmp(which, "scan_dense")) return VRQ_CAT_SCAN_DENSE;
     return -1;
 }
 

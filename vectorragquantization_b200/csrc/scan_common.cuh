@@ -41,6 +41,7 @@ struct ScanParams {
     int* counts;      // [list_strips][nq]
     const int* tau0;  // [nq] or null
     const int* guard;  // nullable: the launch does nothing when *guard == 0 (fallback passes enqueued ahead of knowing they are needed)
+    int compact_limit; // tensor-core kernel: compact a list once it holds more than this many keys (0 = cap - group_tiles * 128)
     int tau_bias;      // added to tau0 (1 turns a k'-th distance T of a sample into the inclusive bound "d <= T")
     int64_t tile_step; // tensor-core kernel: rows between the starts of consecutive tiles (128 = dense scan; larger = strided sample)
     int32_t* dbg;     // tests only: every (query, row) Hamming distance of the launch, [nq][dbg_stride] (tensor-core kernel)

@@ -290,7 +290,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         int cnt = 0;
         int thr = qvalid ? pcq - sm->tau_s[q] : 0x7fffffff;  // survivor <=> dot > thr <=> hamming < tau
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16) + TMEM_D_COL;
-        const int limit = p.cap - p.group_tiles * MROWS;
+        const int limit = p.compact_limit > 0 ? min(p.compact_limit, p.cap - p.group_tiles * MROWS) : p.cap - p.group_tiles * MROWS;
         for (int t = 0; t < ntiles; t++) {
             const int as = t & 1;
             mbar_wait(smem_u32(&sm->acc_full[as]), ((uint32_t)t >> 1) & 1u);

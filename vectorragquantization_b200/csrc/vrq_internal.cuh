@@ -40,7 +40,7 @@ struct vrq_timed {
     cudaEvent_t e0, e1;
 };
 
-enum { VRQ_CAT_SCAN = 0, VRQ_CAT_ENCODE = 1, VRQ_CAT_RESCORE = 2, VRQ_CAT_MERGE = 3, VRQ_CAT_COUNT = 4 };
+enum { VRQ_CAT_SCAN = 0, VRQ_CAT_ENCODE = 1, VRQ_CAT_RESCORE = 2, VRQ_CAT_MERGE = 3, VRQ_CAT_SCAN_DENSE = 4, VRQ_CAT_COUNT = 5 };
 
 // Growable device scratch.  Several named slots so that nested users do not trample each other.
 struct vrq_buf {
