@@ -146,6 +146,7 @@ struct MmaPlan {
     int qtiles, strips, group_tiles, cap, raw_stages, b_stages;
     int64_t rows_per_strip;
     size_t smem, smem_limit;
+    bool f4;  // packed e2m1 operands (kind::mxf4) instead of int8
 };
 constexpr int MMA_TILE_ROWS = 128;
 int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl);

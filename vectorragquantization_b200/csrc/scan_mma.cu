@@ -25,7 +25,17 @@ namespace {
 
 constexpr int MQ = 128;      // queries per CTA  (MMA M)
 constexpr int MROWS = 128;   // database rows per tile (MMA N)
-constexpr int KBLOCKS = 8;   // K-blocks of 128 int8 (= 16 code bytes) per row
+// Operand kinds.  I8: int8 operands, 8 K-blocks of 128 elements per row (16 code bytes -> 128 bytes).  F4: packed e2m1
+// (4-bit float: +1 = 0x2, -1 = 0xA, 0 = 0x0) under kind::mxf4 with every block scale = 1.0, 4 K-blocks of 256 elements
+// per row (32 code bytes -> 128 bytes), twice the tensor rate and half the shared-memory bytes per row.  Either way one
+// MMA consumes 32 bytes of K per operand row (8 TMEM columns of A, a 32-byte step of the B descriptor).
+constexpr int KIND_I8 = 8, KIND_F4 = 4;
+template <int KIND>
+struct KindCfg {
+    static constexpr int KBLOCKS = KIND == KIND_I8 ? 8 : 4;         // shared-memory stages per 128-row tile
+    static constexpr int CODE_BYTES_PER_KBLOCK = KIND == KIND_I8 ? 16 : 32;
+    static constexpr uint32_t A_COLS = KIND == KIND_I8 ? 256 : 128;  // TMEM columns of the query operand
+};
 constexpr int STAGE_BYTES_B = MROWS * 128;
 constexpr int STAGE_BYTES_RAW = MROWS * CODE_BYTES;
 constexpr int EPI_WARPS = 4;
@@ -34,10 +44,14 @@ constexpr int WARP_MMA = 4, WARP_TMA = 5, WARP_EXP0 = 6;
 constexpr int MMA_KERNEL_THREADS = (WARP_EXP0 + EXP_WARPS) * 32;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr uint32_t TMEM_COLS = 512, TMEM_A_COL = 0, TMEM_D_COL = 256;
+constexpr uint32_t TMEM_SFA_COL = 128, TMEM_SFB_COL = 160, TMEM_SF_COLS = 32;  // F4 only: block scales, all 1.0 (UE8M0 0x7F)
 constexpr int MAX_B_STAGES = 12, MAX_RAW_STAGES = 4;
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = signed 8 bit, both K-major, N = 128, M = 128
 constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MROWS >> 3) << 17) | ((uint32_t)(MQ >> 4) << 24);
+// block-scaled descriptor (cute::UMMA::InstrDescriptorBlockScaled): A = B = e2m1 (MXF4 format 1), K-major, scale format
+// UE8M0 (bit 23), scale-factor ids 0, N = 128, M = 128, K = 64 (bit 31 = 0); D is always f32
+constexpr uint32_t IDESC_F4 = (1u << 7) | (1u << 10) | ((uint32_t)(MROWS >> 3) << 17) | (1u << 23) | ((uint32_t)(MQ >> 4) << 24);
 
 // ---- tcgen05 wrappers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -57,6 +71,17 @@ __device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uin
         "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
         "}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f4_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t sfa, uint32_t sfb,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], [%1], %2, %3, [%4], [%5], p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(sfa), "r"(sfb), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
@@ -117,8 +142,11 @@ struct MmaSmem {
     SelectScratch sc;
 };
 
+template <int KIND>
 __global__ void __launch_bounds__(MMA_KERNEL_THREADS, 1)
 hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, int raw_stages, int b_stages) {
+    constexpr bool F4 = KIND == KIND_F4;
+    constexpr int KBLOCKS = KindCfg<KIND>::KBLOCKS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* raw_mem = base;
@@ -179,12 +207,34 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
             const uint32_t w = qvalid ? __ldg(qrow + W) : 0u;
             pcq += __popc(w);
             uint32_t v[8];
+            if constexpr (!F4) {
+                // columns 8 W + t: byte b = bit (t + 8 b) of word W as +1 (0x01) / -1 (0xFF)
 #pragma unroll
-            for (int t = 0; t < 8; t++) {
-                const uint32_t m = (w >> t) & 0x01010101u;           // bit set   -> +1
-                v[t] = qvalid ? (m | ((m ^ 0x01010101u) * 0xFFu)) : 0u;  // bit clear -> -1 (0xFF)
+                for (int t = 0; t < 8; t++) {
+                    const uint32_t m = (w >> t) & 0x01010101u;
+                    v[t] = qvalid ? (m | ((m ^ 0x01010101u) * 0xFFu)) : 0u;
+                }
+                tmem_st8(lane_base + 8 * W, v);
+            } else {
+                // columns 4 W + t: nibble j = bit (t + 4 j) of word W as e2m1 +1.0 (0x2) / -1.0 (0xA); two words per store
+                const uint32_t w2 = qvalid ? __ldg(qrow + W + 1) : 0u;
+                pcq += __popc(w2);
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    v[t] = qvalid ? (0xAAAAAAAAu ^ (((w >> t) & 0x11111111u) << 3)) : 0u;
+                    v[4 + t] = qvalid ? (0xAAAAAAAAu ^ (((w2 >> t) & 0x11111111u) << 3)) : 0u;
+                }
+                tmem_st8(lane_base + 4 * W, v);
+                W++;
             }
-            tmem_st8(lane_base + 8 * W, v);
+        }
+        if constexpr (F4) {
+            // every block scale (UE8M0) = 0x7F = 2^0: with one constant the scale-factor layout does not matter
+            uint32_t one[8];
+#pragma unroll
+            for (int t = 0; t < 8; t++) one[t] = 0x7F7F7F7Fu;
+#pragma unroll
+            for (int c = 0; c < (int)(2 * TMEM_SF_COLS); c += 8) tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + TMEM_SFA_COL + c, one);
         }
         tmem_wait_st();
         sm->tau_s[q] = qvalid ? (p.tau0 ? min(p.tau0[q0 + q], TAU_INF - 1) + p.tau_bias : TAU_INF) : 0;
@@ -223,9 +273,14 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                 if (elect_one()) {
                     const uint64_t desc = desc0 + (uint64_t)(s * (uint32_t)(STAGE_BYTES_B >> 4));
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; k4++)
-                        umma_i8_ts(d_tmem, tmem + TMEM_A_COL + (uint32_t)(kb * 4 + k4) * 8, desc + (uint64_t)(k4 * 2), IDESC_I8,
-                                   (kb | k4) != 0);
+                    for (int k4 = 0; k4 < 4; k4++) {
+                        if constexpr (F4)
+                            umma_f4_ts(d_tmem, tmem + TMEM_A_COL + (uint32_t)(kb * 4 + k4) * 8, desc + (uint64_t)(k4 * 2), IDESC_F4,
+                                       tmem + TMEM_SFA_COL, tmem + TMEM_SFB_COL, (kb | k4) != 0);
+                        else
+                            umma_i8_ts(d_tmem, tmem + TMEM_A_COL + (uint32_t)(kb * 4 + k4) * 8, desc + (uint64_t)(k4 * 2), IDESC_I8,
+                                       (kb | k4) != 0);
+                    }
                     tc_commit(smem_u32(&sm->b_empty[s]));
                     if (kb == KBLOCKS - 1) tc_commit(smem_u32(&sm->acc_full[as]));
                 }
@@ -240,7 +295,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         // ===================== expanders: 16 code bytes -> one 128-byte K-block row of {0,1} int8 =====================
         const int et = tid - WARP_EXP0 * 32;
         const int row = et & (MROWS - 1);
-        const int par = et >> 7;  // this thread expands K-blocks par, par + 2, par + 4, par + 6
+        const int par = et >> 7;  // this thread expands K-blocks par, par + 2, ... of its row
         const uint32_t sw = (uint32_t)(row & 7);
         const uint32_t row_off = (uint32_t)row * 128u;
         uint32_t rs = 0, rph = 0;                 // raw ring
@@ -249,21 +304,35 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
             mbar_wait(smem_u32(&sm->raw_full[rs]), rph);
             const uint32_t raddr = smem_u32(raw_mem) + rs * (uint32_t)STAGE_BYTES_RAW + row_off;
             uint4 c[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) c[j] = lds128(raddr + ((((uint32_t)(2 * j + par)) ^ sw) << 4));
+            // I8: K-block kb = raw chunk kb (16 bytes);  F4: K-block kb = raw chunks 2 kb, 2 kb + 1 (32 bytes)
 #pragma unroll
             for (int j = 0; j < 4; j++) {
+                const uint32_t chunk = F4 ? (uint32_t)(4 * (j >> 1) + 2 * par + (j & 1)) : (uint32_t)(2 * j + par);
+                c[j] = lds128(raddr + ((chunk ^ sw) << 4));
+            }
+#pragma unroll
+            for (int j = 0; j < KBLOCKS / 2; j++) {
                 mbar_wait(smem_u32(&sm->b_empty[s]), ph ^ 1u);
                 const uint32_t baddr = smem_u32(b_mem) + s * (uint32_t)STAGE_BYTES_B + row_off;
-                const uint32_t w[4] = {c[j].x, c[j].y, c[j].z, c[j].w};
+                if constexpr (!F4) {
+                    const uint32_t w[4] = {c[j].x, c[j].y, c[j].z, c[j].w};
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
+                    for (int i = 0; i < 4; i++) {
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const uint32_t ch = (uint32_t)(2 * i + h);
-                        sts128(baddr + ((ch ^ sw) << 4), (w[i] >> (4 * h)) & 0x01010101u, (w[i] >> (4 * h + 1)) & 0x01010101u,
-                               (w[i] >> (4 * h + 2)) & 0x01010101u, (w[i] >> (4 * h + 3)) & 0x01010101u);
+                        for (int h = 0; h < 2; h++) {
+                            const uint32_t ch = (uint32_t)(2 * i + h);
+                            sts128(baddr + ((ch ^ sw) << 4), (w[i] >> (4 * h)) & 0x01010101u, (w[i] >> (4 * h + 1)) & 0x01010101u,
+                                   (w[i] >> (4 * h + 2)) & 0x01010101u, (w[i] >> (4 * h + 3)) & 0x01010101u);
+                        }
                     }
+                } else {
+                    // word i of the 32 code bytes -> 16-byte chunk i: plane t (nibble j = bit t + 4 j) as e2m1 1.0 = 0x2
+                    const uint32_t w[8] = {c[2 * j].x, c[2 * j].y, c[2 * j].z, c[2 * j].w, c[2 * j + 1].x, c[2 * j + 1].y, c[2 * j + 1].z,
+                                           c[2 * j + 1].w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        sts128(baddr + (((uint32_t)i ^ sw) << 4), (w[i] << 1) & 0x22222222u, w[i] & 0x22222222u, (w[i] >> 1) & 0x22222222u,
+                               (w[i] >> 2) & 0x22222222u);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -289,6 +358,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         uint64_t* my_list = p.lists + ((size_t)strip * p.nq + q0 + (qvalid ? q : 0)) * p.cap;
         int cnt = 0;
         int thr = qvalid ? pcq - sm->tau_s[q] : 0x7fffffff;  // survivor <=> dot > thr <=> hamming < tau
+        float thr_f = (float)thr;
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16) + TMEM_D_COL;
         const int limit = p.compact_limit > 0 ? min(p.compact_limit, p.cap - p.group_tiles * MROWS) : p.cap - p.group_tiles * MROWS;
         for (int t = 0; t < ntiles; t++) {
@@ -310,21 +380,37 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                     if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[as]));
                 }
                 const int nv = nvalid - 32 * cc;  // valid columns in this group (>= 32: all)
+                // F4 accumulates in f32: the dots are integers of magnitude <= 1024, exact in binary32
+                auto dot_of = [&](int j) -> int { return F4 ? (int)__int_as_float(v[j]) : v[j]; };
                 if (p.dbg) {
                     if (qvalid)
                         for (int j = 0; j < 32; j++)
-                            if (j < nv) p.dbg[(size_t)(q0 + q) * p.dbg_stride + (lrow0 + 32 * cc + j)] = pcq - v[j];
+                            if (j < nv) p.dbg[(size_t)(q0 + q) * p.dbg_stride + (lrow0 + 32 * cc + j)] = pcq - dot_of(j);
                 }
-                int m = v[0];
+                bool any;
+                int m;
+                if constexpr (F4) {
+                    float mf = __int_as_float(v[0]);
 #pragma unroll
-                for (int j = 1; j < 32; j++) m = max(m, v[j]);
-                if (m > thr) {
+                    for (int j = 1; j < 32; j++) mf = fmaxf(mf, __int_as_float(v[j]));
+                    any = mf > thr_f;
+                    m = (int)mf;
+                } else {
+                    m = v[0];
+#pragma unroll
+                    for (int j = 1; j < 32; j++) m = max(m, v[j]);
+                    any = m > thr;
+                }
+                if (any) {
                     // Some column of this lane survives.  bit (31 - j) of mask <=> v[j] > thr: the sign of thr - v[j] is
                     // shifted in with one funnel shift per column (2 instructions per column, no branches).
                     const unsigned long long pos0 = (unsigned long long)(p.pos_base + lrow0 + 32 * cc);
                     uint32_t mask = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) mask = __funnelshift_l((uint32_t)(thr - v[j]), mask, 1);
+                    for (int j = 0; j < 32; j++) {
+                        const uint32_t sgn = F4 ? __float_as_uint(thr_f - __int_as_float(v[j])) : (uint32_t)(thr - v[j]);
+                        mask = __funnelshift_l(sgn, mask, 1);
+                    }
                     if (nv < 32) mask = nv <= 0 ? 0u : (mask & ~(0xFFFFFFFFu >> nv));
                     if (__popc(mask) == 1 && nv >= 32) {
                         // the usual case once tau has converged: the single survivor is the maximum itself
@@ -334,7 +420,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
                             if ((mask >> (31 - j)) & 1u) {
-                                my_list[cnt] = ((unsigned long long)(pcq - v[j]) << VRQ_KEY_POS_BITS) | (pos0 + j);
+                                my_list[cnt] = ((unsigned long long)(pcq - dot_of(j)) << VRQ_KEY_POS_BITS) | (pos0 + j);
                                 cnt++;
                             }
                         }
@@ -354,6 +440,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                     group_sync<EPI_THREADS>(BAR_CONSUMERS);
                     cnt = sm->cnt_s[q];
                     if (qvalid) thr = pcq - sm->tau_s[q];
+                    thr_f = (float)thr;
                 }
             }
         }
@@ -387,6 +474,7 @@ size_t mma_smem_bytes(int raw_stages, int b_stages, int cap) {
 
 int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
     const int sms = ctx->sm_count;
+    pl->f4 = env_int("VRQ_MMA_KIND", 8) == 4;
     pl->qtiles = (nq + MQ - 1) / MQ;
     pl->group_tiles = env_int("VRQ_MMA_GROUP_TILES", 2);
     if (pl->group_tiles < 1) pl->group_tiles = 1;
@@ -435,8 +523,13 @@ int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const ScanParams& 
         return VRQ_ERR_UNSUPPORTED;
     }
     dim3 grid(pl.qtiles, pl.strips);
-    VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    hamming_scan_mma_kernel<<<grid, MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, pl.b_stages);
+    if (pl.f4) {
+        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_kernel<KIND_F4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        hamming_scan_mma_kernel<KIND_F4><<<grid, MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, pl.b_stages);
+    } else {
+        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_kernel<KIND_I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        hamming_scan_mma_kernel<KIND_I8><<<grid, MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, pl.b_stages);
+    }
     vrq_count_launch(ctx);
     VRQ_CUDA(cudaGetLastError());
     return 0;
