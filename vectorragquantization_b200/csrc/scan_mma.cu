@@ -38,14 +38,14 @@ struct KindCfg {
 };
 constexpr int STAGE_BYTES_B = MROWS * 128;
 constexpr int STAGE_BYTES_RAW = MROWS * CODE_BYTES;
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;
 constexpr int EXP_WARPS = 8;
-constexpr int WARP_MMA = 4, WARP_TMA = 5, WARP_EXP0 = 6;
+constexpr int WARP_MMA = 8, WARP_TMA = 9, WARP_EXP0 = 10;
 constexpr int MMA_KERNEL_THREADS = (WARP_EXP0 + EXP_WARPS) * 32;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr uint32_t TMEM_COLS = 512, TMEM_A_COL = 0, TMEM_D_COL = 256;
 constexpr uint32_t TMEM_SFA_COL = 128, TMEM_SFB_COL = 160, TMEM_SF_COLS = 32;  // F4 only: block scales, all 1.0 (UE8M0 0x7F)
-constexpr int MAX_B_STAGES = 12, MAX_RAW_STAGES = 4;
+constexpr int B_STAGES = 8, MAX_RAW_STAGES = 4;
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = signed 8 bit, both K-major, N = 128, M = 128
 constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MROWS >> 3) << 17) | ((uint32_t)(MQ >> 4) << 24);
@@ -134,7 +134,7 @@ __device__ __forceinline__ int epi_sync_or(int pred) {
 
 struct MmaSmem {
     unsigned long long raw_full[MAX_RAW_STAGES], raw_empty[MAX_RAW_STAGES];
-    unsigned long long b_full[MAX_B_STAGES], b_empty[MAX_B_STAGES];
+    unsigned long long b_full[B_STAGES], b_empty[B_STAGES];
     unsigned long long acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     int tau_s[MQ];
@@ -144,14 +144,17 @@ struct MmaSmem {
 
 template <int KIND>
 __global__ void __launch_bounds__(MMA_KERNEL_THREADS, 1)
-hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, int raw_stages, int b_stages) {
+hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, int raw_stages) {
     constexpr bool F4 = KIND == KIND_F4;
     constexpr int KBLOCKS = KindCfg<KIND>::KBLOCKS;
+    // The B ring has exactly 8 stages of one K-block (16 KB) each, so a tile's stages are compile-time offsets from one
+    // per-tile base: I8 tiles use all 8 (stage = K-block, parity = tile & 1); F4 tiles alternate between stages 0-3 and 4-7.
+    constexpr int GROUPS = B_STAGES / KBLOCKS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* raw_mem = base;
     uint8_t* b_mem = raw_mem + (size_t)raw_stages * STAGE_BYTES_RAW;
-    unsigned long long* scratch = (unsigned long long*)(b_mem + (size_t)b_stages * STAGE_BYTES_B);
+    unsigned long long* scratch = (unsigned long long*)(b_mem + (size_t)B_STAGES * STAGE_BYTES_B);
     MmaSmem* sm = (MmaSmem*)(scratch + p.cap);
 
     const int tid = threadIdx.x;
@@ -174,7 +177,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
             mbar_init(smem_u32(&sm->raw_full[s]), 1);
             mbar_init(smem_u32(&sm->raw_empty[s]), EXP_WARPS);
         }
-        for (int s = 0; s < b_stages; s++) {
+        for (int s = 0; s < B_STAGES; s++) {
             mbar_init(smem_u32(&sm->b_full[s]), EXP_WARPS / 2);
             mbar_init(smem_u32(&sm->b_empty[s]), 1);
         }
@@ -195,50 +198,60 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
     tc_fence_after();
     const uint32_t tmem = sm->tmem_base;
 
-    // ---- the query tile becomes the A operand in tensor memory: lane = query, column 8 W + t = plane t of code word W
+    // ---- the query tile becomes the A operand in tensor memory (lane = query); warps 0-3 write it, every epilogue
+    //      thread keeps popc(query) of the query it filters
     int pcq = 0;
     if (warp < EPI_WARPS) {
-        const int q = tid;
+        const int q = tid & (MQ - 1);
         const bool qvalid = q < qt;
+        const bool writer = warp < 4;
         const uint32_t* qrow = reinterpret_cast<const uint32_t*>(p.queries + (size_t)(q0 + (qvalid ? q : 0)) * CODE_BYTES);
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16) + TMEM_A_COL;
-#pragma unroll 4
-        for (int W = 0; W < 32; W++) {
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + TMEM_A_COL;
+#pragma unroll 2
+        for (int W = 0; W < 32; W += 2) {
             const uint32_t w = qvalid ? __ldg(qrow + W) : 0u;
-            pcq += __popc(w);
-            uint32_t v[8];
-            if constexpr (!F4) {
-                // columns 8 W + t: byte b = bit (t + 8 b) of word W as +1 (0x01) / -1 (0xFF)
+            const uint32_t w2 = qvalid ? __ldg(qrow + W + 1) : 0u;
+            pcq += __popc(w) + __popc(w2);
+            if (writer) {
+                uint32_t v[8];
+                if constexpr (!F4) {
+                    // columns 8 W + t: byte b = bit (t + 8 b) of word W as +1 (0x01) / -1 (0xFF)
 #pragma unroll
-                for (int t = 0; t < 8; t++) {
-                    const uint32_t m = (w >> t) & 0x01010101u;
-                    v[t] = qvalid ? (m | ((m ^ 0x01010101u) * 0xFFu)) : 0u;
-                }
-                tmem_st8(lane_base + 8 * W, v);
-            } else {
-                // columns 4 W + t: nibble j = bit (t + 4 j) of word W as e2m1 +1.0 (0x2) / -1.0 (0xA); two words per store
-                const uint32_t w2 = qvalid ? __ldg(qrow + W + 1) : 0u;
-                pcq += __popc(w2);
+                    for (int t = 0; t < 8; t++) {
+                        const uint32_t m = (w >> t) & 0x01010101u;
+                        v[t] = qvalid ? (m | ((m ^ 0x01010101u) * 0xFFu)) : 0u;
+                    }
+                    tmem_st8(lane_base + 8 * W, v);
 #pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    v[t] = qvalid ? (0xAAAAAAAAu ^ (((w >> t) & 0x11111111u) << 3)) : 0u;
-                    v[4 + t] = qvalid ? (0xAAAAAAAAu ^ (((w2 >> t) & 0x11111111u) << 3)) : 0u;
+                    for (int t = 0; t < 8; t++) {
+                        const uint32_t m = (w2 >> t) & 0x01010101u;
+                        v[t] = qvalid ? (m | ((m ^ 0x01010101u) * 0xFFu)) : 0u;
+                    }
+                    tmem_st8(lane_base + 8 * W + 8, v);
+                } else {
+                    // columns 4 W + t: nibble j = bit (t + 4 j) of word W as e2m1 +1.0 (0x2) / -1.0 (0xA)
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        v[t] = qvalid ? (0xAAAAAAAAu ^ (((w >> t) & 0x11111111u) << 3)) : 0u;
+                        v[4 + t] = qvalid ? (0xAAAAAAAAu ^ (((w2 >> t) & 0x11111111u) << 3)) : 0u;
+                    }
+                    tmem_st8(lane_base + 4 * W, v);
                 }
-                tmem_st8(lane_base + 4 * W, v);
-                W++;
             }
         }
-        if constexpr (F4) {
-            // every block scale (UE8M0) = 0x7F = 2^0: with one constant the scale-factor layout does not matter
-            uint32_t one[8];
+        if (writer) {
+            if constexpr (F4) {
+                // every block scale (UE8M0) = 0x7F = 2^0: with one constant the scale-factor layout does not matter
+                uint32_t one[8];
 #pragma unroll
-            for (int t = 0; t < 8; t++) one[t] = 0x7F7F7F7Fu;
+                for (int t = 0; t < 8; t++) one[t] = 0x7F7F7F7Fu;
 #pragma unroll
-            for (int c = 0; c < (int)(2 * TMEM_SF_COLS); c += 8) tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + TMEM_SFA_COL + c, one);
+                for (int c = 0; c < (int)(2 * TMEM_SF_COLS); c += 8) tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + TMEM_SFA_COL + c, one);
+            }
+            tmem_wait_st();
+            sm->tau_s[q] = qvalid ? (p.tau0 ? min(p.tau0[q0 + q], TAU_INF - 1) + p.tau_bias : TAU_INF) : 0;
+            sm->cnt_s[q] = 0;
         }
-        tmem_wait_st();
-        sm->tau_s[q] = qvalid ? (p.tau0 ? min(p.tau0[q0 + q], TAU_INF - 1) + p.tau_bias : TAU_INF) : 0;
-        sm->cnt_s[q] = 0;
     }
     tc_fence_before();
     __syncthreads();
@@ -248,59 +261,66 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         // ===================== raw-code producer =====================
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
-            for (int t = 0; t < ntiles; t++, s = (s + 1 == (uint32_t)raw_stages) ? 0 : s + 1, ph ^= (s == 0)) {
+            for (int t = 0; t < ntiles; t++) {
                 mbar_wait(smem_u32(&sm->raw_empty[s]), ph ^ 1u);
                 mbar_expect_tx(smem_u32(&sm->raw_full[s]), STAGE_BYTES_RAW);
-                tma_load_2d(smem_u32(raw_mem + (size_t)s * STAGE_BYTES_RAW), &tmap, 0, (int)(s_begin + (int64_t)t * p.tile_step),
+                tma_load_2d(smem_u32(raw_mem) + s * (uint32_t)STAGE_BYTES_RAW, &tmap, 0, (int)(s_begin + (int64_t)t * p.tile_step),
                             smem_u32(&sm->raw_full[s]));
-            }
-        }
-    } else if (warp == WARP_MMA) {
-        // ===================== MMA issuer =====================
-        // The whole warp walks the loop (ring positions stay warp-uniform, i.e. in uniform registers); one elected lane
-        // issues.  Per K-block: 4 MMAs (K = 32 each) whose B descriptors differ by 32 bytes, one commit.
-        uint32_t s = 0, ph = 0;  // B-ring stage and the parity of its current use
-        const uint64_t desc0 = umma_desc_sw128(smem_u32(b_mem));
-        for (int t = 0; t < ntiles; t++) {
-            const int as = t & 1;
-            mbar_wait(smem_u32(&sm->acc_empty[as]), (((uint32_t)t >> 1) & 1u) ^ 1u);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem + TMEM_D_COL + (uint32_t)as * MROWS;
-#pragma unroll
-            for (int kb = 0; kb < KBLOCKS; kb++) {
-                mbar_wait(smem_u32(&sm->b_full[s]), ph);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t desc = desc0 + (uint64_t)(s * (uint32_t)(STAGE_BYTES_B >> 4));
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; k4++) {
-                        if constexpr (F4)
-                            umma_f4_ts(d_tmem, tmem + TMEM_A_COL + (uint32_t)(kb * 4 + k4) * 8, desc + (uint64_t)(k4 * 2), IDESC_F4,
-                                       tmem + TMEM_SFA_COL, tmem + TMEM_SFB_COL, (kb | k4) != 0);
-                        else
-                            umma_i8_ts(d_tmem, tmem + TMEM_A_COL + (uint32_t)(kb * 4 + k4) * 8, desc + (uint64_t)(k4 * 2), IDESC_I8,
-                                       (kb | k4) != 0);
-                    }
-                    tc_commit(smem_u32(&sm->b_empty[s]));
-                    if (kb == KBLOCKS - 1) tc_commit(smem_u32(&sm->acc_full[as]));
-                }
-                __syncwarp();
-                if (++s == (uint32_t)b_stages) {
+                if (++s == (uint32_t)raw_stages) {
                     s = 0;
                     ph ^= 1u;
                 }
             }
         }
+    } else if (warp == WARP_MMA) {
+        // ===================== MMA issuer =====================
+        // The whole warp walks the loop (everything stays warp-uniform); one elected lane issues.  Per K-block: one wait,
+        // 4 MMAs (32 bytes of K each) whose descriptors are immediates off the tile's base, one commit.
+        const uint64_t desc0 = umma_desc_sw128(smem_u32(b_mem));
+        const uint32_t full0 = smem_u32(&sm->b_full[0]), empty0 = smem_u32(&sm->b_empty[0]);
+        for (int t = 0; t < ntiles; t++) {
+            const int as = t & 1;
+            const uint32_t grp = (uint32_t)t & (uint32_t)(GROUPS - 1);
+            const uint32_t ph = ((uint32_t)t / (uint32_t)GROUPS) & 1u;
+            const uint64_t desc_t = desc0 + (uint64_t)(grp * (uint32_t)(KBLOCKS * (STAGE_BYTES_B >> 4)));
+            const uint32_t full_t = full0 + grp * (uint32_t)(KBLOCKS * 8), empty_t = empty0 + grp * (uint32_t)(KBLOCKS * 8);
+            mbar_wait(smem_u32(&sm->acc_empty[as]), (((uint32_t)t >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem + TMEM_D_COL + (uint32_t)as * MROWS;
+#pragma unroll
+            for (int kb = 0; kb < KBLOCKS; kb++) {
+                mbar_wait(full_t + kb * 8, ph);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; k4++) {
+                        const uint64_t desc = desc_t + (uint64_t)(kb * (STAGE_BYTES_B >> 4) + k4 * 2);
+                        const uint32_t a_tmem = tmem + TMEM_A_COL + (uint32_t)(kb * 4 + k4) * 8;
+                        if constexpr (F4)
+                            umma_f4_ts(d_tmem, a_tmem, desc, IDESC_F4, tmem + TMEM_SFA_COL, tmem + TMEM_SFB_COL, (kb | k4) != 0);
+                        else
+                            umma_i8_ts(d_tmem, a_tmem, desc, IDESC_I8, (kb | k4) != 0);
+                    }
+                    tc_commit(empty_t + kb * 8);
+                    if (kb == KBLOCKS - 1) tc_commit(smem_u32(&sm->acc_full[as]));
+                }
+                __syncwarp();
+            }
+        }
     } else if (warp >= WARP_EXP0) {
-        // ===================== expanders: 16 code bytes -> one 128-byte K-block row of {0,1} int8 =====================
+        // ===================== expanders: code bits -> one 128-byte K-block row of the B operand =====================
         const int et = tid - WARP_EXP0 * 32;
         const int row = et & (MROWS - 1);
         const int par = et >> 7;  // this thread expands K-blocks par, par + 2, ... of its row
         const uint32_t sw = (uint32_t)(row & 7);
         const uint32_t row_off = (uint32_t)row * 128u;
-        uint32_t rs = 0, rph = 0;                 // raw ring
-        uint32_t s = (uint32_t)par, ph = 0;       // B ring: this thread's stages advance by 2 (b_stages >= 4 > par)
+        const uint32_t full0 = smem_u32(&sm->b_full[0]), empty0 = smem_u32(&sm->b_empty[0]);
+        const uint32_t bmem0 = smem_u32(b_mem) + row_off;
+        uint32_t rs = 0, rph = 0;  // raw ring
         for (int t = 0; t < ntiles; t++) {
+            const uint32_t grp = (uint32_t)t & (uint32_t)(GROUPS - 1);
+            const uint32_t ph = ((uint32_t)t / (uint32_t)GROUPS) & 1u;
+            const uint32_t stage0 = grp * (uint32_t)KBLOCKS + (uint32_t)par;
             mbar_wait(smem_u32(&sm->raw_full[rs]), rph);
             const uint32_t raddr = smem_u32(raw_mem) + rs * (uint32_t)STAGE_BYTES_RAW + row_off;
             uint4 c[4];
@@ -312,8 +332,9 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
             }
 #pragma unroll
             for (int j = 0; j < KBLOCKS / 2; j++) {
-                mbar_wait(smem_u32(&sm->b_empty[s]), ph ^ 1u);
-                const uint32_t baddr = smem_u32(b_mem) + s * (uint32_t)STAGE_BYTES_B + row_off;
+                const uint32_t s = stage0 + 2 * j;
+                mbar_wait(empty0 + s * 8, ph ^ 1u);
+                const uint32_t baddr = bmem0 + s * (uint32_t)STAGE_BYTES_B;
                 if constexpr (!F4) {
                     const uint32_t w[4] = {c[j].x, c[j].y, c[j].z, c[j].w};
 #pragma unroll
@@ -336,12 +357,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&sm->b_full[s]));
-                s += 2;
-                if (s >= (uint32_t)b_stages) {
-                    s -= (uint32_t)b_stages;
-                    ph ^= 1u;
-                }
+                if (lane == 0) mbar_arrive(full0 + s * 8);
             }
             // the raw tile goes back to the producer only now: every c[j] has been consumed by real instructions, so the
             // shared-memory reads above are known to have completed (an arrive right after the ld.shared can overtake them)
@@ -353,27 +369,29 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         }
     } else {
         // ===================== epilogue: lane = query, columns = database rows =====================
-        const int q = tid;
+        // 8 warps: warp & 3 = TMEM lane quadrant (32 queries), warp >> 2 = which 64 of the tile's 128 columns.  The two
+        // threads that share a query append to the same list through a shared-memory counter.
+        const int q = tid & (MQ - 1);
+        const int half = warp >> 2;
         const bool qvalid = q < qt;
         uint64_t* my_list = p.lists + ((size_t)strip * p.nq + q0 + (qvalid ? q : 0)) * p.cap;
-        int cnt = 0;
         int thr = qvalid ? pcq - sm->tau_s[q] : 0x7fffffff;  // survivor <=> dot > thr <=> hamming < tau
         float thr_f = (float)thr;
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16) + TMEM_D_COL;
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + TMEM_D_COL + (uint32_t)(half * 64);
         const int limit = p.compact_limit > 0 ? min(p.compact_limit, p.cap - p.group_tiles * MROWS) : p.cap - p.group_tiles * MROWS;
         for (int t = 0; t < ntiles; t++) {
             const int as = t & 1;
             mbar_wait(smem_u32(&sm->acc_full[as]), ((uint32_t)t >> 1) & 1u);
             tc_fence_after();
-            const int64_t lrow0 = s_begin + (int64_t)t * p.tile_step;
-            const int nvalid = (int)min((int64_t)MROWS, s_end - lrow0);
+            const int64_t lrow0 = s_begin + (int64_t)t * p.tile_step + half * 64;
+            const int nvalid = (int)min((int64_t)64, s_end - lrow0);
 #pragma unroll 1
-            for (int cc = 0; cc < MROWS / 32; cc++) {
+            for (int cc = 0; cc < 2; cc++) {
                 int v[32];
                 __syncwarp();
                 tmem_ld32(lane_base + (uint32_t)as * MROWS + 32 * cc, v);
                 tmem_wait_ld();
-                if (cc == MROWS / 32 - 1) {
+                if (cc == 1) {
                     // the accumulator is in registers: hand the TMEM stage back to the MMA issuer
                     tc_fence_before();
                     __syncwarp();
@@ -414,14 +432,14 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                     if (nv < 32) mask = nv <= 0 ? 0u : (mask & ~(0xFFFFFFFFu >> nv));
                     if (__popc(mask) == 1 && nv >= 32) {
                         // the usual case once tau has converged: the single survivor is the maximum itself
-                        my_list[cnt] = ((unsigned long long)(pcq - m) << VRQ_KEY_POS_BITS) | (pos0 + __clz((int)mask));
-                        cnt++;
+                        my_list[atomicAdd(&sm->cnt_s[q], 1)] = ((unsigned long long)(pcq - m) << VRQ_KEY_POS_BITS) | (pos0 + __clz((int)mask));
                     } else if (mask) {
+                        int slot = atomicAdd(&sm->cnt_s[q], __popc(mask));
 #pragma unroll
                         for (int j = 0; j < 32; j++) {
                             if ((mask >> (31 - j)) & 1u) {
-                                my_list[cnt] = ((unsigned long long)(pcq - dot_of(j)) << VRQ_KEY_POS_BITS) | (pos0 + j);
-                                cnt++;
+                                my_list[slot] = ((unsigned long long)(pcq - dot_of(j)) << VRQ_KEY_POS_BITS) | (pos0 + j);
+                                slot++;
                             }
                         }
                     }
@@ -429,8 +447,8 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
             }
             // ---- overflow check every group_tiles tiles: no list may exceed cap during the next group ----
             if ((t + 1) % p.group_tiles == 0 && t + 1 < ntiles) {
-                sm->cnt_s[q] = cnt;
-                if (epi_sync_or(cnt > limit)) {
+                group_sync<EPI_THREADS>(BAR_CONSUMERS);  // every append of this group of tiles is in its list
+                if (epi_sync_or(sm->cnt_s[q] > limit)) {
                     for (int qq = 0; qq < qt; qq++) {
                         const int n = sm->cnt_s[qq];
                         if (n > limit)
@@ -438,13 +456,11 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                                                       &sm->cnt_s[qq], &sm->tau_s[qq]);
                     }
                     group_sync<EPI_THREADS>(BAR_CONSUMERS);
-                    cnt = sm->cnt_s[q];
                     if (qvalid) thr = pcq - sm->tau_s[q];
                     thr_f = (float)thr;
                 }
             }
         }
-        sm->cnt_s[q] = cnt;
         group_sync<EPI_THREADS>(BAR_CONSUMERS);
         // final compaction: every list leaves the kernel with at most k keys (bounds the merge's working set)
         for (int qq = 0; qq < qt; qq++) {
@@ -454,7 +470,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                                           &sm->tau_s[qq]);
         }
         group_sync<EPI_THREADS>(BAR_CONSUMERS);
-        if (qvalid) p.counts[(size_t)strip * p.nq + q0 + q] = sm->cnt_s[q];
+        if (qvalid && half == 0) p.counts[(size_t)strip * p.nq + q0 + q] = sm->cnt_s[q];
     }
 
     tc_fence_before();
@@ -465,8 +481,8 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
     }
 }
 
-size_t mma_smem_bytes(int raw_stages, int b_stages, int cap) {
-    return 1024 + (size_t)raw_stages * STAGE_BYTES_RAW + (size_t)b_stages * STAGE_BYTES_B + sizeof(unsigned long long) * (size_t)cap +
+size_t mma_smem_bytes(int raw_stages, int cap) {
+    return 1024 + (size_t)raw_stages * STAGE_BYTES_RAW + (size_t)B_STAGES * STAGE_BYTES_B + sizeof(unsigned long long) * (size_t)cap +
            sizeof(MmaSmem) + 16;
 }
 
@@ -488,32 +504,24 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
     const int64_t tps = (tiles + strips - 1) / strips;
     pl->rows_per_strip = tps * MROWS;
     pl->strips = (int)((tiles + tps - 1) / tps);
+    const size_t limit = ctx->smem_optin ? ctx->smem_optin : 227 * 1024;
+    pl->smem_limit = limit;
     pl->raw_stages = env_int("VRQ_MMA_RAW_STAGES", 3);
     if (pl->raw_stages < 1) pl->raw_stages = 1;
     if (pl->raw_stages > MAX_RAW_STAGES) pl->raw_stages = MAX_RAW_STAGES;
-    const size_t limit = ctx->smem_optin ? ctx->smem_optin : 227 * 1024;
-    pl->smem_limit = limit;
-    int max_b = env_int("VRQ_MMA_B_STAGES", MAX_B_STAGES);
-    if (max_b > MAX_B_STAGES) max_b = MAX_B_STAGES;
-    pl->b_stages = 0;
-    for (int s = max_b; s >= 4; s--) {
-        if (mma_smem_bytes(pl->raw_stages, s, pl->cap) <= limit) {
-            pl->b_stages = s;
-            break;
-        }
-    }
-    if (pl->b_stages == 0) {
+    pl->b_stages = B_STAGES;
+    mma_plan_set_cap(pl, pl->cap);
+    if (pl->smem > limit) {
         vrq_set_error("tensor-core Hamming top-k with k=%d does not fit the shared-memory plan", k);
         return VRQ_ERR_UNSUPPORTED;
     }
-    pl->smem = mma_smem_bytes(pl->raw_stages, pl->b_stages, pl->cap);
     return 0;
 }
 
 void mma_plan_set_cap(MmaPlan* pl, int cap) {
     pl->cap = cap;
-    while (pl->b_stages > 4 && mma_smem_bytes(pl->raw_stages, pl->b_stages, cap) > pl->smem_limit) pl->b_stages--;
-    pl->smem = mma_smem_bytes(pl->raw_stages, pl->b_stages, cap);
+    while (pl->raw_stages > 1 && mma_smem_bytes(pl->raw_stages, cap) > pl->smem_limit) pl->raw_stages--;
+    pl->smem = mma_smem_bytes(pl->raw_stages, cap);
 }
 
 int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const ScanParams& sp, const MmaPlan& pl, cudaStream_t st) {
@@ -525,10 +533,10 @@ int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const ScanParams& 
     dim3 grid(pl.qtiles, pl.strips);
     if (pl.f4) {
         VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_kernel<KIND_F4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        hamming_scan_mma_kernel<KIND_F4><<<grid, MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, pl.b_stages);
+        hamming_scan_mma_kernel<KIND_F4><<<grid, MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages);
     } else {
         VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_kernel<KIND_I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        hamming_scan_mma_kernel<KIND_I8><<<grid, MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, pl.b_stages);
+        hamming_scan_mma_kernel<KIND_I8><<<grid, MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages);
     }
     vrq_count_launch(ctx);
     VRQ_CUDA(cudaGetLastError());
