@@ -40,7 +40,7 @@ constexpr int STAGE_BYTES_B = MROWS * 128;
 constexpr int STAGE_BYTES_RAW = MROWS * CODE_BYTES;
 constexpr int EPI_WARPS = 8;
 constexpr int EXP_WARPS = 8;
-constexpr int WARP_MMA = 8, WARP_TMA = 9, WARP_EXP0 = 10;
+constexpr int WARP_MMA = 8, MMA_WARPS = 2, WARP_TMA = 10, WARP_EXP0 = 11;  // issuer warp 8 takes even tiles, warp 9 odd tiles
 constexpr int MMA_KERNEL_THREADS = (WARP_EXP0 + EXP_WARPS) * 32;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr uint32_t TMEM_COLS = 512, TMEM_A_COL = 0, TMEM_D_COL = 256;
@@ -229,11 +229,13 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                     }
                     tmem_st8(lane_base + 8 * W + 8, v);
                 } else {
-                    // columns 4 W + t: nibble j = bit (t + 4 j) of word W as e2m1 +1.0 (0x2) / -1.0 (0xA)
+                    // columns 4 W + t: nibble j = bit (t + 4 j) of word W as e2m1 +-(1 / b_t), b_t = the value the expanders
+                    // give a set database bit of plane t (0.5, 1, 2, 2): +-2.0 = 0x4/0xC, +-1.0 = 0x2/0xA, +-0.5 = 0x1/0x9
 #pragma unroll
                     for (int t = 0; t < 4; t++) {
-                        v[t] = qvalid ? (0xAAAAAAAAu ^ (((w >> t) & 0x11111111u) << 3)) : 0u;
-                        v[4 + t] = qvalid ? (0xAAAAAAAAu ^ (((w2 >> t) & 0x11111111u) << 3)) : 0u;
+                        const uint32_t mag = t == 0 ? 0x44444444u : (t == 1 ? 0x22222222u : 0x11111111u);
+                        v[t] = qvalid ? ((mag | 0x88888888u) ^ (((w >> t) & 0x11111111u) << 3)) : 0u;
+                        v[4 + t] = qvalid ? ((mag | 0x88888888u) ^ (((w2 >> t) & 0x11111111u) << 3)) : 0u;
                     }
                     tmem_st8(lane_base + 4 * W, v);
                 }
@@ -272,13 +274,19 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                 }
             }
         }
-    } else if (warp == WARP_MMA) {
-        // ===================== MMA issuer =====================
+    } else if (warp >= WARP_MMA && warp < WARP_MMA + MMA_WARPS) {
+        // ===================== MMA issuers =====================
+        // Two issuer warps alternate tiles (the single-thread issue path - waits, descriptor arithmetic, 4 MMAs and a
+        // commit per K-block - costs about as many cycles per tile as the e2m1 MMAs themselves take to execute).  Tiles
+        // of different issuers use different accumulators and barrier-guarded B stages, so their order is free.
         // The whole warp walks the loop (everything stays warp-uniform); one elected lane issues.  Per K-block: one wait,
         // 4 MMAs (32 bytes of K each) whose descriptors are immediates off the tile's base, one commit.
         const uint64_t desc0 = umma_desc_sw128(smem_u32(b_mem));
         const uint32_t full0 = smem_u32(&sm->b_full[0]), empty0 = smem_u32(&sm->b_empty[0]);
-        for (int t = 0; t < ntiles; t++) {
+        // (int8 tiles all share the same 8 stages: a second issuer would wait on a barrier phase two ahead of the completed
+        // one, which a parity wait cannot express - so the int8 kind keeps a single issuer.)
+        constexpr int ISSUERS = F4 ? MMA_WARPS : 1;
+        for (int t = warp - WARP_MMA; t < ntiles && warp - WARP_MMA < ISSUERS; t += ISSUERS) {
             const int as = t & 1;
             const uint32_t grp = (uint32_t)t & (uint32_t)(GROUPS - 1);
             const uint32_t ph = ((uint32_t)t / (uint32_t)GROUPS) & 1u;
@@ -347,13 +355,15 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                         }
                     }
                 } else {
-                    // word i of the 32 code bytes -> 16-byte chunk i: plane t (nibble j = bit t + 4 j) as e2m1 1.0 = 0x2
+                    // word i of the 32 code bytes -> 16-byte chunk i: plane t holds bit (t + 4 j) of the word in nibble j.  Planes
+                    // 0-2 keep the bit where it is - as e2m1 that reads 0.5 (0x1), 1.0 (0x2), 2.0 (0x4) - and the query side
+                    // carries +-2, +-1, +-0.5 so every product is +-1; only plane 3 (bit 3 = the sign bit) needs a shift.
                     const uint32_t w[8] = {c[2 * j].x, c[2 * j].y, c[2 * j].z, c[2 * j].w, c[2 * j + 1].x, c[2 * j + 1].y, c[2 * j + 1].z,
                                            c[2 * j + 1].w};
 #pragma unroll
                     for (int i = 0; i < 8; i++)
-                        sts128(baddr + (((uint32_t)i ^ sw) << 4), (w[i] << 1) & 0x22222222u, w[i] & 0x22222222u, (w[i] >> 1) & 0x22222222u,
-                               (w[i] >> 2) & 0x22222222u);
+                        sts128(baddr + (((uint32_t)i ^ sw) << 4), w[i] & 0x11111111u, w[i] & 0x22222222u, w[i] & 0x44444444u,
+                               (w[i] >> 1) & 0x44444444u);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -490,9 +500,9 @@ size_t mma_smem_bytes(int raw_stages, int cap) {
 
 int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
     const int sms = ctx->sm_count;
-    pl->f4 = env_int("VRQ_MMA_KIND", 8) == 4;
+    pl->f4 = env_int("VRQ_MMA_KIND", 4) != 8;  // 4 (default): packed e2m1 operands, 8: int8 operands
     pl->qtiles = (nq + MQ - 1) / MQ;
-    pl->group_tiles = env_int("VRQ_MMA_GROUP_TILES", 2);
+    pl->group_tiles = env_int("VRQ_MMA_GROUP_TILES", 4);
     if (pl->group_tiles < 1) pl->group_tiles = 1;
     const int slack = k < 256 ? 256 : (k > 2048 ? 2048 : k);
     pl->cap = k + slack + pl->group_tiles * MROWS;
