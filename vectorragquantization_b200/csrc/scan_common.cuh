@@ -111,6 +111,30 @@ __device__ void compact_list(uint64_t* glist, int n, int k, unsigned long long* 
     }
 }
 
+// One WARP keeps the k smallest keys of a list, in place in global memory (the tensor-core kernel compacts 8 lists at a
+// time, one per epilogue warp; a block-wide select per list serialises 128 lists behind ~15 barriers each).
+// bar_id: a named barrier private to the calling warp.  Keys are unique, so "key <= k-th smallest" keeps exactly k.
+__device__ __forceinline__ void compact_list_warp(uint64_t* glist, int n, int k, SelectScratch* sc, int lane, int bar_id, int* cnt_q,
+                                                  int* tau_q) {
+    const unsigned long long kth = radix_select_kth<32>([&](int i) { return (unsigned long long)glist[i]; }, n, k, lane, sc, bar_id);
+    // in-place stable-free compaction, 32 keys per step: step i writes below the end of the chunk it has just read
+    int out = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const unsigned long long key = i < n ? (unsigned long long)glist[i] : ~0ull;
+        const bool keep = i < n && key <= kth;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) glist[out + __popc(m & ((1u << lane) - 1u))] = key;
+        out += __popc(m);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        *cnt_q = out;
+        *tau_q = (int)(kth >> VRQ_KEY_POS_BITS);
+    }
+    __syncwarp();
+}
+
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -46,6 +46,7 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr uint32_t TMEM_COLS = 512, TMEM_A_COL = 0, TMEM_D_COL = 256;
 constexpr uint32_t TMEM_SFA_COL = 128, TMEM_SFB_COL = 160, TMEM_SF_COLS = 32;  // F4 only: block scales, all 1.0 (UE8M0 0x7F)
 constexpr int B_STAGES = 8, MAX_RAW_STAGES = 4;
+constexpr int BAR_WARP0 = 2;  // named barriers 2..9: one per epilogue warp (list compaction)
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = signed 8 bit, both K-major, N = 128, M = 128
 constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MROWS >> 3) << 17) | ((uint32_t)(MQ >> 4) << 24);
@@ -139,7 +140,7 @@ struct MmaSmem {
     uint32_t tmem_base;
     int tau_s[MQ];
     int cnt_s[MQ];
-    SelectScratch sc;
+    SelectScratch sc[EPI_WARPS];  // one radix-select scratch per epilogue warp
 };
 
 template <int KIND>
@@ -154,8 +155,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* raw_mem = base;
     uint8_t* b_mem = raw_mem + (size_t)raw_stages * STAGE_BYTES_RAW;
-    unsigned long long* scratch = (unsigned long long*)(b_mem + (size_t)B_STAGES * STAGE_BYTES_B);
-    MmaSmem* sm = (MmaSmem*)(scratch + p.cap);
+    MmaSmem* sm = (MmaSmem*)(b_mem + (size_t)B_STAGES * STAGE_BYTES_B);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -459,11 +459,11 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
             if ((t + 1) % p.group_tiles == 0 && t + 1 < ntiles) {
                 group_sync<EPI_THREADS>(BAR_CONSUMERS);  // every append of this group of tiles is in its list
                 if (epi_sync_or(sm->cnt_s[q] > limit)) {
-                    for (int qq = 0; qq < qt; qq++) {
+                    for (int qq = warp; qq < qt; qq += EPI_WARPS) {  // one list per warp, 8 lists at a time
                         const int n = sm->cnt_s[qq];
                         if (n > limit)
-                            compact_list<EPI_THREADS>(p.lists + ((size_t)strip * p.nq + q0 + qq) * p.cap, n, p.k, scratch, &sm->sc, tid,
-                                                      &sm->cnt_s[qq], &sm->tau_s[qq]);
+                            compact_list_warp(p.lists + ((size_t)strip * p.nq + q0 + qq) * p.cap, n, p.k, &sm->sc[warp], lane, BAR_WARP0 + warp,
+                                              &sm->cnt_s[qq], &sm->tau_s[qq]);
                     }
                     group_sync<EPI_THREADS>(BAR_CONSUMERS);
                     if (qvalid) thr = pcq - sm->tau_s[q];
@@ -473,11 +473,11 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         }
         group_sync<EPI_THREADS>(BAR_CONSUMERS);
         // final compaction: every list leaves the kernel with at most k keys (bounds the merge's working set)
-        for (int qq = 0; qq < qt; qq++) {
+        for (int qq = warp; qq < qt; qq += EPI_WARPS) {
             const int n = sm->cnt_s[qq];
             if (n > p.k)
-                compact_list<EPI_THREADS>(p.lists + ((size_t)strip * p.nq + q0 + qq) * p.cap, n, p.k, scratch, &sm->sc, tid, &sm->cnt_s[qq],
-                                          &sm->tau_s[qq]);
+                compact_list_warp(p.lists + ((size_t)strip * p.nq + q0 + qq) * p.cap, n, p.k, &sm->sc[warp], lane, BAR_WARP0 + warp,
+                                  &sm->cnt_s[qq], &sm->tau_s[qq]);
         }
         group_sync<EPI_THREADS>(BAR_CONSUMERS);
         if (qvalid && half == 0) p.counts[(size_t)strip * p.nq + q0 + q] = sm->cnt_s[q];
@@ -492,8 +492,8 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
 }
 
 size_t mma_smem_bytes(int raw_stages, int cap) {
-    return 1024 + (size_t)raw_stages * STAGE_BYTES_RAW + (size_t)B_STAGES * STAGE_BYTES_B + sizeof(unsigned long long) * (size_t)cap +
-           sizeof(MmaSmem) + 16;
+    (void)cap;  // lists are compacted in place in global memory: no shared-memory copy
+    return 1024 + (size_t)raw_stages * STAGE_BYTES_RAW + (size_t)B_STAGES * STAGE_BYTES_B + sizeof(MmaSmem) + 16;
 }
 
 }  // namespace
@@ -516,7 +516,7 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
     pl->strips = (int)((tiles + tps - 1) / tps);
     const size_t limit = ctx->smem_optin ? ctx->smem_optin : 227 * 1024;
     pl->smem_limit = limit;
-    pl->raw_stages = env_int("VRQ_MMA_RAW_STAGES", 3);
+    pl->raw_stages = env_int("VRQ_MMA_RAW_STAGES", 4);
     if (pl->raw_stages < 1) pl->raw_stages = 1;
     if (pl->raw_stages > MAX_RAW_STAGES) pl->raw_stages = MAX_RAW_STAGES;
     pl->b_stages = B_STAGES;
