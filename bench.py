@@ -46,6 +46,7 @@ UNIT = "queries/s per 100M codes"
 
 
 INT8_DENSE_NOMINAL_TOPS = 4500.0  # B200 dense int8 / fp8 tensor rate (B200_PROFILING.md, nominal table)
+FP4_DENSE_NOMINAL_TOPS = 9000.0   # B200 dense fp4 tensor rate (same table)
 
 
 def peaks():
@@ -221,7 +222,7 @@ def run_gpu(args):
 
     # ---- queries: a different batch every step, resident on the device (value) and in pinned host memory (e2e) ----
     total_steps = args.warmup_actual + args.steps
-    n_e2e = max(1, min(3, args.steps))
+    n_e2e = max(1, min(5, args.steps))
     qf_d = torch.empty((total_steps + n_e2e + 2, NQ, D), dtype=torch.float32, device=dev)
     qb_d = torch.empty((total_steps + n_e2e + 2, NQ, D // 8), dtype=torch.uint8, device=dev)
     for s in range(qf_d.shape[0]):
@@ -313,28 +314,34 @@ def run_gpu(args):
     alu_peak = LOP3_PER_CLK_PER_SM * 148 * sm_mhz * 1e6 / LOP3_PER_PAIR  # (query, code) pairs per second at the measured clock
     popc_ceiling = POPC_PER_CLK_PER_SM * 148 * sm_mhz * 1e6 / 32.0
     mma_path = os.environ.get("VRQ_SCAN_MMA", "1") != "0"
+    f4 = os.environ.get("VRQ_MMA_KIND", "4") != "8"
     if mma_path and dense_n > 0:
         dense_s = dense_ms / 1e3 / dense_n
-        ops = 2.0 * D * pairs_per_step  # one int8 multiply-add per (query bit, code bit) = 2 ops
+        ops = 2.0 * D * pairs_per_step  # one multiply-add per (query bit, code bit) = 2 ops
         bf16_burst, bf16_sust, bf16_src = bf16_peaks()
+        nominal = FP4_DENSE_NOMINAL_TOPS if f4 else INT8_DENSE_NOMINAL_TOPS
+        ratio = 4 if f4 else 2  # nominal rate of the operand kind relative to bf16
+        kind = ("tcgen05.mma.cta_group::1.kind::mxf4.block_scale (packed e2m1 operands, unit UE8M0 scales, f32 accumulate - exact: "
+                "every product is +-1 and |sum| <= 1024)" if f4 else "tcgen05.mma.cta_group::1.kind::i8 (int8 operands, s32 accumulate)")
         roofline = {
-            "kernel": "hamming_scan_mma_kernel, dense pass (tcgen05.mma.cta_group::1.kind::i8, M=128 queries in TMEM x N=128 codes "
-                      "expanded to {0,1} int8 in shared memory, K=1024; 1024-query batch)",
-            "bound": "tensor", "unit": "TFLOP/s", "ops": "int8 multiply-add = 2 ops",
-            "achieved": ops / dense_s / 1e12, "peak": INT8_DENSE_NOMINAL_TOPS, "frac": ops / dense_s / 1e12 / INT8_DENSE_NOMINAL_TOPS,
-            "peak_source": "nominal dense int8 tensor rate (B200_PROFILING.md table; MEASURED_PEAKS.json holds no int8 figure). "
-                           f"For reference 2 x the {bf16_src} cuBLAS bf16 numbers = {2 * bf16_burst:.0f} (burst) / {2 * bf16_sust:.0f} "
-                           "(sustained) TFLOP/s: the +-1 / {0,1} operands of a Hamming contraction toggle few datapath bits, so "
-                           "this kernel holds a higher SM clock under the power cap than a dense bf16 GEMM does (see clocks)",
-            "frac_of_2x_measured_bf16_sustained": ops / dense_s / 1e12 / (2 * bf16_sust),
+            "kernel": f"hamming_scan_mma_kernel<{'e2m1' if f4 else 'int8'}>, dense pass: {kind}; M=128 queries resident in TMEM x N=128 "
+                      "codes expanded from bits in shared memory, K=1024; 1024-query batch",
+            "bound": "tensor", "unit": "TFLOP/s", "ops": "multiply-add of a query bit and a code bit = 2 ops",
+            "achieved": ops / dense_s / 1e12, "peak": nominal, "frac": ops / dense_s / 1e12 / nominal,
+            "peak_source": f"nominal dense {'fp4' if f4 else 'int8'} tensor rate (B200_PROFILING.md table; MEASURED_PEAKS.json holds only a "
+                           f"cuBLAS bf16 figure). {ratio} x the {bf16_src} bf16 numbers would be {ratio * bf16_burst:.0f} (burst) / "
+                           f"{ratio * bf16_sust:.0f} (sustained) TFLOP/s - see frac_of_scaled_measured_bf16. The kernel is bound by the "
+                           "shared-memory bandwidth that feeds the B operand (expanded in place, never in HBM) before the tensor pipe",
+            "frac_of_scaled_measured_bf16": {"burst": ops / dense_s / 1e12 / (ratio * bf16_burst),
+                                             "sustained": ops / dense_s / 1e12 / (ratio * bf16_sust)},
             "kernel_ms": dense_s * 1e3, "pairs_per_s": pairs_per_step / dense_s,
             "traffic": None,
             "hbm": {"bound": "hbm", "unit": "GB/s", "achieved": n_local * 128 * 8 / dense_s / 1e9, "peak": hbm_peak,
                     "frac": n_local * 128 * 8 / dense_s / 1e9 / hbm_peak, "peak_source": peak_src,
-                    "note": "algorithmic bytes = 128 B per code per 128-query tile (8 tiles per 1024-query batch, mostly served by "
-                            "L2); not the binding resource for a query batch"},
+                    "note": "algorithmic bytes = 128 B per code per 128-query tile (8 tiles per 1024-query batch, 7 of them served by "
+                            "L2: ncu dram__bytes_read ~ 13-15 GB per 102 GB requested); not the binding resource for a query batch"},
             "integer_pipe_kernel": {"note": "scan.cu (XOR + carry-save POPC) handles <= 31 queries per pass and VRQ_SCAN_MMA=0; "
-                                            "its 1024-query rate measured in round 1 was 216 Gpair/s (profiles/r01)",
+                                            "its 1024-query rate measured earlier in round 1 was 216 Gpair/s (profiles/r01)",
                                     "alu_peak_Gpair_s": alu_peak / 1e9},
             "scan_ms_per_step": scan_ms / args.steps, "rescore_ms_per_step": resc_ms / args.steps,
             "merge_ms_per_step": merge_ms / args.steps,
@@ -361,7 +368,7 @@ def run_gpu(args):
         cb, _ = cpu_baseline()
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8 tensor-core contraction of u8 bit codes (Phase I) / f64 (Phases II-III)",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "e2m1/int8 tensor-core contraction of u8 bit codes, exact (Phase I) / f64 (Phases II-III)",
             "data": "synthetic",
             "config": {"workload": "cfg3: CohereEnhancedVectorDB 3-phase search, Hamming top-1000 over 100M x 1024-bit codes per GPU, "
                                    "1024-query batch, k=100, binary_oversample=10, int8_oversample=3",
@@ -478,7 +485,7 @@ def hbm_bound_kernels(torch, ctx, lib, L, index, qb_d, dev, stream, hbm_peak, pe
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=N_PER_GPU, help="rows per GPU (default: the 100M of the headline config)")

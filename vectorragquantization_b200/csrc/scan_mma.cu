@@ -264,7 +264,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
             for (int t = 0; t < ntiles; t++) {
-                mbar_wait(smem_u32(&sm->raw_empty[s]), ph ^ 1u);
+                mbar_wait_relaxed(smem_u32(&sm->raw_empty[s]), ph ^ 1u, 256);
                 mbar_expect_tx(smem_u32(&sm->raw_full[s]), STAGE_BYTES_RAW);
                 tma_load_2d(smem_u32(raw_mem) + s * (uint32_t)STAGE_BYTES_RAW, &tmap, 0, (int)(s_begin + (int64_t)t * p.tile_step),
                             smem_u32(&sm->raw_full[s]));
@@ -329,7 +329,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
             const uint32_t grp = (uint32_t)t & (uint32_t)(GROUPS - 1);
             const uint32_t ph = ((uint32_t)t / (uint32_t)GROUPS) & 1u;
             const uint32_t stage0 = grp * (uint32_t)KBLOCKS + (uint32_t)par;
-            mbar_wait(smem_u32(&sm->raw_full[rs]), rph);
+            mbar_wait_relaxed(smem_u32(&sm->raw_full[rs]), rph, 64);
             const uint32_t raddr = smem_u32(raw_mem) + rs * (uint32_t)STAGE_BYTES_RAW + row_off;
             uint4 c[4];
             // I8: K-block kb = raw chunk kb (16 bytes);  F4: K-block kb = raw chunks 2 kb, 2 kb + 1 (32 bytes)
@@ -341,7 +341,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
 #pragma unroll
             for (int j = 0; j < KBLOCKS / 2; j++) {
                 const uint32_t s = stage0 + 2 * j;
-                mbar_wait(empty0 + s * 8, ph ^ 1u);
+                mbar_wait_relaxed(empty0 + s * 8, ph ^ 1u, 64);
                 const uint32_t baddr = bmem0 + s * (uint32_t)STAGE_BYTES_B;
                 if constexpr (!F4) {
                     const uint32_t w[4] = {c[j].x, c[j].y, c[j].z, c[j].w};
