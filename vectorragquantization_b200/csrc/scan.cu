@@ -589,7 +589,7 @@ static int plan_pass(vrq_ctx* ctx, bool tma, bool mma, int code_bytes, int64_t r
     return plan_scan(ctx, tma, code_bytes, rows, nq, k, &pl->sp);
 }
 
-static int launch_pass(vrq_ctx* ctx, bool tma, const CUtensorMap& tmap, const CUtensorMap& tmap_mma, ScanParams sp, const PassPlan& pl,
+static int launch_pass(vrq_ctx* ctx, bool tma, const CUtensorMap& tmap, const CUtensorMap* tmap_mma, ScanParams sp, const PassPlan& pl,
                        cudaStream_t st) {
     sp.num_strips = pl.strips();
     sp.rows_per_strip = pl.rows_per_strip();
@@ -598,7 +598,7 @@ static int launch_pass(vrq_ctx* ctx, bool tma, const CUtensorMap& tmap, const CU
         sp.qtile = 128;
         sp.group_tiles = pl.mp.group_tiles;
         if (sp.tile_step == 0) sp.tile_step = MMA_TILE_ROWS;
-        return launch_scan_mma(ctx, tmap_mma, sp, pl.mp, st);
+        return launch_scan_mma(ctx, tmap_mma[0], tmap_mma[1], sp, pl.mp, st);
     }
     sp.qtile = pl.sp.qtile;
     sp.group_tiles = pl.sp.group_tiles;
@@ -617,11 +617,12 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
         vrq_set_error("the distance dump is only available on the tensor-core scan path");
         return VRQ_ERR_UNSUPPORTED;
     }
-    CUtensorMap tmap, tmap_mma;
+    CUtensorMap tmap, tmap_mma[2];  // tmap_mma: 128-row boxes (one CTA per tile), 64-row boxes (CTA pairs)
     memset(&tmap, 0, sizeof(tmap));
-    memset(&tmap_mma, 0, sizeof(tmap_mma));
+    memset(tmap_mma, 0, sizeof(tmap_mma));
     if (tma) VRQ_TRY(make_codes_tmap(codes, n, TMA_BOX_ROWS, &tmap));
-    if (mma) VRQ_TRY(make_codes_tmap(codes, n, MMA_TILE_ROWS, &tmap_mma));
+    if (mma) VRQ_TRY(make_codes_tmap(codes, n, MMA_TILE_ROWS, &tmap_mma[0]));
+    if (mma) VRQ_TRY(make_codes_tmap(codes, n, MMA_TILE_ROWS / 2, &tmap_mma[1]));
 
     if (mma) {
         // ---- thresholds from a strided sample (tensor-core path) ------------------------------------------------

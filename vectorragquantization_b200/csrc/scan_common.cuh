@@ -196,12 +196,14 @@ struct MmaPlan {
     int qtiles, strips, group_tiles, cap, raw_stages, b_stages;
     int64_t rows_per_strip;
     size_t smem, smem_limit;
-    bool f4;  // packed e2m1 operands (kind::mxf4) instead of int8
+    bool f4;    // packed e2m1 operands (kind::mxf4) instead of int8
+    bool pair;  // CTA pairs (tcgen05 cta_group::2): two query tiles share every tile of database rows
 };
 constexpr int MMA_TILE_ROWS = 128;
 int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl);
 void mma_plan_set_cap(MmaPlan* pl, int cap);
-int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const ScanParams& sp, const MmaPlan& pl, cudaStream_t st);
+int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const CUtensorMap& tmap64, const ScanParams& sp, const MmaPlan& pl,
+                    cudaStream_t st);
 
 inline int env_int(const char* name, int dflt) {
     const char* v = getenv(name);

@@ -52,6 +52,8 @@ constexpr int BAR_WARP0 = 2;  // named barriers 2..9: one per epilogue warp (lis
 constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MROWS >> 3) << 17) | ((uint32_t)(MQ >> 4) << 24);
 // block-scaled descriptor (cute::UMMA::InstrDescriptorBlockScaled): A = B = e2m1 (MXF4 format 1), K-major, scale format
 // UE8M0 (bit 23), scale-factor ids 0, N = 128, M = 128, K = 64 (bit 31 = 0); D is always f32
+// the same for a CTA pair: M = 256 (128 queries in each CTA's TMEM), N = 128 (64 database rows in each CTA's shared memory)
+constexpr uint32_t IDESC_F4_PAIR = (1u << 7) | (1u << 10) | ((uint32_t)(MROWS >> 3) << 17) | (1u << 23) | ((uint32_t)(256 >> 4) << 24);
 constexpr uint32_t IDESC_F4 = (1u << 7) | (1u << 10) | ((uint32_t)(MROWS >> 3) << 17) | (1u << 23) | ((uint32_t)(MQ >> 4) << 24);
 
 // ---- tcgen05 wrappers ------------------------------------------------------------------------------------------
@@ -81,6 +83,44 @@ __device__ __forceinline__ void umma_f4_ts(uint32_t d_tmem, uint32_t a_tmem, uin
         ".reg .pred p;\n"
         "setp.ne.b32 p, %6, 0;\n"
         "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], [%1], %2, %3, [%4], [%5], p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(sfa), "r"(sfb), "r"(accumulate)
+        : "memory");
+}
+// ---- CTA-pair (cta_group::2) helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory object in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(saddr), "r"(rank));
+    return ra;
+}
+// Remote arrive with the default (.release.cta) semantics, as CUTLASS's ClusterBarrier::arrive(cta_id) does.  What the
+// arrive publishes here is never read by the other CTA's THREADS: B stages are read by the tensor core through the async
+// proxy (made visible by fence.proxy.async before the arrive) and accumulator hand-backs carry no memory at all.  The
+// .release.cluster form costs MEMBAR.ALL.GPU + ERRBAR per arrive (measured: the pair kernel ran 35 % slower with it).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_f4_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t sfa, uint32_t sfb,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.scale_vec::2X [%0], [%1], %2, %3, [%4], [%5], p;\n"
         "}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(sfa), "r"(sfb), "r"(accumulate)
         : "memory");
@@ -143,11 +183,19 @@ struct MmaSmem {
     SelectScratch sc[EPI_WARPS];  // one radix-select scratch per epilogue warp
 };
 
-template <int KIND>
+// CG = 1: one CTA per 128-query tile.  CG = 2 (e2m1 only): a CTA pair shares every tile of database rows - each CTA
+// holds its own 128 queries in TMEM, loads and expands HALF of the tile's rows (64), the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256, N = 128) which reads both halves; per SM the shared-memory traffic per tile halves.
+template <int KIND, int CG>
 __global__ void __launch_bounds__(MMA_KERNEL_THREADS, 1)
 hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, int raw_stages) {
     constexpr bool F4 = KIND == KIND_F4;
     constexpr int KBLOCKS = KindCfg<KIND>::KBLOCKS;
+    static_assert(CG == 1 || F4, "CTA pairs are built for the e2m1 kind only");
+    constexpr int MY_ROWS = MROWS / CG;                    // database rows this CTA loads and expands per tile
+    constexpr int STAGE_BYTES_RAW = MY_ROWS * CODE_BYTES;  // shadows the namespace constant: per-CTA bytes
+    constexpr int STAGE_BYTES_B = MY_ROWS * 128;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
     // The B ring has exactly 8 stages of one K-block (16 KB) each, so a tile's stages are compile-time offsets from one
     // per-tile base: I8 tiles use all 8 (stage = K-block, parity = tile & 1); F4 tiles alternate between stages 0-3 and 4-7.
     constexpr int GROUPS = B_STAGES / KBLOCKS;
@@ -183,18 +231,25 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(smem_u32(&sm->acc_full[s]), 1);
-            mbar_init(smem_u32(&sm->acc_empty[s]), EPI_WARPS);
+            mbar_init(smem_u32(&sm->acc_empty[s]), EPI_WARPS * CG);  // pair: both CTAs' epilogues release the leader's MMA
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == WARP_MMA) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "r"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "r"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "r"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers exist before anyone arrives on them remotely
     tc_fence_after();
     const uint32_t tmem = sm->tmem_base;
 
@@ -266,8 +321,8 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
             for (int t = 0; t < ntiles; t++) {
                 mbar_wait_relaxed(smem_u32(&sm->raw_empty[s]), ph ^ 1u, 256);
                 mbar_expect_tx(smem_u32(&sm->raw_full[s]), STAGE_BYTES_RAW);
-                tma_load_2d(smem_u32(raw_mem) + s * (uint32_t)STAGE_BYTES_RAW, &tmap, 0, (int)(s_begin + (int64_t)t * p.tile_step),
-                            smem_u32(&sm->raw_full[s]));
+                tma_load_2d(smem_u32(raw_mem) + s * (uint32_t)STAGE_BYTES_RAW, &tmap, 0,
+                            (int)(s_begin + (int64_t)t * p.tile_step + (int64_t)rank * MY_ROWS), smem_u32(&sm->raw_full[s]));
                 if (++s == (uint32_t)raw_stages) {
                     s = 0;
                     ph ^= 1u;
@@ -286,7 +341,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         // (int8 tiles all share the same 8 stages: a second issuer would wait on a barrier phase two ahead of the completed
         // one, which a parity wait cannot express - so the int8 kind keeps a single issuer.)
         constexpr int ISSUERS = F4 ? MMA_WARPS : 1;
-        for (int t = warp - WARP_MMA; t < ntiles && warp - WARP_MMA < ISSUERS; t += ISSUERS) {
+        for (int t = warp - WARP_MMA; t < ntiles && warp - WARP_MMA < ISSUERS && rank == 0; t += ISSUERS) {
             const int as = t & 1;
             const uint32_t grp = (uint32_t)t & (uint32_t)(GROUPS - 1);
             const uint32_t ph = ((uint32_t)t / (uint32_t)GROUPS) & 1u;
@@ -304,13 +359,20 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                     for (int k4 = 0; k4 < 4; k4++) {
                         const uint64_t desc = desc_t + (uint64_t)(kb * (STAGE_BYTES_B >> 4) + k4 * 2);
                         const uint32_t a_tmem = tmem + TMEM_A_COL + (uint32_t)(kb * 4 + k4) * 8;
-                        if constexpr (F4)
+                        if constexpr (CG == 2)
+                            umma_f4_ts_pair(d_tmem, a_tmem, desc, IDESC_F4_PAIR, tmem + TMEM_SFA_COL, tmem + TMEM_SFB_COL, (kb | k4) != 0);
+                        else if constexpr (F4)
                             umma_f4_ts(d_tmem, a_tmem, desc, IDESC_F4, tmem + TMEM_SFA_COL, tmem + TMEM_SFB_COL, (kb | k4) != 0);
                         else
                             umma_i8_ts(d_tmem, a_tmem, desc, IDESC_I8, (kb | k4) != 0);
                     }
-                    tc_commit(empty_t + kb * 8);
-                    if (kb == KBLOCKS - 1) tc_commit(smem_u32(&sm->acc_full[as]));
+                    if constexpr (CG == 2) {
+                        tc_commit_pair(empty_t + kb * 8);  // frees the stage in BOTH CTAs
+                        if (kb == KBLOCKS - 1) tc_commit_pair(smem_u32(&sm->acc_full[as]));
+                    } else {
+                        tc_commit(empty_t + kb * 8);
+                        if (kb == KBLOCKS - 1) tc_commit(smem_u32(&sm->acc_full[as]));
+                    }
                 }
                 __syncwarp();
             }
@@ -318,11 +380,15 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
     } else if (warp >= WARP_EXP0) {
         // ===================== expanders: code bits -> one 128-byte K-block row of the B operand =====================
         const int et = tid - WARP_EXP0 * 32;
-        const int row = et & (MROWS - 1);
-        const int par = et >> 7;  // this thread expands K-blocks par, par + 2, ... of its row
+        constexpr int KB_STEP = (EXP_WARPS * 32) / MY_ROWS;  // K-blocks in flight across the 256 expander threads (2; pair: 4)
+        constexpr int UNITS = KBLOCKS / KB_STEP;             // K-blocks per thread per tile
+        const int row = et & (MY_ROWS - 1);
+        const int par = et / MY_ROWS;  // this thread expands K-blocks par, par + KB_STEP, ... of its row
         const uint32_t sw = (uint32_t)(row & 7);
         const uint32_t row_off = (uint32_t)row * 128u;
-        const uint32_t full0 = smem_u32(&sm->b_full[0]), empty0 = smem_u32(&sm->b_empty[0]);
+        const uint32_t empty0 = smem_u32(&sm->b_empty[0]);
+        // the "stage full" barriers the MMA issuer waits on live in the leader CTA
+        const uint32_t full0 = CG == 2 ? mapa_rank(smem_u32(&sm->b_full[0]), 0) : smem_u32(&sm->b_full[0]);
         const uint32_t bmem0 = smem_u32(b_mem) + row_off;
         uint32_t rs = 0, rph = 0;  // raw ring
         for (int t = 0; t < ntiles; t++) {
@@ -334,13 +400,13 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
             uint4 c[4];
             // I8: K-block kb = raw chunk kb (16 bytes);  F4: K-block kb = raw chunks 2 kb, 2 kb + 1 (32 bytes)
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t chunk = F4 ? (uint32_t)(4 * (j >> 1) + 2 * par + (j & 1)) : (uint32_t)(2 * j + par);
+            for (int j = 0; j < (F4 ? 2 * UNITS : UNITS); j++) {
+                const uint32_t chunk = F4 ? (uint32_t)(2 * (par + KB_STEP * (j >> 1)) + (j & 1)) : (uint32_t)(par + KB_STEP * j);
                 c[j] = lds128(raddr + ((chunk ^ sw) << 4));
             }
 #pragma unroll
-            for (int j = 0; j < KBLOCKS / 2; j++) {
-                const uint32_t s = stage0 + 2 * j;
+            for (int j = 0; j < UNITS; j++) {
+                const uint32_t s = stage0 + KB_STEP * j;
                 mbar_wait_relaxed(empty0 + s * 8, ph ^ 1u, 64);
                 const uint32_t baddr = bmem0 + s * (uint32_t)STAGE_BYTES_B;
                 if constexpr (!F4) {
@@ -367,7 +433,12 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(full0 + s * 8);
+                if (lane == 0) {
+                    if constexpr (CG == 2)
+                        mbar_arrive_cluster(full0 + s * 8);
+                    else
+                        mbar_arrive(full0 + s * 8);
+                }
             }
             // the raw tile goes back to the producer only now: every c[j] has been consumed by real instructions, so the
             // shared-memory reads above are known to have completed (an arrive right after the ld.shared can overtake them)
@@ -405,7 +476,12 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                     // the accumulator is in registers: hand the TMEM stage back to the MMA issuer
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[as]));
+                    if (lane == 0) {
+                        if constexpr (CG == 2)
+                            mbar_arrive_cluster(mapa_rank(smem_u32(&sm->acc_empty[as]), 0));
+                        else
+                            mbar_arrive(smem_u32(&sm->acc_empty[as]));
+                    }
                 }
                 const int nv = nvalid - 32 * cc;  // valid columns in this group (>= 32: all)
                 // F4 accumulates in f32: the dots are integers of magnitude <= 1024, exact in binary32
@@ -485,9 +561,13 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared memory and TMEM until the very end
     if (warp == WARP_MMA) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+        if constexpr (CG == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -502,6 +582,8 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
     const int sms = ctx->sm_count;
     pl->f4 = env_int("VRQ_MMA_KIND", 4) != 8;  // 4 (default): packed e2m1 operands, 8: int8 operands
     pl->qtiles = (nq + MQ - 1) / MQ;
+    // CTA pairs need an even number of query tiles (a pair = two neighbouring tiles); VRQ_MMA_PAIR=0 switches them off
+    pl->pair = pl->f4 && pl->qtiles % 2 == 0 && env_int("VRQ_MMA_PAIR", 1) != 0;
     pl->group_tiles = env_int("VRQ_MMA_GROUP_TILES", 4);
     if (pl->group_tiles < 1) pl->group_tiles = 1;
     const int slack = k < 256 ? 256 : (k > 2048 ? 2048 : k);
@@ -534,19 +616,37 @@ void mma_plan_set_cap(MmaPlan* pl, int cap) {
     pl->smem = mma_smem_bytes(pl->raw_stages, cap);
 }
 
-int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const ScanParams& sp, const MmaPlan& pl, cudaStream_t st) {
+int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const CUtensorMap& tmap64, const ScanParams& sp, const MmaPlan& pl,
+                    cudaStream_t st) {
     const size_t limit = ctx->smem_optin ? ctx->smem_optin : 227 * 1024;
     if (pl.smem > limit) {
         vrq_set_error("tensor-core Hamming top-k: shared-memory plan of %zu bytes exceeds %zu", pl.smem, limit);
         return VRQ_ERR_UNSUPPORTED;
     }
     dim3 grid(pl.qtiles, pl.strips);
-    if (pl.f4) {
-        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_kernel<KIND_F4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        hamming_scan_mma_kernel<KIND_F4><<<grid, MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages);
+    if (pl.f4 && pl.pair) {
+        // CTA pairs: clusters of 2 along x = two neighbouring query tiles of the same strip
+        auto kern = hamming_scan_mma_kernel<KIND_F4, 2>;
+        VRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(MMA_KERNEL_THREADS);
+        cfg.dynamicSmemBytes = pl.smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        VRQ_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap64, sp, pl.raw_stages));
+    } else if (pl.f4) {
+        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_kernel<KIND_F4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        hamming_scan_mma_kernel<KIND_F4, 1><<<grid, MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages);
     } else {
-        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_kernel<KIND_I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        hamming_scan_mma_kernel<KIND_I8><<<grid, MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages);
+        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_kernel<KIND_I8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        hamming_scan_mma_kernel<KIND_I8, 1><<<grid, MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages);
     }
     vrq_count_launch(ctx);
     VRQ_CUDA(cudaGetLastError());
