@@ -152,6 +152,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
@@ -460,20 +468,26 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         float thr_f = (float)thr;
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + TMEM_D_COL + (uint32_t)(half * 64);
         const int limit = p.compact_limit > 0 ? min(p.compact_limit, p.cap - p.group_tiles * MROWS) : p.cap - p.group_tiles * MROWS;
+        int until_check = p.group_tiles;
         for (int t = 0; t < ntiles; t++) {
             const int as = t & 1;
             mbar_wait(smem_u32(&sm->acc_full[as]), ((uint32_t)t >> 1) & 1u);
             tc_fence_after();
             const int64_t lrow0 = s_begin + (int64_t)t * p.tile_step + half * 64;
             const int nvalid = (int)min((int64_t)64, s_end - lrow0);
-#pragma unroll 1
-            for (int cc = 0; cc < 2; cc++) {
-                int v[32];
-                __syncwarp();
-                tmem_ld32(lane_base + (uint32_t)as * MROWS + 32 * cc, v);
+            const uint32_t acc = lane_base + (uint32_t)as * MROWS;
+            // 64 columns in 4 groups of 16, software-pipelined over two register sets: the tcgen05.ld of group g + 1 is
+            // in flight while group g is examined; the accumulator goes back to the MMA issuer as soon as the last
+            // group has landed.
+            int v[2][16];
+            __syncwarp();
+            tmem_ld16(acc, v[0]);
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
                 tmem_wait_ld();
-                if (cc == 1) {
-                    // the accumulator is in registers: hand the TMEM stage back to the MMA issuer
+                if (g < 3) {
+                    tmem_ld16(acc + 16 * (g + 1), v[(g + 1) & 1]);
+                } else {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
@@ -483,47 +497,49 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                             mbar_arrive(smem_u32(&sm->acc_empty[as]));
                     }
                 }
-                const int nv = nvalid - 32 * cc;  // valid columns in this group (>= 32: all)
+                const int(&w)[16] = v[g & 1];
+                const int nv = nvalid - 16 * g;  // valid columns in this group (>= 16: all)
                 // F4 accumulates in f32: the dots are integers of magnitude <= 1024, exact in binary32
-                auto dot_of = [&](int j) -> int { return F4 ? (int)__int_as_float(v[j]) : v[j]; };
+                auto dot_of = [&](int j) -> int { return F4 ? (int)__int_as_float(w[j]) : w[j]; };
                 if (p.dbg) {
                     if (qvalid)
-                        for (int j = 0; j < 32; j++)
-                            if (j < nv) p.dbg[(size_t)(q0 + q) * p.dbg_stride + (lrow0 + 32 * cc + j)] = pcq - dot_of(j);
+                        for (int j = 0; j < 16; j++)
+                            if (j < nv) p.dbg[(size_t)(q0 + q) * p.dbg_stride + (lrow0 + 16 * g + j)] = pcq - dot_of(j);
                 }
                 bool any;
                 int m;
                 if constexpr (F4) {
-                    float mf = __int_as_float(v[0]);
+                    float mf = __int_as_float(w[0]);
 #pragma unroll
-                    for (int j = 1; j < 32; j++) mf = fmaxf(mf, __int_as_float(v[j]));
+                    for (int j = 1; j < 16; j++) mf = fmaxf(mf, __int_as_float(w[j]));
                     any = mf > thr_f;
                     m = (int)mf;
                 } else {
-                    m = v[0];
+                    m = w[0];
 #pragma unroll
-                    for (int j = 1; j < 32; j++) m = max(m, v[j]);
+                    for (int j = 1; j < 16; j++) m = max(m, w[j]);
                     any = m > thr;
                 }
                 if (any) {
-                    // Some column of this lane survives.  bit (31 - j) of mask <=> v[j] > thr: the sign of thr - v[j] is
+                    // Some column of this lane survives.  bit (15 - j) of mask <=> w[j] > thr: the sign of thr - w[j] is
                     // shifted in with one funnel shift per column (2 instructions per column, no branches).
-                    const unsigned long long pos0 = (unsigned long long)(p.pos_base + lrow0 + 32 * cc);
+                    const unsigned long long pos0 = (unsigned long long)(p.pos_base + lrow0 + 16 * g);
                     uint32_t mask = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const uint32_t sgn = F4 ? __float_as_uint(thr_f - __int_as_float(v[j])) : (uint32_t)(thr - v[j]);
+                    for (int j = 0; j < 16; j++) {
+                        const uint32_t sgn = F4 ? __float_as_uint(thr_f - __int_as_float(w[j])) : (uint32_t)(thr - w[j]);
                         mask = __funnelshift_l(sgn, mask, 1);
                     }
-                    if (nv < 32) mask = nv <= 0 ? 0u : (mask & ~(0xFFFFFFFFu >> nv));
-                    if (__popc(mask) == 1 && nv >= 32) {
+                    if (nv < 16) mask = nv <= 0 ? 0u : (mask & ~(0xFFFFu >> nv));
+                    if (__popc(mask) == 1 && nv >= 16) {
                         // the usual case once tau has converged: the single survivor is the maximum itself
-                        my_list[atomicAdd(&sm->cnt_s[q], 1)] = ((unsigned long long)(pcq - m) << VRQ_KEY_POS_BITS) | (pos0 + __clz((int)mask));
+                        my_list[atomicAdd(&sm->cnt_s[q], 1)] =
+                            ((unsigned long long)(pcq - m) << VRQ_KEY_POS_BITS) | (pos0 + (__clz((int)mask) - 16));
                     } else if (mask) {
                         int slot = atomicAdd(&sm->cnt_s[q], __popc(mask));
 #pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            if ((mask >> (31 - j)) & 1u) {
+                        for (int j = 0; j < 16; j++) {
+                            if ((mask >> (15 - j)) & 1u) {
                                 my_list[slot] = ((unsigned long long)(pcq - dot_of(j)) << VRQ_KEY_POS_BITS) | (pos0 + j);
                                 slot++;
                             }
@@ -532,7 +548,8 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                 }
             }
             // ---- overflow check every group_tiles tiles: no list may exceed cap during the next group ----
-            if ((t + 1) % p.group_tiles == 0 && t + 1 < ntiles) {
+            if (--until_check == 0 && t + 1 < ntiles) {
+                until_check = p.group_tiles;
                 group_sync<EPI_THREADS>(BAR_CONSUMERS);  // every append of this group of tiles is in its list
                 if (epi_sync_or(sm->cnt_s[q] > limit)) {
                     for (int qq = warp; qq < qt; qq += EPI_WARPS) {  // one list per warp, 8 lists at a time
@@ -584,7 +601,7 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
     pl->qtiles = (nq + MQ - 1) / MQ;
     // CTA pairs need an even number of query tiles (a pair = two neighbouring tiles); VRQ_MMA_PAIR=0 switches them off
     pl->pair = pl->f4 && pl->qtiles % 2 == 0 && env_int("VRQ_MMA_PAIR", 1) != 0;
-    pl->group_tiles = env_int("VRQ_MMA_GROUP_TILES", 4);
+    pl->group_tiles = env_int("VRQ_MMA_GROUP_TILES", 8);
     if (pl->group_tiles < 1) pl->group_tiles = 1;
     const int slack = k < 256 ? 256 : (k > 2048 ? 2048 : k);
     pl->cap = k + slack + pl->group_tiles * MROWS;
