@@ -597,7 +597,11 @@ static int launch_pass(vrq_ctx* ctx, bool tma, const CUtensorMap& tmap, const CU
     if (pl.mma) {
         sp.qtile = 128;
         sp.group_tiles = pl.mp.group_tiles;
-        if (sp.tile_step == 0) sp.tile_step = MMA_TILE_ROWS;
+        if (sp.run_stride == 0) {  // dense scan of [row_begin, row_end)
+            sp.run_stride = MMA_TILE_ROWS;
+            sp.run_shift = 0;
+            sp.total_tiles = sp.row_end > sp.row_begin ? (sp.row_end - sp.row_begin + MMA_TILE_ROWS - 1) / MMA_TILE_ROWS : 0;
+        }
         return launch_scan_mma(ctx, tmap_mma[0], tmap_mma[1], sp, pl.mp, st);
     }
     sp.qtile = pl.sp.qtile;
@@ -641,9 +645,12 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
             if (sample_tiles * 16 > total_tiles || sample_tiles * MMA_TILE_ROWS < (int64_t)64 * kp) sample_tiles = 0;
         }
         if (sample_tiles > 0) {
-            const int64_t step_tiles = total_tiles / sample_tiles;
-            const int64_t tile_step = step_tiles * MMA_TILE_ROWS;
-            const int64_t actual_tiles = (n + tile_step - 1) / tile_step;
+            // the sample = runs of 16 consecutive tiles (one 32 KB stretch of codes) spread evenly over the database: single
+            // tiles 4 MB apart cost a fresh DRAM page / TLB entry per 16 KB (measured: 2.2 ms for 0.4 % of the rows)
+            const int run_shift = 4;
+            const int64_t runs = (sample_tiles + 15) / 16;
+            const int64_t run_stride = (total_tiles / runs) * MMA_TILE_ROWS;  // >= 16 tiles: runs never overlap
+            const int64_t actual_tiles = runs * 16;
             PassPlan s_pl, m_pl;
             VRQ_TRY(plan_pass(ctx, tma, true, code_bytes, actual_tiles * MMA_TILE_ROWS, nq, kp, &s_pl));
             VRQ_TRY(plan_pass(ctx, tma, true, code_bytes, n, nq, k, &m_pl));
@@ -676,14 +683,17 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
             vrq_timer_scope ts(ctx, VRQ_CAT_SCAN, st);
             // 1. sample pass: exact top-k' of the sampled tiles -> tau[q] = k'-th best distance
             sp.k = kp;
-            sp.tile_step = tile_step;
-            sp.compact_limit = kp + 256;  // thresholds start at infinity: tighten them after the first few tiles
+            sp.run_stride = run_stride;
+            sp.run_shift = run_shift;
+            sp.total_tiles = actual_tiles;
+            sp.compact_limit = kp + 256;  // thresholds start at infinity: tighten them after the first two tiles
+            s_pl.mp.group_tiles = 2;
             VRQ_TRY(launch_pass(ctx, tma, tmap, tmap_mma, sp, s_pl, st));
             sp.compact_limit = 0;
             VRQ_TRY(launch_merge(ctx, lists, counts, s_pl.strips(), nq, cap, kp, (uint64_t*)skeys_v, tau, st));
             // 2. dense pass with the inclusive threshold d <= T
             sp.k = k;
-            sp.tile_step = MMA_TILE_ROWS;
+            sp.run_stride = 0;  // dense
             sp.tau0 = tau;
             sp.tau_bias = 1;
             sp.dbg = dbg;

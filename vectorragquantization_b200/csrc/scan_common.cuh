@@ -43,7 +43,11 @@ struct ScanParams {
     const int* guard;  // nullable: the launch does nothing when *guard == 0 (fallback passes enqueued ahead of knowing they are needed)
     int compact_limit; // tensor-core kernel: compact a list once it holds more than this many keys (0 = cap - group_tiles * 128)
     int tau_bias;      // added to tau0 (1 turns a k'-th distance T of a sample into the inclusive bound "d <= T")
-    int64_t tile_step; // tensor-core kernel: rows between the starts of consecutive tiles (128 = dense scan; larger = strided sample)
+    // tensor-core kernel: tile i of the launch starts at row_begin + (i >> run_shift) * run_stride + (i & run_mask) * 128:
+    // dense scan = runs of 1 tile, stride 128; strided sample = runs of 2^run_shift consecutive tiles, run_stride rows apart
+    int64_t run_stride;
+    int run_shift;
+    int64_t total_tiles;
     int32_t* dbg;     // tests only: every (query, row) Hamming distance of the launch, [nq][dbg_stride] (tensor-core kernel)
     int64_t dbg_stride;
     int one;          // == 1, opaque to the compiler: multiplier that keeps the popcount accumulation on the FMA pipe (IMAD)
@@ -143,15 +147,25 @@ __device__ void compact_list(uint64_t* glist, int n, int k, unsigned long long* 
 __device__ __forceinline__ void compact_list_warp(uint64_t* glist, int n, int k, SelectScratch* sc, int lane, int bar_id, int* cnt_q,
                                                   int* tau_q) {
     const unsigned long long kth = radix_select_kth<32>([&](int i) { return (unsigned long long)glist[i]; }, n, k, lane, sc, bar_id);
-    // in-place stable-free compaction, 32 keys per step: step i writes below the end of the chunk it has just read
+    // in-place compaction, 128 keys per step (4 independent loads per lane): a step writes below the end of the chunk it
+    // has just read
     int out = 0;
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        const unsigned long long key = i < n ? (unsigned long long)glist[i] : ~0ull;
-        const bool keep = i < n && key <= kth;
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (keep) glist[out + __popc(m & ((1u << lane) - 1u))] = key;
-        out += __popc(m);
+    for (int base = 0; base < n; base += 128) {
+        unsigned long long key[4];
+        bool keep[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = base + 32 * u + lane;
+            key[u] = i < n ? (unsigned long long)glist[i] : ~0ull;
+            keep[u] = i < n && key[u] <= kth;
+        }
+        __syncwarp();  // the whole 128-key chunk is in registers before anything is written below its end
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned m = __ballot_sync(0xffffffffu, keep[u]);
+            if (keep[u]) glist[out + __popc(m & ((1u << lane) - 1u))] = key[u];
+            out += __popc(m);
+        }
         __syncwarp();
     }
     if (lane == 0) {

@@ -218,13 +218,16 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
     const int q0 = blockIdx.x * MQ;
     const int qt = min(MQ, p.nq - q0);
     const int strip = blockIdx.y;
-    // tiles of this launch start at row_begin + i * tile_step (tile_step == MROWS: a dense scan; larger: a strided sample
-    // of the database); a strip owns tiles_per_strip consecutive tiles
+    // a strip owns tiles_per_strip consecutive tiles of the launch (dense scan: consecutive rows; strided sample: runs of
+    // consecutive tiles spread over the database, see ScanParams)
     const int tiles_per_strip = (int)(p.rows_per_strip / MROWS);
-    const int64_t total_tiles = p.row_end > p.row_begin ? (p.row_end - p.row_begin + p.tile_step - 1) / p.tile_step : 0;
     const int64_t tile0 = (int64_t)strip * tiles_per_strip;
-    const int ntiles = (int)max((int64_t)0, min((int64_t)tiles_per_strip, total_tiles - tile0));
-    const int64_t s_begin = p.row_begin + tile0 * p.tile_step;
+    const int ntiles = (int)max((int64_t)0, min((int64_t)tiles_per_strip, p.total_tiles - tile0));
+    const int64_t run_mask = ((int64_t)1 << p.run_shift) - 1;
+    auto tile_row = [&](int t) -> int64_t {
+        const int64_t i = tile0 + t;
+        return p.row_begin + (i >> p.run_shift) * p.run_stride + (i & run_mask) * MROWS;
+    };
     const int64_t s_end = p.row_end;
     if (p.guard && *p.guard == 0) return;
 
@@ -330,7 +333,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                 mbar_wait_relaxed(smem_u32(&sm->raw_empty[s]), ph ^ 1u, 256);
                 mbar_expect_tx(smem_u32(&sm->raw_full[s]), STAGE_BYTES_RAW);
                 tma_load_2d(smem_u32(raw_mem) + s * (uint32_t)STAGE_BYTES_RAW, &tmap, 0,
-                            (int)(s_begin + (int64_t)t * p.tile_step + (int64_t)rank * MY_ROWS), smem_u32(&sm->raw_full[s]));
+                            (int)(tile_row(t) + (int64_t)rank * MY_ROWS), smem_u32(&sm->raw_full[s]));
                 if (++s == (uint32_t)raw_stages) {
                     s = 0;
                     ph ^= 1u;
@@ -473,7 +476,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
             const int as = t & 1;
             mbar_wait(smem_u32(&sm->acc_full[as]), ((uint32_t)t >> 1) & 1u);
             tc_fence_after();
-            const int64_t lrow0 = s_begin + (int64_t)t * p.tile_step + half * 64;
+            const int64_t lrow0 = tile_row(t) + half * 64;
             const int nvalid = (int)min((int64_t)64, s_end - lrow0);
             const uint32_t acc = lane_base + (uint32_t)as * MROWS;
             // 64 columns in 4 groups of 16, software-pipelined over two register sets: the tcgen05.ld of group g + 1 is

@@ -37,11 +37,17 @@ __device__ unsigned long long radix_select_kth(Load load, int n, int k, int tid,
         sc->kk = k;
     }
     group_sync<NT>(bar_id);
+    // (loads are issued four at a time: when load() reads global memory a dependent one-key-per-trip loop is pure latency)
     unsigned long long lo = ~0ull, hi = 0ull;
-    for (int i = tid; i < n; i += NT) {
-        const unsigned long long key = load(i);
-        lo = key < lo ? key : lo;
-        hi = key > hi ? key : hi;
+    for (int i = tid; i < n; i += 4 * NT) {
+        unsigned long long key[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) key[u] = (i + u * NT < n) ? load(i + u * NT) : load(i);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            lo = key[u] < lo ? key[u] : lo;
+            hi = key[u] > hi ? key[u] : hi;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -66,6 +72,7 @@ __device__ unsigned long long radix_select_kth(Load load, int n, int k, int tid,
         for (int i = tid; i < 256; i += NT) sc->hist[i] = 0;
         group_sync<NT>(bar_id);
         const unsigned long long prefix = sc->prefix, mask = sc->mask;
+#ifdef VRQ_SELECT_MATCH_ANY
         for (int i = tid; i < n_round; i += NT) {
             unsigned long long key = 0ull;
             bool ok = false;
@@ -73,14 +80,20 @@ __device__ unsigned long long radix_select_kth(Load load, int n, int k, int tid,
                 key = load(i);
                 ok = (key & mask) == prefix;
             }
-#ifdef VRQ_SELECT_MATCH_ANY
             const unsigned digit = ok ? ((unsigned)(key >> shift) & 255u) : (256u + (unsigned)lane);
             const unsigned peers = __match_any_sync(0xffffffffu, digit);
             if (ok && lane == (__ffs(peers) - 1)) atomicAdd(&sc->hist[digit], (uint32_t)__popc(peers));
-#else
-            if (ok) atomicAdd(&sc->hist[(unsigned)(key >> shift) & 255u], 1u);
-#endif
         }
+#else
+        for (int i = tid; i < n; i += 4 * NT) {
+            unsigned long long key[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) key[u] = (i + u * NT < n) ? load(i + u * NT) : ~prefix;  // ~prefix never matches
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (i + u * NT < n && (key[u] & mask) == prefix) atomicAdd(&sc->hist[(unsigned)(key[u] >> shift) & 255u], 1u);
+        }
+#endif
         group_sync<NT>(bar_id);
         if (tid < 32) {
             // 8 bins per lane, inclusive scan over lanes, locate the bin holding rank kk
