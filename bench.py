@@ -321,8 +321,10 @@ def run_gpu(args):
         bf16_burst, bf16_sust, bf16_src = bf16_peaks()
         nominal = FP4_DENSE_NOMINAL_TOPS if f4 else INT8_DENSE_NOMINAL_TOPS
         ratio = 4 if f4 else 2  # nominal rate of the operand kind relative to bf16
-        kind = ("tcgen05.mma.cta_group::1.kind::mxf4.block_scale (packed e2m1 operands, unit UE8M0 scales, f32 accumulate - exact: "
-                "every product is +-1 and |sum| <= 1024)" if f4 else "tcgen05.mma.cta_group::1.kind::i8 (int8 operands, s32 accumulate)")
+        pair = f4 and os.environ.get("VRQ_MMA_PAIR", "1") != "0"
+        kind = (f"tcgen05.mma.cta_group::{2 if pair else 1}.kind::mxf4.block_scale (packed e2m1 operands, unit UE8M0 scales, f32 "
+                "accumulate - exact: every product is +-1 and |sum| <= 1024" + ("; CTA pairs: M=256 queries, each CTA expands half of "
+                "every 128-row tile)" if pair else ")") if f4 else "tcgen05.mma.cta_group::1.kind::i8 (int8 operands, s32 accumulate)")
         roofline = {
             "kernel": f"hamming_scan_mma_kernel<{'e2m1' if f4 else 'int8'}>, dense pass: {kind}; M=128 queries resident in TMEM x N=128 "
                       "codes expanded from bits in shared memory, K=1024; 1024-query batch",
@@ -340,7 +342,7 @@ def run_gpu(args):
                     "frac": n_local * 128 * 8 / dense_s / 1e9 / hbm_peak, "peak_source": peak_src,
                     "note": "algorithmic bytes = 128 B per code per 128-query tile (8 tiles per 1024-query batch, 7 of them served by "
                             "L2: ncu dram__bytes_read ~ 13-15 GB per 102 GB requested); not the binding resource for a query batch"},
-            "integer_pipe_kernel": {"note": "scan.cu (XOR + carry-save POPC) handles <= 31 queries per pass and VRQ_SCAN_MMA=0; "
+            "integer_pipe_kernel": {"note": "scan.cu (XOR + carry-save POPC) handles <= 5 queries per pass and VRQ_SCAN_MMA=0; "
                                             "its 1024-query rate measured earlier in round 1 was 216 Gpair/s (profiles/r01)",
                                     "alu_peak_Gpair_s": alu_peak / 1e9},
             "scan_ms_per_step": scan_ms / args.steps, "rescore_ms_per_step": resc_ms / args.steps,
