@@ -124,3 +124,37 @@ def test_bulk_encode_device_path_at_scale():
     deq = q8[idx].float() * np.float32(0.3 / 127.0)
     err = (deq - x[idx].clamp(-0.3, 0.3)).abs().max().item()
     assert err <= 0.5 * 0.3 / 127.0 * 1.0001
+
+
+def test_phase1_at_full_baseline_size(monkeypatch):
+    """BASELINE.json configs[2] at its real size: 100 M x 1024-bit codes, 1024 queries, Phase-I k = 1000.  The tensor-core
+    scan (+-1 x {0,1} e2m1 contraction, CTA pairs, sampled thresholds) and the integer-pipe scan (XOR + carry-save POPC,
+    exact prefix pass) share nothing but the merge tree; they must return identical (distance, position) lists, which must
+    be sorted, duplicate-free, and carry distances that recompute from the counter-based generator."""
+    import torch
+    import vectorragquantization_b200 as V
+    if torch.cuda.mem_get_info()[0] < 40 << 30:
+        pytest.skip("needs 40 GB of free device memory")
+    n, nq, k = 100_000_000, 1024, 1000
+    ix = V.BinaryIndex(1024)
+    ix.reserve(n)
+    for off in range(0, n, 10_000_000):
+        ix.add_synthetic(1, off, 10_000_000, off)
+    qf = oc.synth_f32(2, 0, nq)
+    qb = o.synth_ubinary_from_f32(qf)
+    for kk in ("VRQ_SCAN_MMA", "VRQ_MMA_KIND", "VRQ_MMA_PAIR", "VRQ_MMA_SAFETY", "VRQ_MMA_SAMPLE_K"):
+        monkeypatch.delenv(kk, raising=False)
+    dist, lab = ix.search(qb, k)  # tensor cores
+    key = dist.astype(np.int64) << 40 | lab
+    assert np.all(np.diff(key, axis=1) > 0) and lab.min() >= 0 and lab.max() < n
+    monkeypatch.setenv("VRQ_SCAN_MMA", "0")
+    d0, l0 = ix.search(qb, k)  # integer pipes
+    assert np.array_equal(dist, d0) and np.array_equal(lab, l0)
+    monkeypatch.setenv("VRQ_SCAN_MMA", "1")
+    monkeypatch.setenv("VRQ_MMA_KIND", "8")
+    d8, l8 = ix.search(qb[:256], k)  # int8 operand kind
+    assert np.array_equal(dist[:256], d8) and np.array_equal(lab[:256], l8)
+    for qi in (0, 511, 1023):
+        rows = np.stack([oc.synth_codes_int8(1, int(p), 1, want_int8=False)[0][0] for p in lab[qi][::50]])
+        assert np.array_equal(o.hamming_distances(rows, qb[qi])[0], dist[qi][::50])
+    ix.close()
