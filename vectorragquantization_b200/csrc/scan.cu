@@ -517,12 +517,15 @@ int launch_scan(vrq_ctx* ctx, bool tma, const CUtensorMap& tmap, const ScanParam
 }
 
 // Merge tree over `strips` lists per query (each holding <= k keys, row stride cap): returns sorted keys in out.
+// list_max: upper bound of the keys one input list holds (k when the scan kernel compacted its lists; more after a
+// threshold-only pass).
 int launch_merge(vrq_ctx* ctx, const uint64_t* lists, const int* counts, int strips, int nq, int cap, int k, uint64_t* out,
-                 int* tau_out, cudaStream_t st, const int* guard = nullptr) {
+                 int* tau_out, cudaStream_t st, const int* guard = nullptr, int list_max = 0) {
     int n2 = 1;
     while (n2 < k) n2 <<= 1;
+    if (list_max < k) list_max = k;
     const size_t budget = 200 * 1024;
-    int gs = (int)((budget - sizeof(unsigned long long) * (size_t)n2) / (sizeof(unsigned long long) * (size_t)k));
+    int gs = (int)((budget - sizeof(unsigned long long) * (size_t)n2) / (sizeof(unsigned long long) * (size_t)list_max));
     if (gs > 64) gs = 64;
     if (gs < 2) {
         vrq_set_error("merge: k=%d too large for the shared-memory merge", k);
@@ -535,7 +538,7 @@ int launch_merge(vrq_ctx* ctx, const uint64_t* lists, const int* counts, int str
         const bool final_level = cur_strips <= gs;
         const int g = final_level ? 1 : (cur_strips + gs - 1) / gs;
         const int ns = final_level ? cur_strips : gs;
-        const int buf_cap = ns * k;
+        const int buf_cap = ns * (level == 0 ? list_max : k);
         const size_t smem = sizeof(unsigned long long) * ((size_t)buf_cap + (final_level ? (size_t)n2 : 0));
         VRQ_CUDA(cudaFuncSetAttribute(merge_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget + 8192)));
         uint64_t* nxt_lists = nullptr;
@@ -688,10 +691,13 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
             sp.run_shift = run_shift;
             sp.total_tiles = actual_tiles;
             sp.compact_limit = kp + 256;  // thresholds start at infinity: tighten them after the first two tiles
+            sp.sample_mode = 1;           // only tau[q] matters: distance-only compaction, lists left uncompacted
             s_pl.mp.group_tiles = 2;
             VRQ_TRY(launch_pass(ctx, tma, tmap, tmap_mma, sp, s_pl, st));
+            const int sample_list_max = sp.compact_limit + s_pl.mp.group_tiles * MMA_TILE_ROWS;
             sp.compact_limit = 0;
-            VRQ_TRY(launch_merge(ctx, lists, counts, s_pl.strips(), nq, cap, kp, (uint64_t*)skeys_v, tau, st));
+            sp.sample_mode = 0;
+            VRQ_TRY(launch_merge(ctx, lists, counts, s_pl.strips(), nq, cap, kp, (uint64_t*)skeys_v, tau, st, nullptr, sample_list_max));
             // 2. dense pass with the inclusive threshold d <= T
             sp.k = k;
             sp.run_stride = 0;  // dense

@@ -41,6 +41,8 @@ struct ScanParams {
     int* counts;      // [list_strips][nq]
     const int* tau0;  // [nq] or null
     const int* guard;  // nullable: the launch does nothing when *guard == 0 (fallback passes enqueued ahead of knowing they are needed)
+    int sample_mode;   // tensor-core kernel: only the k-th DISTANCE per query matters (threshold-only pass): lists are compacted on
+                       // the distance bits alone and leave the kernel uncompacted (<= compact_limit + group_tiles * 128 keys)
     int compact_limit; // tensor-core kernel: compact a list once it holds more than this many keys (0 = cap - group_tiles * 128)
     int tau_bias;      // added to tau0 (1 turns a k'-th distance T of a sample into the inclusive bound "d <= T")
     // tensor-core kernel: tile i of the launch starts at row_begin + (i >> run_shift) * run_stride + (i & run_mask) * 128:
@@ -144,9 +146,27 @@ __device__ void compact_list(uint64_t* glist, int n, int k, unsigned long long* 
 // One WARP keeps the k smallest keys of a list, in place in global memory (the tensor-core kernel compacts 8 lists at a
 // time, one per epilogue warp; a block-wide select per list serialises 128 lists behind ~15 barriers each).
 // bar_id: a named barrier private to the calling warp.  Keys are unique, so "key <= k-th smallest" keeps exactly k.
+// ties_ok > 0 (threshold-only passes): select on the distance bits alone (2 radix passes instead of 7) and keep every key
+// whose distance ties with the k-th one - unless that would leave more than ties_ok keys, then fall back to the exact k.
 __device__ __forceinline__ void compact_list_warp(uint64_t* glist, int n, int k, SelectScratch* sc, int lane, int bar_id, int* cnt_q,
-                                                  int* tau_q) {
-    const unsigned long long kth = radix_select_kth<32>([&](int i) { return (unsigned long long)glist[i]; }, n, k, lane, sc, bar_id);
+                                                  int* tau_q, int ties_ok = 0) {
+    unsigned long long kth = 0;
+    bool exact = ties_ok <= 0;
+    if (!exact) {
+        kth = radix_select_kth<32>([&](int i) { return (unsigned long long)glist[i]; }, n, k, lane, sc, bar_id, VRQ_KEY_POS_BITS);
+        int kept = 0;
+        for (int base = 0; base < n; base += 128) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + 32 * u + lane;
+                kept += (i < n && (unsigned long long)glist[i] <= kth) ? 1 : 0;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+        exact = kept > ties_ok;
+    }
+    if (exact) kth = radix_select_kth<32>([&](int i) { return (unsigned long long)glist[i]; }, n, k, lane, sc, bar_id);
     // in-place compaction, 128 keys per step (4 independent loads per lane): a step writes below the end of the chunk it
     // has just read
     int out = 0;

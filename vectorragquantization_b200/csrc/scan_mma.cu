@@ -559,7 +559,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                         const int n = sm->cnt_s[qq];
                         if (n > limit)
                             compact_list_warp(p.lists + ((size_t)strip * p.nq + q0 + qq) * p.cap, n, p.k, &sm->sc[warp], lane, BAR_WARP0 + warp,
-                                              &sm->cnt_s[qq], &sm->tau_s[qq]);
+                                              &sm->cnt_s[qq], &sm->tau_s[qq], p.sample_mode ? limit : 0);
                     }
                     group_sync<EPI_THREADS>(BAR_CONSUMERS);
                     if (qvalid) thr = pcq - sm->tau_s[q];
@@ -569,7 +569,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         }
         group_sync<EPI_THREADS>(BAR_CONSUMERS);
         // final compaction: every list leaves the kernel with at most k keys (bounds the merge's working set)
-        for (int qq = warp; qq < qt; qq += EPI_WARPS) {
+        for (int qq = warp; qq < qt && !p.sample_mode; qq += EPI_WARPS) {
             const int n = sm->cnt_s[qq];
             if (n > p.k)
                 compact_list_warp(p.lists + ((size_t)strip * p.nq + q0 + qq) * p.cap, n, p.k, &sm->sc[warp], lane, BAR_WARP0 + warp,

@@ -27,8 +27,10 @@ struct SelectScratch {
 //     cost nothing;
 //   * lanes that hold the same digit are merged with match.any before the shared-memory atomic, so a digit on which
 //     most keys agree (the distance byte near the threshold) does not serialise the whole block on one address.
+// min_shift > 0 stops the refinement above that bit: the result is the k-th smallest value of (key >> min_shift) with all
+// lower bits SET, i.e. "key <= result" keeps every key that ties with the k-th one in its upper bits (>= k keys).
 template <int NT, class Load>
-__device__ unsigned long long radix_select_kth(Load load, int n, int k, int tid, SelectScratch* sc, int bar_id) {
+__device__ unsigned long long radix_select_kth(Load load, int n, int k, int tid, SelectScratch* sc, int bar_id, int min_shift = 0) {
     const int lane = tid & 31;
     group_sync<NT>(bar_id);  // nobody is still reading the scratch of a previous call
     if (tid == 0) {
@@ -62,13 +64,14 @@ __device__ unsigned long long radix_select_kth(Load load, int n, int k, int tid,
     group_sync<NT>(bar_id);
     const unsigned long long diff = sc->kmin ^ sc->kmax;
     if (diff == 0ull) return sc->kmin;  // every key identical
+    if (min_shift > 0 && (diff >> min_shift) == 0ull) return sc->kmin | ((1ull << min_shift) - 1ull);  // identical upper bits
     const int top_shift = ((63 - __clzll((long long)diff)) >> 3) << 3;
     if (tid == 0) {
         sc->mask = (top_shift >= 56) ? 0ull : (~0ull << (top_shift + 8));
         sc->prefix = sc->kmin & sc->mask;
     }
     const int n_round = ((n + 31) >> 5) << 5;  // whole warps stay converged for match.any
-    for (int shift = top_shift; shift >= 0; shift -= 8) {
+    for (int shift = top_shift; shift >= min_shift; shift -= 8) {
         for (int i = tid; i < 256; i += NT) sc->hist[i] = 0;
         group_sync<NT>(bar_id);
         const unsigned long long prefix = sc->prefix, mask = sc->mask;
@@ -132,7 +135,7 @@ __device__ unsigned long long radix_select_kth(Load load, int n, int k, int tid,
         }
         group_sync<NT>(bar_id);
     }
-    return sc->prefix;
+    return min_shift > 0 ? (sc->prefix | ((1ull << min_shift) - 1ull)) : sc->prefix;
 }
 
 // In-place ascending bitonic sort of n2 (power of two) keys in shared memory, optional 32-bit payload.
