@@ -13,6 +13,8 @@ from oracle import vrq_oracle as o  # noqa: E402
 
 ENVS = {
     "default": {},
+    "int8_kind": {"VRQ_MMA_KIND": "8"},
+    "single_ctas": {"VRQ_MMA_PAIR": "0"},
     "forced_fallback": {"VRQ_MMA_SAMPLE_K": "1", "VRQ_MMA_SAFETY": "1"},  # a threshold far too tight -> verification fails
     "no_sampling": {"VRQ_MMA_SAFETY": "0"},
     "force_mma_small_batch": {"VRQ_SCAN_MMA": "2"},
@@ -27,7 +29,8 @@ def V():
 
 
 def set_env(monkeypatch, name):
-    for k in ("VRQ_MMA_SAMPLE_K", "VRQ_MMA_SAFETY", "VRQ_SCAN_MMA", "VRQ_MMA_B_STAGES", "VRQ_MMA_RAW_STAGES"):
+    for k in ("VRQ_MMA_SAMPLE_K", "VRQ_MMA_SAFETY", "VRQ_SCAN_MMA", "VRQ_MMA_RAW_STAGES", "VRQ_MMA_KIND", "VRQ_MMA_PAIR",
+              "VRQ_MMA_GROUP_TILES"):
         monkeypatch.delenv(k, raising=False)
     for k, v in ENVS[name].items():
         monkeypatch.setenv(k, v)
@@ -56,27 +59,29 @@ def test_mma_distance_matrix_exact(V, monkeypatch, n, nq):
     assert np.array_equal(d, ref_distances(q, codes))
 
 
-@pytest.mark.parametrize("stages", [("4", "1"), ("7", "2"), ("12", "4")])
-def test_mma_pipeline_depths(V, monkeypatch, stages):
-    """Ring depths (B stages, raw stages) must not change a single distance: the hazards are in the hand-offs."""
+@pytest.mark.parametrize("cfg", [("1", "4", "1"), ("2", "4", "0"), ("4", "8", "0"), ("3", "4", "1"), ("1", "8", "0")])
+def test_mma_pipeline_variants(V, monkeypatch, cfg):
+    """Raw-ring depth, operand kind (e2m1 / int8) and CTA pairs on / off must not change a single distance: the hazards
+    are in the hand-offs between TMA, expanders, MMA issuers and epilogue."""
     set_env(monkeypatch, "force_mma_small_batch")
-    monkeypatch.setenv("VRQ_MMA_B_STAGES", stages[0])
-    monkeypatch.setenv("VRQ_MMA_RAW_STAGES", stages[1])
+    monkeypatch.setenv("VRQ_MMA_RAW_STAGES", cfg[0])
+    monkeypatch.setenv("VRQ_MMA_KIND", cfg[1])
+    monkeypatch.setenv("VRQ_MMA_PAIR", cfg[2])
     rng = np.random.default_rng(7)
-    n, nq = 200000, 128
+    n, nq = 200000, 256
     codes = rng.integers(0, 256, (n, 128), dtype=np.uint8)
     q = rng.integers(0, 256, (nq, 128), dtype=np.uint8)
     ix = V.BinaryIndex(1024)
     ix.add_with_ids(codes, np.arange(n))
     d = ix.distances(q)
-    sel = [0, 1, 63, 64, 127]
+    sel = [0, 1, 63, 64, 127, 128, 200, 255]
     assert np.array_equal(d[sel], ref_distances(q[sel], codes))
 
 
-@pytest.mark.parametrize("env", ["default", "forced_fallback", "no_sampling", "integer_pipes"])
+@pytest.mark.parametrize("env", ["default", "int8_kind", "single_ctas", "forced_fallback", "no_sampling", "integer_pipes"])
 def test_mma_topk_matches_oracle_all_paths(V, monkeypatch, env):
     set_env(monkeypatch, env)
-    n, nq = 2_000_000, 300
+    n, nq = 2_000_000, 256  # two 128-query tiles: the default path runs them as one CTA pair
     codes, _ = oc.synth_codes_int8(61, 0, n, want_int8=False)
     qx = oc.synth_f32(62, 0, nq)
     q = o.synth_ubinary_from_f32(qx)
