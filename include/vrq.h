@@ -135,7 +135,10 @@ int vrq_index_search(vrq_index*, int64_t nq, const uint8_t* q, int k, int32_t* d
 int vrq_index_distances(vrq_index*, int64_t nq, const uint8_t* q, int32_t* dist);
 /* .reconstruct(id) (CohereEnhancedVectorDB.py:286); last added wins on duplicate ids; host output. */
 int vrq_index_reconstruct(vrq_index*, int64_t id, uint8_t* code_out);
-/* .remove_ids (CohereEnhancedVectorDB.py:334): order-preserving compaction; returns the number removed (>= 0). */
+/* .remove_ids (CohereEnhancedVectorDB.py:334): returns the number of rows removed (>= 0; every row carrying a listed id,
+ * as IDMap2 does).  The removal is recorded and the device arrays are compacted once - in place, order-preserving like
+ * faiss, through a 64 MB bounce buffer - before the next call that reads them, so the reference's one-id-per-call
+ * remove_document loop costs one pass instead of one O(N) pass per id.  vrq_index_ntotal reflects it immediately. */
 int64_t vrq_index_remove_ids(vrq_index*, int64_t n, const int64_t* ids);
 /* faiss.write_index_binary / read_index_binary (CohereEnhancedVectorDB.py:346,123): byte-compatible "IBM2"/"IBxF". */
 int vrq_index_write(vrq_index*, const char* path);

@@ -319,3 +319,53 @@ def test_search3_other_dim(V):
         rc = np.array([h["score_cosine"] for h in ref])
         fl = o.rescore_int8cos_absfloor(qf[qi], i8[labels[qi]])
         assert np.all(np.abs(sc[qi] - rc) <= 1e-5 * np.abs(rc) + fl)
+
+
+@pytest.mark.parametrize("explicit_ids", [False, True])
+def test_remove_ids_lazy_compaction(V, explicit_ids, tmp_path):
+    """remove_ids (CohereEnhancedVectorDB.py:334) records the rows and compacts the device arrays once, in place, before
+    the next read: many single-id removals (the reference removes one document per call) cost one pass.  Every
+    observable - ntotal, search order incl. ties, reconstruct, payload, index.bin - is what faiss's immediate
+    order-preserving compaction gives."""
+    from vectorragquantization_b200 import _lib as L
+    rng = np.random.default_rng(5)
+    n = 300_000
+    base = rng.integers(0, 256, (64, 128), dtype=np.uint8)
+    codes = base[rng.integers(0, 64, n)]  # few distinct codes: tie order across removed rows matters
+    codes[::7] = rng.integers(0, 256, (len(codes[::7]), 128), dtype=np.uint8)
+    payload = rng.integers(-128, 128, (n, 1024), dtype=np.int8)
+    ids = (np.arange(n, dtype=np.int64) if not explicit_ids else rng.permutation(n).astype(np.int64) * 5 + 1)
+    ix = V.BinaryIndex(1024, payload_kind=L.PAYLOAD_INT8_RAW)
+    ix.add_with_ids(codes, ids, payload=payload)
+    kill_pos = np.unique(np.concatenate([rng.integers(0, n, 500), [0, 1, 2, n - 1, n - 2, 77777]]))
+    removed = 0
+    for chunk in np.array_split(ids[kill_pos], 40):  # 40 calls, nothing read in between
+        removed += ix.remove_ids(chunk)
+    assert removed == len(kill_pos)
+    assert ix.remove_ids(ids[kill_pos[:10]]) == 0  # already gone
+    assert ix.ntotal == n - len(kill_pos)
+    keep = np.setdiff1d(np.arange(n), kill_pos)
+    q = np.concatenate([base[:8], codes[kill_pos[:4]], rng.integers(0, 256, (28, 128), dtype=np.uint8)])
+    for nq in (3, 40):  # integer-pipe and tensor-core scans
+        d, lab = ix.search(q[:nq], 300)
+        rd, rp = oc.hamming_topk(codes[keep], q[:nq], 300)
+        assert np.array_equal(d, rd) and np.array_equal(lab, ids[keep][rp])
+    with pytest.raises(V.VrqError):
+        ix.reconstruct(int(ids[kill_pos[3]]))
+    assert np.array_equal(ix.reconstruct(int(ids[keep[12345]])), codes[keep[12345]])
+    got = ix.get_payload(np.array([0, 1, len(keep) - 1, 4242]), np.int8, 1024)
+    got = got[0] if isinstance(got, tuple) else got
+    assert np.array_equal(got, payload[keep][[0, 1, len(keep) - 1, 4242]])
+    # remove + re-add (the dedupe path of add_documents), then the file is byte-identical to a fresh index of the same rows
+    ix.remove_ids(ids[keep[:3]])
+    ix.add_with_ids(codes[keep[:3]], ids[keep[:3]], payload=payload[keep[:3]])
+    order = np.concatenate([keep[3:], keep[:3]])
+    p = str(tmp_path / "index.bin")
+    V.write_index_binary(ix, p)
+    assert open(p, "rb").read() == o.write_index_binary_bytes(1024, codes[order], ids[order])
+    # duplicate ids: IDMap2 removes every row carrying the id
+    dup = V.BinaryIndex(1024)
+    dup.add_with_ids(codes[:10], np.array([1, 2, 3, 1, 2, 3, 1, 9, 9, 4], dtype=np.int64))
+    assert dup.remove_ids(np.array([1, 9])) == 5 and dup.ntotal == 5
+    d, lab = dup.search(codes[:1], 5)
+    assert sorted(lab[0].tolist()) == [2, 2, 3, 3, 4]

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <iterator>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -29,6 +30,10 @@ struct vrq_index {
     bool host_ids_valid = false;
     std::unordered_map<int64_t, int64_t> rev;  // id -> last position
     bool rev_valid = false;
+    // remove_ids is lazy: removed positions (sorted, unique, in the coordinates of the arrays as they are) wait here and
+    // the arrays are compacted once, in place, before the next call that reads them.  `ntotal` counts the rows in the
+    // arrays, ntotal - dead.size() is what the caller sees.
+    std::vector<int64_t> dead;
 };
 
 namespace {
@@ -148,6 +153,75 @@ int gather_rows(vrq_ctx* ctx, const uint8_t* src, const int64_t* pos_dev, int64_
     return 0;
 }
 
+// dst row (i - #dead below i) of the compacted array <- row i, for the kept rows i of [a, b); written to a bounce buffer
+// whose row 0 is compacted row `out` (an in-place forward shift cannot be done by an unordered grid).
+__global__ void compact_chunk_kernel(const uint8_t* __restrict__ src, int64_t a, int64_t b, const int64_t* __restrict__ dead, int64_t m,
+                                     int row_bytes, int64_t out, uint8_t* __restrict__ bounce) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t i = a + (int64_t)blockIdx.x * 8 + warp; i < b; i += (int64_t)gridDim.x * 8) {
+        int64_t lo = 0, hi = m;  // lower_bound(dead, i)
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (dead[mid] < i) lo = mid + 1; else hi = mid;
+        }
+        if (lo < m && dead[lo] == i) continue;
+        const uint8_t* s = src + (size_t)i * row_bytes;
+        uint8_t* o = bounce + (size_t)(i - lo - out) * row_bytes;
+        if ((row_bytes & 15) == 0) {
+            for (int w = lane; w < row_bytes / 16; w += 32) reinterpret_cast<uint4*>(o)[w] = reinterpret_cast<const uint4*>(s)[w];
+        } else if ((row_bytes & 3) == 0) {
+            for (int w = lane; w < row_bytes / 4; w += 32) reinterpret_cast<uint32_t*>(o)[w] = reinterpret_cast<const uint32_t*>(s)[w];
+        } else {
+            for (int w = lane; w < row_bytes; w += 32) o[w] = s[w];
+        }
+    }
+}
+
+// Apply the pending removals: order-preserving, in place (faiss shifts the tail down; survivors keep their relative
+// order, so the (distance, position) tie order of every later search is the one faiss would give).  Rows before the first
+// removed position do not move; the rest goes through a 64 MB bounce buffer chunk by chunk in ascending order, so no
+// second copy of a 100 GB payload is ever needed.
+int flush_dead(vrq_index* ix) {
+    if (ix->dead.empty()) return 0;
+    vrq_ctx* ctx = ix->ctx;
+    VRQ_CUDA(cudaSetDevice(ctx->device));
+    VRQ_TRY(materialise_ids(ix));
+    const int64_t m = (int64_t)ix->dead.size();
+    void* dead_dev = nullptr;
+    VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_SEARCH_B, sizeof(int64_t) * (size_t)m, &dead_dev));
+    VRQ_CUDA(cudaMemcpyAsync(dead_dev, ix->dead.data(), sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+    auto compact = [&](uint8_t* buf, size_t row) -> int {
+        if (row == 0 || !buf) return 0;
+        const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)((64u << 20) / row));
+        void* bounce = nullptr;
+        VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_STAGE_OUT0, (size_t)chunk_rows * row, &bounce));
+        for (int64_t a = ix->dead[0]; a < ix->ntotal; a += chunk_rows) {
+            const int64_t b = std::min(ix->ntotal, a + chunk_rows);
+            const int64_t dead_below_a = std::lower_bound(ix->dead.begin(), ix->dead.end(), a) - ix->dead.begin();
+            const int64_t dead_below_b = std::lower_bound(ix->dead.begin(), ix->dead.end(), b) - ix->dead.begin();
+            const int64_t out = a - dead_below_a, kept = (b - a) - (dead_below_b - dead_below_a);
+            if (kept == 0) continue;
+            const int64_t blocks = std::min<int64_t>((b - a + 7) / 8, (int64_t)ctx->sm_count * 16);
+            compact_chunk_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(buf, a, b, (const int64_t*)dead_dev, m, (int)row, out,
+                                                                            (uint8_t*)bounce);
+            vrq_count_launch(ctx);
+            VRQ_CUDA(cudaGetLastError());
+            VRQ_CUDA(cudaMemcpyAsync(buf + (size_t)out * row, bounce, (size_t)kept * row, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        return 0;
+    };
+    VRQ_TRY(compact(ix->codes, (size_t)ix->code_bytes));
+    VRQ_TRY(compact((uint8_t*)ix->ids, sizeof(int64_t)));
+    VRQ_TRY(compact(ix->payload, ix->payload_row));
+    VRQ_TRY(compact(ix->aux, ix->aux_row));
+    VRQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    ix->ntotal -= m;
+    ix->dead.clear();
+    ix->host_ids_valid = false;
+    ix->rev_valid = false;
+    return 0;
+}
+
 struct DevIO {
     // Stages host arguments of one index call into scratch, remembers host outputs to copy back.
     vrq_ctx* ctx;
@@ -213,12 +287,13 @@ extern "C" int vrq_index_free(vrq_index* ix) {
     return 0;
 }
 
-extern "C" int64_t vrq_index_ntotal(const vrq_index* ix) { return ix ? ix->ntotal : 0; }
+extern "C" int64_t vrq_index_ntotal(const vrq_index* ix) { return ix ? ix->ntotal - (int64_t)ix->dead.size() : 0; }
 extern "C" int vrq_index_d(const vrq_index* ix) { return ix ? ix->d : 0; }
 extern "C" int vrq_index_payload_kind(const vrq_index* ix) { return ix ? ix->payload_kind : 0; }
 
 extern "C" int vrq_index_device_ptrs(vrq_index* ix, void** codes, void** ids, void** payload, void** aux) {
     VRQ_CHECK_ARG(ix != nullptr, "index is null");
+    VRQ_TRY(flush_dead(ix));
     if (codes) *codes = ix->codes;
     if (ids) *ids = ix->ids;
     if (payload) *payload = ix->payload;
@@ -256,6 +331,7 @@ extern "C" int vrq_index_set_payload(vrq_index* ix, int kind, double global_limi
 extern "C" int vrq_index_add_with_ids(vrq_index* ix, int64_t n, const uint8_t* codes, const int64_t* ids, const void* payload,
                                       const void* aux) {
     VRQ_CHECK_ARG(ix != nullptr && n >= 0, "bad argument");
+    if (ix) VRQ_TRY(flush_dead(ix));
     if (n == 0) return 0;
     VRQ_CHECK_ARG(codes != nullptr && ids != nullptr, "codes / ids are null");
     VRQ_CHECK_ARG((ix->payload_row == 0) == (payload == nullptr), "payload must be given exactly when a payload kind is set");
@@ -282,6 +358,7 @@ extern "C" int vrq_index_add_with_ids(vrq_index* ix, int64_t n, const uint8_t* c
 
 extern "C" int vrq_index_add_synthetic(vrq_index* ix, uint64_t seed, int64_t row0, int64_t nrows, int64_t id0) {
     VRQ_CHECK_ARG(ix != nullptr && nrows >= 0, "bad argument");
+    if (ix) VRQ_TRY(flush_dead(ix));
     if (ix->payload_kind != VRQ_PAYLOAD_NONE && ix->payload_kind != VRQ_PAYLOAD_INT8_RAW) {
         vrq_set_error("add_synthetic fills codes (+ INT8_RAW payload) only");
         return VRQ_ERR_STATE;
@@ -307,6 +384,7 @@ extern "C" int vrq_index_add_synthetic(vrq_index* ix, uint64_t seed, int64_t row
 
 extern "C" int vrq_index_search(vrq_index* ix, int64_t nq, const uint8_t* q, int k, int32_t* dist, int64_t* labels) {
     VRQ_CHECK_ARG(ix != nullptr && nq >= 0, "bad argument");
+    VRQ_TRY(flush_dead(ix));
     if (nq == 0) return 0;
     VRQ_CHECK_ARG(q != nullptr && dist != nullptr && labels != nullptr, "null pointer");
     VRQ_CHECK_ARG(k > 0, "k must be > 0");
@@ -330,6 +408,7 @@ extern "C" int vrq_index_search(vrq_index* ix, int64_t nq, const uint8_t* q, int
 
 extern "C" int vrq_index_distances(vrq_index* ix, int64_t nq, const uint8_t* q, int32_t* dist) {
     VRQ_CHECK_ARG(ix != nullptr && nq >= 0, "bad argument");
+    VRQ_TRY(flush_dead(ix));
     if (nq == 0 || ix->ntotal == 0) return 0;
     VRQ_CHECK_ARG(q != nullptr && dist != nullptr, "null pointer");
     const void* all[2] = {q, dist};
@@ -350,6 +429,7 @@ extern "C" int vrq_index_distances(vrq_index* ix, int64_t nq, const uint8_t* q, 
 
 extern "C" int64_t vrq_index_position_of(vrq_index* ix, int64_t id) {
     if (!ix) return -1;
+    if (flush_dead(ix) != 0) return -1;
     if (ix->implicit_ids) return (id >= ix->id0 && id < ix->id0 + ix->ntotal) ? id - ix->id0 : -1;
     if (build_rev(ix) != 0) return -1;
     auto it = ix->rev.find(id);
@@ -371,6 +451,7 @@ extern "C" int vrq_index_reconstruct(vrq_index* ix, int64_t id, uint8_t* code_ou
 
 extern "C" int vrq_index_get_payload(vrq_index* ix, int64_t m, const int64_t* positions, void* payload_out, void* aux_out) {
     VRQ_CHECK_ARG(ix != nullptr && m >= 0, "bad argument");
+    if (ix) VRQ_TRY(flush_dead(ix));
     if (m == 0) return 0;
     VRQ_CHECK_ARG(positions != nullptr, "positions is null");
     if (ix->payload_kind == VRQ_PAYLOAD_NONE) {
@@ -411,47 +492,33 @@ extern "C" int64_t vrq_index_remove_ids(vrq_index* ix, int64_t n, const int64_t*
     } else {
         memcpy(hids.data(), ids, sizeof(int64_t) * (size_t)n);
     }
-    if (load_host_ids(ix) != 0) return VRQ_ERR_STATE;
-    std::unordered_set<int64_t> kill(hids.begin(), hids.end());
-    std::vector<int64_t> keep;
-    keep.reserve((size_t)ix->ntotal);
-    for (int64_t i = 0; i < ix->ntotal; i++)
-        if (!kill.count(ix->host_ids[(size_t)i])) keep.push_back(i);
-    const int64_t removed = ix->ntotal - (int64_t)keep.size();
-    if (removed == 0) return 0;
-    if (materialise_ids(ix) != 0) return VRQ_ERR_STATE;
-    const int64_t m = (int64_t)keep.size();
-    // order-preserving compaction (faiss shifts the tail down; ids keep their relative order)
-    void* kp = nullptr;
-    if (m > 0) {
-        if (vrq_ws_get(ctx, VRQ_WS_SEARCH_B, sizeof(int64_t) * (size_t)m, &kp) != 0) return VRQ_ERR_NOMEM;
-        if (cudaMemcpyAsync(kp, keep.data(), sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return VRQ_ERR_STATE;
+    // positions (in the coordinates of the arrays as they are now) of every row whose id is listed
+    std::vector<int64_t> pos;
+    if (ix->implicit_ids) {
+        for (int64_t id : hids)
+            if (id >= ix->id0 && id < ix->id0 + ix->ntotal) pos.push_back(id - ix->id0);
+    } else {
+        // explicit ids may repeat (IDMap2 keeps duplicates and removes all of them): scan the id column on the host
+        if (load_host_ids(ix) != 0) return VRQ_ERR_STATE;
+        std::unordered_set<int64_t> kill(hids.begin(), hids.end());
+        for (int64_t i = 0; i < ix->ntotal; i++)
+            if (kill.count(ix->host_ids[(size_t)i])) pos.push_back(i);
     }
-    auto compact = [&](uint8_t** buf, size_t row) -> int {
-        if (row == 0 || !*buf) return 0;
-        uint8_t* nb = nullptr;
-        if (cudaMalloc((void**)&nb, row * (size_t)std::max<int64_t>(ix->capacity, 1)) != cudaSuccess) return VRQ_ERR_NOMEM;
-        int r = gather_rows(ctx, *buf, (const int64_t*)kp, m, row, nb, ctx->stream);
-        if (r != 0) return r;
-        cudaStreamSynchronize(ctx->stream);
-        cudaFree(*buf);
-        *buf = nb;
-        return 0;
-    };
-    if (compact(&ix->codes, (size_t)ix->code_bytes) != 0) return VRQ_ERR_NOMEM;
-    if (compact((uint8_t**)&ix->ids, sizeof(int64_t)) != 0) return VRQ_ERR_NOMEM;
-    if (compact(&ix->payload, ix->payload_row) != 0) return VRQ_ERR_NOMEM;
-    if (compact(&ix->aux, ix->aux_row) != 0) return VRQ_ERR_NOMEM;
-    cudaStreamSynchronize(ctx->stream);
-    ix->ntotal = m;
-    ix->host_ids_valid = false;
-    ix->rev_valid = false;
+    std::sort(pos.begin(), pos.end());
+    pos.erase(std::unique(pos.begin(), pos.end()), pos.end());
+    std::vector<int64_t> merged;
+    merged.reserve(ix->dead.size() + pos.size());
+    std::set_union(ix->dead.begin(), ix->dead.end(), pos.begin(), pos.end(), std::back_inserter(merged));
+    const int64_t removed = (int64_t)merged.size() - (int64_t)ix->dead.size();
+    ix->dead.swap(merged);
+    ix->rev_valid = false;  // position_of / reconstruct must not find the removed rows
     return removed;
 }
 
 // ---- faiss file format ("IBM2" wrapping "IBxF"), SURVEY App. B.1 ----------------------------------------------------
 extern "C" int vrq_index_write(vrq_index* ix, const char* path) {
     VRQ_CHECK_ARG(ix != nullptr && path != nullptr, "null argument");
+    VRQ_TRY(flush_dead(ix));
     VRQ_CUDA(cudaSetDevice(ix->ctx->device));
     FILE* f = fopen(path, "wb");
     if (!f) {
@@ -571,6 +638,7 @@ extern "C" int vrq_index_search3_local(vrq_index* ix, int64_t nq, const float* q
                                        int64_t pos_base, uint64_t* keys, int64_t* labels, double* score_binary,
                                        double* score_cosine) {
     VRQ_CHECK_ARG(ix && q_float && q_ubin && keys && labels && score_binary && score_cosine, "null argument");
+    if (ix) VRQ_TRY(flush_dead(ix));
     VRQ_CHECK_ARG(nq >= 0 && binary_k > 0, "bad sizes");
     if (ix->payload_kind != VRQ_PAYLOAD_INT8_RAW) {
         vrq_set_error("search3 needs an index with the INT8_RAW payload (CohereEnhancedVectorDB layout)");
@@ -593,6 +661,7 @@ extern "C" int vrq_index_search3(vrq_index* ix, int64_t nq, const float* q_float
                                  int binary_oversample, int int8_oversample, int64_t* labels, int32_t* hamming,
                                  double* score_binary, double* score_cosine, int32_t* out_count) {
     VRQ_CHECK_ARG(ix && q_float && q_ubin && labels && hamming && score_binary && score_cosine && out_count, "null argument");
+    VRQ_TRY(flush_dead(ix));
     VRQ_CHECK_ARG(nq >= 0 && k > 0 && binary_oversample > 0 && int8_oversample > 0, "bad sizes");
     if (nq == 0) return 0;
     const void* all[7] = {q_float, q_ubin, labels, hamming, score_binary, score_cosine, out_count};
@@ -639,6 +708,7 @@ extern "C" int vrq_index_search3(vrq_index* ix, int64_t nq, const float* q_float
 extern "C" int vrq_index_search2(vrq_index* ix, int64_t nq, const float* q_float, const uint8_t* q_ubin, int k,
                                  int binary_oversample, int64_t* labels, float* score, int32_t* out_count) {
     VRQ_CHECK_ARG(ix && q_float && q_ubin && labels && score && out_count, "null argument");
+    VRQ_TRY(flush_dead(ix));
     VRQ_CHECK_ARG(nq >= 0 && k > 0 && binary_oversample > 0, "bad sizes");
     if (ix->payload_kind == VRQ_PAYLOAD_NONE || ix->payload_kind == VRQ_PAYLOAD_INT8_RAW) {
         vrq_set_error("search2 needs a quantised (or float32) payload");
