@@ -1,23 +1,31 @@
 // Phase I for query batches on the 5th-generation tensor cores (tcgen05, sm_100a): the same exact Hamming top-k as
 // scan.cu (faiss IndexBinaryFlat::search, CohereEnhancedVectorDB.py:268 / VectorDBInt8.py:218), with the
-// (query, code) bit contraction done by tcgen05.mma.kind::i8 instead of XOR + POPC on the integer pipes.
+// (query, code) bit contraction done by tcgen05.mma instead of XOR + POPC on the integer pipes.
 //
-// Arithmetic (exact, int32 accumulation):  with database bits c_k in {0, 1} and query bits mapped to s_k in {+1, -1}
+// Arithmetic (exact):  with database bits c_k in {0, 1} and query bits mapped to s_k in {+1, -1}
 //     dot(q, c) = sum_k s_k c_k = #(c=1, q=1) - #(c=1, q=0)      and      hamming(q, c) = popc(q) - dot(q, c)
-// so "hamming < tau" is "dot > popc(q) - tau", one integer compare per accumulator element.
+// so "hamming < tau" is "dot > popc(q) - tau", one compare per accumulator element.  Two operand kinds: packed e2m1
+// under kind::mxf4 with unit block scales (default; f32 accumulation of +-1 products, |sum| <= 1024: exact) and int8
+// under kind::i8 (s32 accumulation).
 //
-// Kernel (one CTA per SM, grid = query tiles x row strips; a CTA walks its strip in ascending row order):
-//   * A operand = 128 queries x 1024 (+-1 int8), written ONCE into tensor memory (256 TMEM columns) with tcgen05.st
-//     and read from there by every MMA (the ".ts" form): shared-memory bandwidth is left to the B operand.
-//   * B operand = 128 database rows x 1024 {0,1} int8, never materialised in HBM: a producer warp TMA-loads the raw
-//     128-byte codes (16 KB per tile), eight expander warps blow each 16 code bytes up to one 128-byte K-block row
-//     ((w >> t) & 0x01010101 - the bit -> byte permutation inside a K-block is arbitrary as long as the query side
-//     uses the same one) and store it with the 128-byte swizzle the UMMA shared-memory descriptor expects.
-//   * One thread issues 32 MMAs (M=128, N=128, K=32) per tile into one of two 128-column TMEM accumulators.
-//   * Four epilogue warps read the accumulator with tcgen05.ld (lane = query, 32 columns = 32 database rows per
-//     load), take the maximum of the 32 dots and compare it with the query's threshold held in a register; only
-//     when a group holds a survivor are the 32 values looked at individually and appended to the (strip, query)
-//     list.  Lists, thresholds, compaction and the merge tree are exactly those of scan.cu.
+// Kernel (one CTA per SM, grid = query tiles x row strips; a CTA walks its strip in ascending row order; with the e2m1
+// kind two neighbouring query tiles form a CTA pair - cta_group::2 - and share every tile of database rows):
+//   * A operand = the CTA's 128 queries, written ONCE into tensor memory with tcgen05.st and read from there by every
+//     MMA (the ".ts" form): shared-memory bandwidth is left to the B operand.
+//   * B operand = 128 database rows per tile, never materialised in HBM: a producer warp TMA-loads the raw 128-byte codes
+//     (the CTA's half of the tile when paired), eight expander warps turn each K-block of code bits into one 128-byte
+//     operand row (w & mask planes - the bit -> element permutation inside a K-block is arbitrary as long as the query
+//     side uses the same one) and store it with the 128-byte swizzle the UMMA shared-memory descriptor expects, into an
+//     8-stage ring of K-block stages.
+//   * Two issuer warps (one elected lane each; the leader CTA of a pair) issue 4 MMAs per K-block into one of two
+//     128-column TMEM accumulators; tcgen05.commit frees the stage / publishes the accumulator (multicast to both CTAs).
+//   * Eight epilogue warps read the accumulator with software-pipelined tcgen05.ld (lane = query, 16 columns = 16
+//     database rows per load), take the maximum of the 16 dots and compare it with the query's threshold held in a
+//     register; only when a group holds a survivor are the values looked at individually and appended to the
+//     (strip, query) list.  Lists, thresholds and the merge tree are those of scan.cu; overflowing lists are compacted in
+//     place by one warp per list.
+// Host side (scan.cu: topk_batch): thresholds come from a strided sample pass of this kernel, one dense pass collects the
+// candidates, a verification kernel un-gates an exact fallback pass if a query came up short.  DESIGN.md section 3.2.1.
 #include "scan_common.cuh"
 
 namespace vrq {
@@ -32,9 +40,7 @@ constexpr int MROWS = 128;   // database rows per tile (MMA N)
 constexpr int KIND_I8 = 8, KIND_F4 = 4;
 template <int KIND>
 struct KindCfg {
-    static constexpr int KBLOCKS = KIND == KIND_I8 ? 8 : 4;         // shared-memory stages per 128-row tile
-    static constexpr int CODE_BYTES_PER_KBLOCK = KIND == KIND_I8 ? 16 : 32;
-    static constexpr uint32_t A_COLS = KIND == KIND_I8 ? 256 : 128;  // TMEM columns of the query operand
+    static constexpr int KBLOCKS = KIND == KIND_I8 ? 8 : 4;  // shared-memory stages per 128-row tile
 };
 constexpr int STAGE_BYTES_B = MROWS * 128;
 constexpr int STAGE_BYTES_RAW = MROWS * CODE_BYTES;
@@ -48,13 +54,14 @@ constexpr uint32_t TMEM_SFA_COL = 128, TMEM_SFB_COL = 160, TMEM_SF_COLS = 32;  /
 constexpr int B_STAGES = 8, MAX_RAW_STAGES = 4;
 constexpr int BAR_WARP0 = 2;  // named barriers 2..9: one per epilogue warp (list compaction)
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = signed 8 bit, both K-major, N = 128, M = 128
+// instruction descriptor (bit layout of cute::UMMA::InstrDescriptor): D = s32 (bits 4-5 = 2), A = B = signed 8 bit (bits
+// 7-9, 10-12 = 1), both K-major, N >> 3 in bits 17-22, M >> 4 in bits 24-28
 constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MROWS >> 3) << 17) | ((uint32_t)(MQ >> 4) << 24);
 // block-scaled descriptor (cute::UMMA::InstrDescriptorBlockScaled): A = B = e2m1 (MXF4 format 1), K-major, scale format
 // UE8M0 (bit 23), scale-factor ids 0, N = 128, M = 128, K = 64 (bit 31 = 0); D is always f32
+constexpr uint32_t IDESC_F4 = (1u << 7) | (1u << 10) | ((uint32_t)(MROWS >> 3) << 17) | (1u << 23) | ((uint32_t)(MQ >> 4) << 24);
 // the same for a CTA pair: M = 256 (128 queries in each CTA's TMEM), N = 128 (64 database rows in each CTA's shared memory)
 constexpr uint32_t IDESC_F4_PAIR = (1u << 7) | (1u << 10) | ((uint32_t)(MROWS >> 3) << 17) | (1u << 23) | ((uint32_t)(256 >> 4) << 24);
-constexpr uint32_t IDESC_F4 = (1u << 7) | (1u << 10) | ((uint32_t)(MROWS >> 3) << 17) | (1u << 23) | ((uint32_t)(MQ >> 4) << 24);
 
 // ---- tcgen05 wrappers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
