@@ -479,13 +479,36 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + TMEM_D_COL + (uint32_t)(half * 64);
         const int limit = p.compact_limit > 0 ? min(p.compact_limit, p.cap - p.group_tiles * MROWS) : p.cap - p.group_tiles * MROWS;
         int until_check = p.group_tiles;
+        int64_t cur_row = tile_row(0) + half * 64;
+        int in_run = (int)(tile0 & run_mask);
         for (int t = 0; t < ntiles; t++) {
             const int as = t & 1;
             mbar_wait(smem_u32(&sm->acc_full[as]), ((uint32_t)t >> 1) & 1u);
             tc_fence_after();
-            const int64_t lrow0 = tile_row(t) + half * 64;
-            const int nvalid = (int)min((int64_t)64, s_end - lrow0);
+            const int64_t lrow0 = cur_row;  // first database row of this warp's 64 columns
+            const int64_t left = s_end - lrow0;
+            const int nvalid = left >= 64 ? 64 : (int)max(left, (int64_t)0);
+            // advance the tile cursor (dense scan: +128 rows; strided sample: +128 inside a run, a jump at its end)
+            if (++in_run > (int)run_mask) {
+                in_run = 0;
+                cur_row += p.run_stride - run_mask * MROWS;
+            } else {
+                cur_row += MROWS;
+            }
             const uint32_t acc = lane_base + (uint32_t)as * MROWS;
+            if (p.dbg) {
+                // tests only: every distance of the tile (a second, unpipelined read of the accumulator)
+                for (int g = 0; g < 4; g++) {
+                    int w[16];
+                    __syncwarp();
+                    tmem_ld16(acc + 16 * g, w);
+                    tmem_wait_ld();
+                    if (qvalid)
+                        for (int j = 0; j < 16; j++)
+                            if (16 * g + j < nvalid)
+                                p.dbg[(size_t)(q0 + q) * p.dbg_stride + (lrow0 + 16 * g + j)] = pcq - (F4 ? (int)__int_as_float(w[j]) : w[j]);
+                }
+            }
             // 64 columns in 4 groups of 16, software-pipelined over two register sets: the tcgen05.ld of group g + 1 is
             // in flight while group g is examined; the accumulator goes back to the MMA issuer as soon as the last
             // group has landed.
@@ -511,11 +534,6 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                 const int nv = nvalid - 16 * g;  // valid columns in this group (>= 16: all)
                 // F4 accumulates in f32: the dots are integers of magnitude <= 1024, exact in binary32
                 auto dot_of = [&](int j) -> int { return F4 ? (int)__int_as_float(w[j]) : w[j]; };
-                if (p.dbg) {
-                    if (qvalid)
-                        for (int j = 0; j < 16; j++)
-                            if (j < nv) p.dbg[(size_t)(q0 + q) * p.dbg_stride + (lrow0 + 16 * g + j)] = pcq - dot_of(j);
-                }
                 bool any;
                 int m;
                 if constexpr (F4) {
