@@ -432,11 +432,12 @@ def hbm_bound_kernels(torch, ctx, lib, L, index, qb_d, dev, stream, hbm_peak, pe
         s3 = timed(lambda: L.check(lib.vrq_rescore_int8cos(h, pay_p, n_local, D, L.ptr(pos5), nq5, m5, L.ptr(qf5), L.ptr(sc5))), 5)
         s2 = timed(lambda: L.check(lib.vrq_rescore_binary(h, codes_p, n_local, D, L.ptr(pos5), nq5, m5, L.ptr(qf5), L.ptr(sc5))), 5)
         gb3 = nq5 * m5 * 1024 / s3 / 1e9
-        out["roofline_rescore_int8cos"] = {"kernel": "rescore_int8cos_kernel<d=1024> (CUDA-core path, float64 accumulation)",
+        out["roofline_rescore_int8cos"] = {"kernel": "rescore_int8cos_async_kernel<d=1024> (CUDA-core path, float64 accumulation, cp.async shared-memory ring: 128 KB in flight per SM)",
                                            "workload": "cfg5: 4096 queries x 1000 gathered int8 candidates, random positions over the resident rows",
                                            "bound": "hbm", "unit": "GB/s", "achieved": gb3, "peak": hbm_peak, "frac": gb3 / hbm_peak,
                                            "peak_source": peak_src, "ms": s3 * 1e3, "traffic": None,
                                            "pairs_per_s": nq5 * m5 / s3,
+                                           "gather_roofline": "random 1 KB rows stream at 6.8 TB/s with >= 128 KB in flight per SM (profiles/microbench/gather_bench_r01.txt)",
                                            "imma_path": "not built: 1 KB gathered per (query, candidate) with no operand reuse, so the kernel is "
                                                         "bound by the gather; tensor cores have nothing to amortise (DESIGN.md 3.3)"}
         out["rescore_binary_cfg5"] = {"ms": s2 * 1e3, "pairs_per_s": nq5 * m5 / s2, "GB/s": nq5 * m5 * 128 / s2 / 1e9}

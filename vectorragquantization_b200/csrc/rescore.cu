@@ -5,6 +5,7 @@
 // Every sort here reproduces a STABLE descending list.sort: the sort key is (score descending, previous rank
 // ascending), which is a total order, so the result is unique and equals the stable sort.
 #include <math.h>
+#include <stdlib.h>
 
 #include "topk_utils.cuh"
 #include "vrq_internal.cuh"
@@ -264,6 +265,94 @@ __global__ void __launch_bounds__(256, 2) rescore_int8cos_kernel(const int8_t* _
             for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(FULL, n2, o);
             if (lane == 0) score[idx] = (n2 == 0) ? -INFINITY : (acc - offset) / sqrt((double)n2);
         }
+    }
+}
+
+// ---- Phase III, d == 1024, rows in flight parked in shared memory ---------------------------------------------------
+// Random 1 KB rows stream at the full HBM rate only with >= 128 KB in flight per SM (profiles/microbench/
+// gather_bench_r01.txt: 6.8 TB/s; 4.4 TB/s at 64 KB).  The register ring of the kernel above holds 64 KB per SM and cannot
+// grow (the float64 query slice takes 64 registers).  Here every lane parks its own 2 x 16 bytes of each row in shared
+// memory with cp.async (LDGSTS) - a ring of P3_RING rows per warp, 8 KB - and reads back exactly the bytes it copied, so
+// the ring needs no barrier at all: cp.async.wait_group orders a lane's own copies.  Same arithmetic as above.
+constexpr int P3_RING = 8;
+
+__global__ void __launch_bounds__(256, 2) rescore_int8cos_async_kernel(const int8_t* __restrict__ rows, const uint64_t* __restrict__ keys,
+                                                                       const int64_t* __restrict__ pos, int64_t pos_base, int m,
+                                                                       const float* __restrict__ qf, double* __restrict__ score) {
+    extern __shared__ __align__(16) uint8_t p3_ring[];  // [8 warps][P3_RING][2][32 lanes][16 bytes]
+    const int q = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t my_slot0 = (uint32_t)__cvta_generic_to_shared(p3_ring) + (uint32_t)(warp * P3_RING * 1024 + lane * 16);
+    double qr[32];
+    double qsum = 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const float f = qf[(size_t)q * 1024 + 512 * h + 16 * lane + e];
+            asm volatile("cvt.f64.f32 %0, %1;" : "=d"(qr[16 * h + e]) : "f"(f));
+            qsum += qr[16 * h + e];
+        }
+    qsum = warp_sum_f64(qsum);
+    const double offset = 4224.0 * qsum;  // sum_i q_i * (4096 + 128)
+    const int step = gridDim.x * 8, first = blockIdx.x * 8 + warp;
+    const int ncand = first < m ? (m - first + step - 1) / step : 0;
+    for (int c0 = 0; c0 < ncand; c0 += 32) {
+        const int nchunk = min(32, ncand - c0);
+        const size_t myidx = (size_t)q * m + first + (size_t)(c0 + lane) * step;
+        const int64_t myrow = (lane < nchunk) ? cand_row(keys, pos, myidx, pos_base) : -1;
+        double my_acc = 0.0;
+        int my_n2 = 0;
+        auto issue = [&](int j) {  // park row j of this chunk in ring slot j % P3_RING (one commit group per row, even if empty)
+            const int64_t r = __shfl_sync(FULL, myrow, j & 31);
+            if (j < nchunk && r >= 0) {
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(rows) + (size_t)r * 1024 + lane * 16;
+                const uint32_t dst = my_slot0 + (uint32_t)((j % P3_RING) * 1024);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512), "l"(src + 512) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+#pragma unroll
+        for (int j = 0; j < P3_RING; j++) issue(j);
+#pragma unroll 1
+        for (int j = 0; j < nchunk; j++) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(P3_RING - 1) : "memory");
+            const int64_t row = __shfl_sync(FULL, myrow, j);
+            const uint32_t src = my_slot0 + (uint32_t)((j % P3_RING) * 1024);
+            uint4 v0, v1;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v0.x), "=r"(v0.y), "=r"(v0.z), "=r"(v0.w) : "r"(src) : "memory");
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v1.x), "=r"(v1.y), "=r"(v1.z), "=r"(v1.w) : "r"(src + 512) : "memory");
+            if (row >= 0) {
+                double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+                int n2 = 0;
+                const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w}, w1[4] = {v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    n2 = __dp4a((int)w0[c], (int)w0[c], n2);
+                    n2 = __dp4a((int)w1[c], (int)w1[c], n2);
+                    const uint32_t u0 = w0[c] ^ 0x80808080u, u1 = w1[c] ^ 0x80808080u;  // bytes + 128, unsigned
+#pragma unroll
+                    for (int b = 0; b < 4; b += 2) {
+                        acc0 = fma(qr[4 * c + b], __hiloint2double((int)__byte_perm(0x40B00000u, u0, 0x3200 | ((4 + b) << 4)), 0), acc0);
+                        acc1 = fma(qr[16 + 4 * c + b], __hiloint2double((int)__byte_perm(0x40B00000u, u1, 0x3200 | ((4 + b) << 4)), 0), acc1);
+                        acc2 = fma(qr[4 * c + b + 1], __hiloint2double((int)__byte_perm(0x40B00000u, u0, 0x3200 | ((5 + b) << 4)), 0), acc2);
+                        acc3 = fma(qr[16 + 4 * c + b + 1], __hiloint2double((int)__byte_perm(0x40B00000u, u1, 0x3200 | ((5 + b) << 4)), 0), acc3);
+                    }
+                }
+                const double acc = warp_sum_f64((acc0 + acc1) + (acc2 + acc3));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(FULL, n2, o);
+                if (lane == j) {
+                    my_acc = acc;
+                    my_n2 = n2;
+                }
+            }
+            issue(j + P3_RING);  // the slot just read is free again (this lane's own reads are complete: v0 / v1 were consumed)
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (lane < nchunk)
+            score[myidx] = (myrow < 0 || my_n2 == 0) ? -INFINITY : (my_acc - offset) / sqrt((double)my_n2);
     }
 }
 
@@ -533,7 +622,12 @@ int vrq_launch_rescore_int8cos(vrq_ctx* ctx, const int8_t* rows, int d, const ui
     }
     vrq_timer_scope ts(ctx, VRQ_CAT_RESCORE, st);
     dim3 grid(grid_x_for(ctx, nq, m), (unsigned)nq);
-    if (d == 1024)
+    static const bool use_async = !(getenv("VRQ_RESCORE_ASYNC") && atoi(getenv("VRQ_RESCORE_ASYNC")) == 0);
+    if (d == 1024 && use_async) {
+        const size_t smem = (size_t)8 * P3_RING * 1024;
+        VRQ_CUDA(cudaFuncSetAttribute(rescore_int8cos_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rescore_int8cos_async_kernel<<<grid, 256, smem, st>>>(rows, keys, pos, pos_base, m, qf, score);
+    } else if (d == 1024)
         rescore_int8cos_kernel<true><<<grid, 256, 0, st>>>(rows, d, keys, pos, pos_base, m, qf, score);
     else
         rescore_int8cos_kernel<false><<<grid, 256, sizeof(double) * d, st>>>(rows, d, keys, pos, pos_base, m, qf, score);
