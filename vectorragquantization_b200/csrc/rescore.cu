@@ -91,23 +91,30 @@ __global__ void __launch_bounds__(256, 2) rescore_binary1024_kernel(const uint8_
         qhi[e + 2] = __double2hiint(d2), qlo[e + 2] = __double2loint(d2);
         qhi[e + 3] = __double2hiint(d3), qlo[e + 3] = __double2loint(d3);
     }
-    constexpr int U = 4;  // candidates in flight per warp (16 measured slower: 1.82 vs 1.56 ms on BASELINE config 5)
-    const int step = gridDim.x * 8;
-    for (int i0 = blockIdx.x * 8 + warp; i0 < m; i0 += U * step) {
-        uint32_t nw[U];
-        uint32_t okmask = 0;
+    // Candidates are processed in chunks of 32 per warp: lane j fetches the position of candidate j (one load per
+    // chunk), the code words of candidates j .. j + 7 are in flight in a register ring (one register per slot), and lane j
+    // keeps the score of candidate j so that the chunk's 32 scores leave in one store.
+    constexpr int R = 8;
+    const int step = gridDim.x * 8, first = blockIdx.x * 8 + warp;
+    const int ncand = first < m ? (m - first + step - 1) / step : 0;
+    for (int c0 = 0; c0 < ncand; c0 += 32) {
+        const int nchunk = min(32, ncand - c0);
+        const size_t myidx = (size_t)q * m + first + (size_t)(c0 + lane) * step;
+        const int64_t myrow = (lane < nchunk) ? cand_row(keys, pos, myidx, pos_base) : -1;
+        double my_acc = 0.0;
+        uint32_t ring[R];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int i = i0 + u * step;
-            int64_t row = -1;
-            if (i < m) row = cand_row(keys, pos, (size_t)q * m + i, pos_base);
-            okmask |= (row >= 0 ? 1u : 0u) << u;
-            nw[u] = row >= 0 ? ~__ldg(reinterpret_cast<const uint32_t*>(codes + (size_t)row * 128) + lane) : 0u;
+        for (int p = 0; p < R; p++) {
+            const int64_t r = __shfl_sync(FULL, myrow, p);
+            ring[p] = (p < nchunk && r >= 0) ? ~__ldg(reinterpret_cast<const uint32_t*>(codes + (size_t)r * 128) + lane) : 0u;
         }
+#pragma unroll 1
+        for (int j = 0; j < nchunk; j++) {
+            const uint32_t nw = ring[0];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int i = i0 + u * step;
-            if (i >= m) break;
+            for (int p = 0; p < R - 1; p++) ring[p] = ring[p + 1];
+            const int64_t rn = __shfl_sync(FULL, myrow, (j + R) & 31);
+            ring[R - 1] = (j + R < nchunk && rn >= 0) ? ~__ldg(reinterpret_cast<const uint32_t*>(codes + (size_t)rn * 128) + lane) : 0u;
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
             for (int b = 0; b < 32; b += 4) {
@@ -115,7 +122,7 @@ __global__ void __launch_bounds__(256, 2) rescore_binary1024_kernel(const uint8_
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
                     const int bit = b + t, e = 8 * (bit >> 3) + 7 - (bit & 7);
-                    const int hi = qhi[e] ^ (int)((nw[u] << (31 - bit)) & 0x80000000u);
+                    const int hi = qhi[e] ^ (int)((nw << (31 - bit)) & 0x80000000u);
                     const double v = __hiloint2double(hi, qlo[e]);
                     if (t == 0) a0 += v;
                     if (t == 1) a1 += v;
@@ -124,8 +131,9 @@ __global__ void __launch_bounds__(256, 2) rescore_binary1024_kernel(const uint8_
                 }
             }
             const double acc = warp_sum_f64((a0 + a1) + (a2 + a3));
-            if (lane == 0) score[(size_t)q * m + i] = ((okmask >> u) & 1u) ? acc : -INFINITY;
+            if (lane == j) my_acc = acc;
         }
+        if (lane < nchunk) score[myidx] = myrow < 0 ? -INFINITY : my_acc;
     }
 }
 
