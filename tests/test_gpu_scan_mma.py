@@ -30,7 +30,7 @@ def V():
 
 def set_env(monkeypatch, name):
     for k in ("VRQ_MMA_SAMPLE_K", "VRQ_MMA_SAFETY", "VRQ_SCAN_MMA", "VRQ_MMA_RAW_STAGES", "VRQ_MMA_KIND", "VRQ_MMA_PAIR",
-              "VRQ_MMA_GROUP_TILES"):
+              "VRQ_MMA_GROUP_TILES", "VRQ_MMA_FEW"):
         monkeypatch.delenv(k, raising=False)
     for k, v in ENVS[name].items():
         monkeypatch.setenv(k, v)
@@ -155,3 +155,57 @@ def test_mma_and_integer_kernels_agree_with_ids(V, monkeypatch):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     rd, rp = oc.hamming_topk(codes, q[:8], k)
     assert np.array_equal(a[0][:8], rd) and np.array_equal(a[1][:8], ids[rp])
+
+
+# ---- <= 32 queries per pass: the swapped-operand kernel (database rows = MMA M, expanded straight into tensor memory) ----
+@pytest.mark.parametrize("n,nq", [(1, 6), (127, 8), (129, 7), (5000, 17), (40000, 32), (300001, 24)])
+def test_few_queries_distance_matrix_exact(V, monkeypatch, n, nq):
+    set_env(monkeypatch, "default")
+    rng = np.random.default_rng(n * 77 + nq)
+    codes = rng.integers(0, 256, (n, 128), dtype=np.uint8)
+    q = rng.integers(0, 256, (nq, 128), dtype=np.uint8)
+    q[0] = 0
+    q[-1] = 255
+    ix = V.BinaryIndex(1024)
+    ix.add_with_ids(codes, np.arange(n))
+    assert np.array_equal(ix.distances(q), ref_distances(q, codes))
+
+
+@pytest.mark.parametrize("env", ["default", "forced_fallback", "no_sampling"])
+@pytest.mark.parametrize("nq", [6, 20, 32])
+def test_few_queries_topk_matches_oracle(V, monkeypatch, env, nq):
+    set_env(monkeypatch, env)
+    n = 2_000_000
+    codes, _ = oc.synth_codes_int8(61, 0, n, want_int8=False)
+    q = o.synth_ubinary_from_f32(oc.synth_f32(62, 0, nq))
+    q[0] = codes[n - 5]
+    ix = V.BinaryIndex(1024)
+    ix.add_with_ids(codes, np.arange(n))
+    for k in (10, 1000):
+        dist, labels = ix.search(q, k)
+        rd, rp = oc.hamming_topk(codes, q, k)
+        assert np.array_equal(dist, rd) and np.array_equal(labels, rp)
+    monkeypatch.setenv("VRQ_MMA_FEW", "0")  # the 128-query-tile kernel on the same batch
+    d2, l2 = ix.search(q, 1000)
+    assert np.array_equal(d2, rd) and np.array_equal(l2, rp)
+
+
+def test_few_queries_ties_and_sorted_database(V, monkeypatch):
+    set_env(monkeypatch, "default")
+    rng = np.random.default_rng(43)
+    n = 500000
+    base = rng.integers(0, 256, (16, 128), dtype=np.uint8)
+    codes = base[rng.integers(0, 16, n)]
+    q = np.concatenate([base[:3], rng.integers(0, 256, (9, 128), dtype=np.uint8)])
+    ix = V.BinaryIndex(1024)
+    ix.add_with_ids(codes, np.arange(n))
+    for k in (1, 100, 4096):
+        dist, labels = ix.search(q, k)
+        rd, rp = oc.hamming_topk(codes, q, k)
+        assert np.array_equal(dist, rd) and np.array_equal(labels, rp)
+    codes[:] = base[0]
+    ix2 = V.BinaryIndex(1024)
+    ix2.add_with_ids(codes, np.arange(n))
+    dist, labels = ix2.search(q, 1000)
+    rd, rp = oc.hamming_topk(codes, q, 1000)
+    assert np.array_equal(dist, rd) and np.array_equal(labels, rp)

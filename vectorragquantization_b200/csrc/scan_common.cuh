@@ -231,6 +231,7 @@ struct MmaPlan {
     int64_t rows_per_strip;
     size_t smem, smem_limit;
     bool f4;    // packed e2m1 operands (kind::mxf4) instead of int8
+    bool few;   // <= 64 queries: swapped-operand kernel (database rows = M, expanded straight into tensor memory)
     bool pair;  // CTA pairs (tcgen05 cta_group::2): two query tiles share every tile of database rows
 };
 constexpr int MMA_TILE_ROWS = 128;

@@ -148,6 +148,15 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                  "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+        "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+        "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
@@ -616,6 +625,296 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
     }
 }
 
+// =====================================================================================================================
+// Few queries per pass (6 .. 32): the operand roles are swapped.  The MMA of the kernel above costs 8 cycles per database
+// row whatever the number of queries, which caps a single 128-query tile at 4.5 TB/s of codes (measured 3.5 TB/s).  Here
+// the DATABASE rows are the M dimension and the queries the N dimension (N = nq rounded up to 8), so one tile costs
+// 8 N cycles of tensor time and the scan goes back to being bound by HBM:
+//   * B operand = the queries (+-2, +-1, +-0.5 e2m1), expanded once into shared memory (N x 512 bytes);
+//   * A operand = 128 database rows, expanded by the expander threads straight into TENSOR MEMORY with tcgen05.st
+//     (thread = row = TMEM lane; two 128-column buffers), so the expansion never touches shared memory;
+//   * D = 128 rows x N queries (two buffers); epilogue lane = database row, column = query, thresholds per column.
+// Same lists / counts / thresholds contract as the kernels above, e2m1 kind only.
+constexpr int FEW_MAXQ = 32;
+constexpr int FEW_WARP_MMA = 4, FEW_WARP_TMA = 5, FEW_WARP_EXP0 = 6, FEW_EXP_WARPS = 8;
+constexpr int FEW_THREADS = (FEW_WARP_EXP0 + FEW_EXP_WARPS) * 32;
+constexpr int FEW_EPI_WARPS = 4, FEW_EPI_THREADS = FEW_EPI_WARPS * 32;
+constexpr uint32_t FEW_A_COL = 0, FEW_D_COL = 256, FEW_SF_COL = 384;  // A: 2 x 128 columns, D: 2 x 64 (32 used), scales: 64
+constexpr int FEW_MAX_RAW = 8;
+
+struct FewSmem {
+    unsigned long long raw_full[FEW_MAX_RAW], raw_empty[FEW_MAX_RAW];
+    unsigned long long a_full[2], a_empty[2], acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    int tau_s[FEW_MAXQ];
+    int cnt_s[FEW_MAXQ];
+    int pcq_s[FEW_MAXQ];
+    float thr_s[FEW_MAXQ];
+    SelectScratch sc[FEW_EPI_WARPS];
+};
+
+__global__ void __launch_bounds__(FEW_THREADS, 1)
+hamming_scan_mma_few_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, int raw_stages, int npad) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* raw_mem = base;                                      // [raw_stages][128 rows][128 B], TMA SWIZZLE_128B
+    uint8_t* q_mem = raw_mem + (size_t)raw_stages * STAGE_BYTES_RAW;  // [4 K-blocks][npad queries][128 B], same swizzle
+    FewSmem* sm = (FewSmem*)(q_mem + (size_t)4 * FEW_MAXQ * 128);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nq = p.nq;  // <= FEW_MAXQ, one query tile
+    const int strip = blockIdx.y;
+    const int tiles_per_strip = (int)(p.rows_per_strip / MROWS);
+    const int64_t tile0 = (int64_t)strip * tiles_per_strip;
+    const int ntiles = (int)max((int64_t)0, min((int64_t)tiles_per_strip, p.total_tiles - tile0));
+    const int64_t run_mask = ((int64_t)1 << p.run_shift) - 1;
+    auto tile_row = [&](int t) -> int64_t {
+        const int64_t i = tile0 + t;
+        return p.row_begin + (i >> p.run_shift) * p.run_stride + (i & run_mask) * MROWS;
+    };
+    const int64_t s_end = p.row_end;
+    if (p.guard && *p.guard == 0) return;
+
+    if (tid == 0) {
+        for (int s = 0; s < raw_stages; s++) {
+            mbar_init(smem_u32(&sm->raw_full[s]), 1);
+            mbar_init(smem_u32(&sm->raw_empty[s]), 4);  // the four expander warps of one group
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(smem_u32(&sm->a_full[s]), 4);
+            mbar_init(smem_u32(&sm->a_empty[s]), 1);
+            mbar_init(smem_u32(&sm->acc_full[s]), 1);
+            mbar_init(smem_u32(&sm->acc_empty[s]), FEW_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (tid < FEW_MAXQ) {
+        sm->pcq_s[tid] = 0;
+        sm->cnt_s[tid] = 0;
+        sm->tau_s[tid] = tid < nq ? (p.tau0 ? min(p.tau0[tid], TAU_INF - 1) + p.tau_bias : TAU_INF) : 0;
+    }
+    if (warp == FEW_WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm->tmem_base;
+
+    // ---- the queries become the B operand in shared memory: row = query, K-block kb = code words 8 kb .. 8 kb + 7, chunk i
+    //      of the 128-byte row = word 8 kb + i as four planes (nibble j of plane t = bit t + 4 j) of +-(1 / plane value)
+    for (int idx = tid; idx < npad * 32; idx += FEW_THREADS) {
+        const int q = idx >> 5, W = idx & 31;
+        const bool qvalid = q < nq;
+        const uint32_t w = qvalid ? __ldg(reinterpret_cast<const uint32_t*>(p.queries + (size_t)q * CODE_BYTES) + W) : 0u;
+        if (qvalid) atomicAdd(&sm->pcq_s[q], __popc(w));
+        uint32_t v[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const uint32_t mag = t == 0 ? 0x44444444u : (t == 1 ? 0x22222222u : 0x11111111u);
+            v[t] = qvalid ? ((mag | 0x88888888u) ^ (((w >> t) & 0x11111111u) << 3)) : 0u;
+        }
+        const int kb = W >> 3, i = W & 7;
+        sts128(smem_u32(q_mem) + (uint32_t)(kb * npad * 128 + q * 128 + ((i ^ (q & 7)) << 4)), v[0], v[1], v[2], v[3]);
+    }
+    if (warp < FEW_EPI_WARPS) {
+        // every block scale (UE8M0) = 0x7F = 2^0
+        uint32_t one[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) one[t] = 0x7F7F7F7Fu;
+#pragma unroll
+        for (int c = 0; c < 64; c += 8) tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + FEW_SF_COL + c, one);
+        tmem_wait_st();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid < FEW_MAXQ) sm->thr_s[tid] = tid < nq ? (float)(sm->pcq_s[tid] - sm->tau_s[tid]) : 3.0e9f;
+    __syncthreads();
+
+    if (warp == FEW_WARP_TMA) {
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (int t = 0; t < ntiles; t++) {
+                mbar_wait_relaxed(smem_u32(&sm->raw_empty[s]), ph ^ 1u, 128);
+                mbar_expect_tx(smem_u32(&sm->raw_full[s]), STAGE_BYTES_RAW);
+                tma_load_2d(smem_u32(raw_mem) + s * (uint32_t)STAGE_BYTES_RAW, &tmap, 0, (int)tile_row(t), smem_u32(&sm->raw_full[s]));
+                if (++s == (uint32_t)raw_stages) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+    } else if (warp == FEW_WARP_MMA) {
+        // ===================== MMA issuer: 16 MMAs (M = 128 rows, N = npad queries, K = 64) per tile =====================
+        const uint32_t idesc = (1u << 7) | (1u << 10) | ((uint32_t)(npad >> 3) << 17) | (1u << 23) | ((uint32_t)(MQ >> 4) << 24);
+        const uint64_t qdesc0 = umma_desc_sw128(smem_u32(q_mem));
+        const uint32_t kb_step = (uint32_t)(npad * 128) >> 4;
+        for (int t = 0; t < ntiles; t++) {
+            const uint32_t ab = (uint32_t)t & 1u, ph = ((uint32_t)t >> 1) & 1u;
+            mbar_wait(smem_u32(&sm->a_full[ab]), ph);
+            mbar_wait(smem_u32(&sm->acc_empty[ab]), ph ^ 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d_tmem = tmem + FEW_D_COL + ab * 64, a0 = tmem + FEW_A_COL + ab * 128;
+#pragma unroll
+                for (int s = 0; s < 16; s++)
+                    umma_f4_ts(d_tmem, a0 + 8 * s, qdesc0 + (uint64_t)((s >> 2) * kb_step + (s & 3) * 2), idesc, tmem + FEW_SF_COL,
+                               tmem + FEW_SF_COL + 32, s != 0);
+                tc_commit(smem_u32(&sm->a_empty[ab]));
+                tc_commit(smem_u32(&sm->acc_full[ab]));
+            }
+            __syncwarp();
+        }
+    } else if (warp >= FEW_WARP_EXP0) {
+        // ===================== expanders: thread = database row = TMEM lane; group g writes A buffer g ================
+        const int g = (warp - FEW_WARP_EXP0) >> 2;
+        const int row = (warp & 3) * 32 + lane;  // a warp may only touch the TMEM lane quadrant warp_id % 4
+        const uint32_t sw = (uint32_t)(row & 7);
+        const uint32_t a_buf = tmem + ((uint32_t)((warp & 3) * 32) << 16) + FEW_A_COL + (uint32_t)g * 128;
+        for (int t = g; t < ntiles; t += 2) {
+            const uint32_t rs = (uint32_t)t % (uint32_t)raw_stages, rph = ((uint32_t)t / (uint32_t)raw_stages) & 1u;
+            const uint32_t ph = ((uint32_t)t >> 1) & 1u;
+            mbar_wait_relaxed(smem_u32(&sm->raw_full[rs]), rph, 32);
+            const uint32_t raddr = smem_u32(raw_mem) + rs * (uint32_t)STAGE_BYTES_RAW + (uint32_t)row * 128u;
+            uint4 c[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) c[j] = lds128(raddr + (((uint32_t)j ^ sw) << 4));
+            mbar_wait(smem_u32(&sm->a_empty[g]), ph ^ 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int part = 0; part < 4; part++) {
+                // words 8 part .. 8 part + 7 -> columns 32 part .. 32 part + 31 (column 4 W + t = plane t of word W)
+                const uint32_t w[8] = {c[2 * part].x, c[2 * part].y, c[2 * part].z, c[2 * part].w,
+                                       c[2 * part + 1].x, c[2 * part + 1].y, c[2 * part + 1].z, c[2 * part + 1].w};
+                uint32_t v[32];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    v[4 * i + 0] = w[i] & 0x11111111u;
+                    v[4 * i + 1] = w[i] & 0x22222222u;
+                    v[4 * i + 2] = w[i] & 0x44444444u;
+                    v[4 * i + 3] = (w[i] >> 1) & 0x44444444u;
+                }
+                tmem_st32(a_buf + 32 * part, v);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(smem_u32(&sm->a_full[g]));
+                mbar_arrive(smem_u32(&sm->raw_empty[rs]));  // every c[j] has been consumed by real instructions
+            }
+        }
+    } else {
+        // ===================== epilogue: lane = database row, column = query ==========================================
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16) + FEW_D_COL;
+        const int limit = p.compact_limit > 0 ? min(p.compact_limit, p.cap - p.group_tiles * MROWS) : p.cap - p.group_tiles * MROWS;
+        uint64_t* const lists0 = p.lists + (size_t)strip * p.nq * p.cap;
+        int until_check = p.group_tiles;
+        // the per-query thresholds (survivor <=> dot > popc(q) - tau) live in registers between compactions
+        float thr[FEW_MAXQ / 16][16];
+        auto load_thr = [&]() {
+#pragma unroll
+            for (int ch = 0; ch < FEW_MAXQ / 16; ch++)
+#pragma unroll
+                for (int j = 0; j < 16; j++) thr[ch][j] = (16 * ch < npad) ? sm->thr_s[16 * ch + j] : 3.0e9f;
+        };
+        load_thr();
+        for (int t = 0; t < ntiles; t++) {
+            const uint32_t ab = (uint32_t)t & 1u;
+            mbar_wait(smem_u32(&sm->acc_full[ab]), ((uint32_t)t >> 1) & 1u);
+            tc_fence_after();
+            const int64_t lrow = tile_row(t) + warp * 32 + lane;
+            const bool rvalid = lrow < s_end;
+#pragma unroll
+            for (int ch = 0; ch < FEW_MAXQ / 16; ch++) {
+                const int cb = 16 * ch;
+                if (cb >= npad) break;
+                int v[16];
+                __syncwarp();
+                tmem_ld16(lane_base + ab * 64 + cb, v);
+                tmem_wait_ld();
+                if (cb + 16 >= npad) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[ab]));
+                }
+                float mx = -3.0e9f;
+#pragma unroll
+                for (int j = 0; j < 16; j++) mx = fmaxf(mx, __int_as_float(v[j]) - thr[ch][j]);
+                if (p.dbg && rvalid) {
+                    for (int j = 0; j < 16; j++)
+                        if (cb + j < nq) p.dbg[(size_t)(cb + j) * p.dbg_stride + lrow] = sm->pcq_s[cb + j] - (int)__int_as_float(v[j]);
+                }
+                if (mx > 0.0f && rvalid) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const float f = __int_as_float(v[j]);
+                        if (f > thr[ch][j]) {
+                            const int q = cb + j;
+                            const int slot = atomicAdd(&sm->cnt_s[q], 1);
+                            lists0[(size_t)q * p.cap + slot] =
+                                ((unsigned long long)(sm->pcq_s[q] - (int)f) << VRQ_KEY_POS_BITS) | (unsigned long long)(p.pos_base + lrow);
+                        }
+                    }
+                }
+            }
+            if (--until_check == 0 && t + 1 < ntiles) {
+                until_check = p.group_tiles;
+                group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
+                const int over = (tid < nq && sm->cnt_s[tid] > limit) ? 1 : 0;
+                int any;
+                asm volatile(
+                    "{\n"
+                    ".reg .pred p, q;\n"
+                    "setp.ne.s32 q, %1, 0;\n"
+                    "bar.red.or.pred p, %2, %3, q;\n"
+                    "selp.s32 %0, 1, 0, p;\n"
+                    "}\n"
+                    : "=r"(any)
+                    : "r"(over), "n"(BAR_CONSUMERS), "n"(FEW_EPI_THREADS)
+                    : "memory");
+                if (any) {
+                    for (int qq = warp; qq < nq; qq += FEW_EPI_WARPS) {
+                        const int n = sm->cnt_s[qq];
+                        if (n > limit)
+                            compact_list_warp(lists0 + (size_t)qq * p.cap, n, p.k, &sm->sc[warp], lane, BAR_WARP0 + warp, &sm->cnt_s[qq],
+                                              &sm->tau_s[qq], p.sample_mode ? limit : 0);
+                    }
+                    group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
+                    if (tid < nq) sm->thr_s[tid] = (float)(sm->pcq_s[tid] - sm->tau_s[tid]);
+                    group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
+                    load_thr();
+                }
+            }
+        }
+        group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
+        for (int qq = warp; qq < nq && !p.sample_mode; qq += FEW_EPI_WARPS) {
+            const int n = sm->cnt_s[qq];
+            if (n > p.k)
+                compact_list_warp(lists0 + (size_t)qq * p.cap, n, p.k, &sm->sc[warp], lane, BAR_WARP0 + warp, &sm->cnt_s[qq], &sm->tau_s[qq]);
+        }
+        group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
+        if (tid < nq) p.counts[(size_t)strip * p.nq + tid] = sm->cnt_s[tid];
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == FEW_WARP_MMA) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+size_t few_smem_bytes(int raw_stages) {
+    return 1024 + (size_t)raw_stages * STAGE_BYTES_RAW + (size_t)4 * FEW_MAXQ * 128 + sizeof(FewSmem) + 16;
+}
+
 size_t mma_smem_bytes(int raw_stages, int cap) {
     (void)cap;  // lists are compacted in place in global memory: no shared-memory copy
     return 1024 + (size_t)raw_stages * STAGE_BYTES_RAW + (size_t)B_STAGES * STAGE_BYTES_B + sizeof(MmaSmem) + 16;
@@ -627,6 +926,8 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
     const int sms = ctx->sm_count;
     pl->f4 = env_int("VRQ_MMA_KIND", 4) != 8;  // 4 (default): packed e2m1 operands, 8: int8 operands
     pl->qtiles = (nq + MQ - 1) / MQ;
+    // <= 64 queries: the swapped-operand kernel (database rows = M), HBM-bound instead of bound by 8 tensor cycles per row
+    pl->few = pl->f4 && nq <= FEW_MAXQ && env_int("VRQ_MMA_FEW", 1) != 0;
     // CTA pairs need an even number of query tiles (a pair = two neighbouring tiles); VRQ_MMA_PAIR=0 switches them off
     pl->pair = pl->f4 && pl->qtiles % 2 == 0 && env_int("VRQ_MMA_PAIR", 1) != 0;
     pl->group_tiles = env_int("VRQ_MMA_GROUP_TILES", 8);
@@ -643,9 +944,9 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
     pl->strips = (int)((tiles + tps - 1) / tps);
     const size_t limit = ctx->smem_optin ? ctx->smem_optin : 227 * 1024;
     pl->smem_limit = limit;
-    pl->raw_stages = env_int("VRQ_MMA_RAW_STAGES", 4);
+    pl->raw_stages = env_int("VRQ_MMA_RAW_STAGES", pl->few ? FEW_MAX_RAW : 4);
     if (pl->raw_stages < 1) pl->raw_stages = 1;
-    if (pl->raw_stages > MAX_RAW_STAGES) pl->raw_stages = MAX_RAW_STAGES;
+    if (pl->raw_stages > (pl->few ? FEW_MAX_RAW : MAX_RAW_STAGES)) pl->raw_stages = pl->few ? FEW_MAX_RAW : MAX_RAW_STAGES;
     pl->b_stages = B_STAGES;
     mma_plan_set_cap(pl, pl->cap);
     if (pl->smem > limit) {
@@ -657,6 +958,10 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
 
 void mma_plan_set_cap(MmaPlan* pl, int cap) {
     pl->cap = cap;
+    if (pl->few) {
+        pl->smem = few_smem_bytes(pl->raw_stages);
+        return;
+    }
     while (pl->raw_stages > 1 && mma_smem_bytes(pl->raw_stages, cap) > pl->smem_limit) pl->raw_stages--;
     pl->smem = mma_smem_bytes(pl->raw_stages, cap);
 }
@@ -669,7 +974,11 @@ int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const CUtensorMap&
         return VRQ_ERR_UNSUPPORTED;
     }
     dim3 grid(pl.qtiles, pl.strips);
-    if (pl.f4 && pl.pair) {
+    if (pl.few) {
+        const int npad = ((sp.nq + 7) / 8) * 8;
+        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_few_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        hamming_scan_mma_few_kernel<<<grid, FEW_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, npad);
+    } else if (pl.f4 && pl.pair) {
         // CTA pairs: clusters of 2 along x = two neighbouring query tiles of the same strip
         auto kern = hamming_scan_mma_kernel<KIND_F4, 2>;
         VRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
