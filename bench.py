@@ -342,7 +342,7 @@ def run_gpu(args):
                     "frac": n_local * 128 * 8 / dense_s / 1e9 / hbm_peak, "peak_source": peak_src,
                     "note": "algorithmic bytes = 128 B per code per 128-query tile (8 tiles per 1024-query batch, 7 of them served by "
                             "L2: ncu dram__bytes_read ~ 13-15 GB per 102 GB requested); not the binding resource for a query batch"},
-            "integer_pipe_kernel": {"note": "scan.cu (XOR + carry-save POPC) handles <= 5 queries per pass and VRQ_SCAN_MMA=0; "
+            "integer_pipe_kernel": {"note": "scan.cu (XOR + carry-save POPC) handles <= 3 queries per pass and VRQ_SCAN_MMA=0; "
                                             "its 1024-query rate measured earlier in round 1 was 216 Gpair/s (profiles/r01)",
                                     "alu_peak_Gpair_s": alu_peak / 1e9},
             "scan_ms_per_step": scan_ms / args.steps, "rescore_ms_per_step": resc_ms / args.steps,
