@@ -13,7 +13,7 @@ shard (weak scaling: the database is N x 100 M rows), each query is answered exa
 per second, i.e. it is plain QPS@100M at N=1 and total pair throughput in the same unit for N>1.
 
 The JSON line carries, besides the base contract: `roofline` (dominant kernel = the dense pass of the batched Hamming
-scan, a tcgen05 int8 contraction bound by the tensor pipe, with its HBM figures alongside), `roofline_scan_stream` /
+scan, a tcgen05 e2m1 contraction bound by the tensor pipe, with its HBM figures alongside), `roofline_scan_stream` /
 `roofline_encode` (the two HBM-bound kernels the metric names: scan at <=2 queries per pass, fused int8 encode),
 `cpu_baseline`, `e2e`, `clocks`, `gpu_launches`.
 """
@@ -410,13 +410,15 @@ def hbm_bound_kernels(torch, ctx, lib, L, index, qb_d, dev, stream, hbm_peak, pe
         return e0.elapsed_time(e1) / reps / 1e3
 
     kk = K * BO
-    dist_d = torch.empty((2, kk), dtype=torch.int32, device=dev)
-    lab_d = torch.empty((2, kk), dtype=torch.int64, device=dev)
-    for nq in (1, 2):
+    dist_d = torch.empty((16, kk), dtype=torch.int32, device=dev)
+    lab_d = torch.empty((16, kk), dtype=torch.int64, device=dev)
+    for nq in (1, 2, 16):
         q = qb_d[0][:nq].contiguous()
         s = timed(lambda: L.check(lib.vrq_index_search(index._h, nq, L.ptr(q), kk, L.ptr(dist_d), L.ptr(lab_d))), 5)
         gbs = n_local * 128 / s / 1e9
-        out[f"roofline_scan_stream_nq{nq}"] = {"kernel": f"hamming_scan_kernel<true> + merge, {nq} query/pass, top-{kk}", "bound": "hbm",
+        kern = ("hamming_scan_kernel<true> (XOR + POPC)" if nq < 4 else
+                "hamming_scan_mma_few_kernel (tcgen05, database rows = M expanded into TMEM) incl. its sample pass")
+        out[f"roofline_scan_stream_nq{nq}"] = {"kernel": f"{kern} + merge, {nq} query/pass, top-{kk}", "bound": "hbm",
                                                 "unit": "GB/s", "achieved": gbs, "peak": hbm_peak, "frac": gbs / hbm_peak,
                                                 "peak_source": peak_src, "ms": s * 1e3, "traffic": None}
     # BASELINE config 5: Phase III micro - 4096 queries x 1000 gathered int8 candidates each (HBM-gather-bound)
