@@ -154,6 +154,7 @@ __device__ __forceinline__ int hamming128_csa14(const uint4 (&c)[8], uint32_t qa
 // the hot loop carries no address arithmetic for it.
 __device__ __noinline__ void append_candidate(int* cnt_s, uint64_t* lists, int q, int cap, int d, unsigned long long pos) {
     const int slot = atomicAdd(&cnt_s[q], 1);
+    if (slot >= cap) __trap();  // cannot happen (overflow check every group_tiles tiles); never write past a list
     lists[(size_t)q * cap + slot] = ((unsigned long long)d << VRQ_KEY_POS_BITS) | pos;
 }
 

@@ -570,10 +570,12 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                     if (nv < 16) mask = nv <= 0 ? 0u : (mask & ~(0xFFFFu >> nv));
                     if (__popc(mask) == 1 && nv >= 16) {
                         // the usual case once tau has converged: the single survivor is the maximum itself
-                        my_list[atomicAdd(&sm->cnt_s[q], 1)] =
-                            ((unsigned long long)(pcq - m) << VRQ_KEY_POS_BITS) | (pos0 + (__clz((int)mask) - 16));
+                        const int slot = atomicAdd(&sm->cnt_s[q], 1);
+                        if (slot >= p.cap) __trap();  // cannot happen (overflow check every group_tiles tiles); never write past a list
+                        my_list[slot] = ((unsigned long long)(pcq - m) << VRQ_KEY_POS_BITS) | (pos0 + (__clz((int)mask) - 16));
                     } else if (mask) {
                         int slot = atomicAdd(&sm->cnt_s[q], __popc(mask));
+                        if (slot + __popc(mask) > p.cap) __trap();
 #pragma unroll
                         for (int j = 0; j < 16; j++) {
                             if ((mask >> (15 - j)) & 1u) {
@@ -858,6 +860,7 @@ hamming_scan_mma_few_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams
                         if (f > thr[ch][j]) {
                             const int q = cb + j;
                             const int slot = atomicAdd(&sm->cnt_s[q], 1);
+                            if (slot >= p.cap) __trap();
                             lists0[(size_t)q * p.cap + slot] =
                                 ((unsigned long long)(sm->pcq_s[q] - (int)f) << VRQ_KEY_POS_BITS) | (unsigned long long)(p.pos_base + lrow);
                         }
