@@ -209,3 +209,27 @@ def test_few_queries_ties_and_sorted_database(V, monkeypatch):
     dist, labels = ix2.search(q, 1000)
     rd, rp = oc.hamming_topk(codes, q, 1000)
     assert np.array_equal(dist, rd) and np.array_equal(labels, rp)
+
+
+@pytest.mark.parametrize("nq", [12, 40, 256])
+def test_mma_clustered_rows_partial_fallback(V, monkeypatch, nq):
+    """A tight cluster that the strided sample happens to cover (the first 2048 rows are near-copies of query 0) makes the
+    sampled threshold of THAT query far too small: the verification must catch it and the fallback pass must redo it (with
+    an infinite threshold for that query only) while every other query keeps its result."""
+    set_env(monkeypatch, "default")
+    rng = np.random.default_rng(17)
+    n = 3_000_000
+    codes = rng.integers(0, 256, (n, 128), dtype=np.uint8)
+    q = rng.integers(0, 256, (nq, 128), dtype=np.uint8)
+    bits = np.unpackbits(np.repeat(q[:1], 2048, 0), axis=1)
+    flips = rng.integers(0, 1024, (2048, 40))
+    nflip = np.arange(2048) % 40
+    for i in range(2048):
+        bits[i, flips[i, :nflip[i]]] ^= 1
+    codes[:2048] = np.packbits(bits, axis=1)
+    ix = V.BinaryIndex(1024)
+    ix.add_with_ids(codes, np.arange(n))
+    for k in (100, 1000):
+        dist, labels = ix.search(q, k)
+        rd, rp = oc.hamming_topk(codes, q, k)
+        assert np.array_equal(dist, rd) and np.array_equal(labels, rp)

@@ -399,12 +399,17 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_group_kernel(const uint64
 
 // After a pass whose thresholds came from a sample: does every query hold at least `need` candidates over all strips?
 // (A list that was compacted holds k >= need keys on its own.)  Sets *flag otherwise - the exact fallback pass runs.
-__global__ void verify_counts_kernel(const int* __restrict__ counts, int strips, int nq, int need, int* flag) {
+// A query that came up short gets an infinite threshold for the fallback pass; the others keep theirs, so the fallback
+// floods only the lists of the queries that need it.
+__global__ void verify_counts_kernel(const int* __restrict__ counts, int strips, int nq, int need, int* flag, int* tau) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     long long total = 0;
     for (int s = 0; s < strips; s++) total += counts[(size_t)s * nq + q];
-    if (total < need) atomicOr(flag, 1);
+    if (total < need) {
+        atomicOr(flag, 1);
+        tau[q] = 0x7fffffff;
+    }
 }
 
 __global__ void fill_int_kernel(int* p, int n, int v) {
@@ -639,7 +644,7 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
         // at about k' n / m; m is chosen so that this is `safety` x k.  One dense pass with tau = T + 1 then collects a
         // few thousand candidates per query instead of k per strip, with no list compaction.  The result stays exact:
         // a verification kernel checks that every query collected >= min(k, n) candidates and otherwise raises a flag
-        // that un-gates an exact fallback pass (tau starts at infinity) enqueued right behind.
+        // that un-gates an exact fallback pass (tau of the short queries starts at infinity) enqueued right behind.
         const int kp = env_int("VRQ_MMA_SAMPLE_K", 32);
         const int safety = env_int("VRQ_MMA_SAFETY", 8);
         const int64_t total_tiles = (n + MMA_TILE_ROWS - 1) / MMA_TILE_ROWS;
@@ -711,12 +716,11 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
             }
             VRQ_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
             const int need = (int)((int64_t)k < n ? (int64_t)k : n);
-            verify_counts_kernel<<<(nq + 127) / 128, 128, 0, st>>>(counts, m_pl.strips(), nq, need, flag);
+            verify_counts_kernel<<<(nq + 127) / 128, 128, 0, st>>>(counts, m_pl.strips(), nq, need, flag, tau);
             vrq_count_launch(ctx);
             VRQ_TRY(launch_merge(ctx, lists, counts, m_pl.strips(), nq, cap, k, keys_out, nullptr, st));
-            // 3. exact fallback, a no-op unless the verification raised the flag
-            sp.tau0 = nullptr;
-            sp.tau_bias = 0;
+            // 3. exact fallback, a no-op unless the verification raised the flag: the same dense pass again, with the
+            //    thresholds of the queries that came up short set to infinity (the others collect the same lists again)
             sp.guard = flag;
             VRQ_TRY(launch_pass(ctx, tma, tmap, tmap_mma, sp, m_pl, st));
             VRQ_TRY(launch_merge(ctx, lists, counts, m_pl.strips(), nq, cap, k, keys_out, nullptr, st, flag));
