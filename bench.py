@@ -337,7 +337,10 @@ def run_gpu(args):
             "frac_of_scaled_measured_bf16": {"burst": ops / dense_s / 1e12 / (ratio * bf16_burst),
                                              "sustained": ops / dense_s / 1e12 / (ratio * bf16_sust)},
             "kernel_ms": dense_s * 1e3, "pairs_per_s": pairs_per_step / dense_s,
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch at 100 M rows x 1024 queries from one
+            # `ncu --set full` capture (profiles/r01/ncu_scan_mma_final_raw.csv): 25.54 GB + 0.15 GB, against 12.8 GB of codes
+            # requested 8 times (once per 128-query tile) = 102 GB: most re-reads are served by L2
+            "traffic": 25.70e9 if (f4 and pair and n_local == N_PER_GPU) else None, "traffic_unit": "bytes per launch (DRAM)",
             "hbm": {"bound": "hbm", "unit": "GB/s", "achieved": n_local * 128 * 8 / dense_s / 1e9, "peak": hbm_peak,
                     "frac": n_local * 128 * 8 / dense_s / 1e9 / hbm_peak, "peak_source": peak_src,
                     "note": "algorithmic bytes = 128 B per code per 128-query tile (8 tiles per 1024-query batch, 7 of them served by "
