@@ -483,7 +483,7 @@ def hbm_bound_kernels(torch, ctx, lib, L, index, qb_d, dev, stream, hbm_peak, pe
     th = time.perf_counter() - t0
     enc["int8_global+ubinary_host_buffers"] = {"GB/s": n_h * 5248 / th / 1e9, "ms": th * 1e3, "rows": n_h,
                                                "note": "end to end with pinned host input/output: PCIe-bound (4096 B in + 1152 B out per row)"}
-    out["roofline_encode"] = {"kernel": "encode1024_kernel<INT8_GLOBAL, ubinary fused>", "bound": "hbm", "unit": "GB/s",
+    out["roofline_encode"] = {"kernel": "encode1024_ring_kernel<INT8_GLOBAL, ubinary fused> (cp.async ring of rows per warp, magic-number rounding)", "bound": "hbm", "unit": "GB/s",
                               "achieved": enc["int8_global+ubinary"]["GB/s"], "peak": hbm_peak,
                               "frac": enc["int8_global+ubinary"]["frac"], "peak_source": peak_src, "rows": n_enc, "traffic": None,
                               "workload": "cfg2: 10M x 1024 float32 rows resident in HBM", "all_codecs": enc}

@@ -81,6 +81,37 @@ def test_encoders_bit_exact(K, d):
     assert q1.shape == (d,) and np.array_equal(q1, rq[20]) and a1 == rlo[20] and b1 == rhi[20]
 
 
+@pytest.mark.parametrize("shape", ["register", "ring_8x2", "ring_8x4", "ring_4x6", "ring_3x3", "ring_1x2"])
+@pytest.mark.parametrize("n", [1, 7, 1201])
+def test_encoder_launch_shapes_bit_exact(K, monkeypatch, shape, n):
+    """d = 1024 has two kernels (encode1024_kernel: registers; encode1024_ring_kernel: cp.async ring, magic-number rounding)
+    and the ring kernel several launch shapes; every one must give the oracle's bytes, ragged row counts included."""
+    if shape == "register":
+        monkeypatch.setenv("VRQ_ENCODE_RING", "0")
+    else:
+        w, s = shape.split("_")[1].split("x")
+        monkeypatch.setenv("VRQ_ENCODE_RING", "1")
+        monkeypatch.setenv("VRQ_ENCODE_WARPS", w)
+        monkeypatch.setenv("VRQ_ENCODE_STAGES", s)
+    x = np.ascontiguousarray(make_x(max(n, 16), 1024, seed=n)[:n])  # the adversarial rows come first
+    rub = o.to_binary_f32(x)
+    q, lo, hi, ub = K.quantize_int8_perdoc(x, want_binary=True)
+    rq, rlo, rhi = o.quantize_int8_perdoc(x)
+    assert np.array_equal(q, rq) and np.array_equal(lo, rlo) and np.array_equal(hi, rhi) and np.array_equal(ub, rub)
+    for lim in (0.18, 0.3, 1.0):
+        q8, ub8 = K.quantize_int8_global(x, lim, want_binary=True)
+        assert np.array_equal(q8, o.quantize_int8_global(x, lim)) and np.array_equal(ub8, rub)
+        q16, ub16 = K.quantize_int16_global(x, lim, want_binary=True)
+        assert np.array_equal(q16, o.quantize_int16_global(x, lim)) and np.array_equal(ub16, rub)
+        assert np.array_equal(K.quantize_int8_global(x, lim), q8)  # without the fused code
+    p4, l4, h4, ub4 = K.quantize_int4(x, want_binary=True)
+    r4, rl4, rh4 = o.quantize_int4(x)
+    assert np.array_equal(p4, r4) and np.array_equal(l4, rl4) and np.array_equal(h4, rh4) and np.array_equal(ub4, rub)
+    assert np.array_equal(K.quantize_int4(x)[0], r4) and np.array_equal(K.quantize_int8_perdoc(x)[0], rq)
+    assert np.array_equal(K.to_binary(x), rub)
+    assert np.array_equal(K.to_binary(x, ge=True), o.to_binary_f32(x, ge=True))
+
+
 def test_encoders_golden(K, golden_static):
     g = golden_static
     x = g["x"]

@@ -8,12 +8,18 @@
 // __fdiv_rn, no FMA contraction, file compiled with --fmad=false as a second fence); np.mean's float32 pairwise
 // summation tree is reproduced add for add (A.2).
 #include <math.h>
+#include <stdlib.h>
 
 #include "vrq_internal.cuh"
 
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+
+inline int vrq_env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
 
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
     float4 r;
@@ -211,6 +217,321 @@ __global__ void __launch_bounds__(256) encode1024_kernel(EncParams p) {
             reinterpret_cast<uint32_t*>(p.ubin + row * 128)[4 * jsel + (lane >> 3)] = word;
         }
     }
+}
+
+// =====================================================================================================
+// Fast path with a prefetch ring, d == 1024 (the default).  The register kernel above keeps at most one row per warp
+// in flight and stalls on it (ncu r01: 40 % warps active, long-scoreboard bound, 5.1-5.8 TB/s).  Here every warp owns a
+// ring of RING_STAGES rows in shared memory filled by cp.async (LDGSTS), so RING_STAGES-1 .. RING_STAGES rows per warp
+// are always on their way from HBM while one is encoded.  A row sits in the ring as 256 16-byte chunks, chunk c stored
+// at c ^ ring_swz(c >> 3): with that XOR all three access patterns are bank-conflict free -
+//   fill   : lane l copies chunks 32j + l (coalesced 512 B global reads),
+//   mean   : lane (b, jp) walks its two strided accumulator chains of 128-block b with LDS.64 (np.mean's tree, A.2),
+//   encode : lane l reads its 32 CONSECUTIVE elements 32l .. 32l+31 with 8 LDS.128.
+// Owning consecutive elements is what makes the rest cheap: the packbits word of the lane is one 32-bit store and
+// the quantised elements go out as 16-byte stores, with no shuffles.  Rounding uses the 1.5 * 2^23 magic-number add
+// (round-half-even of the FADD itself, the integer lands in the low mantissa bits) instead of FRND + F2I, which run at
+// quarter rate; clipping to the integer bounds commutes with rint, so it is done first and the result is the same for
+// every finite input.  Rows whose scale is not an ordinary float (max|x| outside [1e-36, 1e36], NaN) take the
+// literal formulas of the register kernel.
+// =====================================================================================================
+constexpr int RING_MAX_WARPS = 8;  // warps per block (run-time: blockDim.x / 32)
+constexpr int RING_MAX_STAGES = 6;
+
+__device__ __forceinline__ int ring_swz(int line) { return (line & 7) ^ (((line >> 3) & 1) << 1); }
+
+template <int STAGES>
+__device__ __forceinline__ void ring_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack4_low_bytes(int a, int b, int c, int d) {
+    const uint32_t lo = __byte_perm((uint32_t)a, (uint32_t)b, 0x0040);
+    const uint32_t hi = __byte_perm((uint32_t)c, (uint32_t)d, 0x0040);
+    return __byte_perm(lo, hi, 0x5410);
+}
+
+// w |= BIT if a > b (a >= b): FSETP + predicated LOP3, exact IEEE comparison (false for NaN, -0 == +0)
+template <uint32_t BIT>
+__device__ __forceinline__ void or_if_gt(uint32_t& w, float a, float b) {
+    asm("{\n\t.reg .pred q;\n\tsetp.gt.f32 q, %1, %2;\n\t@q or.b32 %0, %0, %3;\n\t}" : "+r"(w) : "f"(a), "f"(b), "n"(BIT));
+}
+template <uint32_t BIT>
+__device__ __forceinline__ void or_if_ge(uint32_t& w, float a, float b) {
+    asm("{\n\t.reg .pred q;\n\tsetp.ge.f32 q, %1, %2;\n\t@q or.b32 %0, %0, %3;\n\t}" : "+r"(w) : "f"(a), "f"(b), "n"(BIT));
+}
+// the four bits of chunk U of a run (elements 4U .. 4U+3): bit 7 - (4(U&1) + c) of byte U/2
+template <int U, bool GE>
+__device__ __forceinline__ uint32_t chunk_bits(const float4& f, float mean) {
+    constexpr int BASE = 8 * (U >> 1) + 7 - 4 * (U & 1);
+    uint32_t w = 0;
+    if (GE) {
+        or_if_ge<1u << BASE>(w, f.x, mean);
+        or_if_ge<1u << (BASE - 1)>(w, f.y, mean);
+        or_if_ge<1u << (BASE - 2)>(w, f.z, mean);
+        or_if_ge<1u << (BASE - 3)>(w, f.w, mean);
+    } else {
+        or_if_gt<1u << BASE>(w, f.x, mean);
+        or_if_gt<1u << (BASE - 1)>(w, f.y, mean);
+        or_if_gt<1u << (BASE - 2)>(w, f.z, mean);
+        or_if_gt<1u << (BASE - 3)>(w, f.w, mean);
+    }
+    return w;
+}
+template <int CPR, bool GE>
+__device__ __forceinline__ uint32_t run_bits(const float4* v, float mean) {
+    uint32_t w = chunk_bits<0, GE>(v[0], mean);
+    if (CPR > 1) w |= chunk_bits<1, GE>(v[1 % CPR], mean);
+    if (CPR > 2) w |= chunk_bits<2, GE>(v[2 % CPR], mean) | chunk_bits<3, GE>(v[3 % CPR], mean);
+    if (CPR > 4)
+        w |= (chunk_bits<4, GE>(v[4 % CPR], mean) | chunk_bits<5, GE>(v[5 % CPR], mean)) |
+             (chunk_bits<6, GE>(v[6 % CPR], mean) | chunk_bits<7, GE>(v[7 % CPR], mean));
+    return w;
+}
+
+// np.clip(x, -lim, lim) for lim > 0 in one instruction: min(|x|, lim) carrying the sign of x
+__device__ __forceinline__ float clip_sym(float x, float lim) {
+    float r;
+    asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(lim));
+    return r;
+}
+
+constexpr float MAGIC_RINT = 12582912.f;  // 1.5 * 2^23: (t + MAGIC) has ulp 1, so the add rounds t half-to-even
+
+template <int CODEC, bool UBIN, int STAGES>
+__global__ void __launch_bounds__(RING_MAX_WARPS * 32, 3) encode1024_ring_kernel(EncParams p) {
+    extern __shared__ __align__(1024) unsigned char ring_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // 32-bit shared address of this warp's ring; 1024-byte aligned, so the XOR parts below (< 512) never carry into it
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring_raw) + (uint32_t)warp * STAGES * 4096;
+    const int nwarps = blockDim.x >> 5;
+    const int64_t stride = (int64_t)gridDim.x * nwarps;
+    const int64_t row0 = (int64_t)blockIdx.x * nwarps + warp;
+
+    // Every swizzled byte offset splits into (lane part) ^ (compile-time part) + (compile-time add); only the lane
+    // parts live in registers (checked against ring_swz for all lanes in profiles/debug/check_ring_swizzle.py):
+    //   fill, chunk 32j + lane          : 512j + (fill_l ^ 16 * (4(j&1) ^ 2((j>>1)&1)))
+    //   mean, lane (b, jp), step s      : (mean_l ^ 16 * (2(s&3) ^ (s>>2))) + 128 (s>>2)
+    //   encode, run k, chunk u          : (4096/K) k + (enc_l ^ 16u)          [K = 4: 1024k + (enc_l ^ 16 (u ^ 2(k&1)))]
+    constexpr int K = (CODEC == VRQ_CODEC_INT16_GLOBAL) ? 4 : (CODEC == VRQ_CODEC_INT8_PERDOC || CODEC == VRQ_CODEC_INT8_GLOBAL) ? 2 : 1;
+    constexpr int CPR = 8 / K;  // chunks per run
+    const uint32_t fill_l = (uint32_t)(lane ^ (lane >> 3)) * 16;
+    const int mb = lane >> 2, mjp = lane & 3;
+    const uint32_t mean_l = 512u * mb + (uint32_t)((mjp >> 1) ^ (4 * (mb & 1)) ^ (2 * ((mb >> 1) & 1))) * 16 + (mjp & 1) * 8;
+    const uint32_t enc_l = K == 1   ? (uint32_t)((8 * lane) ^ ((lane & 7) ^ (((lane >> 3) & 1) << 1))) * 16
+                           : K == 2 ? (uint32_t)((4 * lane) ^ (((lane >> 1) & 7) ^ (((lane >> 4) & 1) << 1))) * 16
+                                    : (uint32_t)((2 * lane) ^ ((lane >> 2) & 7)) * 16;
+
+    auto fill = [&](int64_t row, int stage) {
+        if (row < p.n) {
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(p.x + row * 1024) + lane * 16;
+            const uint32_t dst = ring_s + stage * 4096;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512 * j + (fill_l ^ (16u * ((4 * (j & 1)) ^ (2 * ((j >> 1) & 1)))))),
+                             "l"(src + 512 * j)
+                             : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) fill(row0 + s * stride, s);
+
+    int stage = 0;
+    for (int64_t row = row0; row < p.n; row += stride) {
+        ring_wait<STAGES>();
+        __syncwarp();
+        const uint32_t sb = ring_s + stage * 4096;
+
+        // ---- np.mean(x): same tree as encode1024_kernel, read through the swizzle ------------------------------
+        float mean = 0.f;
+        if (UBIN) {
+            const uint32_t a1 = sb + mean_l;
+            float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+            for (int s = 0; s < 16; s++) {
+                float2 e;
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                             : "=f"(e.x), "=f"(e.y)
+                             : "r"((a1 ^ (16u * ((2 * (s & 3)) ^ (s >> 2)))) + 128 * (s >> 2)));
+                r0 = s ? __fadd_rn(r0, e.x) : e.x;
+                r1 = s ? __fadd_rn(r1, e.y) : e.y;
+            }
+            float t = __fadd_rn(r0, r1);
+            t = __fadd_rn(t, __shfl_xor_sync(FULL, t, 1));
+            t = __fadd_rn(t, __shfl_xor_sync(FULL, t, 2));
+            t = __fadd_rn(t, __shfl_xor_sync(FULL, t, 4));
+            t = __fadd_rn(t, __shfl_xor_sync(FULL, t, 8));
+            t = __fadd_rn(t, __shfl_xor_sync(FULL, t, 16));
+            mean = __fmul_rn(t, 0.0009765625f);  // == t / 1024 for every t (a power-of-two scaling rounds the same way)
+        }
+
+        // ---- the lane's elements: K runs of 32/K CONSECUTIVE elements, run k = elements 1024k/K + (32/K) * lane .. -------
+        // K = 16-byte stores the quantised row takes per lane (int4: 1, int8: 2, int16: 4), so every store instruction
+        // of the warp writes 512 contiguous bytes.  v[k * 8/K + u] = chunk k * 256/K + lane * 8/K + u (conflict-free too).
+        float4 v[8];
+        {
+            const uint32_t a2 = sb + enc_l;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int k = i / CPR, u = i % CPR;
+                const uint32_t addr = (K == 4) ? (a2 ^ (16u * (u ^ (2 * (k & 1))))) + 1024 * k : (a2 ^ (16u * u)) + (4096 / K) * k;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(addr));
+            }
+        }
+
+        // np.packbits(x > mean), MSB first: FSETP + predicated OR per element (run_bits)
+        if (UBIN) {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const uint32_t word = p.ge ? run_bits<CPR, true>(v + k * CPR, mean) : run_bits<CPR, false>(v + k * CPR, mean);
+                uint8_t* code = p.ubin + row * 128;
+                if (K == 1)
+                    reinterpret_cast<uint32_t*>(code)[lane] = word;
+                else if (K == 2)
+                    reinterpret_cast<uint16_t*>(code)[32 * k + lane] = (uint16_t)word;
+                else
+                    code[32 * k + lane] = (uint8_t)word;
+            }
+        }
+
+        // ---- per-row statistics (they consume every loaded register: the stage can be refilled after them) -----
+        float scale = p.scale;
+        bool constant = false, ordinary = true;
+        if (CODEC == VRQ_CODEC_INT8_PERDOC || CODEC == VRQ_CODEC_INT4) {
+            float lo = v[0].x, hi = v[0].x;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                lo = fminf(fminf(fminf(lo, v[u].x), fminf(v[u].y, v[u].z)), v[u].w);
+                hi = fmaxf(fmaxf(fmaxf(hi, v[u].x), fmaxf(v[u].y, v[u].z)), v[u].w);
+            }
+            lo = warp_min(lo);
+            hi = warp_max(hi);
+            constant = (lo == hi);
+            const float m = fmaxf(fabsf(lo), fabsf(hi));
+            ordinary = (m >= 1e-36f) && (m <= 1e36f);
+            if (CODEC == VRQ_CODEC_INT8_PERDOC) {
+                scale = __fdiv_rn(127.f, m);
+                if (lane == 0) {
+                    if (p.mn) static_cast<float*>(p.mn)[row] = lo;
+                    if (p.mx) static_cast<float*>(p.mx)[row] = hi;
+                }
+            } else {
+                scale = (float)(7.0 / (double)m);
+                if (lane == 0) {
+                    if (p.mn) static_cast<double*>(p.mn)[row] = (double)lo;
+                    if (p.mx) static_cast<double*>(p.mx)[row] = (double)hi;
+                }
+            }
+        }
+
+        // every lane's loads from this stage have been consumed by the arithmetic above (packbits compares / min-max):
+        // hand the stage back now; without either the refill waits until the quantiser below has used the registers
+        constexpr bool EARLY = UBIN || CODEC == VRQ_CODEC_INT8_PERDOC || CODEC == VRQ_CODEC_INT4;
+        if (EARLY) {
+            __syncwarp();
+            fill(row + (int64_t)STAGES * stride, stage);
+        }
+
+        // ---- quantise + store ------------------------------------------------------------------------------------
+        if (CODEC == VRQ_CODEC_INT8_PERDOC) {
+            uint32_t w[8];
+            if (ordinary) {
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    w[u] = pack4_low_bytes(__float2int_rz(__fmul_rn(v[u].x, scale)), __float2int_rz(__fmul_rn(v[u].y, scale)),
+                                           __float2int_rz(__fmul_rn(v[u].z, scale)), __float2int_rz(__fmul_rn(v[u].w, scale)));
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    w[u] = pack4_low_bytes(q_perdoc8(v[u].x, scale), q_perdoc8(v[u].y, scale), q_perdoc8(v[u].z, scale),
+                                           q_perdoc8(v[u].w, scale));
+            }
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<int8_t*>(p.q) + row * 1024) + lane;
+            dst[0] = constant ? make_uint4(0, 0, 0, 0) : make_uint4(w[0], w[1], w[2], w[3]);
+            dst[32] = constant ? make_uint4(0, 0, 0, 0) : make_uint4(w[4], w[5], w[6], w[7]);
+        } else if (CODEC == VRQ_CODEC_INT8_GLOBAL) {
+            uint32_t w[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                int b[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const float cl = clip_sym(e[c], p.lim);
+                    b[c] = __float_as_int(__fadd_rn(__fmul_rn(cl, scale), MAGIC_RINT));
+                }
+                w[u] = pack4_low_bytes(b[0], b[1], b[2], b[3]);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<int8_t*>(p.q) + row * 1024) + lane;
+            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            dst[32] = make_uint4(w[4], w[5], w[6], w[7]);
+        } else if (CODEC == VRQ_CODEC_INT16_GLOBAL) {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<int16_t*>(p.q) + row * 1024) + lane;
+#pragma unroll
+            for (int h = 0; h < 4; h++) {
+                uint32_t w[4];
+#pragma unroll
+                for (int t = 0; t < 2; t++) {
+                    const float4 f = v[2 * h + t];
+                    const float e[4] = {f.x, f.y, f.z, f.w};
+                    int b[4];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const float cl = clip_sym(e[c], p.lim);
+                        b[c] = __float_as_int(__fadd_rn(__fmul_rn(cl, scale), MAGIC_RINT));
+                    }
+                    w[2 * t] = __byte_perm((uint32_t)b[0], (uint32_t)b[1], 0x5410);
+                    w[2 * t + 1] = __byte_perm((uint32_t)b[2], (uint32_t)b[3], 0x5410);
+                }
+                dst[32 * h] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        } else if (CODEC == VRQ_CODEC_INT4) {
+            uint32_t w[4];
+            if (ordinary) {
+                // (c + MAGIC + 8) carries rint(c) + 8 = the nibble in its low 4 bits; two of them make a byte with one IMAD
+#pragma unroll
+                for (int h = 0; h < 4; h++) {
+                    int by[4];
+#pragma unroll
+                    for (int t = 0; t < 2; t++) {
+                        const float4 f = v[2 * h + t];
+                        const float e[4] = {f.x, f.y, f.z, f.w};
+                        int b[4];
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            // |x * scale| <= 7 (1 + 2^-23) on an ordinary row, so np.clip(., -8, 7) never acts
+                            b[c] = __float_as_int(__fadd_rn(__fmul_rn(e[c], scale), MAGIC_RINT + 8.f));
+                        }
+                        by[2 * t] = b[0] * 16 + b[1];
+                        by[2 * t + 1] = b[2] * 16 + b[3];
+                    }
+                    w[h] = pack4_low_bytes(by[0], by[1], by[2], by[3]);
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 4; h++) {
+                    int by[4];
+#pragma unroll
+                    for (int t = 0; t < 2; t++) {
+                        const float4 f = v[2 * h + t];
+                        by[2 * t] = (q_int4(f.x, scale) << 4) | q_int4(f.y, scale);
+                        by[2 * t + 1] = (q_int4(f.z, scale) << 4) | q_int4(f.w, scale);
+                    }
+                    w[h] = pack4_low_bytes(by[0], by[1], by[2], by[3]);
+                }
+            }
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<int8_t*>(p.q) + row * 512) + lane;
+            dst[0] = constant ? make_uint4(0, 0, 0, 0) : make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        if (!EARLY) {
+            __syncwarp();
+            fill(row + (int64_t)STAGES * stride, stage);
+        }
+        stage = (stage + 1 == STAGES) ? 0 : stage + 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // =====================================================================================================
@@ -422,10 +743,58 @@ __global__ void __launch_bounds__(256) dequant_kernel(DeqParams p) {
     }
 }
 
+// The magic-number rounding of the ring kernel needs |clip(x) * scale| to stay below qmax + 0.5 (it always does for a
+// positive, ordinary limit: the product is qmax * (1 +- 2^-23)); anything else goes to the register kernel.
+template <int CODEC>
+bool ring_params_ok(const EncParams& p) {
+    if (CODEC == VRQ_CODEC_INT8_GLOBAL || CODEC == VRQ_CODEC_INT16_GLOBAL) {
+        const float qmax = CODEC == VRQ_CODEC_INT8_GLOBAL ? 127.f : 32767.f;
+        const float top = p.lim * p.scale;
+        return p.lim > 0.f && isfinite(p.scale) && p.scale > 0.f && top < qmax + 0.49f;
+    }
+    return true;
+}
+
+template <int CODEC, bool UBIN, int STAGES>
+int launch_ring(const EncParams& p, int grid, int warps, size_t smem, cudaStream_t st) {
+    auto kern = encode1024_ring_kernel<CODEC, UBIN, STAGES>;
+    VRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, warps * 32, smem, st>>>(p);
+    return 0;
+}
+
 template <int CODEC>
 int launch_codec(vrq_ctx* ctx, const EncParams& p, cudaStream_t st) {
     const bool ub = p.ubin != nullptr;
-    if (p.d == 1024) {
+    if (p.d == 1024 && ring_params_ok<CODEC>(p) && vrq_env_int("VRQ_ENCODE_RING", 1) != 0) {
+        // launch shape (B200 sweep, profiles/r01/encode_ring_sweep.txt): the codecs with per-row statistics need 16 warps per
+        // SM to cover their shuffle chains (2 blocks of 8 warps x 3 stages); the others run best with one block of 8
+        // warps and a deeper ring (4 stages = 3-4 rows per warp in flight)
+        const bool stats = CODEC == VRQ_CODEC_INT8_PERDOC || CODEC == VRQ_CODEC_INT4;
+        int stages = vrq_env_int("VRQ_ENCODE_STAGES", stats ? 3 : 4);
+        stages = stages < 2 ? 2 : (stages > RING_MAX_STAGES ? RING_MAX_STAGES : stages);
+        if (stages == 5) stages = 4;
+        int warps = vrq_env_int("VRQ_ENCODE_WARPS", 8);
+        warps = warps < 1 ? 1 : (warps > RING_MAX_WARPS ? RING_MAX_WARPS : warps);
+        const size_t smem = (size_t)warps * stages * 4096;
+        int per_sm = (int)((size_t)(ctx->smem_optin ? ctx->smem_optin : 227 * 1024) / (smem + 1024));
+        const int by_threads = 2048 / (warps * 32), by_regs = 65536 / (80 * warps * 32);
+        per_sm = per_sm < by_threads ? per_sm : by_threads;
+        per_sm = per_sm < by_regs ? per_sm : by_regs;
+        int64_t blocks = (p.n + warps - 1) / warps;
+        int64_t cap = (int64_t)ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
+        int grid = (int)(blocks < cap ? blocks : cap);
+        int rc;
+        if (stages == 2)
+            rc = ub ? launch_ring<CODEC, true, 2>(p, grid, warps, smem, st) : launch_ring<CODEC, false, 2>(p, grid, warps, smem, st);
+        else if (stages == 3)
+            rc = ub ? launch_ring<CODEC, true, 3>(p, grid, warps, smem, st) : launch_ring<CODEC, false, 3>(p, grid, warps, smem, st);
+        else if (stages == 4)
+            rc = ub ? launch_ring<CODEC, true, 4>(p, grid, warps, smem, st) : launch_ring<CODEC, false, 4>(p, grid, warps, smem, st);
+        else
+            rc = ub ? launch_ring<CODEC, true, 6>(p, grid, warps, smem, st) : launch_ring<CODEC, false, 6>(p, grid, warps, smem, st);
+        if (rc) return rc;
+    } else if (p.d == 1024) {
         int64_t blocks = (p.n + 7) / 8;
         int64_t cap = (int64_t)ctx->sm_count * 6;
         int grid = (int)(blocks < cap ? blocks : cap);
