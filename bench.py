@@ -478,9 +478,12 @@ def hbm_bound_kernels(torch, ctx, lib, L, index, qb_d, dev, stream, hbm_peak, pe
     q8h = torch.empty((n_h, D), dtype=torch.int8).pin_memory()
     ubh = torch.empty((n_h, D // 8), dtype=torch.uint8).pin_memory()
     torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    L.check(lib.vrq_quantize_int8_global(h, L.ptr(xh), n_h, D, 0.3, L.ptr(q8h), L.ptr(ubh)))
-    th = time.perf_counter() - t0
+    th = 1e30
+    for it in range(3):  # the first call allocates the library's staging buffers; report the best warm call
+        t0 = time.perf_counter()
+        L.check(lib.vrq_quantize_int8_global(h, L.ptr(xh), n_h, D, 0.3, L.ptr(q8h), L.ptr(ubh)))
+        if it:
+            th = min(th, time.perf_counter() - t0)
     enc["int8_global+ubinary_host_buffers"] = {"GB/s": n_h * 5248 / th / 1e9, "ms": th * 1e3, "rows": n_h,
                                                "note": "end to end with pinned host input/output: PCIe-bound (4096 B in + 1152 B out per row)"}
     out["roofline_encode"] = {"kernel": "encode1024_ring_kernel<INT8_GLOBAL, ubinary fused> (cp.async ring of rows per warp, magic-number rounding)", "bound": "hbm", "unit": "GB/s",
