@@ -767,11 +767,10 @@ template <int CODEC>
 int launch_codec(vrq_ctx* ctx, const EncParams& p, cudaStream_t st) {
     const bool ub = p.ubin != nullptr;
     if (p.d == 1024 && ring_params_ok<CODEC>(p) && vrq_env_int("VRQ_ENCODE_RING", 1) != 0) {
-        // launch shape (B200 sweep, profiles/r01/encode_ring_sweep.txt): the codecs with per-row statistics need 16 warps per
-        // SM to cover their shuffle chains (2 blocks of 8 warps x 3 stages); the others run best with one block of 8
-        // warps and a deeper ring (4 stages = 3-4 rows per warp in flight)
-        const bool stats = CODEC == VRQ_CODEC_INT8_PERDOC || CODEC == VRQ_CODEC_INT4;
-        int stages = vrq_env_int("VRQ_ENCODE_STAGES", stats ? 3 : 4);
+        // launch shape (B200 sweeps, profiles/r01/encode_ring_sweep*.txt): one block of 8 warps with a 4-stage ring per SM
+        // (3-4 rows per warp in flight) is best for every codec except per-document int8, whose min/max shuffle chain +
+        // float divide + F2I want 16 warps per SM (2 blocks of 8 warps x 3 stages)
+        int stages = vrq_env_int("VRQ_ENCODE_STAGES", CODEC == VRQ_CODEC_INT8_PERDOC ? 3 : 4);
         stages = stages < 2 ? 2 : (stages > RING_MAX_STAGES ? RING_MAX_STAGES : stages);
         if (stages == 5) stages = 4;
         int warps = vrq_env_int("VRQ_ENCODE_WARPS", 8);
