@@ -1,8 +1,9 @@
 // Quantise / dequantise / 1-bit-code kernels (sm_100a).
 //
-// Every encoder is ONE pass over x: a warp owns a row, pulls it with 128-bit coalesced streaming loads, reduces
-// min/max/sum with warp shuffles, and writes the quantised row (+ the packbits code) with full-line stores.
-// HBM-bound: 4096 B read + {1024, 2048, 512} (+128) B written per 1024-d row.
+// Every encoder is ONE pass over x with a warp per row: min/max/sum by warp shuffles, the quantised row (+ the packbits
+// code) written with full-line stores.  d == 1024 runs encode1024_ring_kernel (rows prefetched into a per-warp
+// shared-memory ring with cp.async; encode1024_kernel, the register variant, stays as the literal-formula fallback),
+// any other d % 8 == 0 the generic kernel.  HBM-bound: 4096 B read + {1024, 2048, 512} (+128) B written per 1024-d row.
 //
 // Bit-exactness contract: all float ops are single IEEE roundings (__fmul_rn / __fadd_rn /
 // __fdiv_rn, no FMA contraction, file compiled with --fmad=false as a second fence); np.mean's float32 pairwise
