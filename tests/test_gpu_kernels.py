@@ -136,6 +136,43 @@ def test_kat1_on_gpu(K, golden_dbs):
     assert np.array_equal(K.to_binary(pay), golden_dbs["db_cohere_int8.codes"][: pay.shape[0]])
 
 
+@pytest.mark.parametrize("variant", ["dp2a", "register_ring"])
+def test_rescore_int8cos_kernel_variants(K, monkeypatch, variant):
+    """Phase III has three d = 1024 kernels: the cp.async ring with float64 FMAs (default), the same ring with integer
+    dot products on 16-bit limbs of the fixed-point query (VRQ_RESCORE_DP2A=1) and the register ring
+    (VRQ_RESCORE_ASYNC=0).  All must agree with the float64 evaluation far inside the parity tolerance."""
+    rng = np.random.default_rng(11)
+    n, nq, m = 4000, 9, 257
+    x = o.synth_f32(31, 0, n)
+    i8 = o.synth_int8_from_f32(x)
+    i8[17] = 0
+    qf = o.synth_f32(32, 0, nq)
+    qf[1] = 0                    # all-zero query
+    qf[2, ::2] *= 1e-12          # wide exponent range inside one query
+    qf[3] *= 1e20                # large magnitudes
+    qf[4] *= 1e-25               # small magnitudes
+    pos = rng.integers(0, n, (nq, m))
+    pos[0, 0] = 17
+    pos[5, 3] = -1
+    base = K.rescore_int8cos(i8, pos, qf)
+    if variant == "dp2a":
+        monkeypatch.setenv("VRQ_RESCORE_DP2A", "1")
+    else:
+        monkeypatch.setenv("VRQ_RESCORE_ASYNC", "0")
+    sc = K.rescore_int8cos(i8, pos, qf)
+    for i in range(nq):
+        ok = pos[i] >= 0
+        rc = np.full(m, -np.inf)
+        rc[ok] = o.rescore_int8cos(qf[i], i8[pos[i][ok]], literal=False)
+        fin = np.isfinite(rc)
+        assert np.array_equal(np.isfinite(sc[i]), fin) and np.array_equal(np.isfinite(base[i]), fin)
+        mag = np.zeros(m)
+        mag[ok] = o.rescore_int8cos_absfloor(qf[i], i8[pos[i][ok]]) / (4.0 * 2.0 ** -24)  # sum|q x| / |x|
+        assert np.all(np.abs(sc[i][fin] - rc[fin]) <= 1e-13 * mag[fin]), i
+        assert np.all(np.abs(base[i][fin] - rc[fin]) <= 1e-13 * mag[fin]), i
+    assert sc[0, 0] == -np.inf and sc[5, 3] == -np.inf
+
+
 def test_dequant_int4(K):
     x = make_x(500, 1024, seed=5)
     p, lo, hi = o.quantize_int4(x)

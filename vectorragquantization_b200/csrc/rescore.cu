@@ -364,6 +364,143 @@ __global__ void __launch_bounds__(256, 2) rescore_int8cos_async_kernel(const int
     }
 }
 
+// ---- Phase III, d == 1024, integer dot products ----------------------------------------------------------------------
+// Same ring as above, different arithmetic.  The float64 kernel spends ~93 of its ~180 instructions per row on 32 DFMA +
+// 32 PRMT (byte -> high word of a double) + 29 moves re-zeroing operand pairs.  Here the query is turned ONCE per block
+// into 64-bit fixed point against its own largest exponent E, Q_i = rint(q_i * 2^(61-E)) (|Q_i| < 2^62; exact for every
+// element within 2^-38 of max|q|, i.e. far below float64 accumulation error), and split into four 16-bit limbs
+// (three unsigned, the top one signed).  dp2a multiplies two limbs by two int8 bytes of the packed row word and
+// accumulates in int32 - no byte extraction, no conversion: 64 IDP.2A per row and lane, sums bounded by
+// 32 * 65535 * 128 < 2^31.  sum_i Q_i x_i = A3 2^48 + A2 2^32 + A1 2^16 + A0 is then an exact integer, rounded once into
+// a double per lane, reduced across the warp in float64 and scaled back by 2^(E-61) (a power of two: exact).
+__device__ __forceinline__ int dp2a_lo_us(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_us(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_lo_ss(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_ss(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__global__ void __launch_bounds__(256, 2) rescore_int8cos_dp2a_kernel(const int8_t* __restrict__ rows, const uint64_t* __restrict__ keys,
+                                                                      const int64_t* __restrict__ pos, int64_t pos_base, int m,
+                                                                      const float* __restrict__ qf, double* __restrict__ score) {
+    extern __shared__ __align__(16) uint8_t p3_ring[];  // [8 warps][P3_RING][2][32 lanes][16 bytes]
+    const int q = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t my_slot0 = (uint32_t)__cvta_generic_to_shared(p3_ring) + (uint32_t)(warp * P3_RING * 1024 + lane * 16);
+
+    // ---- the query slice of this lane (elements 16 lane .. +15 and 512 + 16 lane .. +15) as packed 16-bit limbs ------
+    // qa[p][l] = limb l of element 2p (low half) and of element 2p+1 (high half)
+    uint32_t qa[16][4];
+    double unscale;
+    {
+        float qv[32];
+        float amax = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                qv[16 * h + e] = qf[(size_t)q * 1024 + 512 * h + 16 * lane + e];
+                amax = fmaxf(amax, fabsf(qv[16 * h + e]));
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, o));
+        const int bexp = (__float_as_int(amax) >> 23) & 0xFF;  // biased exponent of max|q|; 0: the query is all zero / denormal
+        const int E = bexp - 127;
+        const double sc = bexp == 0 ? 0.0 : __hiloint2double((1023 + 61 - E) << 20, 0);       // 2^(61-E)
+        unscale = bexp == 0 ? 0.0 : __hiloint2double((1023 - 61 + E) << 20, 0);               // 2^(E-61)
+#pragma unroll
+        for (int pr = 0; pr < 16; pr++) {
+            const long long Q0 = __double2ll_rn((double)qv[2 * pr] * sc), Q1 = __double2ll_rn((double)qv[2 * pr + 1] * sc);
+            const uint32_t lo0 = (uint32_t)Q0, hi0 = (uint32_t)((unsigned long long)Q0 >> 32);
+            const uint32_t lo1 = (uint32_t)Q1, hi1 = (uint32_t)((unsigned long long)Q1 >> 32);
+            qa[pr][0] = __byte_perm(lo0, lo1, 0x5410);
+            qa[pr][1] = __byte_perm(lo0, lo1, 0x7632);
+            qa[pr][2] = __byte_perm(hi0, hi1, 0x5410);
+            qa[pr][3] = __byte_perm(hi0, hi1, 0x7632);
+        }
+    }
+
+    const int step = gridDim.x * 8, first = blockIdx.x * 8 + warp;
+    const int ncand = first < m ? (m - first + step - 1) / step : 0;
+    for (int c0 = 0; c0 < ncand; c0 += 32) {
+        const int nchunk = min(32, ncand - c0);
+        const size_t myidx = (size_t)q * m + first + (size_t)(c0 + lane) * step;
+        const int64_t myrow = (lane < nchunk) ? cand_row(keys, pos, myidx, pos_base) : -1;
+        double my_acc = 0.0;
+        int my_n2 = 0;
+        auto issue = [&](int j) {  // park row j of this chunk in ring slot j % P3_RING (one commit group per row, even if empty)
+            const int64_t r = __shfl_sync(FULL, myrow, j & 31);
+            if (j < nchunk && r >= 0) {
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(rows) + (size_t)r * 1024 + lane * 16;
+                const uint32_t dst = my_slot0 + (uint32_t)((j % P3_RING) * 1024);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512), "l"(src + 512) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+#pragma unroll
+        for (int j = 0; j < P3_RING; j++) issue(j);
+#pragma unroll 1
+        for (int j = 0; j < nchunk; j++) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(P3_RING - 1) : "memory");
+            const int64_t row = __shfl_sync(FULL, myrow, j);
+            const uint32_t src = my_slot0 + (uint32_t)((j % P3_RING) * 1024);
+            uint4 v0, v1;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v0.x), "=r"(v0.y), "=r"(v0.z), "=r"(v0.w) : "r"(src) : "memory");
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v1.x), "=r"(v1.y), "=r"(v1.z), "=r"(v1.w) : "r"(src + 512) : "memory");
+            if (row >= 0) {
+                int a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+                int n2 = 0;
+                const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w}, w1[4] = {v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    n2 = __dp4a((int)w0[c], (int)w0[c], n2);
+                    n2 = __dp4a((int)w1[c], (int)w1[c], n2);
+#pragma unroll
+                    for (int l = 0; l < 3; l++) {
+                        a0[l] = dp2a_lo_us(qa[2 * c][l], w0[c], a0[l]);
+                        a0[l] = dp2a_hi_us(qa[2 * c + 1][l], w0[c], a0[l]);
+                        a1[l] = dp2a_lo_us(qa[8 + 2 * c][l], w1[c], a1[l]);
+                        a1[l] = dp2a_hi_us(qa[8 + 2 * c + 1][l], w1[c], a1[l]);
+                    }
+                    a0[3] = dp2a_lo_ss(qa[2 * c][3], w0[c], a0[3]);
+                    a0[3] = dp2a_hi_ss(qa[2 * c + 1][3], w0[c], a0[3]);
+                    a1[3] = dp2a_lo_ss(qa[8 + 2 * c][3], w1[c], a1[3]);
+                    a1[3] = dp2a_hi_ss(qa[8 + 2 * c + 1][3], w1[c], a1[3]);
+                }
+                double s = (double)(a0[3] + a1[3]);
+                s = fma(s, 65536.0, (double)(a0[2] + a1[2]));
+                s = fma(s, 65536.0, (double)(a0[1] + a1[1]));
+                s = fma(s, 65536.0, (double)(a0[0] + a1[0]));
+                const double acc = warp_sum_f64(s);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(FULL, n2, o);
+                if (lane == j) {
+                    my_acc = acc;
+                    my_n2 = n2;
+                }
+            }
+            issue(j + P3_RING);  // the slot just read is free again (this lane's own reads are complete: v0 / v1 were consumed)
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (lane < nchunk) score[myidx] = (myrow < 0 || my_n2 == 0) ? -INFINITY : (my_acc * unscale) / sqrt((double)my_n2);
+    }
+}
+
 // ---- 2-phase rescoring of the VectorDB* classes: float32 dot(q, dequantised payload row) -------------------------
 struct PayloadParams {
     int kind;
@@ -630,8 +767,13 @@ int vrq_launch_rescore_int8cos(vrq_ctx* ctx, const int8_t* rows, int d, const ui
     }
     vrq_timer_scope ts(ctx, VRQ_CAT_RESCORE, st);
     dim3 grid(grid_x_for(ctx, nq, m), (unsigned)nq);
-    static const bool use_async = !(getenv("VRQ_RESCORE_ASYNC") && atoi(getenv("VRQ_RESCORE_ASYNC")) == 0);
-    if (d == 1024 && use_async) {
+    const bool use_async = !(getenv("VRQ_RESCORE_ASYNC") && atoi(getenv("VRQ_RESCORE_ASYNC")) == 0);  // read per call (tests switch it)
+    const bool use_dp2a = getenv("VRQ_RESCORE_DP2A") && atoi(getenv("VRQ_RESCORE_DP2A")) != 0;  // opt-in: integer dot products
+    if (d == 1024 && use_async && use_dp2a) {
+        const size_t smem = (size_t)8 * P3_RING * 1024;
+        VRQ_CUDA(cudaFuncSetAttribute(rescore_int8cos_dp2a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rescore_int8cos_dp2a_kernel<<<grid, 256, smem, st>>>(rows, keys, pos, pos_base, m, qf, score);
+    } else if (d == 1024 && use_async) {
         const size_t smem = (size_t)8 * P3_RING * 1024;
         VRQ_CUDA(cudaFuncSetAttribute(rescore_int8cos_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         rescore_int8cos_async_kernel<<<grid, 256, smem, st>>>(rows, keys, pos, pos_base, m, qf, score);
