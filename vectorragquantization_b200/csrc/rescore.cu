@@ -284,6 +284,12 @@ __global__ void __launch_bounds__(256, 2) rescore_int8cos_kernel(const int8_t* _
 // the ring needs no barrier at all: cp.async.wait_group orders a lane's own copies.  Same arithmetic as above.
 constexpr int P3_RING = 8;
 
+// BATCH (opt-in, VRQ_RESCORE_BATCHRED=1; written at the end of round 1, NOT yet run on a GPU): the per-row butterfly
+// reductions (15 shuffles + 10 adds per row, the top stall of the ncu capture) are replaced by a transpose through shared
+// memory - every lane parks its partial dot / partial norm of row j in red[j & 7][lane]; after 8 rows lane (qd, r) adds
+// the 8 partials of quarter qd of row r (columns visited in the skewed order 8 qd + ((i + r) & 7): conflict-free), two
+// xor-shuffle steps close the sum over the quarters, and lane j picks up the total of row j.
+template <bool BATCH>
 __global__ void __launch_bounds__(256, 2) rescore_int8cos_async_kernel(const int8_t* __restrict__ rows, const uint64_t* __restrict__ keys,
                                                                        const int64_t* __restrict__ pos, int64_t pos_base, int m,
                                                                        const float* __restrict__ qf, double* __restrict__ score) {
@@ -291,6 +297,9 @@ __global__ void __launch_bounds__(256, 2) rescore_int8cos_async_kernel(const int
     const int q = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t my_slot0 = (uint32_t)__cvta_generic_to_shared(p3_ring) + (uint32_t)(warp * P3_RING * 1024 + lane * 16);
+    // BATCH: [8 warps][8 rows][32 lanes] doubles, then the same shape of ints, behind the ring
+    double* red_acc = reinterpret_cast<double*>(p3_ring + 8 * P3_RING * 1024) + warp * 256;
+    int* red_n2 = reinterpret_cast<int*>(p3_ring + 8 * P3_RING * 1024 + 8 * 256 * sizeof(double)) + warp * 256;
     double qr[32];
     double qsum = 0.0;
 #pragma unroll
@@ -348,13 +357,42 @@ __global__ void __launch_bounds__(256, 2) rescore_int8cos_async_kernel(const int
                         acc3 = fma(qr[16 + 4 * c + b + 1], __hiloint2double((int)__byte_perm(0x40B00000u, u1, 0x3200 | ((5 + b) << 4)), 0), acc3);
                     }
                 }
-                const double acc = warp_sum_f64((acc0 + acc1) + (acc2 + acc3));
+                if (BATCH) {
+                    red_acc[(j & 7) * 32 + lane] = (acc0 + acc1) + (acc2 + acc3);
+                    red_n2[(j & 7) * 32 + lane] = n2;
+                } else {
+                    const double acc = warp_sum_f64((acc0 + acc1) + (acc2 + acc3));
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(FULL, n2, o);
-                if (lane == j) {
-                    my_acc = acc;
-                    my_n2 = n2;
+                    for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(FULL, n2, o);
+                    if (lane == j) {
+                        my_acc = acc;
+                        my_n2 = n2;
+                    }
                 }
+            } else if (BATCH) {
+                red_acc[(j & 7) * 32 + lane] = 0.0;
+                red_n2[(j & 7) * 32 + lane] = 0;
+            }
+            if (BATCH && ((j & 7) == 7 || j == nchunk - 1)) {
+                __syncwarp();
+                const int r = lane & 7, qd = lane >> 3;
+                double a = 0.0;
+                int nn = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int col = 8 * qd + ((i + r) & 7);
+                    a += red_acc[r * 32 + col];
+                    nn += red_n2[r * 32 + col];
+                }
+                a += __shfl_xor_sync(FULL, a, 8);
+                a += __shfl_xor_sync(FULL, a, 16);
+                nn += __shfl_xor_sync(FULL, nn, 8);
+                nn += __shfl_xor_sync(FULL, nn, 16);
+                if ((lane >> 3) == (j >> 3)) {  // lanes 8 (j/8) .. +7 take the totals of rows 8 (j/8) + (lane & 7)
+                    my_acc = a;
+                    my_n2 = nn;
+                }
+                __syncwarp();
             }
             issue(j + P3_RING);  // the slot just read is free again (this lane's own reads are complete: v0 / v1 were consumed)
         }
@@ -775,8 +813,14 @@ int vrq_launch_rescore_int8cos(vrq_ctx* ctx, const int8_t* rows, int d, const ui
         rescore_int8cos_dp2a_kernel<<<grid, 256, smem, st>>>(rows, keys, pos, pos_base, m, qf, score);
     } else if (d == 1024 && use_async) {
         const size_t smem = (size_t)8 * P3_RING * 1024;
-        VRQ_CUDA(cudaFuncSetAttribute(rescore_int8cos_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rescore_int8cos_async_kernel<<<grid, 256, smem, st>>>(rows, keys, pos, pos_base, m, qf, score);
+        if (getenv("VRQ_RESCORE_BATCHRED") && atoi(getenv("VRQ_RESCORE_BATCHRED")) != 0) {  // opt-in, see the kernel's comment
+            const size_t smem_b = smem + 8 * 256 * (sizeof(double) + sizeof(int));
+            VRQ_CUDA(cudaFuncSetAttribute(rescore_int8cos_async_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+            rescore_int8cos_async_kernel<true><<<grid, 256, smem_b, st>>>(rows, keys, pos, pos_base, m, qf, score);
+        } else {
+            VRQ_CUDA(cudaFuncSetAttribute(rescore_int8cos_async_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            rescore_int8cos_async_kernel<false><<<grid, 256, smem, st>>>(rows, keys, pos, pos_base, m, qf, score);
+        }
     } else if (d == 1024)
         rescore_int8cos_kernel<true><<<grid, 256, 0, st>>>(rows, d, keys, pos, pos_base, m, qf, score);
     else
