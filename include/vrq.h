@@ -58,7 +58,8 @@ int vrq_ctx_device(const vrq_ctx* ctx);
 /* ---------------------------------------------------------------- encoders ------------------------
  * x: float32[n, d].  ubin (nullable): uint8[n, d/8] = np.packbits(x > np.mean(x)) of the same row, fused
  * into the same pass over x (the reference calls _quantize_* and _to_binary back to back on every
- * embedding: VectorDBInt8.py:103-106). */
+ * embedding: VectorDBInt8.py:103-106).  Device pointers: x and q 16-byte aligned, ubin 4-byte aligned (any torch /
+ * cudaMalloc allocation is; VRQ_ERR_ARG otherwise).  Host pointers: no alignment requirement. */
 
 /* VectorDBInt8._quantize_to_int8 (VectorDBInt8.py:114-126): scale = f32(127)/max(|min|,|max|) (f32 divide),
  * q = trunc(x*scale); max == min -> zeros.  q int8[n,d]; mn, mx float32[n]. */

@@ -9,6 +9,7 @@
 // __fdiv_rn, no FMA contraction, file compiled with --fmad=false as a second fence); np.mean's float32 pairwise
 // summation tree is reproduced add for add (A.2).
 #include <math.h>
+#include <stdint.h>
 #include <stdlib.h>
 
 #include "vrq_internal.cuh"
@@ -834,6 +835,12 @@ int vrq_launch_encode(vrq_ctx* ctx, const vrq_encode_args& a, cudaStream_t st) {
     if (a.d != 1024 && a.d > GEN_MAX_D) {
         vrq_set_error("embedding_dim %d > %d is not supported by the encode kernels", a.d, GEN_MAX_D);
         return VRQ_ERR_UNSUPPORTED;
+    }
+    // every kernel moves rows with 16-byte vector accesses (torch allocations and the library's staging buffers are
+    // 256-byte aligned; a caller-made sub-view might not be): refuse instead of faulting
+    if (((uintptr_t)a.x | (uintptr_t)a.q) & 15u || ((uintptr_t)a.ubin & 3u)) {
+        vrq_set_error("encode: x and q must be 16-byte aligned and ubinary 4-byte aligned device pointers");
+        return VRQ_ERR_ARG;
     }
     EncParams p{a.x, a.n, a.d, a.limit_f32, a.scale_f32, a.q, a.mn, a.mx, a.ubin, a.ge};
     vrq_timer_scope ts(ctx, VRQ_CAT_ENCODE, st);
