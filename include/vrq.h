@@ -141,9 +141,26 @@ int vrq_index_reconstruct(vrq_index*, int64_t id, uint8_t* code_out);
  * faiss, through a 64 MB bounce buffer - before the next call that reads them, so the reference's one-id-per-call
  * remove_document loop costs one pass instead of one O(N) pass per id.  vrq_index_ntotal reflects it immediately. */
 int64_t vrq_index_remove_ids(vrq_index*, int64_t n, const int64_t* ids);
-/* faiss.write_index_binary / read_index_binary (CohereEnhancedVectorDB.py:346,123): byte-compatible "IBM2"/"IBxF". */
+/* faiss.write_index_binary / read_index_binary (CohereEnhancedVectorDB.py:346,123): byte-compatible "IBM2"/"IBxF".
+ * Both stream between the file and device memory in 64 MB chunks (13.6 GB at 100 M codes never sits in host memory);
+ * the writer goes through "<path>.tmp" + fsync + rename, so a crash leaves the old file or the new one. */
 int vrq_index_write(vrq_index*, const char* path);
 int vrq_index_read(vrq_ctx*, const char* path, vrq_index** out);
+/* The quantised vectors the reference keeps in RocksDB pickles beside index.bin (CohereEnhancedVectorDB.py:221 {"int8"},
+ * VectorDBInt8.py:179 {"emb_int8","min_max"}) as one flat sidecar file ("VRQP": header, payload rows, aux rows), streamed
+ * the same way.  read_payload attaches the rows to an index that came from vrq_index_read (same ntotal, no payload yet). */
+int vrq_index_write_payload(vrq_index*, const char* path);
+int vrq_index_read_payload(vrq_index*, const char* path);
+/* Give a payload-less index (e.g. one read from a reference-written index.bin) zero-filled payload rows of `kind`, to be
+ * filled with vrq_index_write_rows: how the importer of the reference's docs/ store re-attaches its int8 vectors. */
+int vrq_index_attach_payload(vrq_index*, int kind, double global_limit);
+/* `count` consecutive rows starting at position `offset` of one resident array, to / from a host or device buffer. */
+#define VRQ_ROWS_CODES 0   /* uint8[d/8]              */
+#define VRQ_ROWS_IDS 1     /* int64                   */
+#define VRQ_ROWS_PAYLOAD 2 /* row type of the payload kind */
+#define VRQ_ROWS_AUX 3     /* {min,max} pairs         */
+int vrq_index_read_rows(vrq_index*, int which, int64_t offset, int64_t count, void* out);
+int vrq_index_write_rows(vrq_index*, int which, int64_t offset, int64_t count, const void* src); /* codes / payload / aux */
 /* Copy payload rows (and aux) of the given positions to host/device buffers (doc_db.get replacement). */
 int vrq_index_get_payload(vrq_index*, int64_t m, const int64_t* positions, void* payload_out, void* aux_out);
 int64_t vrq_index_position_of(vrq_index*, int64_t id); /* -1 if absent */
@@ -187,6 +204,12 @@ int vrq_synth_f32(vrq_ctx*, uint64_t seed, int64_t row0, int64_t nrows, int d, i
 int vrq_synth_codes_int8(vrq_ctx*, uint64_t seed, int64_t row0, int64_t nrows, int d, uint8_t* codes, int8_t* int8_rows);
 /* Append nrows synthetic rows straight into a device-resident index (ids = id0 + i), payload INT8_RAW or NONE. */
 int vrq_index_add_synthetic(vrq_index*, uint64_t seed, int64_t row0, int64_t nrows, int64_t id0);
+
+/* Benchmark-only stand-in for an INT8_RAW payload that does not fit in HBM (1 billion rows x 1 KB on fewer than 8 GPUs,
+ * SURVEY.md H6): nothing is stored, Phase III regenerates the int8 row of position p from the counter-based generator
+ * (seed, row0 + p) - the bytes vrq_index_add_synthetic would have stored.  Only on an empty index whose payload kind is
+ * INT8_RAW; afterwards the index accepts vrq_index_add_synthetic(seed, row0 + ntotal, ...) only, and no removals. */
+int vrq_index_set_synthetic_payload(vrq_index*, uint64_t seed, int64_t row0);
 
 /* CUDA-event timing of the library's own kernels on the launching stream (bench.py's roofline.achieved).
  * After vrq_ctx_enable_timing(ctx, 1) every scan / encode / rescore / merge launch group is bracketed by events;

@@ -57,6 +57,29 @@ def quantize_int8_perdoc(x: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndar
     return q, lo, hi
 
 
+def quantize_int8_perdoc_one(v: np.ndarray):
+    """VectorDBInt8._quantize_to_int8 (VectorDBInt8.py:114-126) for ONE vector with the reference's own NumPy call
+    sequence (np.min, np.max, Python max/abs on NumPy scalars, one multiply, astype) - the per-document cost the
+    reference pays; used by bench.py's cfg1 CPU leg.  Same result as quantize_int8_perdoc (tests/test_oracle_golden.py)."""
+    lo, hi = np.min(v), np.max(v)
+    if hi == lo:
+        return np.zeros_like(v, dtype=np.int8), lo, hi
+    scale = 127 / max(abs(lo), abs(hi))
+    return (v * scale).astype(np.int8), lo, hi
+
+
+def dequantize_int8_perdoc_one(q: np.ndarray, lo, hi) -> np.ndarray:
+    """VectorDBInt8._dequantize_int8 (VectorDBInt8.py:128-138) for ONE vector."""
+    if hi == lo:
+        return np.zeros_like(q, dtype=np.float32)
+    return q.astype(np.float32) * (max(abs(lo), abs(hi)) / 127)
+
+
+def to_binary_one(v: np.ndarray) -> np.ndarray:
+    """``_to_binary`` (VectorDBInt8.py:140-146) for ONE vector."""
+    return np.packbits((v > np.mean(v)).astype(np.uint8))
+
+
 def dequantize_int8_perdoc(q: np.ndarray, lo: np.ndarray, hi: np.ndarray) -> np.ndarray:
     """VectorDBInt8._dequantize_int8 (VectorDBInt8.py:128-138): q.astype(f32) * (max(|min|,|max|)/127), f32."""
     q = np.asarray(q, dtype=np.int8)
@@ -336,14 +359,27 @@ def search3(codes: np.ndarray, ids: np.ndarray, int8_rows, q_float: np.ndarray, 
         return []
     binary_k = min(k * binary_oversample, n)
     dist, pos = hamming_topk(codes, q_ubinary, binary_k, pos_base=0)
-    hits = [{"doc_id": int(ids[p]), "pos": int(p) + pos_base, "score_hamming": int(d)}
-            for d, p in zip(dist[0], pos[0]) if p != -1]
+    return search3_after_phase1(dist[0], pos[0], lambda p: ids[p], lambda p: codes[p], int8_rows, q_float, k,
+                                binary_oversample, int8_oversample, literal, pos_base)
+
+
+def search3_after_phase1(dist: np.ndarray, pos: np.ndarray, ids_of, codes_of, int8_rows, q_float: np.ndarray,
+                         k: int = 10, binary_oversample: int = 10, int8_oversample: int = 3, literal: bool = True,
+                         pos_base: int = 0) -> List[dict]:
+    """Everything of CohereEnhancedVectorDB.search that follows ``index.search`` (:269-322), given faiss's answer
+    (dist int32[binary_k], pos int64[binary_k], -1 padded) for one query.  ``ids_of`` / ``codes_of`` / ``int8_rows``:
+    callables positions -> int64[m] / uint8[m, D/8] / int8[m, D] (``int8_rows`` may also be an array).  Used by the
+    scale tests, where phase I comes from the C scan over database chunks and the rows are regenerated on demand."""
+    keep = pos != -1
+    lab = ids_of(pos[keep])
+    hits = [{"doc_id": int(i), "pos": int(p) + pos_base, "score_hamming": int(d)}
+            for d, p, i in zip(dist[keep], pos[keep], lab)]
     hits.sort(key=lambda h: h["score_hamming"])  # stable (:274)
     cand = hits[:k * binary_oversample]
     if not cand:
         return []
     p = np.array([h["pos"] - pos_base for h in cand], np.int64)
-    sb = rescore_binary(q_float, codes[p], literal)
+    sb = rescore_binary(q_float, codes_of(p), literal)
     for h, s in zip(cand, sb):
         h["score_binary"] = float(s)
     cand.sort(key=lambda h: h["score_binary"], reverse=True)  # stable (:296)

@@ -156,7 +156,27 @@ def load_reference_module(name):
     return __import__(name)
 
 
+def copy_fixture_dbs():
+    """Two of the reference's committed 1000-document database folders, byte for byte (DATA, not source: config.json,
+    index.bin and the RocksDB files of docs/), so that the GPU box - which never sees /root/reference - can check that
+    a folder WRITTEN BY THE REFERENCE opens in this package (tests/test_gpu_classes.py::test_open_reference_written_*)."""
+    import shutil
+    for db in ("db_cohere_enhanced", "db_int8"):
+        dst = os.path.join(OUT, db)
+        if os.path.exists(dst):
+            shutil.rmtree(dst)
+        os.makedirs(os.path.join(dst, "docs"))
+        for f in ("config.json", "index.bin"):
+            shutil.copyfile(f"{REF}/{db}/{f}", os.path.join(dst, f))
+        for f in os.listdir(f"{REF}/{db}/docs"):
+            if f.endswith(".sst") or f in ("CURRENT", "rocksdict-config.json") or f.startswith("MANIFEST"):
+                shutil.copyfile(f"{REF}/{db}/docs/{f}", os.path.join(dst, "docs", f))
+        os.chmod(dst, 0o755)
+        print("copied", db, sum(os.path.getsize(os.path.join(r, x)) for r, _, fs in os.walk(dst) for x in fs), "bytes")
+
+
 def main():
+    copy_fixture_dbs()
     rows = {}
     dbs = ["db_int8", "db_int8_global", "db_int4", "db_int4_global", "db_int16", "db_int16_global",
            "db_cohere_int8", "db_cohere_enhanced"]

@@ -218,3 +218,106 @@ def test_cohere_int8_class(tmp_path):
     assert [r["doc_id"] for r in res] == p[0][:10].tolist() and [r["score"] for r in res] == d[0][:10].tolist()
     with pytest.raises(NotImplementedError):
         db.search_rerank_cohere(QUERY)
+
+
+def _golden_walker():
+    """tests/golden/make_golden.py's own decoder of the reference's database files (test infrastructure, independent of the
+    product's importer)."""
+    import importlib.util
+    from conftest import GOLDEN
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m, GOLDEN
+
+
+def test_open_reference_written_cohere_enhanced(tmp_path):
+    """A database folder WRITTEN BY THE REFERENCE (config.json + faiss index.bin + rocksdict docs/, committed in the
+    reference repo as db_cohere_enhanced) opens as-is (CohereEnhancedVectorDB.py:116-128); the 3-phase search over it equals
+    the oracle run on the arrays decoded independently from the same files.  Queries: Cohere-like (float, ubinary) pairs
+    derived from stored documents, so there are true neighbours."""
+    import shutil
+    import vectorragquantization_b200 as V
+    g, GOLDEN = _golden_walker()
+    folder = os.path.join(tmp_path, "db_cohere_enhanced")
+    shutil.copytree(os.path.join(GOLDEN, "db_cohere_enhanced"), folder)
+    d, codes, ids, _ = g.read_index_bin(os.path.join(folder, "index.bin"))
+    docs = g.read_docs(os.path.join(folder, "docs", "000009.sst"))
+    i8 = np.stack([np.asarray(docs[int(i)]["int8"]) for i in ids])
+    rng = np.random.default_rng(3)
+    qsrc = [5, 123, 777, 999]
+    qf = np.stack([(i8[j].astype(np.float32) + rng.normal(0, 12, 1024).astype(np.float32)) / np.float32(1259.0) for j in qsrc])
+    qb = np.packbits(qf > 0, axis=1)
+    table = {f"q{j}": i for i, j in enumerate(qsrc)}
+
+    def embedder(texts, input_type, embedding_types):
+        sel = [table[t] for t in texts]
+        return {"float": qf[sel], "ubinary": qb[sel]}
+
+    db = V.CohereEnhancedVectorDB(folder, embedder=embedder)
+    assert len(db) == 1000 and db.index.payload_kind == V._lib.PAYLOAD_INT8_RAW
+    assert np.array_equal(db.index.read_rows(V._lib.ROWS_PAYLOAD, 0, 1000), i8)
+    for k, bo, io in ((10, 10, 3), (50, 10, 3)):
+        for qi, j in enumerate(qsrc):
+            ref = o.search3(codes, ids, i8, qf[qi], qb[qi], k, bo, io)
+            res = db.search(f"q{j}", k=k, binary_oversample=bo, int8_oversample=io)
+            assert [r["doc_id"] for r in res] == [h["doc_id"] for h in ref]
+            assert [r["score_hamming"] for r in res] == [h["score_hamming"] for h in ref]
+            for r, h in zip(res, ref):
+                assert r["doc"] == docs[r["doc_id"]]["doc"]
+                assert close(r["score_binary"], h["score_binary"], 1e-12)
+                assert close(r["score_cosine"], h["score_cosine"], float(o.rescore_int8cos_absfloor(qf[qi], i8[[h["doc_id"]]])[0]))
+    # save() next to the reference's files (index.bin byte-identical, streamed sidecar, docs.log overlay), reopen, same answers
+    before = open(os.path.join(folder, "index.bin"), "rb").read()
+    db.remove_document(int(ids[17]), save=False)
+    db.add_embeddings([5000], i8[17:18], codes[17:18], docs=["re-added"], save=True)
+    db2 = V.CohereEnhancedVectorDB(folder, embedder=embedder)
+    assert len(db2) == 1000 and os.path.exists(os.path.join(folder, "payload.vrqp"))
+    assert db2.search("q5", k=10) == db.search("q5", k=10)
+    assert db2.doc_db.get("5000")["doc"] == "re-added" and "17" not in db2.doc_db
+    assert len(before) == 136066 and g.read_index_bin(os.path.join(folder, "index.bin"))[2][-1] == 5000
+
+
+def test_open_reference_written_int8(tmp_path):
+    """The reference's committed db_int8 folder (VectorDBInt8: per-document int8 + min_max in the docs store) opens and its
+    2-phase search equals the oracle on the independently decoded arrays."""
+    import shutil
+    import vectorragquantization_b200 as V
+    g, GOLDEN = _golden_walker()
+    folder = os.path.join(tmp_path, "db_int8")
+    shutil.copytree(os.path.join(GOLDEN, "db_int8"), folder)
+    d, codes, ids, _ = g.read_index_bin(os.path.join(folder, "index.bin"))
+    docs = g.read_docs(os.path.join(folder, "docs", "000009.sst"))
+    q8 = np.stack([np.asarray(docs[int(i)]["emb_int8"]) for i in ids])
+    lo = np.array([docs[int(i)]["min_max"][0] for i in ids], np.float32)
+    hi = np.array([docs[int(i)]["min_max"][1] for i in ids], np.float32)
+    emb = o.dequantize_int8_perdoc(q8, lo, hi)
+    db = V.VectorDBInt8(folder, embedder=lambda texts: np.stack([emb[int(t)] for t in texts]))
+    assert len(db) == 1000
+    for j in (3, 500, 998):
+        qf = emb[j]
+        qb = o.to_binary_f32(qf)
+        for k, bo in ((10, 10), (100, 10)):
+            check_search2(db.search(str(j), k=k, binary_oversample=bo), o.search2(codes, ids, lambda p: emb[p], qf, qb, k, bo))
+    assert db.search("3", k=1)[0]["doc"] == docs[db.search("3", k=1)[0]["doc_id"]]["doc"]
+    db.save()
+    db2 = V.VectorDBInt8(folder, embedder=lambda texts: np.stack([emb[int(t)] for t in texts]))
+    assert db2.search("500", k=10) == db.search("500", k=10)
+
+
+def test_remove_and_readd_without_float_rows(tmp_path):
+    """add_embeddings(keep_float=False) with a duplicate id, and a re-add after a reopen, must neither raise nor
+    leave the document half removed (the reference raises KeyError from `del float_embeddings[id]` after a reopen)."""
+    import vectorragquantization_b200 as V
+    folder = os.path.join(tmp_path, "db")
+    db = V.VectorDBInt8Global(folder, global_limit=0.3)
+    x = synth_rows(DOCS[:50])
+    db.add_embeddings(IDS[:50], x, DOCS[:50], keep_float=False)
+    db.add_embeddings([7], x[8:9], ["seven again"], keep_float=False)  # duplicate id: replaced, not an exception
+    assert len(db) == 50 and db.doc_db.get("7")["doc"] == "seven again" and db.index.position_of(7) == 49
+    db.save()
+    db2 = V.VectorDBInt8Global(folder)
+    db2.add_documents([3], ["a replaced document"])  # re-add after a reopen (float_embeddings is empty)
+    assert len(db2) == 50 and db2.index.position_of(3) == 49
+    db2.remove_document(4)
+    assert len(db2) == 49 and "4" not in db2.doc_db

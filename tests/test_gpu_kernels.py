@@ -136,11 +136,13 @@ def test_kat1_on_gpu(K, golden_dbs):
     assert np.array_equal(K.to_binary(pay), golden_dbs["db_cohere_int8.codes"][: pay.shape[0]])
 
 
-@pytest.mark.parametrize("variant", ["dp2a", "register_ring"])
+@pytest.mark.parametrize("variant", ["dp2a", "register_ring", "batchred", "cuda_core", "imma", "imma43", "imma62", "imma13"])
 def test_rescore_int8cos_kernel_variants(K, monkeypatch, variant):
-    """Phase III has three d = 1024 kernels: the cp.async ring with float64 FMAs (default), the same ring with integer
-    dot products on 16-bit limbs of the fixed-point query (VRQ_RESCORE_DP2A=1) and the register ring
-    (VRQ_RESCORE_ASYNC=0).  All must agree with the float64 evaluation far inside the parity tolerance."""
+    """Phase III has several d = 1024 kernels: the cp.async ring with float64 FMAs, the same ring with integer dot
+    products on 16-bit limbs of the fixed-point query (VRQ_RESCORE_DP2A=1), with batched reductions
+    (VRQ_RESCORE_BATCHRED=1), the register ring (VRQ_RESCORE_ASYNC=0) and the tensor-core kernel (mma.sync s8 over eight
+    base-256 digits of the fixed-point query, VRQ_RESCORE_IMMA=1, several launch shapes).  All must agree with the
+    float64 evaluation far inside the parity tolerance."""
     rng = np.random.default_rng(11)
     n, nq, m = 4000, 9, 257
     x = o.synth_f32(31, 0, n)
@@ -154,11 +156,17 @@ def test_rescore_int8cos_kernel_variants(K, monkeypatch, variant):
     pos = rng.integers(0, n, (nq, m))
     pos[0, 0] = 17
     pos[5, 3] = -1
+    pos[6, -40:] = -1            # a whole 16-row group without a valid row
     base = K.rescore_int8cos(i8, pos, qf)
+    monkeypatch.setenv("VRQ_RESCORE_IMMA", "1" if variant.startswith("imma") else "0")
     if variant == "dp2a":
         monkeypatch.setenv("VRQ_RESCORE_DP2A", "1")
-    else:
+    elif variant == "batchred":
+        monkeypatch.setenv("VRQ_RESCORE_BATCHRED", "1")
+    elif variant == "register_ring":
         monkeypatch.setenv("VRQ_RESCORE_ASYNC", "0")
+    elif variant.startswith("imma") and len(variant) > 4:
+        monkeypatch.setenv("VRQ_RESCORE_IMMA_SHAPE", variant[4:])
     sc = K.rescore_int8cos(i8, pos, qf)
     for i in range(nq):
         ok = pos[i] >= 0
@@ -171,6 +179,34 @@ def test_rescore_int8cos_kernel_variants(K, monkeypatch, variant):
         assert np.all(np.abs(sc[i][fin] - rc[fin]) <= 1e-13 * mag[fin]), i
         assert np.all(np.abs(base[i][fin] - rc[fin]) <= 1e-13 * mag[fin]), i
     assert sc[0, 0] == -np.inf and sc[5, 3] == -np.inf
+
+
+def test_rescore_binary_lut_equals_register_kernel(K, monkeypatch):
+    """Phase II for d = 1024: the nibble-table kernel (default) and the register kernel agree with the float64 evaluation
+    to rounding, incl. invalid positions, all-zero and wide-range queries, m not a multiple of the block size."""
+    rng = np.random.default_rng(12)
+    n, nq, m = 3000, 6, 1000
+    codes = rng.integers(0, 256, (n, 128)).astype(np.uint8)
+    codes[5] = 0
+    codes[6] = 255
+    qf = o.synth_f32(33, 0, nq)
+    qf[1] = 0
+    qf[2, ::2] *= 1e-12
+    qf[3] *= 1e20
+    pos = rng.integers(0, n, (nq, m))
+    pos[0, :2] = (5, 6)
+    pos[4, 7] = -1
+    got = {}
+    for lut in ("1", "0"):
+        monkeypatch.setenv("VRQ_RESCORE_BIN_LUT", lut)
+        got[lut] = K.rescore_binary(codes, pos, qf)
+    for i in range(nq):
+        ok = pos[i] >= 0
+        ref = o.rescore_binary(qf[i], codes[pos[i][ok]], literal=False)
+        mag = np.abs(qf[i].astype(np.float64)).sum()
+        for lut in ("1", "0"):
+            assert np.all(np.abs(got[lut][i][ok] - ref) <= 1e-13 * mag + 1e-300), (lut, i)
+            assert np.all(got[lut][i][~ok] == -np.inf)
 
 
 def test_dequant_int4(K):

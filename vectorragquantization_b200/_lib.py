@@ -22,6 +22,8 @@ PAYLOAD_NONE, PAYLOAD_INT8_RAW, PAYLOAD_INT8_PERDOC, PAYLOAD_INT8_GLOBAL = 0, 1,
 PAYLOAD_INT16_GLOBAL, PAYLOAD_INT4_PERDOC, PAYLOAD_INT4_GLOBAL, PAYLOAD_F32 = 4, 5, 6, 7
 PAYLOAD_CODES_PM1 = 8
 
+ROWS_CODES, ROWS_IDS, ROWS_PAYLOAD, ROWS_AUX = 0, 1, 2, 3
+
 KEY_POS_BITS = 40
 KEY_NONE = 0xFFFFFFFFFFFFFFFF
 MAX_K = 4096
@@ -78,6 +80,11 @@ SIGNATURES = {
     "vrq_index_remove_ids": (_i64, [_vp, _i64, _vp]),
     "vrq_index_write": (_i32, [_vp, C.c_char_p]),
     "vrq_index_read": (_i32, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "vrq_index_write_payload": (_i32, [_vp, C.c_char_p]),
+    "vrq_index_read_payload": (_i32, [_vp, C.c_char_p]),
+    "vrq_index_attach_payload": (_i32, [_vp, _i32, _dbl]),
+    "vrq_index_read_rows": (_i32, [_vp, _i32, _i64, _i64, _vp]),
+    "vrq_index_write_rows": (_i32, [_vp, _i32, _i64, _i64, _vp]),
     "vrq_index_get_payload": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "vrq_index_position_of": (_i64, [_vp, _i64]),
     "vrq_index_search3": (_i32, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
@@ -89,6 +96,7 @@ SIGNATURES = {
     "vrq_synth_f32": (_i32, [_vp, _u64, _i64, _i64, _i32, _i32, _vp]),
     "vrq_synth_codes_int8": (_i32, [_vp, _u64, _i64, _i64, _i32, _vp, _vp]),
     "vrq_index_add_synthetic": (_i32, [_vp, _u64, _i64, _i64, _i64]),
+    "vrq_index_set_synthetic_payload": (_i32, [_vp, _u64, _i64]),
 }
 
 

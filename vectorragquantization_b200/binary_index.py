@@ -129,6 +129,45 @@ class BinaryIndex:
     def add_synthetic(self, seed: int, row0: int, nrows: int, id0: int) -> None:
         L.check(self._lib.vrq_index_add_synthetic(self._h, C.c_uint64(seed), int(row0), int(nrows), int(id0)))
 
+    # ---- resident rows and the payload sidecar file ------------------------------------------------------------------
+    def payload_layout(self):
+        """(row dtype, row length, aux dtype or None) of this index's payload kind."""
+        d = self.d
+        return {L.PAYLOAD_INT8_RAW: (np.int8, d, None), L.PAYLOAD_INT8_PERDOC: (np.int8, d, np.float32),
+                L.PAYLOAD_INT8_GLOBAL: (np.int8, d, None), L.PAYLOAD_INT16_GLOBAL: (np.int16, d, None),
+                L.PAYLOAD_INT4_PERDOC: (np.int8, d // 2, np.float64), L.PAYLOAD_INT4_GLOBAL: (np.int8, d // 2, None),
+                L.PAYLOAD_F32: (np.float32, d, None)}[self.payload_kind]
+
+    def read_rows(self, which: int, offset: int, count: int) -> np.ndarray:
+        """``count`` consecutive rows of the resident codes / ids / payload / aux arrays (L.ROWS_*), copied to the host."""
+        if which == L.ROWS_CODES:
+            out = np.empty((count, self.code_size), np.uint8)
+        elif which == L.ROWS_IDS:
+            out = np.empty(count, np.int64)
+        else:
+            dt, ln, adt = self.payload_layout()
+            out = np.empty((count, ln), dt) if which == L.ROWS_PAYLOAD else np.empty((count, 2), adt)
+        L.check(self._lib.vrq_index_read_rows(self._h, int(which), int(offset), int(count), L.ptr(out)))
+        return out
+
+    def write_rows(self, which: int, offset: int, rows) -> None:
+        rows = np.ascontiguousarray(rows)
+        L.check(self._lib.vrq_index_write_rows(self._h, int(which), int(offset), int(rows.shape[0]), L.ptr(rows)))
+
+    def attach_payload(self, kind: int, global_limit: float = 0.0) -> None:
+        L.check(self._lib.vrq_index_attach_payload(self._h, int(kind), float(global_limit)))
+
+    def write_payload(self, path: str) -> None:
+        """Stream the payload (+ aux) rows to a sidecar file next to index.bin (vrq_index_write_payload)."""
+        L.check(self._lib.vrq_index_write_payload(self._h, str(path).encode()))
+
+    def read_payload(self, path: str) -> None:
+        L.check(self._lib.vrq_index_read_payload(self._h, str(path).encode()))
+
+    def set_synthetic_payload(self, seed: int, row0: int) -> None:
+        """Benchmark-only: INT8_RAW rows are regenerated on demand instead of stored (vrq_index_set_synthetic_payload)."""
+        L.check(self._lib.vrq_index_set_synthetic_payload(self._h, C.c_uint64(seed), int(row0)))
+
     def search3(self, q_float, q_ubinary, k: int, binary_oversample: int = 10, int8_oversample: int = 3):
         """Phases I-III of CohereEnhancedVectorDB.search (:267-322) for a batch of queries.
         Returns (labels i64[nq,k], hamming i32, score_binary f64, score_cosine f64, count i32[nq])."""

@@ -28,7 +28,7 @@ import numpy as np
 from . import _lib as L
 from .binary_index import BinaryIndex, IndexBinaryFlat, read_index_binary, write_index_binary
 from .docstore import DocStore
-from .embedder import SyntheticCohereEmbedder
+from .embedder import CohereHttpEmbedder, SyntheticCohereEmbedder, warn_synthetic
 
 logger = logging.getLogger(__name__)
 
@@ -54,10 +54,16 @@ class CohereEnhancedVectorDB:
         self.model = model
         self.folder = folder
         self._ctx = ctx if ctx is not None else L.default_context()
-        self._embedder = embedder if embedder is not None else SyntheticCohereEmbedder(embedding_dim, ctx=self._ctx)
+        if embedder == "http":
+            embedder = CohereHttpEmbedder(self.endpoint, self.api_key, model)
+        elif embedder is None:
+            warn_synthetic(type(self).__name__, "COHERE_EMBED_ENDPOINT / COHERE_EMBED_KEY")
+            embedder = SyntheticCohereEmbedder(embedding_dim, ctx=self._ctx)
+        self._embedder = embedder
         self._setup_config(folder, model, embedding_dim)
-        self.index = self._initialize_faiss_index(folder, embedding_dim, index_type, index_args)
         self.doc_db = DocStore(os.path.join(folder, "docs"), rdict_options)
+        self.index = self._initialize_faiss_index(folder, embedding_dim, index_type, index_args)
+        self.doc_db.imported_raw = None  # the vectors of an imported reference store are in the index now
 
     # ---- config.json (:90-115): a mismatch is overwritten with a warning -------------------------------------
     def _setup_config(self, folder: str, model: str, embedding_dim: int):
@@ -80,30 +86,49 @@ class CohereEnhancedVectorDB:
                     json.dump(config, fOut)
         self.config = config
 
-    def _int8_path(self):
-        return os.path.join(self.folder, "int8.npy")
+    def _payload_path(self):
+        return os.path.join(self.folder, "payload.vrqp")
 
     def _initialize_faiss_index(self, folder, embedding_dim, index_type, index_args) -> BinaryIndex:
+        """:116-128.  index.bin is faiss's layout (codes + ids) and is streamed straight into device memory.  The int8 rows
+        the reference keeps in RocksDB pickles come from, in this order: the streamed sidecar ``payload.vrqp`` written by
+        ``save()``; round 1's ``int8.npy``; or - a folder written by the REFERENCE - its ``docs/`` store, imported
+        read-only by rocks_import.py."""
         path = os.path.join(folder, "index.bin")
-        new = BinaryIndex(index_type(*index_args), ctx=self._ctx, payload_kind=L.PAYLOAD_INT8_RAW)
-        if os.path.exists(path):
-            # index.bin is faiss's layout (codes + ids); the int8 rows the reference keeps in RocksDB pickles are
-            # stored as int8.npy beside it and re-attached to the device-resident index here
-            import struct
-            raw = open(path, "rb").read()
-            if raw[:4] != b"IBM2" or raw[25:29] != b"IBxF":
-                raise Exception(f"{path} is not an IndexBinaryIDMap2(IndexBinaryFlat) file")
-            d, cs, n = struct.unpack_from("<iiq", raw, 4)
-            if n > 0:
-                codes = np.frombuffer(raw, np.uint8, n * cs, 58).reshape(n, cs)
-                ids = np.frombuffer(raw, np.int64, n, 66 + n * cs)
-                if not os.path.exists(os.path.join(folder, "int8.npy")):
-                    raise Exception(f"{folder}/int8.npy is missing: index.bin has {n} codes but no int8 vectors")
-                new.add_with_ids(codes, ids, payload=np.load(os.path.join(folder, "int8.npy")))
-            logger.info("Existing FAISS binary index loaded.")
-        else:
+        if not os.path.exists(path):
             logger.info(f"New FAISS binary index created with embedding dimension {embedding_dim}.")
-        return new
+            return BinaryIndex(index_type(*index_args), ctx=self._ctx, payload_kind=L.PAYLOAD_INT8_RAW)
+        index = read_index_binary(path, ctx=self._ctx)
+        if index.d != embedding_dim:
+            raise Exception(f"{path} holds {index.d}-bit codes, expected {embedding_dim}")
+        n = index.ntotal
+        legacy = os.path.join(folder, "int8.npy")
+        if os.path.exists(self._payload_path()):
+            index.read_payload(self._payload_path())
+            if index.payload_kind != L.PAYLOAD_INT8_RAW:
+                raise Exception(f"{self._payload_path()} does not hold int8 vectors")
+        else:
+            index.attach_payload(L.PAYLOAD_INT8_RAW)
+            if n > 0 and os.path.exists(legacy):
+                rows = np.load(legacy, mmap_mode="r")
+                if rows.shape != (n, embedding_dim):
+                    raise Exception(f"{legacy} has shape {rows.shape}, index.bin has {n} codes")
+                for a in range(0, n, 65536):
+                    index.write_rows(L.ROWS_PAYLOAD, a, np.ascontiguousarray(rows[a:a + 65536], np.int8))
+            elif n > 0 and self.doc_db.imported_raw is not None:
+                ids = index.read_rows(L.ROWS_IDS, 0, n)
+                for a in range(0, n, 65536):
+                    chunk = []
+                    for i in ids[a:a + 65536]:
+                        entry = self.doc_db.imported_raw.get(str(int(i)))
+                        if entry is None or "int8" not in entry:
+                            raise Exception(f"document {int(i)} of index.bin has no int8 vector in {folder}/docs")
+                        chunk.append(np.asarray(entry["int8"], np.int8))
+                    index.write_rows(L.ROWS_PAYLOAD, a, np.stack(chunk))
+            elif n > 0:
+                raise Exception(f"{folder}: index.bin has {n} codes but there are no int8 vectors (payload.vrqp / docs store)")
+        logger.info("Existing FAISS binary index loaded.")
+        return index
 
     def _to_binary(self, emb_int8: np.ndarray) -> np.ndarray:
         """:130-134 (dead code in the reference; kept for API parity)."""
@@ -139,8 +164,7 @@ class CohereEnhancedVectorDB:
                 logger.error("Error processing embeddings: %s", str(e))
                 continue
             self.index.add_with_ids(ubinary_embs, np.array(batch_ids, dtype=np.int64), payload=int8_embs)
-            for doc_id, doc in zip(batch_ids, batch_docs):
-                self.doc_db[str(doc_id)] = {"doc": doc}
+            self.doc_db.set_many((str(doc_id), {"doc": doc}) for doc_id, doc in zip(batch_ids, batch_docs))
         if save:
             self.save()
 
@@ -156,8 +180,7 @@ class CohereEnhancedVectorDB:
             if str(doc_id) in self.doc_db:
                 self.remove_document(doc_id, save=False)
         self.index.add_with_ids(ubinary_embs, np.array(doc_ids, dtype=np.int64), payload=np.ascontiguousarray(int8_embs, np.int8))
-        for i, doc_id in enumerate(doc_ids):
-            self.doc_db[str(doc_id)] = {"doc": docs[i] if docs is not None else ""}
+        self.doc_db.set_many((str(doc_id), {"doc": docs[i] if docs is not None else ""}) for i, doc_id in enumerate(doc_ids))
         if save:
             self.save()
 
@@ -210,11 +233,13 @@ class CohereEnhancedVectorDB:
             self.save()
 
     def save(self):
+        """:342-347.  index.bin (faiss layout) + the int8 sidecar, both streamed from device memory in 64 MB chunks and
+        renamed into place (no whole-matrix host copy, no second device copy)."""
         write_index_binary(self.index, os.path.join(self.folder, "index.bin"))
-        n = self.index.ntotal
-        pay, _ = self.index.get_payload(np.arange(n, dtype=np.int64), np.int8, self.embedding_dim) if n else (
-            np.empty((0, self.embedding_dim), np.int8), None)
-        np.save(self._int8_path(), pay)
+        self.index.write_payload(self._payload_path())
+        legacy = os.path.join(self.folder, "int8.npy")
+        if os.path.exists(legacy):
+            os.remove(legacy)
         logger.info("FAISS binary index saved.")
 
     def __len__(self):

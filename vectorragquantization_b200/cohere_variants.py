@@ -29,7 +29,8 @@ class CohereVectorDBInt8(_VectorDBBase):
     def __init__(self, folder: str, model: str = "embed-english-v3.0", embedding_dim: int = 1024, rdict_options=None,
                  embedder: Optional[Callable] = None, ctx=None):
         if embedder is None:
-            from .embedder import SyntheticCohereEmbedder
+            from .embedder import SyntheticCohereEmbedder, warn_synthetic
+            warn_synthetic(type(self).__name__, "the Cohere endpoint")
             coh = SyntheticCohereEmbedder(embedding_dim, ctx=ctx)
             embedder = lambda texts, input_type="search_document": coh(texts, input_type, ["int8"])["int8"]  # noqa: E731
         super().__init__(folder, model, embedding_dim, rdict_options, "", embedder, ctx)

@@ -1,11 +1,15 @@
 // Device-resident binary index: the faiss.IndexBinaryIDMap2(faiss.IndexBinaryFlat(d)) surface the reference
 // classes call, plus an optional per-position payload matrix that replaces the RocksDB
 // point-gets inside the reference's rescoring loops, and the fused multi-phase searches.
+#include <errno.h>
 #include <stdio.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <iterator>
+#include <string>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -34,6 +38,11 @@ struct vrq_index {
     // the arrays are compacted once, in place, before the next call that reads them.  `ntotal` counts the rows in the
     // arrays, ntotal - dead.size() is what the caller sees.
     std::vector<int64_t> dead;
+    // Benchmark-only "virtual" INT8_RAW payload: no rows in HBM, Phase III regenerates row p from the counter-based
+    // generator (seed, synth_row0 + p).  For the 1-billion-row legs on fewer than 8 GPUs.
+    bool synth_payload = false;
+    uint64_t synth_seed = 0;
+    int64_t synth_row0 = 0;
 };
 
 namespace {
@@ -328,9 +337,26 @@ extern "C" int vrq_index_set_payload(vrq_index* ix, int kind, double global_limi
     return 0;
 }
 
+extern "C" int vrq_index_set_synthetic_payload(vrq_index* ix, uint64_t seed, int64_t row0) {
+    VRQ_CHECK_ARG(ix != nullptr, "index is null");
+    if (ix->ntotal != 0 || ix->capacity != 0 || ix->payload_kind != VRQ_PAYLOAD_INT8_RAW) {
+        vrq_set_error("a synthetic payload can only replace the INT8_RAW payload of an empty, unreserved index");
+        return VRQ_ERR_STATE;
+    }
+    ix->synth_payload = true;
+    ix->synth_seed = seed;
+    ix->synth_row0 = row0;
+    ix->payload_row = 0;  // nothing is stored
+    return 0;
+}
+
 extern "C" int vrq_index_add_with_ids(vrq_index* ix, int64_t n, const uint8_t* codes, const int64_t* ids, const void* payload,
                                       const void* aux) {
     VRQ_CHECK_ARG(ix != nullptr && n >= 0, "bad argument");
+    if (ix && ix->synth_payload) {
+        vrq_set_error("an index with a synthetic payload only accepts vrq_index_add_synthetic");
+        return VRQ_ERR_STATE;
+    }
     if (ix) VRQ_TRY(flush_dead(ix));
     if (n == 0) return 0;
     VRQ_CHECK_ARG(codes != nullptr && ids != nullptr, "codes / ids are null");
@@ -364,6 +390,10 @@ extern "C" int vrq_index_add_synthetic(vrq_index* ix, uint64_t seed, int64_t row
         return VRQ_ERR_STATE;
     }
     if (nrows == 0) return 0;
+    if (ix->synth_payload && (seed != ix->synth_seed || row0 != ix->synth_row0 + ix->ntotal)) {
+        vrq_set_error("add_synthetic: rows must continue the (seed, row0) sequence the synthetic payload was declared with");
+        return VRQ_ERR_ARG;
+    }
     VRQ_CUDA(cudaSetDevice(ix->ctx->device));
     const bool contiguous = ix->implicit_ids && (ix->ntotal == 0 || ix->id0 + ix->ntotal == id0);
     if (ix->ntotal == 0 && ix->implicit_ids) ix->id0 = id0;
@@ -454,8 +484,8 @@ extern "C" int vrq_index_get_payload(vrq_index* ix, int64_t m, const int64_t* po
     if (ix) VRQ_TRY(flush_dead(ix));
     if (m == 0) return 0;
     VRQ_CHECK_ARG(positions != nullptr, "positions is null");
-    if (ix->payload_kind == VRQ_PAYLOAD_NONE) {
-        vrq_set_error("index has no payload");
+    if (ix->payload_kind == VRQ_PAYLOAD_NONE || ix->synth_payload) {
+        vrq_set_error("index has no stored payload");
         return VRQ_ERR_STATE;
     }
     const void* all[3] = {positions, payload_out, aux_out};
@@ -482,6 +512,10 @@ extern "C" int64_t vrq_index_remove_ids(vrq_index* ix, int64_t n, const int64_t*
         return VRQ_ERR_ARG;
     }
     if (n == 0 || ix->ntotal == 0) return 0;
+    if (ix->synth_payload) {
+        vrq_set_error("remove_ids: rows of an index with a synthetic payload cannot be removed (position = generator row)");
+        return VRQ_ERR_STATE;
+    }
     vrq_ctx* ctx = ix->ctx;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return VRQ_ERR_STATE;
     bool is_dev;
@@ -515,60 +549,230 @@ extern "C" int64_t vrq_index_remove_ids(vrq_index* ix, int64_t n, const int64_t*
     return removed;
 }
 
-// ---- faiss file format ("IBM2" wrapping "IBxF"), SURVEY App. B.1 ----------------------------------------------------
+// ---- row access, attachable payloads -------------------------------------------------------------------------------------
+namespace {
+int rows_of(vrq_index* ix, int which, uint8_t** base, size_t* row) {
+    switch (which) {
+        case VRQ_ROWS_CODES: *base = ix->codes; *row = (size_t)ix->code_bytes; return 0;
+        case VRQ_ROWS_IDS: *base = (uint8_t*)ix->ids; *row = sizeof(int64_t); return 0;
+        case VRQ_ROWS_PAYLOAD: *base = ix->payload; *row = ix->payload_row; return 0;
+        case VRQ_ROWS_AUX: *base = ix->aux; *row = ix->aux_row; return 0;
+    }
+    vrq_set_error("unknown row array %d", which);
+    return VRQ_ERR_ARG;
+}
+}  // namespace
+
+extern "C" int vrq_index_read_rows(vrq_index* ix, int which, int64_t offset, int64_t count, void* out) {
+    VRQ_CHECK_ARG(ix != nullptr && offset >= 0 && count >= 0, "bad argument");
+    VRQ_TRY(flush_dead(ix));
+    if (count == 0) return 0;
+    VRQ_CHECK_ARG(out != nullptr, "out is null");
+    VRQ_CHECK_ARG(offset + count <= ix->ntotal, "row range beyond ntotal");
+    VRQ_CUDA(cudaSetDevice(ix->ctx->device));
+    if (which == VRQ_ROWS_IDS) VRQ_TRY(materialise_ids(ix));
+    uint8_t* base;
+    size_t row;
+    VRQ_TRY(rows_of(ix, which, &base, &row));
+    if (row == 0 || base == nullptr) {
+        vrq_set_error("the index holds no such rows");
+        return VRQ_ERR_STATE;
+    }
+    VRQ_CUDA(cudaMemcpyAsync(out, base + (size_t)offset * row, (size_t)count * row, cudaMemcpyDefault, ix->ctx->stream));
+    bool is_dev;
+    vrq_is_device_ptr(out, &is_dev);
+    if (!is_dev) VRQ_CUDA(cudaStreamSynchronize(ix->ctx->stream));
+    return 0;
+}
+
+extern "C" int vrq_index_write_rows(vrq_index* ix, int which, int64_t offset, int64_t count, const void* src) {
+    VRQ_CHECK_ARG(ix != nullptr && offset >= 0 && count >= 0, "bad argument");
+    VRQ_CHECK_ARG(which == VRQ_ROWS_PAYLOAD || which == VRQ_ROWS_AUX || which == VRQ_ROWS_CODES, "ids cannot be overwritten in place");
+    VRQ_TRY(flush_dead(ix));
+    if (count == 0) return 0;
+    VRQ_CHECK_ARG(src != nullptr, "src is null");
+    VRQ_CHECK_ARG(offset + count <= ix->ntotal, "row range beyond ntotal");
+    VRQ_CUDA(cudaSetDevice(ix->ctx->device));
+    uint8_t* base;
+    size_t row;
+    VRQ_TRY(rows_of(ix, which, &base, &row));
+    if (row == 0 || base == nullptr) {
+        vrq_set_error("the index holds no such rows");
+        return VRQ_ERR_STATE;
+    }
+    VRQ_CUDA(cudaMemcpyAsync(base + (size_t)offset * row, src, (size_t)count * row, cudaMemcpyDefault, ix->ctx->stream));
+    bool is_dev;
+    vrq_is_device_ptr(src, &is_dev);
+    if (!is_dev) VRQ_CUDA(cudaStreamSynchronize(ix->ctx->stream));
+    return 0;
+}
+
+extern "C" int vrq_index_attach_payload(vrq_index* ix, int kind, double global_limit) {
+    VRQ_CHECK_ARG(ix != nullptr, "index is null");
+    VRQ_CHECK_ARG(kind > VRQ_PAYLOAD_NONE && kind <= VRQ_PAYLOAD_CODES_PM1, "unknown payload kind");
+    if (ix->payload_kind != VRQ_PAYLOAD_NONE) {
+        vrq_set_error("the index already has a payload");
+        return VRQ_ERR_STATE;
+    }
+    VRQ_TRY(flush_dead(ix));
+    VRQ_CUDA(cudaSetDevice(ix->ctx->device));
+    const size_t prow = payload_row_bytes(kind, ix->d), arow = aux_row_bytes(kind);
+    void *pp = nullptr, *ap = nullptr;
+    if (ix->capacity > 0 && prow) {
+        cudaError_t e = cudaMalloc(&pp, prow * (size_t)ix->capacity);
+        if (e == cudaSuccess && arow) e = cudaMalloc(&ap, arow * (size_t)ix->capacity);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            if (pp) cudaFree(pp);
+            vrq_set_error("cudaMalloc of %zu payload bytes failed: %s", prow * (size_t)ix->capacity, cudaGetErrorString(e));
+            return VRQ_ERR_NOMEM;
+        }
+        VRQ_CUDA(cudaMemsetAsync(pp, 0, prow * (size_t)ix->capacity, ix->ctx->stream));
+        if (ap) VRQ_CUDA(cudaMemsetAsync(ap, 0, arow * (size_t)ix->capacity, ix->ctx->stream));
+    }
+    ix->payload_kind = kind;
+    ix->limit = global_limit;
+    ix->payload_row = prow;
+    ix->aux_row = arow;
+    ix->payload = (uint8_t*)pp;
+    ix->aux = (uint8_t*)ap;
+    return 0;
+}
+
+// ---- files -------------------------------------------------------------------------------------------------------------
+// Every file is written to "<path>.tmp", flushed, fsync'ed and renamed over <path>: a crash leaves the old file or the new
+// one, never a torn one.  Arrays stream between the file and device memory through one pinned 64 MB bounce buffer.
+namespace {
+
+constexpr size_t IO_CHUNK = 64u << 20;
+
+struct PinnedBounce {
+    void* p = nullptr;
+    ~PinnedBounce() {
+        if (p) cudaFreeHost(p);
+    }
+    int get(size_t bytes) {
+        if (p) return 0;
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            vrq_set_error("cudaHostAlloc of the %zu-byte IO bounce buffer failed", bytes);
+            return VRQ_ERR_NOMEM;
+        }
+        return 0;
+    }
+};
+
+struct AtomicFile {
+    std::string path, tmp;
+    FILE* f = nullptr;
+    int open(const char* p) {
+        path = p;
+        tmp = path + ".tmp";
+        f = fopen(tmp.c_str(), "wb");
+        if (!f) {
+            vrq_set_error("cannot open %s for writing: %s", tmp.c_str(), strerror(errno));
+            return VRQ_ERR_IO;
+        }
+        return 0;
+    }
+    bool put(const void* d, size_t n) { return n == 0 || fwrite(d, 1, n, f) == n; }
+    int fail(const char* why) {
+        if (f) fclose(f);
+        f = nullptr;
+        remove(tmp.c_str());
+        vrq_set_error("%s: %s", path.c_str(), why);
+        return VRQ_ERR_IO;
+    }
+    int commit() {
+        if (fflush(f) != 0 || fsync(fileno(f)) != 0) return fail("flush failed");
+        if (fclose(f) != 0) {
+            f = nullptr;
+            return fail("close failed");
+        }
+        f = nullptr;
+        if (rename(tmp.c_str(), path.c_str()) != 0) return fail("rename failed");
+        return 0;
+    }
+    ~AtomicFile() {
+        if (f) {
+            fclose(f);
+            remove(tmp.c_str());
+        }
+    }
+};
+
+// device array -> file
+int stream_out(vrq_index* ix, AtomicFile& af, const uint8_t* dev, size_t nbytes, PinnedBounce& pb) {
+    if (nbytes == 0) return 0;
+    VRQ_TRY(pb.get(IO_CHUNK));
+    for (size_t off = 0; off < nbytes; off += IO_CHUNK) {
+        const size_t len = std::min(IO_CHUNK, nbytes - off);
+        cudaError_t e = cudaMemcpyAsync(pb.p, dev + off, len, cudaMemcpyDeviceToHost, ix->ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ix->ctx->stream);
+        if (e != cudaSuccess) {
+            af.fail(cudaGetErrorString(e));
+            return (int)e;
+        }
+        if (!af.put(pb.p, len)) return af.fail("short write");
+    }
+    return 0;
+}
+
+// file -> device array
+int stream_in(vrq_ctx* ctx, FILE* f, uint8_t* dev, size_t nbytes, PinnedBounce& pb, const char* path) {
+    if (nbytes == 0) return 0;
+    VRQ_TRY(pb.get(IO_CHUNK));
+    for (size_t off = 0; off < nbytes; off += IO_CHUNK) {
+        const size_t len = std::min(IO_CHUNK, nbytes - off);
+        if (fread(pb.p, 1, len, f) != len) {
+            vrq_set_error("%s: truncated file", path);
+            return VRQ_ERR_IO;
+        }
+        VRQ_CUDA(cudaMemcpyAsync(dev + off, pb.p, len, cudaMemcpyHostToDevice, ctx->stream));
+        VRQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+int64_t file_size(FILE* f) {
+    struct stat st;
+    if (fstat(fileno(f), &st) != 0) return -1;
+    return (int64_t)st.st_size;
+}
+
+}  // namespace
+
+// faiss file format ("IBM2" wrapping "IBxF"), SURVEY App. B.1
 extern "C" int vrq_index_write(vrq_index* ix, const char* path) {
     VRQ_CHECK_ARG(ix != nullptr && path != nullptr, "null argument");
     VRQ_TRY(flush_dead(ix));
     VRQ_CUDA(cudaSetDevice(ix->ctx->device));
-    FILE* f = fopen(path, "wb");
-    if (!f) {
-        vrq_set_error("cannot open %s for writing", path);
-        return VRQ_ERR_IO;
-    }
-    auto hdr = [&](const char* fourcc) {
+    AtomicFile af;
+    VRQ_TRY(af.open(path));
+    auto hdr = [&](const char* fourcc) -> bool {
         int32_t d = ix->d, cs = ix->code_bytes, metric = 1;
         int64_t nt = ix->ntotal;
         uint8_t trained = 1;
-        fwrite(fourcc, 1, 4, f);
-        fwrite(&d, 4, 1, f);
-        fwrite(&cs, 4, 1, f);
-        fwrite(&nt, 8, 1, f);
-        fwrite(&trained, 1, 1, f);
-        fwrite(&metric, 4, 1, f);
+        return af.put(fourcc, 4) && af.put(&d, 4) && af.put(&cs, 4) && af.put(&nt, 8) && af.put(&trained, 1) && af.put(&metric, 4);
     };
-    hdr("IBM2");
-    hdr("IBxF");
-    uint64_t nbytes = (uint64_t)ix->ntotal * ix->code_bytes;
-    fwrite(&nbytes, 8, 1, f);
-    const size_t CH = 64u << 20;
-    std::vector<uint8_t> tmp(std::min<size_t>(CH, std::max<size_t>(nbytes, 1)));
-    for (uint64_t off = 0; off < nbytes; off += CH) {
-        size_t len = (size_t)std::min<uint64_t>(CH, nbytes - off);
-        VRQ_CUDA(cudaMemcpyAsync(tmp.data(), ix->codes + off, len, cudaMemcpyDeviceToHost, ix->ctx->stream));
-        VRQ_CUDA(cudaStreamSynchronize(ix->ctx->stream));
-        if (fwrite(tmp.data(), 1, len, f) != len) {
-            fclose(f);
-            vrq_set_error("short write to %s", path);
-            return VRQ_ERR_IO;
+    const uint64_t nbytes = (uint64_t)ix->ntotal * ix->code_bytes, nids = (uint64_t)ix->ntotal;
+    if (!hdr("IBM2") || !hdr("IBxF") || !af.put(&nbytes, 8)) return af.fail("short write");
+    PinnedBounce pb;
+    VRQ_TRY(stream_out(ix, af, ix->codes, (size_t)nbytes, pb));
+    if (!af.put(&nids, 8)) return af.fail("short write");
+    if (ix->implicit_ids) {
+        // ids are id0 + position: produced on the fly, no device or host array needed
+        std::vector<int64_t> tmp(std::min<size_t>((size_t)nids, 1u << 20));
+        for (uint64_t off = 0; off < nids; off += tmp.size()) {
+            const size_t len = (size_t)std::min<uint64_t>(tmp.size(), nids - off);
+            for (size_t i = 0; i < len; i++) tmp[i] = ix->id0 + (int64_t)(off + i);
+            if (!af.put(tmp.data(), 8 * len)) return af.fail("short write");
         }
+    } else {
+        VRQ_TRY(stream_out(ix, af, (const uint8_t*)ix->ids, (size_t)nids * 8, pb));
     }
-    uint64_t nids = (uint64_t)ix->ntotal;
-    fwrite(&nids, 8, 1, f);
-    int r = load_host_ids(ix);
-    if (r != 0) {
-        fclose(f);
-        return r;
-    }
-    if (nids && fwrite(ix->host_ids.data(), 8, nids, f) != nids) {
-        fclose(f);
-        vrq_set_error("short write to %s", path);
-        return VRQ_ERR_IO;
-    }
-    if (fclose(f) != 0) {
-        vrq_set_error("close of %s failed", path);
-        return VRQ_ERR_IO;
-    }
-    return 0;
+    return af.commit();
 }
 
 extern "C" int vrq_index_read(vrq_ctx* ctx, const char* path, vrq_index** out) {
@@ -578,8 +782,10 @@ extern "C" int vrq_index_read(vrq_ctx* ctx, const char* path, vrq_index** out) {
         vrq_set_error("cannot open %s", path);
         return VRQ_ERR_IO;
     }
+    vrq_index* ix = nullptr;
     auto fail = [&](const char* why) {
         fclose(f);
+        if (ix) vrq_index_free(ix);
         vrq_set_error("%s: %s", path, why);
         return VRQ_ERR_IO;
     };
@@ -600,37 +806,103 @@ extern "C" int vrq_index_read(vrq_ctx* ctx, const char* path, vrq_index** out) {
     if (h2.d <= 0 || h2.d % 8 != 0 || h2.cs != h2.d / 8 || h2.nt < 0) return fail("corrupt header");
     uint64_t nbytes = 0;
     if (fread(&nbytes, 8, 1, f) != 1 || nbytes != (uint64_t)h2.nt * h2.cs) return fail("code array size mismatch");
-    vrq_index* ix = nullptr;
+    // the header must agree with the size of the file before anything is allocated from it
+    const int64_t fsz = file_size(f);
+    if (fsz >= 0 && (uint64_t)fsz != 58 + nbytes + 8 + 8 * (uint64_t)h2.nt) return fail("file size does not match its header");
     int r = vrq_index_create(ctx, h2.d, &ix);
     if (r != 0) {
         fclose(f);
         return r;
     }
-    std::vector<uint8_t> codes((size_t)nbytes);
-    if (nbytes && fread(codes.data(), 1, (size_t)nbytes, f) != nbytes) {
-        vrq_index_free(ix);
-        return fail("truncated code array");
-    }
+    r = cudaSetDevice(ctx->device) == cudaSuccess ? 0 : VRQ_ERR_STATE;
+    if (r == 0 && h2.nt > 0) r = ensure_capacity(ix, h2.nt);
+    PinnedBounce pb;
+    if (r == 0) r = stream_in(ctx, f, ix->codes, (size_t)nbytes, pb, path);
     uint64_t nids = 0;
-    if (fread(&nids, 8, 1, f) != 1 || nids != (uint64_t)h2.nt) {
-        vrq_index_free(ix);
-        return fail("id map size mismatch");
-    }
-    std::vector<int64_t> ids((size_t)nids);
-    if (nids && fread(ids.data(), 8, (size_t)nids, f) != nids) {
-        vrq_index_free(ix);
-        return fail("truncated id map");
+    if (r == 0 && (fread(&nids, 8, 1, f) != 1 || nids != (uint64_t)h2.nt)) return fail("id map size mismatch");
+    if (r == 0 && h2.nt > 0) {
+        ix->implicit_ids = false;
+        if (cudaMalloc((void**)&ix->ids, sizeof(int64_t) * (size_t)ix->capacity) != cudaSuccess) {
+            cudaGetLastError();
+            vrq_set_error("cudaMalloc of the id map failed");
+            r = VRQ_ERR_NOMEM;
+        }
+        if (r == 0) r = stream_in(ctx, f, (uint8_t*)ix->ids, (size_t)nids * 8, pb, path);
     }
     fclose(f);
-    if (h2.nt > 0) {
-        r = vrq_index_add_with_ids(ix, h2.nt, codes.data(), ids.data(), nullptr, nullptr);
-        if (r != 0) {
-            vrq_index_free(ix);
-            return r;
-        }
+    if (r != 0) {
+        vrq_index_free(ix);
+        return r;
     }
+    ix->ntotal = h2.nt;
     *out = ix;
     return 0;
+}
+
+// Payload sidecar ("VRQP"): what the reference keeps in RocksDB pickles next to index.bin (CohereEnhancedVectorDB.py:221 {"int8"},
+// VectorDBInt8.py:179 {"emb_int8","min_max"}), as one flat file: header, payload rows, aux rows - streamed like the codes.
+struct VrqpHeader {
+    char magic[4];
+    int32_t version, kind, d;
+    int64_t ntotal;
+    uint64_t payload_row, aux_row;
+    double limit;
+};
+
+extern "C" int vrq_index_write_payload(vrq_index* ix, const char* path) {
+    VRQ_CHECK_ARG(ix != nullptr && path != nullptr, "null argument");
+    VRQ_TRY(flush_dead(ix));
+    if (ix->payload_kind == VRQ_PAYLOAD_NONE || ix->synth_payload) {
+        vrq_set_error("index has no stored payload");
+        return VRQ_ERR_STATE;
+    }
+    VRQ_CUDA(cudaSetDevice(ix->ctx->device));
+    AtomicFile af;
+    VRQ_TRY(af.open(path));
+    VrqpHeader h{};
+    memcpy(h.magic, "VRQP", 4);
+    h.version = 1;
+    h.kind = ix->payload_kind;
+    h.d = ix->d;
+    h.ntotal = ix->ntotal;
+    h.payload_row = ix->payload_row;
+    h.aux_row = ix->aux_row;
+    h.limit = ix->limit;
+    if (!af.put(&h, sizeof(h))) return af.fail("short write");
+    PinnedBounce pb;
+    VRQ_TRY(stream_out(ix, af, ix->payload, ix->payload_row * (size_t)ix->ntotal, pb));
+    VRQ_TRY(stream_out(ix, af, ix->aux, ix->aux_row * (size_t)ix->ntotal, pb));
+    return af.commit();
+}
+
+extern "C" int vrq_index_read_payload(vrq_index* ix, const char* path) {
+    VRQ_CHECK_ARG(ix != nullptr && path != nullptr, "null argument");
+    VRQ_TRY(flush_dead(ix));
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+        vrq_set_error("cannot open %s", path);
+        return VRQ_ERR_IO;
+    }
+    VrqpHeader h{};
+    auto fail = [&](const char* why) {
+        fclose(f);
+        vrq_set_error("%s: %s", path, why);
+        return VRQ_ERR_IO;
+    };
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "VRQP", 4) != 0 || h.version != 1) return fail("not a payload sidecar (VRQP v1)");
+    if (h.d != ix->d) return fail("embedding_dim differs from the index");
+    if (h.ntotal != ix->ntotal) return fail("row count differs from index.bin (the two files are not from the same save)");
+    if (h.kind <= VRQ_PAYLOAD_NONE || h.kind > VRQ_PAYLOAD_CODES_PM1 || h.payload_row != payload_row_bytes(h.kind, h.d) ||
+        h.aux_row != aux_row_bytes(h.kind))
+        return fail("corrupt header");
+    const int64_t fsz = file_size(f);
+    if (fsz >= 0 && (uint64_t)fsz != sizeof(h) + (h.payload_row + h.aux_row) * (uint64_t)h.ntotal) return fail("file size does not match its header");
+    int r = vrq_index_attach_payload(ix, h.kind, h.limit);
+    PinnedBounce pb;
+    if (r == 0) r = stream_in(ix->ctx, f, ix->payload, ix->payload_row * (size_t)ix->ntotal, pb, path);
+    if (r == 0) r = stream_in(ix->ctx, f, ix->aux, ix->aux_row * (size_t)ix->ntotal, pb, path);
+    fclose(f);
+    return r;
 }
 
 // ---- fused searches ---------------------------------------------------------------------------------------------------
@@ -652,6 +924,15 @@ extern "C" int vrq_index_search3_local(vrq_index* ix, int64_t nq, const float* q
     VRQ_TRY(vrq_launch_keys_to_dist_labels(ctx, keys, nq * (int64_t)binary_k, pos_base, ix->implicit_ids ? nullptr : ix->ids,
                                            ix->id0, nullptr, labels, st));
     VRQ_TRY(vrq_launch_rescore_binary(ctx, ix->codes, ix->d, keys, nullptr, pos_base, nq, binary_k, q_float, score_binary, st));
+    if (ix->synth_payload) {
+        if (ix->d != 1024) {
+            vrq_set_error("the synthetic payload needs d == 1024");
+            return VRQ_ERR_UNSUPPORTED;
+        }
+        VRQ_TRY(vrq_launch_rescore_int8cos_synth(ctx, ix->synth_seed, ix->synth_row0, keys, nullptr, pos_base, nq, binary_k, q_float,
+                                                 score_cosine, st));
+        return 0;
+    }
     VRQ_TRY(vrq_launch_rescore_int8cos(ctx, (const int8_t*)ix->payload, ix->d, keys, nullptr, pos_base, nq, binary_k, q_float,
                                        score_cosine, st));
     return 0;

@@ -10,6 +10,10 @@
 #include "topk_utils.cuh"
 #include "vrq_internal.cuh"
 
+#ifndef VRQ_RESCORE_IMMA_DEFAULT
+#define VRQ_RESCORE_IMMA_DEFAULT 0
+#endif
+
 namespace {
 
 using namespace vrq;
@@ -786,6 +790,9 @@ int vrq_launch_rescore_binary(vrq_ctx* ctx, const uint8_t* codes, int d, const u
         return VRQ_ERR_UNSUPPORTED;
     }
     vrq_timer_scope ts(ctx, VRQ_CAT_RESCORE, st);
+    // d == 1024: the nibble-table kernel of rescore_mma.cu (VRQ_RESCORE_BIN_LUT=0 selects the register kernel below)
+    if (d == 1024 && !(getenv("VRQ_RESCORE_BIN_LUT") && atoi(getenv("VRQ_RESCORE_BIN_LUT")) == 0))
+        return vrq_launch_rescore_binary_lut(ctx, codes, keys, pos, pos_base, nq, m, qf, score, st);
     dim3 grid(grid_x_for(ctx, nq, m), (unsigned)nq);
     if (d == 1024)
         rescore_binary1024_kernel<<<grid, 256, 0, st>>>(codes, keys, pos, pos_base, m, qf, score);
@@ -807,6 +814,10 @@ int vrq_launch_rescore_int8cos(vrq_ctx* ctx, const int8_t* rows, int d, const ui
     dim3 grid(grid_x_for(ctx, nq, m), (unsigned)nq);
     const bool use_async = !(getenv("VRQ_RESCORE_ASYNC") && atoi(getenv("VRQ_RESCORE_ASYNC")) == 0);  // read per call (tests switch it)
     const bool use_dp2a = getenv("VRQ_RESCORE_DP2A") && atoi(getenv("VRQ_RESCORE_DP2A")) != 0;  // opt-in: integer dot products
+    // tensor-core path (rescore_mma.cu): VRQ_RESCORE_IMMA=1/0; the default is whichever the cfg5 measurement favours
+    const bool use_imma = getenv("VRQ_RESCORE_IMMA") ? atoi(getenv("VRQ_RESCORE_IMMA")) != 0 : VRQ_RESCORE_IMMA_DEFAULT;
+    if (d == 1024 && use_imma && ((uintptr_t)rows % 16) == 0)
+        return vrq_launch_rescore_int8cos_imma(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st);
     if (d == 1024 && use_async && use_dp2a) {
         const size_t smem = (size_t)8 * P3_RING * 1024;
         VRQ_CUDA(cudaFuncSetAttribute(rescore_int8cos_dp2a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

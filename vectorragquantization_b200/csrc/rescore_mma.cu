@@ -1,0 +1,409 @@
+// Round-2 rescoring kernels for d == 1024 (the other widths stay on rescore.cu):
+//
+//   * Phase II (CohereEnhancedVectorDB.py:283-293): per-query nibble table of float64 partial sums in shared memory.
+//     score = sum_j q_j (2 bit_j - 1) becomes 256 table reads + 256 DADD per (query, candidate) instead of 1024
+//     shift / select / DADD; one THREAD owns one candidate, so there is no per-candidate warp reduction either.
+//   * Phase III (CohereEnhancedVectorDB.py:302-318) on the tensor cores (mma.sync.m16n8k32.s8, SASS IMMA.16832.S8):
+//     the float32 query becomes 64-bit fixed point against its own largest exponent and is split into eight signed
+//     base-256 digits = the eight columns of the B operand; sixteen gathered int8 rows are the A operand.  Two IMMA per
+//     1 KB row replace 64 PRMT + DFMA, the digit sums are exact integers, and the rows travel global -> shared memory as
+//     1 KB bulk copies (UBLKCP) completing on an mbarrier, so no load instruction is issued per row at all.
+//     BASELINE.json configs[4] asks for exactly this comparison (IMMA vs the CUDA-core path of rescore.cu).
+//   * Phase III with the int8 rows REGENERATED from the counter-based generator instead of read from HBM: only for the
+//     1-billion-row benchmark legs on fewer than 8 GPUs, where the int8 store (1 TB) does not fit.
+#include <math.h>
+#include <stdlib.h>
+
+#include "vrq_internal.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ int64_t cand_row(const uint64_t* keys, const int64_t* pos, size_t idx, int64_t pos_base) {
+    if (keys) {
+        const uint64_t k = keys[idx];
+        return k == VRQ_KEY_NONE ? -1 : (int64_t)(k & VRQ_KEY_POS_MASK) - pos_base;
+    }
+    const int64_t p = pos[idx];
+    return p < 0 ? -1 : p - pos_base;
+}
+
+// =====================================================================================================================
+// Phase II, nibble table.  Position p = 2 * byte + (0: high nibble, 1: low nibble) covers dimensions 4p .. 4p + 3, and
+// bit (3 - i) of the nibble is dimension 4p + i (np.packbits is MSB-first).  lut[p][v] = sum_i (+-) q[4p + i].
+// All 32 lanes of a warp read the SAME position at the same time, so the 16 possible addresses are one 128-byte line:
+// broadcast, never a bank conflict, whatever the data.
+// =====================================================================================================================
+constexpr int P2_THREADS = 256;
+
+__global__ void __launch_bounds__(P2_THREADS) rescore_binary_lut_kernel(const uint8_t* __restrict__ codes,
+                                                                        const uint64_t* __restrict__ keys,
+                                                                        const int64_t* __restrict__ pos, int64_t pos_base, int m,
+                                                                        const float* __restrict__ qf, double* __restrict__ score) {
+    __shared__ __align__(128) double lut[256 * 16];
+    const int q = blockIdx.y, tid = threadIdx.x;
+    {
+        // thread (p0 = tid >> 4, v = tid & 15) fills lut[p][v] for p = p0, p0 + 16, ...: consecutive threads write
+        // consecutive doubles
+        const int v = tid & 15;
+        for (int p = tid >> 4; p < 256; p += P2_THREADS / 16) {
+            const float4 f = *reinterpret_cast<const float4*>(qf + (size_t)q * 1024 + 4 * p);
+            const double a = (v & 8) ? (double)f.x : -(double)f.x, b = (v & 4) ? (double)f.y : -(double)f.y;
+            const double c = (v & 2) ? (double)f.z : -(double)f.z, e = (v & 1) ? (double)f.w : -(double)f.w;
+            lut[p * 16 + v] = (a + b) + (c + e);
+        }
+    }
+    __syncthreads();
+    const char* const L = reinterpret_cast<const char*>(lut);
+    for (int i = blockIdx.x * P2_THREADS + tid; i < m; i += gridDim.x * P2_THREADS) {
+        const size_t idx = (size_t)q * m + i;
+        const int64_t row = cand_row(keys, pos, idx, pos_base);
+        if (row < 0) {
+            score[idx] = -INFINITY;
+            continue;
+        }
+        const uint4* src = reinterpret_cast<const uint4*>(codes + (size_t)row * 128);
+        uint4 c[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) c[j] = __ldg(src + j);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t w[4] = {c[j].x, c[j].y, c[j].z, c[j].w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                // byte b of the word = code byte 16 j + 4 t + b; its high nibble is position 2 byte, its low nibble position
+                // 2 byte + 1.  wh / wl hold (nibble * 8) = the byte offset inside the 128-byte table line, one per byte lane
+                const uint32_t wh = (w[t] >> 1) & 0x78787878u, wl = (w[t] << 3) & 0x78787878u;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int byte = 16 * j + 4 * t + b;
+                    const uint32_t hi8 = __byte_perm(wh, 0u, 0x4440u + b), lo8 = __byte_perm(wl, 0u, 0x4440u + b);
+                    const double vh = *reinterpret_cast<const double*>(L + (2 * byte) * 128 + hi8);
+                    const double vl = *reinterpret_cast<const double*>(L + (2 * byte + 1) * 128 + lo8);
+                    if (b & 1) {
+                        a2 += vh;
+                        a3 += vl;
+                    } else {
+                        a0 += vh;
+                        a1 += vl;
+                    }
+                }
+            }
+        }
+        score[idx] = (a0 + a1) + (a2 + a3);
+    }
+}
+
+// =====================================================================================================================
+// Phase III on the tensor cores.
+// =====================================================================================================================
+// One warp owns a private ring of P3M_STAGES stages; a stage holds a GROUP of 16 candidate rows (the M dimension of
+// mma.m16n8k32), each row 1 KB at a stride of 1088 bytes so that the fragment reads below are bank-conflict free.
+// Lane i < 16 starts the bulk copy of row i of the group; lane 0 posts the expected byte count on the stage's mbarrier.
+// Fragment <-> data mapping: a dot product does not care about the order of its terms, so the K index of the MMA is
+// permuted freely as long as A and B agree.  Lane (g = lane / 4, t = lane % 4) reads, for step j = 0 .. 15, the 16
+// bytes [64 j + 16 t, +16) of rows g and g + 8 (two LDS.128) and the same 16 bytes of digit plane n = g of the query
+// (one LDS.128): words 0,1 of the three loads are {a0, a2} / {a1, a3} / {b0, b1} of one MMA, words 2,3 of the next.
+constexpr int P3M_ROW_STRIDE = 1024 + 64;
+constexpr int P3M_GROUP = 16;
+constexpr int P3M_STAGE_BYTES = P3M_GROUP * P3M_ROW_STRIDE;
+constexpr int P3M_DIGITS = 8;
+
+__device__ __forceinline__ void mma_s8_16832(int (&d)[4], const uint32_t a0, const uint32_t a1, const uint32_t a2, const uint32_t a3,
+                                             const uint32_t b0, const uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void mbar_init_(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+
+template <int WARPS, int STAGES>
+struct P3mSmem {
+    static constexpr size_t RING = (size_t)WARPS * STAGES * P3M_STAGE_BYTES;
+    static constexpr size_t DIGITS = (size_t)P3M_DIGITS * P3M_ROW_STRIDE;
+    static constexpr size_t BARS = (size_t)WARPS * STAGES * 8;
+    static constexpr size_t TOTAL = RING + DIGITS + BARS + 64 + 128;
+};
+
+template <int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32) rescore_int8cos_imma_kernel(const int8_t* __restrict__ rows, const uint64_t* __restrict__ keys,
+                                                                          const int64_t* __restrict__ pos, int64_t pos_base, int m,
+                                                                          const float* __restrict__ qf, double* __restrict__ score) {
+    extern __shared__ __align__(128) uint8_t p3m_smem[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)p3m_smem + 127) & ~(uintptr_t)127);
+    uint8_t* ring = base;                                              // [WARPS][STAGES][16 rows][1088]
+    uint8_t* digits = ring + P3mSmem<WARPS, STAGES>::RING;             // [8 digit planes][1088]: plane n, element k -> byte
+    unsigned long long* bars = (unsigned long long*)(digits + P3mSmem<WARPS, STAGES>::DIGITS);  // [WARPS][STAGES]
+    float* red = (float*)(bars + WARPS * STAGES);                      // [WARPS] max |q| partials
+    const int q = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- the query as eight signed base-256 digits of rint(q_i * 2^(61 - E)), E = exponent of max |q| -----------------
+    // |Q_i| < 2^62; exact for every element whose exponent is within 38 of the largest one (below that the dropped bits
+    // are < 2^-61 of max |q| - far under float64 accumulation error).  Digits are in [-128, 127]: Q = sum_n l_n 256^n.
+    float amax = 0.f;
+    for (int i = tid; i < 1024; i += WARPS * 32) amax = fmaxf(amax, fabsf(qf[(size_t)q * 1024 + i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, o));
+    if (lane == 0) red[warp] = amax;
+    if (tid < WARPS * STAGES) mbar_init_((uint32_t)__cvta_generic_to_shared(&bars[tid]), 1);
+    __syncthreads();
+    amax = red[0];
+#pragma unroll
+    for (int w = 1; w < WARPS; w++) amax = fmaxf(amax, red[w]);
+    int bexp = (__float_as_int(amax) >> 23) & 0xFF;
+    if (bexp == 0) bexp = 1;  // zero / denormal queries: the denormal scale
+    const int E = bexp - 127;
+    const double sc = __hiloint2double((1023 + 61 - E) << 20, 0);        // 2^(61 - E)
+    const double unscale = __hiloint2double((1023 - 61 + E) << 20, 0);   // 2^(E - 61)
+    for (int c = tid; c < 256; c += WARPS * 32) {  // four consecutive elements -> one 32-bit store per digit plane
+        const float4 f = *reinterpret_cast<const float4*>(qf + (size_t)q * 1024 + 4 * c);
+        long long Q[4] = {__double2ll_rn((double)f.x * sc), __double2ll_rn((double)f.y * sc), __double2ll_rn((double)f.z * sc),
+                          __double2ll_rn((double)f.w * sc)};
+#pragma unroll
+        for (int n = 0; n < P3M_DIGITS; n++) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const long long dgt = (long long)(signed char)(Q[e] & 0xFF);
+                Q[e] = (Q[e] - dgt) >> 8;
+                word |= ((uint32_t)dgt & 0xFFu) << (8 * e);
+            }
+            *reinterpret_cast<uint32_t*>(digits + n * P3M_ROW_STRIDE + 4 * c) = word;
+        }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t ring_w = (uint32_t)__cvta_generic_to_shared(ring) + (uint32_t)(warp * STAGES * P3M_STAGE_BYTES);
+    const uint32_t bar_w = (uint32_t)__cvta_generic_to_shared(bars) + (uint32_t)(warp * STAGES * 8);
+    const uint32_t a_off = (uint32_t)(g * P3M_ROW_STRIDE + 16 * t);
+    const uint32_t b_addr = (uint32_t)__cvta_generic_to_shared(digits) + (uint32_t)(g * P3M_ROW_STRIDE + 16 * t);
+
+    const int ngroups = (m + P3M_GROUP - 1) / P3M_GROUP;
+    const int wstride = gridDim.x * WARPS, wfirst = blockIdx.x * WARPS + warp;
+    const int mine = wfirst < ngroups ? (ngroups - wfirst + wstride - 1) / wstride : 0;  // groups of this warp
+
+    // lane i < 16 keeps, per stage, the local row of candidate i of the group parked there (-1: none)
+    int64_t srow[STAGES];
+    auto issue = [&](int it, int s) {  // start the copies of this warp's it-th group into stage s
+        const int grp = wfirst + it * wstride;
+        int64_t r = -1;
+        if (it < mine && lane < P3M_GROUP) {
+            const int i = grp * P3M_GROUP + lane;
+            if (i < m) r = cand_row(keys, pos, (size_t)q * m + i, pos_base);
+        }
+        srow[s] = r;
+        if (it >= mine) return;
+        const unsigned valid = __ballot_sync(FULL, r >= 0);
+        const uint32_t bar = bar_w + (uint32_t)s * 8u;
+        if (lane == 0) mbar_expect_tx_(bar, (uint32_t)__popc(valid) * 1024u);
+        __syncwarp();
+        if (r >= 0) bulk_g2s(ring_w + (uint32_t)(s * P3M_STAGE_BYTES + lane * P3M_ROW_STRIDE), rows + (size_t)r * 1024, 1024u, bar);
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) issue(s, s);
+
+    for (int it0 = 0; it0 < mine; it0 += STAGES) {
+#pragma unroll
+        for (int s = 0; s < STAGES; s++) {
+            const int it = it0 + s;
+            if (it >= mine) break;
+            mbar_wait_(bar_w + (uint32_t)s * 8u, (uint32_t)(it0 / STAGES) & 1u);
+            const uint32_t a_addr = ring_w + (uint32_t)(s * P3M_STAGE_BYTES) + a_off;
+            int acc[4] = {0, 0, 0, 0};
+            int n2a = 0, n2b = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint4 x = lds128u(a_addr + 64 * j);
+                const uint4 y = lds128u(a_addr + 8 * P3M_ROW_STRIDE + 64 * j);
+                const uint4 b = lds128u(b_addr + 64 * j);
+                mma_s8_16832(acc, x.x, y.x, x.y, y.y, b.x, b.y);
+                mma_s8_16832(acc, x.z, y.z, x.w, y.w, b.z, b.w);
+                n2a = __dp4a((int)x.x, (int)x.x, n2a);
+                n2a = __dp4a((int)x.y, (int)x.y, n2a);
+                n2a = __dp4a((int)x.z, (int)x.z, n2a);
+                n2a = __dp4a((int)x.w, (int)x.w, n2a);
+                n2b = __dp4a((int)y.x, (int)y.x, n2b);
+                n2b = __dp4a((int)y.y, (int)y.y, n2b);
+                n2b = __dp4a((int)y.z, (int)y.z, n2b);
+                n2b = __dp4a((int)y.w, (int)y.w, n2b);
+            }
+            // acc[0], acc[1] = row g, digit columns 2t, 2t + 1; acc[2], acc[3] = row g + 8.  sum_n c_n 256^n: every partial
+            // below is an exact integer in a double (< 2^40 before the power-of-two scale)
+            const double wgt = __hiloint2double((1023 + 16 * t) << 20, 0);  // 256^(2t)
+            double da = (double)((long long)acc[0] + 256ll * (long long)acc[1]) * wgt;
+            double db = (double)((long long)acc[2] + 256ll * (long long)acc[3]) * wgt;
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                da += __shfl_xor_sync(FULL, da, o);
+                db += __shfl_xor_sync(FULL, db, o);
+                n2a += __shfl_xor_sync(FULL, n2a, o);
+                n2b += __shfl_xor_sync(FULL, n2b, o);
+            }
+            const int grp = wfirst + it * wstride;
+            const int64_t ra = __shfl_sync(FULL, srow[s], g), rb = __shfl_sync(FULL, srow[s], g + 8);
+            if (t < 2) {
+                const int r = t == 0 ? g : g + 8;
+                const int i = grp * P3M_GROUP + r;
+                const int64_t rw = t == 0 ? ra : rb;
+                const double dot = t == 0 ? da : db;
+                const int n2 = t == 0 ? n2a : n2b;
+                if (i < m) score[(size_t)q * m + i] = (rw < 0 || n2 == 0) ? -INFINITY : (dot * unscale) / sqrt((double)n2);
+            }
+            // the stage is free again: every byte of it that this warp reads has been consumed by the instructions above
+            __syncwarp();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(it + STAGES, s);
+        }
+    }
+}
+
+// =====================================================================================================================
+// Phase III with regenerated rows (benchmark-only payload: the int8 row of position p is clip(rint(1259 x - 0.69)) of the
+// counter-based synthetic row seed/row0 + p, exactly what vrq_index_add_synthetic would have stored).
+// =====================================================================================================================
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) rescore_int8cos_synth_kernel(uint64_t seed, int64_t synth_row0, const uint64_t* __restrict__ keys,
+                                                                    const int64_t* __restrict__ pos, int64_t pos_base, int m,
+                                                                    const float* __restrict__ qf, double* __restrict__ score) {
+    __shared__ double qd[1024];
+    __shared__ int mc_s[1024];
+    const int q = blockIdx.y;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+        qd[i] = (double)qf[(size_t)q * 1024 + i];
+        mc_s[i] = (int)(splitmix64((uint64_t)i ^ 0xC01DBEEFCAFEF00Dull) & 0x7FFF) - 16384;
+    }
+    __syncthreads();
+    const uint64_t sbase = seed * 0xD1342543DE82EF95ull;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = blockIdx.x * 8 + warp; i < m; i += gridDim.x * 8) {
+        const size_t idx = (size_t)q * m + i;
+        const int64_t row = cand_row(keys, pos, idx, pos_base);
+        if (row < 0) {
+            if (lane == 0) score[idx] = -INFINITY;
+            continue;
+        }
+        const uint64_t rbase = sbase + (uint64_t)(synth_row0 + row) * 1024ull;
+        double acc = 0.0;
+        int n2 = 0;
+#pragma unroll 4
+        for (int c = lane; c < 1024; c += 32) {
+            const uint64_t h = splitmix64(rbase + (uint64_t)c);
+            const int s = (int)((h & 0xFFFF) + ((h >> 16) & 0xFFFF) + ((h >> 32) & 0xFFFF) + (h >> 48));
+            const float x = __fmul_rn((float)(s - 131070 + mc_s[c]), 0x1p-20f);
+            float v = __fsub_rn(__fmul_rn(x, 1259.0f), 0.69f);
+            v = fminf(fmaxf(rintf(v), -128.f), 127.f);
+            const int iv = __float2int_rz(v);
+            n2 += iv * iv;
+            acc = fma(qd[c], (double)iv, acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(FULL, acc, o);
+            n2 += __shfl_xor_sync(FULL, n2, o);
+        }
+        if (lane == 0) score[idx] = n2 == 0 ? -INFINITY : acc / sqrt((double)n2);
+    }
+}
+
+template <int WARPS, int STAGES>
+int launch_imma(vrq_ctx* ctx, const int8_t* rows, const uint64_t* keys, const int64_t* pos, int64_t pos_base, int64_t nq, int m,
+                const float* qf, double* score, cudaStream_t st) {
+    const size_t smem = P3mSmem<WARPS, STAGES>::TOTAL;
+    auto kern = rescore_int8cos_imma_kernel<WARPS, STAGES>;
+    VRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = (int)((ctx->smem_optin ? ctx->smem_optin : 227 * 1024) / (smem + 1024));
+    const int ngroups = (m + P3M_GROUP - 1) / P3M_GROUP;
+    // enough blocks per query to fill the GPU when there are few queries, never more warps than groups
+    int64_t gx = ((int64_t)ctx->sm_count * (per_sm < 1 ? 1 : per_sm) + nq - 1) / nq;
+    const int64_t gmax = (ngroups + WARPS - 1) / WARPS;
+    if (gx > gmax) gx = gmax;
+    if (gx < 1) gx = 1;
+    kern<<<dim3((unsigned)gx, (unsigned)nq), WARPS * 32, smem, st>>>(rows, keys, pos, pos_base, m, qf, score);
+    return 0;
+}
+
+}  // namespace
+
+int vrq_launch_rescore_binary_lut(vrq_ctx* ctx, const uint8_t* codes, const uint64_t* keys, const int64_t* pos, int64_t pos_base,
+                                  int64_t nq, int m, const float* qf, double* score, cudaStream_t st) {
+    int64_t gx = (m + P2_THREADS - 1) / P2_THREADS;
+    const int64_t cap = ((int64_t)ctx->sm_count * 5 + nq - 1) / nq;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    rescore_binary_lut_kernel<<<dim3((unsigned)gx, (unsigned)nq), P2_THREADS, 0, st>>>(codes, keys, pos, pos_base, m, qf, score);
+    vrq_count_launch(ctx);
+    VRQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int vrq_launch_rescore_int8cos_imma(vrq_ctx* ctx, const int8_t* rows, const uint64_t* keys, const int64_t* pos, int64_t pos_base,
+                                    int64_t nq, int m, const float* qf, double* score, cudaStream_t st) {
+    // launch shape: VRQ_RESCORE_IMMA_SHAPE = 10 * warps + stages (default 23: two warps x three stages, two blocks per SM)
+    const char* e = getenv("VRQ_RESCORE_IMMA_SHAPE");
+    const int shape = (e && *e) ? atoi(e) : 23;
+    int r;
+    switch (shape) {
+        case 43: r = launch_imma<4, 3>(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st); break;
+        case 34: r = launch_imma<3, 4>(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st); break;
+        case 62: r = launch_imma<6, 2>(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st); break;
+        case 24: r = launch_imma<2, 4>(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st); break;
+        case 13: r = launch_imma<1, 3>(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st); break;
+        case 22: r = launch_imma<2, 2>(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st); break;
+        default: r = launch_imma<2, 3>(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st); break;
+    }
+    if (r != 0) return r;
+    vrq_count_launch(ctx);
+    VRQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int vrq_launch_rescore_int8cos_synth(vrq_ctx* ctx, uint64_t seed, int64_t synth_row0, const uint64_t* keys, const int64_t* pos,
+                                     int64_t pos_base, int64_t nq, int m, const float* qf, double* score, cudaStream_t st) {
+    int64_t gx = (m + 7) / 8;
+    const int64_t cap = ((int64_t)ctx->sm_count * 8 + nq - 1) / nq;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    rescore_int8cos_synth_kernel<<<dim3((unsigned)gx, (unsigned)nq), 256, 0, st>>>(seed, synth_row0, keys, pos, pos_base, m, qf, score);
+    vrq_count_launch(ctx);
+    VRQ_CUDA(cudaGetLastError());
+    return 0;
+}

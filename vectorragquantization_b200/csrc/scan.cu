@@ -21,6 +21,10 @@
 // the integer pipes (32 x (LOP3 + POPC + IADD) per (query, code) pair).  See DESIGN.md section 3.
 #include "scan_common.cuh"
 
+#ifndef VRQ_MMA_LOCKSTEP_DEFAULT
+#define VRQ_MMA_LOCKSTEP_DEFAULT 0
+#endif
+
 namespace {
 
 using namespace vrq;
@@ -710,10 +714,20 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
             sp.tau0 = tau;
             sp.tau_bias = 1;
             sp.dbg = dbg;
+            const int lock_window = env_int("VRQ_MMA_LOCKSTEP", VRQ_MMA_LOCKSTEP_DEFAULT);
+            if (lock_window > 0 && m_pl.mp.pair && m_pl.mp.qtiles > 2) {
+                void* prog_v;
+                const size_t pbytes = sizeof(int) * (size_t)m_pl.strips() * (size_t)(m_pl.mp.qtiles / 2);
+                VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_PROGRESS, pbytes, &prog_v));
+                VRQ_CUDA(cudaMemsetAsync(prog_v, 0, pbytes, st));
+                sp.progress = (int*)prog_v;
+                sp.lock_window = lock_window;
+            }
             {
                 vrq_timer_scope td(ctx, VRQ_CAT_SCAN_DENSE, st);  // the dominant launch on its own (bench.py's roofline)
                 VRQ_TRY(launch_pass(ctx, tma, tmap, tmap_mma, sp, m_pl, st));
             }
+            sp.progress = nullptr;  // the gated fallback pass runs unthrottled (its counters would have to be reset)
             VRQ_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
             const int need = (int)((int64_t)k < n ? (int64_t)k : n);
             verify_counts_kernel<<<(nq + 127) / 128, 128, 0, st>>>(counts, m_pl.strips(), nq, need, flag, tau);

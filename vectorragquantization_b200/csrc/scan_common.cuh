@@ -52,6 +52,8 @@ struct ScanParams {
     int64_t total_tiles;
     int32_t* dbg;     // tests only: every (query, row) Hamming distance of the launch, [nq][dbg_stride] (tensor-core kernel)
     int64_t dbg_stride;
+    int* progress;    // tensor-core pair kernel, dense pass: [strip][query-tile pair] tile counters (lockstep throttle), or null
+    int lock_window;  // a pair's TMA producer stays within this many tiles of the slowest pair of its strip
     int one;          // == 1, opaque to the compiler: multiplier that keeps the popcount accumulation on the FMA pipe (IMAD)
 };
 

@@ -334,7 +334,22 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         // ===================== raw-code producer =====================
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
+            // Lockstep throttle (dense pass, CTA pairs): the pairs of one strip read the same rows, and only the first read
+            // of a row comes from HBM as long as the others follow within the L2's reach.  Left alone the pairs drift apart
+            // (ncu: DRAM reads 2x the code array); here the leader's producer publishes its tile counter every 16 tiles and
+            // does not run more than lock_window tiles ahead of the slowest pair of its strip - which costs nothing, since
+            // the launch ends with the slowest pair anyway.
+            const int ncols = (int)(gridDim.x / CG);
+            volatile int* prog = (p.progress && rank == 0 && ncols > 1) ? p.progress + (size_t)strip * ncols : nullptr;
+            const int mycol = (int)(blockIdx.x / CG);
             for (int t = 0; t < ntiles; t++) {
+                if (prog && (t & 15) == 0) {
+                    prog[mycol] = t;
+                    const int lim = t - p.lock_window;
+                    if (lim > 0)
+                        for (int c = 0; c < ncols; c++)
+                            while (prog[c] < lim) __nanosleep(256);
+                }
                 mbar_wait_relaxed(smem_u32(&sm->raw_empty[s]), ph ^ 1u, 256);
                 mbar_expect_tx(smem_u32(&sm->raw_full[s]), STAGE_BYTES_RAW);
                 tma_load_2d(smem_u32(raw_mem) + s * (uint32_t)STAGE_BYTES_RAW, &tmap, 0,
@@ -344,6 +359,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                     ph ^= 1u;
                 }
             }
+            if (prog) prog[mycol] = 0x7fffffff;
         }
     } else if (warp >= WARP_MMA && warp < WARP_MMA + MMA_WARPS) {
         // ===================== MMA issuers =====================

@@ -50,7 +50,7 @@ struct vrq_buf {
 enum { VRQ_WS_STAGE_IN0 = 0, VRQ_WS_STAGE_IN1, VRQ_WS_STAGE_OUT0, VRQ_WS_STAGE_OUT1, VRQ_WS_LISTS, VRQ_WS_COUNTS,
        VRQ_WS_TOPK, VRQ_WS_SEARCH_A, VRQ_WS_SEARCH_B, VRQ_WS_SEARCH_C, VRQ_WS_SEARCH_D, VRQ_WS_SEARCH_E,
        VRQ_WS_QUERY_A, VRQ_WS_QUERY_B, VRQ_WS_OUT_A, VRQ_WS_OUT_B, VRQ_WS_OUT_C, VRQ_WS_OUT_D, VRQ_WS_OUT_E,
-       VRQ_WS_MISC, VRQ_WS_TAU, VRQ_WS_MERGE_A, VRQ_WS_MERGE_B, VRQ_WS_MERGE_CA, VRQ_WS_MERGE_CB, VRQ_WS_SAMPLE_KEYS, VRQ_WS_FLAG, VRQ_WS_SLOTS };
+       VRQ_WS_MISC, VRQ_WS_TAU, VRQ_WS_MERGE_A, VRQ_WS_MERGE_B, VRQ_WS_MERGE_CA, VRQ_WS_MERGE_CB, VRQ_WS_SAMPLE_KEYS, VRQ_WS_FLAG, VRQ_WS_PROGRESS, VRQ_WS_SLOTS };
 
 struct vrq_ctx {
     int device = 0;
@@ -129,6 +129,13 @@ int vrq_launch_rescore_binary(vrq_ctx* ctx, const uint8_t* codes, int d, const u
                               int64_t pos_base, int64_t nq, int m, const float* qf, double* score, cudaStream_t st);
 int vrq_launch_rescore_int8cos(vrq_ctx* ctx, const int8_t* rows, int d, const uint64_t* keys, const int64_t* pos,
                                int64_t pos_base, int64_t nq, int m, const float* qf, double* score, cudaStream_t st);
+// rescore_mma.cu (d == 1024): nibble-table Phase II, tensor-core (mma.sync s8) Phase III, Phase III over regenerated rows
+int vrq_launch_rescore_binary_lut(vrq_ctx* ctx, const uint8_t* codes, const uint64_t* keys, const int64_t* pos, int64_t pos_base,
+                                  int64_t nq, int m, const float* qf, double* score, cudaStream_t st);
+int vrq_launch_rescore_int8cos_imma(vrq_ctx* ctx, const int8_t* rows, const uint64_t* keys, const int64_t* pos, int64_t pos_base,
+                                    int64_t nq, int m, const float* qf, double* score, cudaStream_t st);
+int vrq_launch_rescore_int8cos_synth(vrq_ctx* ctx, uint64_t seed, int64_t synth_row0, const uint64_t* keys, const int64_t* pos,
+                                     int64_t pos_base, int64_t nq, int m, const float* qf, double* score, cudaStream_t st);
 struct vrq_rescore2_args {
     int kind;  // payload kind
     const void* payload;

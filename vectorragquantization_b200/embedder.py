@@ -9,11 +9,66 @@ variant returns the three types the Cohere API returns: float, int8 = clip(rint(
 from __future__ import annotations
 
 import hashlib
-from typing import Dict, List, Sequence
+import logging
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
 from . import kernels as K
+
+logger = logging.getLogger(__name__)
+_warned = set()
+
+
+def warn_synthetic(cls_name: str, what: str) -> None:
+    """Logged once per class: the default embedder produces NON-SEMANTIC vectors (a hash of the text picks a row of the
+    counter-based generator).  Pass ``embedder=`` (any callable) or ``embedder="http"`` to reach a real service."""
+    if cls_name in _warned:
+        return
+    _warned.add(cls_name)
+    logger.warning("%s: no embedder was injected - using the SYNTHETIC embedder (%s is ignored); search results are not "
+                   "semantically meaningful.  Pass embedder=<callable> or embedder='http'.", cls_name, what)
+
+
+class OllamaHttpEmbedder:
+    """The reference's embedding call (VectorDBInt8.py:76-100): POST {"model", "input"} to ``embed_url``, read
+    ``["embeddings"]``.  Needs a reachable service; selected with ``embedder="http"``."""
+
+    def __init__(self, embed_url: str, model: str, timeout: float = 60.0):
+        self.embed_url, self.model, self.timeout = embed_url, model, timeout
+
+    def __call__(self, texts: Sequence[str]) -> np.ndarray:
+        import requests
+        rows = []
+        for text in texts:  # one request per text, like the reference; both response shapes it accepts
+            r = requests.post(self.embed_url, json={"model": self.model, "input": text}, timeout=self.timeout)
+            r.raise_for_status()
+            data = r.json()
+            if data.get("data"):
+                e = np.asarray(data["data"][0]["embedding"], dtype=np.float32)
+            else:
+                e = np.asarray(data["embeddings"], dtype=np.float32)
+            rows.append(e[0] if e.ndim > 1 else e)
+        return np.stack(rows)
+
+
+class CohereHttpEmbedder:
+    """The reference's Cohere call (CohereEnhancedVectorDB.py:136-169): POST to COHERE_EMBED_ENDPOINT /v2/embed with a
+    bearer key; returns the ``embeddings`` object ({"float": ..., "int8": ..., "ubinary": ...})."""
+
+    def __init__(self, endpoint: Optional[str], api_key: Optional[str], model: str, timeout: float = 60.0):
+        if not endpoint or not api_key:
+            raise Exception("COHERE_EMBED_ENDPOINT / COHERE_EMBED_KEY are not set in the environment.")
+        self.endpoint, self.api_key, self.model, self.timeout = endpoint, api_key, model, timeout
+
+    def __call__(self, texts: Sequence[str], input_type: str, embedding_types: List[str]) -> Dict:
+        import requests
+        r = requests.post(self.endpoint, headers={"Content-Type": "application/json", "Authorization": f"Bearer {self.api_key}"},
+                          json={"model": self.model, "texts": list(texts), "input_type": input_type, "truncate": "NONE",
+                                "embedding_types": embedding_types},
+                          timeout=self.timeout)
+        r.raise_for_status()
+        return r.json().get("embeddings", {})
 
 
 def text_row(text: str) -> int:

@@ -28,7 +28,7 @@ from . import _lib as L
 from . import kernels as K
 from .binary_index import BinaryIndex, read_index_binary, write_index_binary
 from .docstore import DocStore
-from .embedder import SyntheticEmbedder
+from .embedder import OllamaHttpEmbedder, SyntheticEmbedder, warn_synthetic
 
 logger = logging.getLogger(__name__)
 
@@ -67,14 +67,19 @@ class _VectorDBBase:
         self.embedding_dim = embedding_dim
         self.embed_url = embed_url
         self._ctx = ctx if ctx is not None else L.default_context()
-        self._embedder = embedder if embedder is not None else SyntheticEmbedder(embedding_dim, ctx=self._ctx)
-        self._setup_config(folder, model, embedding_dim)
-        self.index = self._initialize_faiss_index(folder, embedding_dim)
-        self.doc_db = DocStore(os.path.join(folder, "docs"), rdict_options)
+        if embedder == "http":
+            embedder = OllamaHttpEmbedder(embed_url, model)  # the reference's service call (VectorDBInt8.py:76-100)
+        elif embedder is None:
+            warn_synthetic(type(self).__name__, "embed_url")
+            embedder = SyntheticEmbedder(embedding_dim, ctx=self._ctx)
+        self._embedder = embedder
         self.folder = folder
+        self._setup_config(folder, model, embedding_dim)
+        self.doc_db = DocStore(os.path.join(folder, "docs"), rdict_options)
+        self.index = self._initialize_faiss_index(folder, embedding_dim)
+        self.doc_db.imported_raw = None  # the vectors of an imported reference store are in the index now
         self.float_embeddings: Dict[str, np.ndarray] = {}
         self._findex: Optional[BinaryIndex] = None  # codes + float32 rows, backs compare_float32=True
-        self._restore_payload()
 
     # ---- config.json (VectorDBInt8.py:41-58, VectorDBInt8Global.py:50-73) ------------------------------------
     def _config_dict(self, model, embedding_dim):
@@ -102,54 +107,61 @@ class _VectorDBBase:
     def _limit(self) -> float:
         return float(getattr(self, "global_limit", 0.0))
 
+    # key of the quantised vector inside the reference's per-document pickles (VectorDBInt8.py:179-183 and siblings)
+    _ref_payload_key: Optional[str] = None
+
     def _initialize_faiss_index(self, folder: str, embedding_dim: int) -> BinaryIndex:
+        """index.bin holds codes + ids only (faiss layout) and is streamed into device memory.  The quantised rows the
+        reference keeps in RocksDB pickles come from the streamed sidecar ``payload.vrqp`` written by ``save()``, from
+        round 1's ``payload.npz``, or - for a folder written by the REFERENCE - from its ``docs/`` store (rocks_import.py)."""
         path = os.path.join(folder, "index.bin")
-        if os.path.exists(path):
-            loaded = read_index_binary(path, ctx=self._ctx)
-            logger.info("Existing FAISS index loaded.")
-            self._loaded = loaded
-            return loaded  # replaced by _restore_payload() once the quantised rows are re-attached
-        self._loaded = None
-        logger.info(f"New FAISS index created with embedding dimension {embedding_dim}.")
-        return BinaryIndex(embedding_dim, ctx=self._ctx, payload_kind=self._payload_kind, global_limit=self._limit())
+        kind = self._payload_kind
+        if not os.path.exists(path):
+            logger.info(f"New FAISS index created with embedding dimension {embedding_dim}.")
+            return BinaryIndex(embedding_dim, ctx=self._ctx, payload_kind=kind, global_limit=self._limit())
+        index = read_index_binary(path, ctx=self._ctx)
+        logger.info("Existing FAISS index loaded.")
+        n = index.ntotal
+        if kind == L.PAYLOAD_NONE:
+            return index
+        if kind == L.PAYLOAD_CODES_PM1:  # the rescoring payload is the code itself
+            index.attach_payload(kind)
+            return index
+        legacy = os.path.join(folder, "payload.npz")
+        if os.path.exists(self._payload_path()):
+            index.read_payload(self._payload_path())
+            if index.payload_kind != kind:
+                raise Exception(f"{self._payload_path()} holds payload kind {index.payload_kind}, this class needs {kind}")
+            return index
+        index.attach_payload(kind, self._limit())
+        dt, ln, adt = index.payload_layout()
+        if n > 0 and os.path.exists(legacy):
+            z = np.load(legacy)
+            if z["payload"].shape[0] != n:
+                raise Exception(f"{legacy} has {z['payload'].shape[0]} rows, index.bin has {n} codes")
+            index.write_rows(L.ROWS_PAYLOAD, 0, np.ascontiguousarray(z["payload"], dt))
+            if adt is not None:
+                index.write_rows(L.ROWS_AUX, 0, np.ascontiguousarray(z["aux"], adt))
+        elif n > 0 and self.doc_db.imported_raw is not None and self._ref_payload_key:
+            ids = index.read_rows(L.ROWS_IDS, 0, n)
+            for a in range(0, n, 65536):
+                rows, aux = [], []
+                for i in ids[a:a + 65536]:
+                    entry = self.doc_db.imported_raw.get(str(int(i)))
+                    if entry is None or self._ref_payload_key not in entry:
+                        raise Exception(f"document {int(i)} of index.bin has no '{self._ref_payload_key}' vector in {folder}/docs")
+                    rows.append(np.asarray(entry[self._ref_payload_key]).astype(dt, copy=False).reshape(ln))
+                    if adt is not None:
+                        aux.append([entry["min_max"][0], entry["min_max"][1]])
+                index.write_rows(L.ROWS_PAYLOAD, a, np.stack(rows))
+                if adt is not None:
+                    index.write_rows(L.ROWS_AUX, a, np.asarray(aux, adt))
+        elif n > 0:
+            raise Exception(f"{folder}: index.bin has {n} codes but there are no quantised vectors (payload.vrqp / docs store)")
+        return index
 
     def _payload_path(self):
-        return os.path.join(self.folder, "payload.npz")
-
-    def _restore_payload(self):
-        """index.bin holds codes + ids only (faiss layout); the quantised rows the reference keeps in RocksDB pickles
-        are persisted as payload.npz next to it and re-attached to the device index on open."""
-        if self._loaded is None or self._payload_kind == L.PAYLOAD_NONE:
-            return
-        if self._payload_kind == L.PAYLOAD_CODES_PM1:
-            # no side file: the rescoring payload is the code itself; rebuild the index with that kind set
-            import struct
-            raw = open(os.path.join(self.folder, "index.bin"), "rb").read()
-            n = self._loaded.ntotal
-            new = BinaryIndex(self.embedding_dim, ctx=self._ctx, payload_kind=self._payload_kind)
-            if n:
-                cs = self.embedding_dim // 8
-                new.add_with_ids(np.frombuffer(raw, np.uint8, n * cs, 58).reshape(n, cs), np.frombuffer(raw, np.int64, n, 66 + n * cs))
-            self._loaded.close()
-            self.index, self._loaded = new, None
-            return
-        src = self._loaded
-        n = src.ntotal
-        new = BinaryIndex(self.embedding_dim, ctx=self._ctx, payload_kind=self._payload_kind, global_limit=self._limit())
-        if n > 0:
-            if not os.path.exists(self._payload_path()):
-                raise Exception(f"{self._payload_path()} is missing: index.bin has {n} codes but no quantised vectors")
-            z = np.load(self._payload_path())
-            codes = np.stack([src.reconstruct(int(i)) for i in z["ids"]]) if n < 4096 else None
-            if codes is None:
-                import struct
-                raw = open(os.path.join(self.folder, "index.bin"), "rb").read()
-                nb = struct.unpack_from("<Q", raw, 50)[0]
-                codes = np.frombuffer(raw, np.uint8, nb, 58).reshape(n, -1)
-            new.add_with_ids(codes, z["ids"], payload=z["payload"], aux=z["aux"] if "aux" in z.files else None)
-        src.close()
-        self.index = new
-        self._loaded = None
+        return os.path.join(self.folder, "payload.vrqp")
 
     # ---- embedding -----------------------------------------------------------------------------------------
     def _embed_float(self, texts: Sequence[str]) -> Optional[np.ndarray]:
@@ -222,9 +234,9 @@ class _VectorDBBase:
             if self._findex is None:
                 self._findex = BinaryIndex(self.embedding_dim, ctx=self._ctx, payload_kind=L.PAYLOAD_F32)
             self._findex.add_with_ids(ub, ids, payload=x)
-        for i, doc_id in enumerate(batch_ids):
-            self.doc_db[str(doc_id)] = {"doc": batch_docs[i] if batch_docs is not None else ""}
-            if keep_float:
+        self.doc_db.set_many((str(doc_id), {"doc": batch_docs[i] if batch_docs is not None else ""}) for i, doc_id in enumerate(batch_ids))
+        if keep_float:
+            for i, doc_id in enumerate(batch_ids):
                 self.float_embeddings[str(doc_id)] = x[i]
 
     # ---- search ------------------------------------------------------------------------------------------------
@@ -271,7 +283,10 @@ class _VectorDBBase:
             if self._findex is not None:
                 self._findex.remove_ids(np.array([doc_id], dtype=np.int64))
             del self.doc_db[doc_id_str]
-            del self.float_embeddings[doc_id_str]  # KeyError after a reopen, like the reference (VectorDBInt8.py:252)
+            # (the reference does `del self.float_embeddings[id]` here, VectorDBInt8.py:252, and raises KeyError after a reopen
+            # with the document already half removed; popping keeps remove / re-add usable after a reopen and with
+            # add_embeddings(keep_float=False))
+            self.float_embeddings.pop(doc_id_str, None)
             logger.info(f"Document {doc_id} removed from the database.")
         else:
             logger.warning(f"Document {doc_id} not found in the database.")
@@ -279,30 +294,14 @@ class _VectorDBBase:
             self.save()
 
     def save(self):
+        """index.bin (faiss layout) + the payload sidecar, both streamed from device memory and renamed into place."""
         write_index_binary(self.index, os.path.join(self.folder, "index.bin"))
         if self._payload_kind not in (L.PAYLOAD_NONE, L.PAYLOAD_CODES_PM1):
-            self._save_payload()
+            self.index.write_payload(self._payload_path())
+            legacy = os.path.join(self.folder, "payload.npz")
+            if os.path.exists(legacy):
+                os.remove(legacy)
         logger.info("FAISS index saved to disk.")
-
-    def _payload_layout(self):
-        """(row dtype, row length, aux dtype or None) of the payload kind."""
-        d = self.embedding_dim
-        return {L.PAYLOAD_INT8_PERDOC: (np.int8, d, np.float32), L.PAYLOAD_INT8_GLOBAL: (np.int8, d, None),
-                L.PAYLOAD_INT16_GLOBAL: (np.int16, d, None), L.PAYLOAD_INT4_PERDOC: (np.int8, d // 2, np.float64),
-                L.PAYLOAD_INT4_GLOBAL: (np.int8, d // 2, None)}[self._payload_kind]
-
-    def _save_payload(self):
-        n = self.index.ntotal
-        dt, ln, adt = self._payload_layout()
-        pos = np.arange(n, dtype=np.int64)
-        pay, aux = self.index.get_payload(pos, dt, ln, adt) if n else (np.empty((0, ln), dt), None)
-        import struct
-        raw = open(os.path.join(self.folder, "index.bin"), "rb").read()
-        ids = np.frombuffer(raw, np.int64, n, 66 + n * (self.embedding_dim // 8)).copy()
-        arrs = {"ids": ids, "payload": pay}
-        if aux is not None:
-            arrs["aux"] = aux
-        np.savez(self._payload_path(), **arrs)
 
     def __len__(self):
         return self.index.ntotal
@@ -313,6 +312,7 @@ class VectorDBInt8(_VectorDBBase):
     """Per-document symmetric int8 (VectorDBInt8.py): scale = 127/max|x| per vector, truncating cast."""
 
     _payload_kind = L.PAYLOAD_INT8_PERDOC
+    _ref_payload_key = "emb_int8"
     _desc = "Indexing docs (Int8)"
 
     @staticmethod
@@ -343,6 +343,7 @@ class VectorDBInt8Global(_VectorDBBase):
     """Global-limit int8 (VectorDBInt8Global.py): clip to +-limit, scale 127/limit, round half to even."""
 
     _payload_kind = L.PAYLOAD_INT8_GLOBAL
+    _ref_payload_key = "emb_int8"
     _desc = "Indexing docs (Global Int8)"
     _has_global_limit = True
 
@@ -375,6 +376,7 @@ class VectorDBInt16Global(_VectorDBBase):
     """Global-limit int16 (VectorDBInt16Global.py)."""
 
     _payload_kind = L.PAYLOAD_INT16_GLOBAL
+    _ref_payload_key = "emb_int16"
     _desc = "Indexing docs (Global Int16)"
     _has_global_limit = True
 
@@ -407,6 +409,7 @@ class VectorDBInt4(_VectorDBBase):
     """Per-document int4, two nibbles per byte (VectorDBInt4.py)."""
 
     _payload_kind = L.PAYLOAD_INT4_PERDOC
+    _ref_payload_key = "emb_int4"
     _desc = "Indexing docs (Int4)"
 
     @staticmethod
@@ -434,6 +437,7 @@ class VectorDBInt4Global(_VectorDBBase):
     IGNORES the limit and scales per document (VectorDBInt4Global.py:142-149), the decoder uses limit/7 (:177)."""
 
     _payload_kind = L.PAYLOAD_INT4_GLOBAL
+    _ref_payload_key = "emb_int4"
     _desc = "Indexing docs (Global Int4)"
     _has_global_limit = True
 
