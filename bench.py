@@ -646,7 +646,7 @@ def hbm_bound_kernels(env, index, qf_d, qb_d, hbm_peak, peak_src, n_local, ms_pe
         sc5 = torch.empty((nq5, m5), dtype=torch.float64, device=dev)
         sc5b = torch.empty((nq5, m5), dtype=torch.float64, device=dev)
         variants = {}
-        saved = {k_: os.environ.get(k_) for k_ in ("VRQ_RESCORE_IMMA", "VRQ_RESCORE_IMMA_SHAPE", "VRQ_RESCORE_BIN_LUT")}
+        saved = {k_: os.environ.get(k_) for k_ in ("VRQ_RESCORE_IMMA", "VRQ_RESCORE_IMMA_SHAPE", "VRQ_RESCORE_BIN")}
 
         def run3(dst):
             return lambda: L.check(lib.vrq_rescore_int8cos(h, pay_p, n_local, D, L.ptr(pos5), nq5, m5, L.ptr(qf5), L.ptr(dst)))
@@ -654,9 +654,9 @@ def hbm_bound_kernels(env, index, qf_d, qb_d, hbm_peak, peak_src, n_local, ms_pe
         os.environ["VRQ_RESCORE_IMMA"] = "0"
         variants["cuda_core_f64_cp_async_ring"] = _timed(env, run3(sc5), 5)
         os.environ["VRQ_RESCORE_IMMA"] = "1"
-        for shape in ("23", "24", "43", "34", "62"):
-            os.environ["VRQ_RESCORE_IMMA_SHAPE"] = shape
-            variants[f"imma_s8_w{shape[0]}_s{shape[1]}"] = _timed(env, run3(sc5b), 5)
+        for bulk, w_, s_ in ((1, 6, 2), (0, 6, 2), (1, 4, 3), (0, 4, 3), (1, 2, 3), (1, 3, 4), (0, 3, 4), (1, 12, 1), (0, 12, 1), (1, 8, 1), (0, 8, 1)):
+            os.environ["VRQ_RESCORE_IMMA_SHAPE"] = str(100 * bulk + 10 * w_ + s_)
+            variants[f"imma_s8_{'bulk1KB' if bulk else 'cpasync16B'}_w{w_}_s{s_}"] = _timed(env, run3(sc5b), 5)
         for k_, v in saved.items():
             if v is None:
                 os.environ.pop(k_, None)
@@ -665,12 +665,17 @@ def hbm_bound_kernels(env, index, qf_d, qb_d, hbm_peak, peak_src, n_local, ms_pe
         fin = torch.isfinite(sc5) & torch.isfinite(sc5b)
         dev_rel = float(((sc5 - sc5b).abs()[fin] / sc5.abs()[fin].clamp_min(1e-30)).max().item())
         s3 = _timed(env, run3(sc5), 5)  # the default path, whichever it is
-        os.environ["VRQ_RESCORE_BIN_LUT"] = "0"
-        s2_old = _timed(env, lambda: L.check(lib.vrq_rescore_binary(h, codes_p, n_local, D, L.ptr(pos5), nq5, m5, L.ptr(qf5), L.ptr(sc5))), 5)
-        os.environ.pop("VRQ_RESCORE_BIN_LUT", None)
-        if saved["VRQ_RESCORE_BIN_LUT"] is not None:
-            os.environ["VRQ_RESCORE_BIN_LUT"] = saved["VRQ_RESCORE_BIN_LUT"]
-        s2 = _timed(env, lambda: L.check(lib.vrq_rescore_binary(h, codes_p, n_local, D, L.ptr(pos5), nq5, m5, L.ptr(qf5), L.ptr(sc5))), 5)
+        def run2():
+            L.check(lib.vrq_rescore_binary(h, codes_p, n_local, D, L.ptr(pos5), nq5, m5, L.ptr(qf5), L.ptr(sc5)))
+
+        bin_ms = {}
+        for mode, name in (("0", "cuda_core_register_kernel"), ("1", "cuda_core_nibble_table"), ("2", "imma_s8_code_bits")):
+            os.environ["VRQ_RESCORE_BIN"] = mode
+            bin_ms[name] = _timed(env, run2, 5) * 1e3
+        os.environ.pop("VRQ_RESCORE_BIN", None)
+        if saved["VRQ_RESCORE_BIN"] is not None:
+            os.environ["VRQ_RESCORE_BIN"] = saved["VRQ_RESCORE_BIN"]
+        s2 = _timed(env, run2, 5)  # the default path
         gb3 = nq5 * m5 * 1024 / s3 / 1e9
         tr, tr_src = traffic("rescore_int8cos_cfg5")
         best = min(variants, key=variants.get)
@@ -688,10 +693,11 @@ def hbm_bound_kernels(env, index, qf_d, qb_d, hbm_peak, peak_src, n_local, ms_pe
                                   "paths": "cuda_core: float64 FMA of exact products, cp.async ring (rescore.cu); imma: mma.sync.m16n8k32.s8 over eight "
                                            "base-256 digits of the 64-bit fixed-point query, 1 KB bulk copies into a per-warp ring (rescore_mma.cu), "
                                            "w = warps per block, s = ring stages"}}
-        out["rescore_binary_cfg5"] = {"kernel": "rescore_binary_lut_kernel (per-query nibble table of f64 partial sums in shared memory)",
+        out["rescore_binary_cfg5"] = {"kernel": "vrq_rescore_binary, default path (d=1024): mma.sync s8, code bits x digit planes of the fixed-point query",
                                       "ms": s2 * 1e3, "pairs_per_s": nq5 * m5 / s2, "GB/s": nq5 * m5 * 128 / s2 / 1e9,
-                                      "register_kernel_ms": s2_old * 1e3, "speedup": s2_old / s2,
-                                      "gather_roofline_128B_GBs": 4200.0, "frac": nq5 * m5 * 128 / s2 / 1e9 / 4200.0}
+                                      "variants_ms": bin_ms, "speedup_vs_round1_register_kernel": bin_ms["cuda_core_register_kernel"] / (s2 * 1e3),
+                                      "gather_roofline_128B_GBs": 4200.0, "frac": nq5 * m5 * 128 / s2 / 1e9 / 4200.0,
+                                      "peak_source": "random 128-byte rows stream at 4.0-4.4 TB/s (profiles/microbench/gather_bench_r01.txt)"}
         del pos5, qf5, sc5, sc5b
     # adversarial step: 64 of the 1024 queries have 32 exact duplicates each inside the first sampled tiles, so their
     # sampled threshold is 0, the dense pass collects < k candidates for them and the exact fallback pass runs

@@ -267,17 +267,14 @@ def test_limits_and_errors(V):
     from vectorragquantization_b200 import _lib as L
     from vectorragquantization_b200 import kernels as K
     with pytest.raises(V.VrqError) as e:
-        V.BinaryIndex(1000)  # d % 32 != 0
-    assert e.value.code == L.ERR_UNSUPPORTED
-    with pytest.raises(V.VrqError) as e:
-        V.BinaryIndex(1027)
+        V.BinaryIndex(1027)  # faiss's own requirement: d % 8 == 0
     assert e.value.code == L.ERR_ARG
     ix = V.BinaryIndex(1024)
     rng = np.random.default_rng(0)
     codes = rng.integers(0, 256, (5000, 128), dtype=np.uint8)
     ix.add_with_ids(codes, np.arange(5000))
     with pytest.raises(V.VrqError) as e:
-        ix.search(codes[:1], 5000)  # k > 4096
+        ix.search(codes[:1], 20000)  # k > 16384
     assert e.value.code == L.ERR_UNSUPPORTED
     with pytest.raises(V.VrqError):
         ix.search(codes[:1], 0)
@@ -298,6 +295,81 @@ def test_limits_and_errors(V):
     d, l = ix.search(q, 7)
     rd, rp = oc.hamming_topk(codes, q, 7)
     assert np.array_equal(d, rd) and np.array_equal(l, rp)
+
+
+@pytest.mark.parametrize("n,nq,k", [(30000, 3, 5000), (30000, 40, 10000), (9000, 2, 16384), (400000, 5, 10000)])
+def test_hamming_topk_beyond_one_pass(V, n, nq, k):
+    """k above what one scan pass keeps per list (4096): the ranking is produced in chunks, each an exact scan above the last
+    key of the chunk before it (faiss has no limit on k; CohereEnhancedVectorDB.py:267 with k=1000 asks for 10000).  Includes
+    k > ntotal (padding) and heavy ties across chunk boundaries."""
+    rng = np.random.default_rng(n + k)
+    if n == 9000:  # few distinct codes: tie groups far larger than a chunk
+        base = rng.integers(0, 256, (4, 128), dtype=np.uint8)
+        codes = base[rng.integers(0, 4, n)]
+    else:
+        codes = rng.integers(0, 256, (n, 128), dtype=np.uint8)
+    q = rng.integers(0, 256, (nq, 128), dtype=np.uint8)
+    ix = V.BinaryIndex(1024)
+    ix.add_with_ids(codes, np.arange(n))
+    check_topk(ix, codes, q, k)
+
+
+def test_search3_large_binary_k(V):
+    """k * binary_oversample = 10000 (k=1000, oversample 10: a legal call of the reference) through all three phases."""
+    from vectorragquantization_b200 import _lib as L
+    n, nq, k, bo, io = 40000, 4, 1000, 10, 3
+    x = oc.synth_f32(41, 0, n)
+    codes, i8 = oc.synth_codes_int8(41, 0, n)
+    ids = np.arange(n, dtype=np.int64)
+    qf = (x[np.arange(nq) * 997] + oc.synth_f32(42, 0, nq) * np.float32(0.5)).astype(np.float32)
+    qb = o.synth_ubinary_from_f32(qf)
+    ix = V.BinaryIndex(1024, payload_kind=L.PAYLOAD_INT8_RAW)
+    ix.add_with_ids(codes, ids, payload=i8)
+    labels, ham, sb, sc, cnt = ix.search3(qf, qb, k, bo, io)
+    for qi in range(nq):
+        ref = o.search3(codes, ids, i8, qf[qi], qb[qi], k, bo, io, literal=False)
+        assert cnt[qi] == len(ref) == k
+        assert [h["doc_id"] for h in ref] == labels[qi].tolist()
+        assert [h["score_hamming"] for h in ref] == ham[qi].tolist()
+    # the 2-phase classes' search with 12000 phase-I hits
+    ix2 = V.BinaryIndex(1024, payload_kind=L.PAYLOAD_F32)
+    ix2.add_with_ids(codes, ids, payload=x)
+    l2, s2, c2 = ix2.search2(qf[:2], qb[:2], 1200, 10)
+    for qi in range(2):
+        ref = o.search2(codes, ids, lambda p: x[p], qf[qi], qb[qi], 1200, 10)
+        assert c2[qi] == 1200 and len(set(l2[qi].tolist()) ^ {h["doc_id"] for h in ref}) <= 4  # float32 score ties may swap the last ranks
+
+
+@pytest.mark.parametrize("d", [1000, 136, 8])
+def test_code_widths_not_multiple_of_32_bits(V, d):
+    """faiss binary indexes only require d % 8 == 0: index, Hamming top-k, both fused searches and the file round trip with
+    code rows that are not word-aligned (d = 1000 -> 125-byte codes)."""
+    from vectorragquantization_b200 import _lib as L
+    rng = np.random.default_rng(d)
+    n, nq = 5000, 6
+    x = rng.normal(0, 0.05, (n, d)).astype(np.float32)
+    codes = np.packbits(x > 0, axis=1)
+    i8 = np.clip(np.rint(1259 * x - 0.69), -128, 127).astype(np.int8)
+    ids = np.arange(n, dtype=np.int64) * 3
+    qf = (x[:nq] + rng.normal(0, 0.02, (nq, d))).astype(np.float32)
+    qb = np.packbits(qf > 0, axis=1)
+    ix = V.BinaryIndex(d, payload_kind=L.PAYLOAD_INT8_RAW)
+    ix.add_with_ids(codes, ids, payload=i8)
+    check_topk(ix, codes, qb, 100 if d > 8 else 20, ids)
+    assert np.array_equal(ix.reconstruct(int(ids[77])), codes[77])
+    if d >= 136:
+        labels, ham, sb, sc, cnt = ix.search3(qf, qb, 10, 10, 3)
+        for qi in range(nq):
+            ref = o.search3(codes, ids, i8, qf[qi], qb[qi], 10, 10, 3)
+            assert [h["doc_id"] for h in ref] == labels[qi].tolist() and [h["score_hamming"] for h in ref] == ham[qi].tolist()
+            rb = np.array([h["score_binary"] for h in ref])
+            assert np.all(np.abs(sb[qi] - rb) <= 1e-5 * np.abs(rb) + 1e-12)
+    ix2 = V.BinaryIndex(d, payload_kind=L.PAYLOAD_F32)
+    ix2.add_with_ids(codes, ids, payload=x)
+    l2, s2, c2 = ix2.search2(qf, qb, 5, 10)
+    for qi in range(nq):
+        ref = o.search2(codes, ids, lambda p: x[p], qf[qi], qb[qi], 5, 10)
+        assert [h["doc_id"] for h in ref] == l2[qi].tolist()
 
 
 def test_search3_other_dim(V):

@@ -136,7 +136,7 @@ def test_kat1_on_gpu(K, golden_dbs):
     assert np.array_equal(K.to_binary(pay), golden_dbs["db_cohere_int8.codes"][: pay.shape[0]])
 
 
-@pytest.mark.parametrize("variant", ["dp2a", "register_ring", "batchred", "cuda_core", "imma", "imma43", "imma62", "imma13"])
+@pytest.mark.parametrize("variant", ["dp2a", "register_ring", "batchred", "cuda_core", "imma", "imma62", "imma143", "imma43", "imma123", "imma121", "imma81", "imma34"])
 def test_rescore_int8cos_kernel_variants(K, monkeypatch, variant):
     """Phase III has several d = 1024 kernels: the cp.async ring with float64 FMAs, the same ring with integer dot
     products on 16-bit limbs of the fixed-point query (VRQ_RESCORE_DP2A=1), with batched reductions
@@ -181,9 +181,10 @@ def test_rescore_int8cos_kernel_variants(K, monkeypatch, variant):
     assert sc[0, 0] == -np.inf and sc[5, 3] == -np.inf
 
 
-def test_rescore_binary_lut_equals_register_kernel(K, monkeypatch):
-    """Phase II for d = 1024: the nibble-table kernel (default) and the register kernel agree with the float64 evaluation
-    to rounding, incl. invalid positions, all-zero and wide-range queries, m not a multiple of the block size."""
+def test_rescore_binary_kernel_variants(K, monkeypatch):
+    """Phase II for d = 1024: the tensor-core kernel (default: mma.sync s8 over the code bits x digit planes of the fixed-point
+    query), the nibble-table kernel and the register kernel agree with the float64 evaluation to rounding, incl. invalid
+    positions, all-zero and wide-range queries, m not a multiple of the group / block size."""
     rng = np.random.default_rng(12)
     n, nq, m = 3000, 6, 1000
     codes = rng.integers(0, 256, (n, 128)).astype(np.uint8)
@@ -196,15 +197,16 @@ def test_rescore_binary_lut_equals_register_kernel(K, monkeypatch):
     pos = rng.integers(0, n, (nq, m))
     pos[0, :2] = (5, 6)
     pos[4, 7] = -1
+    pos[5, -20:] = -1
     got = {}
-    for lut in ("1", "0"):
-        monkeypatch.setenv("VRQ_RESCORE_BIN_LUT", lut)
+    for lut in ("2", "1", "0"):  # tensor cores (default) / nibble table / register kernel
+        monkeypatch.setenv("VRQ_RESCORE_BIN", lut)
         got[lut] = K.rescore_binary(codes, pos, qf)
     for i in range(nq):
         ok = pos[i] >= 0
         ref = o.rescore_binary(qf[i], codes[pos[i][ok]], literal=False)
         mag = np.abs(qf[i].astype(np.float64)).sum()
-        for lut in ("1", "0"):
+        for lut in ("2", "1", "0"):
             assert np.all(np.abs(got[lut][i][ok] - ref) <= 1e-13 * mag + 1e-300), (lut, i)
             assert np.all(got[lut][i][~ok] == -np.inf)
 

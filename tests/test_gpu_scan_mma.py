@@ -30,7 +30,7 @@ def V():
 
 def set_env(monkeypatch, name):
     for k in ("VRQ_MMA_SAMPLE_K", "VRQ_MMA_SAFETY", "VRQ_SCAN_MMA", "VRQ_MMA_RAW_STAGES", "VRQ_MMA_KIND", "VRQ_MMA_PAIR",
-              "VRQ_MMA_GROUP_TILES", "VRQ_MMA_FEW"):
+              "VRQ_MMA_GROUP_TILES", "VRQ_MMA_FEW", "VRQ_MMA_MID", "VRQ_MMA_TAIL", "VRQ_MMA_LOCKSTEP"):
         monkeypatch.delenv(k, raising=False)
     for k, v in ENVS[name].items():
         monkeypatch.setenv(k, v)
@@ -209,6 +209,78 @@ def test_few_queries_ties_and_sorted_database(V, monkeypatch):
     dist, labels = ix2.search(q, 1000)
     rd, rp = oc.hamming_topk(codes, q, 1000)
     assert np.array_equal(dist, rd) and np.array_equal(labels, rp)
+
+
+# ---- 33 .. 96 queries per pass: the same swapped-operand kernel with thresholds in shared memory -------------------------
+@pytest.mark.parametrize("n,nq", [(1, 33), (127, 48), (129, 50), (5000, 64), (40000, 96), (300001, 81)])
+def test_mid_queries_distance_matrix_exact(V, monkeypatch, n, nq):
+    set_env(monkeypatch, "default")
+    rng = np.random.default_rng(n * 79 + nq)
+    codes = rng.integers(0, 256, (n, 128), dtype=np.uint8)
+    q = rng.integers(0, 256, (nq, 128), dtype=np.uint8)
+    q[0] = 0
+    q[-1] = 255
+    ix = V.BinaryIndex(1024)
+    ix.add_with_ids(codes, np.arange(n))
+    assert np.array_equal(ix.distances(q), ref_distances(q, codes))
+
+
+@pytest.mark.parametrize("env", ["default", "forced_fallback", "no_sampling"])
+@pytest.mark.parametrize("nq", [33, 64, 96])
+def test_mid_queries_topk_matches_oracle(V, monkeypatch, env, nq):
+    set_env(monkeypatch, env)
+    n = 2_000_000
+    codes, _ = oc.synth_codes_int8(61, 0, n, want_int8=False)
+    q = o.synth_ubinary_from_f32(oc.synth_f32(62, 0, nq))
+    q[0] = codes[n - 5]
+    ix = V.BinaryIndex(1024)
+    ix.add_with_ids(codes, np.arange(n))
+    for k in (10, 1000):
+        dist, labels = ix.search(q, k)
+        rd, rp = oc.hamming_topk(codes, q, k)
+        assert np.array_equal(dist, rd) and np.array_equal(labels, rp)
+    monkeypatch.setenv("VRQ_MMA_MID", "0")  # the 128-query-tile kernel on the same batch
+    d2, l2 = ix.search(q, 1000)
+    assert np.array_equal(d2, rd) and np.array_equal(l2, rp)
+
+
+def test_mid_queries_ties_and_sorted_database(V, monkeypatch):
+    set_env(monkeypatch, "default")
+    rng = np.random.default_rng(44)
+    n = 500000
+    base = rng.integers(0, 256, (16, 128), dtype=np.uint8)
+    codes = base[rng.integers(0, 16, n)]
+    q = np.concatenate([base[:3], rng.integers(0, 256, (67, 128), dtype=np.uint8)])
+    ix = V.BinaryIndex(1024)
+    ix.add_with_ids(codes, np.arange(n))
+    for k in (1, 100, 4096):
+        dist, labels = ix.search(q, k)
+        rd, rp = oc.hamming_topk(codes, q, k)
+        assert np.array_equal(dist, rd) and np.array_equal(labels, rp)
+
+
+@pytest.mark.parametrize("tail,lock", [("0", "0"), ("1", "0"), ("1", "64"), ("0", "64")])
+def test_pair_scheduler_variants(V, monkeypatch, tail, lock):
+    """1024 queries = 4 CTA-pair columns: the pair scheduler (full strips + the tail strip shared by the left-over pairs,
+    VRQ_MMA_TAIL) and the lockstep throttle of the TMA producers (VRQ_MMA_LOCKSTEP) must not change a single key."""
+    set_env(monkeypatch, "default")
+    monkeypatch.setenv("VRQ_MMA_TAIL", tail)
+    monkeypatch.setenv("VRQ_MMA_LOCKSTEP", lock)
+    n, nq, k = 3_000_017, 1024, 1000
+    codes, _ = oc.synth_codes_int8(63, 0, n, want_int8=False)
+    q = o.synth_ubinary_from_f32(oc.synth_f32(64, 0, nq))
+    q[5] = codes[n - 3]
+    q[700] = codes[0]
+    ix = V.BinaryIndex(1024)
+    ix.add_with_ids(codes, np.arange(n))
+    dist, labels = ix.search(q, k)
+    sel = [0, 5, 127, 128, 300, 511, 512, 700, 1023]
+    rd, rp = oc.hamming_topk(codes, q[sel], k)
+    assert np.array_equal(dist[sel], rd) and np.array_equal(labels[sel], rp)
+    key = dist.astype(np.int64) << 40 | labels
+    assert np.all(np.diff(key, axis=1) > 0)
+    d768, l768 = ix.search(q[:768], k)  # 3 pair columns: the left-over pairs do not divide them -> fewer tail pairs
+    assert np.array_equal(d768, dist[:768]) and np.array_equal(l768, labels[:768])
 
 
 @pytest.mark.parametrize("nq", [12, 40, 256])

@@ -26,7 +26,7 @@ ROWS_CODES, ROWS_IDS, ROWS_PAYLOAD, ROWS_AUX = 0, 1, 2, 3
 
 KEY_POS_BITS = 40
 KEY_NONE = 0xFFFFFFFFFFFFFFFF
-MAX_K = 4096
+MAX_K = 16384
 
 
 class VrqError(RuntimeError):

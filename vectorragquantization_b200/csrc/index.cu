@@ -272,10 +272,6 @@ struct DevIO {
 extern "C" int vrq_index_create(vrq_ctx* ctx, int d, vrq_index** out) {
     VRQ_CHECK_ARG(ctx != nullptr && out != nullptr, "null argument");
     VRQ_CHECK_ARG(d > 0 && d % 8 == 0, "d must be a positive multiple of 8 (faiss binary indexes require it)");
-    if (d % 32 != 0) {
-        vrq_set_error("d=%d: the Hamming kernels need d %% 32 == 0", d);
-        return VRQ_ERR_UNSUPPORTED;
-    }
     vrq_index* ix = new vrq_index();
     ix->ctx = ctx;
     ix->d = d;

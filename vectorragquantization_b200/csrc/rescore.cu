@@ -5,13 +5,18 @@
 // Every sort here reproduces a STABLE descending list.sort: the sort key is (score descending, previous rank
 // ascending), which is a total order, so the result is unique and equals the stable sort.
 #include <math.h>
+
+#include <algorithm>
 #include <stdlib.h>
 
 #include "topk_utils.cuh"
 #include "vrq_internal.cuh"
 
 #ifndef VRQ_RESCORE_IMMA_DEFAULT
-#define VRQ_RESCORE_IMMA_DEFAULT 0
+#define VRQ_RESCORE_IMMA_DEFAULT 1  // cfg5 measurement (profiles/r02): the tensor-core path beats the CUDA-core path
+#endif
+#ifndef VRQ_RESCORE_BIN_DEFAULT
+#define VRQ_RESCORE_BIN_DEFAULT 2
 #endif
 
 namespace {
@@ -70,6 +75,32 @@ __global__ void __launch_bounds__(256) rescore_binary_kernel(const uint8_t* __re
                 acc += __hiloint2double(hi, __double2loint(v));
             }
         }
+        acc = warp_sum_f64(acc);
+        if (lane == 0) score[idx] = acc;
+    }
+}
+
+// d % 32 != 0 (faiss only asks for d % 8 == 0): code rows are not word-aligned; lane l walks dimensions l, l + 32, ... and
+// picks its bit out of the code byte by byte.  Correct, not tuned - such widths are not on any benchmark path.
+__global__ void __launch_bounds__(256) rescore_binary_bytes_kernel(const uint8_t* __restrict__ codes, int d,
+                                                                   const uint64_t* __restrict__ keys, const int64_t* __restrict__ pos,
+                                                                   int64_t pos_base, int m, const float* __restrict__ qf,
+                                                                   double* __restrict__ score) {
+    extern __shared__ double qd[];
+    const int q = blockIdx.y;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) qd[i] = (double)qf[(size_t)q * d + i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = blockIdx.x * 8 + warp; i < m; i += gridDim.x * 8) {
+        const size_t idx = (size_t)q * m + i;
+        const int64_t row = cand_row(keys, pos, idx, pos_base);
+        if (row < 0) {
+            if (lane == 0) score[idx] = -INFINITY;
+            continue;
+        }
+        const uint8_t* code = codes + (size_t)row * (d >> 3);
+        double acc = 0.0;
+        for (int e = lane; e < d; e += 32) acc += ((__ldg(code + (e >> 3)) >> (7 - (e & 7))) & 1) ? qd[e] : -qd[e];
         acc = warp_sum_f64(acc);
         if (lane == 0) score[idx] = acc;
     }
@@ -649,13 +680,16 @@ __global__ void __launch_bounds__(M3_THREADS) merge3_kernel(int world, int nq, i
                                                             const double* __restrict__ scos, int k, int k2,
                                                             int64_t* __restrict__ out_labels, int32_t* __restrict__ out_ham,
                                                             double* __restrict__ out_sbin, double* __restrict__ out_scos,
-                                                            int32_t* __restrict__ out_count) {
+                                                            int32_t* __restrict__ out_count, uint32_t* __restrict__ g_src1,
+                                                            uint32_t* __restrict__ g_r2) {
     extern __shared__ unsigned long long sm3[];
     const int P = next_pow2(bk);
     unsigned long long* skey = sm3;                   // P
     uint32_t* sval = (uint32_t*)(skey + P);           // P
-    uint32_t* src1 = sval + P;                        // P: phase-I rank -> flat source index (w * bk + j)
-    uint32_t* r2 = src1 + P;                          // P: phase-II rank -> phase-I rank
+    // P: phase-I rank -> flat source index (w * bk + j), and P: phase-II rank -> phase-I rank.  Shared memory up to P = 8192;
+    // for larger candidate lists the two index arrays live in global scratch (written and read by this block only)
+    uint32_t* src1 = g_src1 ? g_src1 + (size_t)blockIdx.x * P : sval + P;
+    uint32_t* r2 = g_r2 ? g_r2 + (size_t)blockIdx.x * P : sval + 2 * P;
     __shared__ SelectScratch sc;
     __shared__ int total_s;
     const int q = blockIdx.x, tid = threadIdx.x;
@@ -785,13 +819,24 @@ int grid_x_for(vrq_ctx* ctx, int64_t nq, int m) {
 int vrq_launch_rescore_binary(vrq_ctx* ctx, const uint8_t* codes, int d, const uint64_t* keys, const int64_t* pos,
                               int64_t pos_base, int64_t nq, int m, const float* qf, double* score, cudaStream_t st) {
     if (nq == 0 || m == 0) return 0;
-    if (d % 32 != 0 || d > 12288) {
-        vrq_set_error("rescore_binary needs d %% 32 == 0 and d <= 12288 (got %d)", d);
+    if (d % 8 != 0 || d > 12288) {
+        vrq_set_error("rescore_binary needs d %% 8 == 0 and d <= 12288 (got %d)", d);
         return VRQ_ERR_UNSUPPORTED;
     }
     vrq_timer_scope ts(ctx, VRQ_CAT_RESCORE, st);
-    // d == 1024: the nibble-table kernel of rescore_mma.cu (VRQ_RESCORE_BIN_LUT=0 selects the register kernel below)
-    if (d == 1024 && !(getenv("VRQ_RESCORE_BIN_LUT") && atoi(getenv("VRQ_RESCORE_BIN_LUT")) == 0))
+    if (d % 32 != 0) {
+        rescore_binary_bytes_kernel<<<dim3(grid_x_for(ctx, nq, m), (unsigned)nq), 256, sizeof(double) * d, st>>>(codes, d, keys, pos, pos_base, m,
+                                                                                                                qf, score);
+        vrq_count_launch(ctx);
+        VRQ_CUDA(cudaGetLastError());
+        return 0;
+    }
+    // d == 1024: the kernels of rescore_mma.cu.  VRQ_RESCORE_BIN = 2 (default): tensor cores (mma.sync s8 over the code bits),
+    // 1: nibble table in shared memory, 0: the register kernel below
+    const int bin_mode = getenv("VRQ_RESCORE_BIN") ? atoi(getenv("VRQ_RESCORE_BIN")) : VRQ_RESCORE_BIN_DEFAULT;
+    if (d == 1024 && bin_mode == 2 && ((uintptr_t)codes % 16) == 0)
+        return vrq_launch_rescore_binary_imma(ctx, codes, keys, pos, pos_base, nq, m, qf, score, st);
+    if (d == 1024 && bin_mode == 1 && ((uintptr_t)codes % 16) == 0)
         return vrq_launch_rescore_binary_lut(ctx, codes, keys, pos, pos_base, nq, m, qf, score, st);
     dim3 grid(grid_x_for(ctx, nq, m), (unsigned)nq);
     if (d == 1024)
@@ -806,8 +851,8 @@ int vrq_launch_rescore_binary(vrq_ctx* ctx, const uint8_t* codes, int d, const u
 int vrq_launch_rescore_int8cos(vrq_ctx* ctx, const int8_t* rows, int d, const uint64_t* keys, const int64_t* pos,
                                int64_t pos_base, int64_t nq, int m, const float* qf, double* score, cudaStream_t st) {
     if (nq == 0 || m == 0) return 0;
-    if (d % 32 != 0 || d > 12288) {
-        vrq_set_error("rescore_int8cos needs d %% 32 == 0 and d <= 12288 (got %d)", d);
+    if (d % 8 != 0 || d > 12288) {
+        vrq_set_error("rescore_int8cos needs d %% 8 == 0 and d <= 12288 (got %d)", d);
         return VRQ_ERR_UNSUPPORTED;
     }
     vrq_timer_scope ts(ctx, VRQ_CAT_RESCORE, st);
@@ -843,8 +888,8 @@ int vrq_launch_rescore_int8cos(vrq_ctx* ctx, const int8_t* rows, int d, const ui
 
 int vrq_launch_rescore_payload_dot(vrq_ctx* ctx, const vrq_rescore2_args& a, cudaStream_t st) {
     if (a.nq == 0 || a.m == 0) return 0;
-    if (a.d % 32 != 0 || a.d > 12288) {
-        vrq_set_error("payload rescoring needs d %% 32 == 0 and d <= 12288 (got %d)", a.d);
+    if (a.d % 8 != 0 || a.d > 12288) {
+        vrq_set_error("payload rescoring needs d %% 8 == 0 and d <= 12288 (got %d)", a.d);
         return VRQ_ERR_UNSUPPORTED;
     }
     PayloadParams p{};
@@ -887,13 +932,19 @@ int vrq_launch_merge3(vrq_ctx* ctx, int world, int64_t nq, int bk, int64_t rank_
     }
     int P = 1;
     while (P < bk) P <<= 1;
-    size_t smem = (size_t)P * (8 + 4 + 4 + 4);
+    const bool big = P > 8192;
+    size_t smem = (size_t)P * (big ? (8 + 4) : (8 + 4 + 4 + 4));
+    void *g1 = nullptr, *g2 = nullptr;
+    if (big) {
+        VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_M3_SRC, sizeof(uint32_t) * (size_t)nq * P, &g1));
+        VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_M3_R2, sizeof(uint32_t) * (size_t)nq * P, &g2));
+    }
     if (smem > 40 * 1024)
-        VRQ_CUDA(cudaFuncSetAttribute(merge3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VRQ_CUDA(cudaFuncSetAttribute(merge3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 160 * 1024)));
     vrq_timer_scope ts(ctx, VRQ_CAT_MERGE, st);
     if (rank_stride <= 0) rank_stride = nq * (int64_t)bk;
     merge3_kernel<<<(unsigned)nq, M3_THREADS, smem, st>>>(world, (int)nq, bk, rank_stride, keys, labels, sbin, scos, k, k2, out_labels,
-                                                          out_ham, out_sbin, out_scos, out_count);
+                                                          out_ham, out_sbin, out_scos, out_count, (uint32_t*)g1, (uint32_t*)g2);
     vrq_count_launch(ctx);
     VRQ_CUDA(cudaGetLastError());
     return 0;
@@ -910,7 +961,7 @@ int vrq_launch_select2(vrq_ctx* ctx, int64_t nq, int m, const uint64_t* keys, co
     while (P < m) P <<= 1;
     size_t smem = (size_t)P * 12;
     if (smem > 40 * 1024)
-        VRQ_CUDA(cudaFuncSetAttribute(select2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VRQ_CUDA(cudaFuncSetAttribute(select2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 96 * 1024)));
     vrq_timer_scope ts(ctx, VRQ_CAT_MERGE, st);
     select2_kernel<<<(unsigned)nq, M3_THREADS, smem, st>>>(m, keys, labels, score, k, out_labels, out_score, out_count);
     vrq_count_launch(ctx);

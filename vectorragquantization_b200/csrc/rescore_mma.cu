@@ -16,6 +16,10 @@
 
 #include "vrq_internal.cuh"
 
+#ifndef VRQ_RESCORE_IMMA_SHAPE_DEFAULT
+#define VRQ_RESCORE_IMMA_SHAPE_DEFAULT 121  // cp.async, 12 warps x 1 stage (cfg5 sweep, profiles/r02)
+#endif
+
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -147,6 +151,41 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  : "memory");
 }
 
+// ---- the query as eight signed base-256 digits of rint(q_i * 2^(61 - E)), E = exponent of max |q| -----------------------
+// |Q_i| < 2^62; exact for every element whose exponent is within 38 of the largest one (below that the dropped bits are
+// < 2^-61 of max |q| - far under float64 accumulation error).  Digits are in [-128, 127]: Q = sum_n l_n 256^n.
+// PLACE(dim) = byte offset of dimension `dim` inside a digit plane (the K permutation the A fragments use).
+// All threads of the block call; ends with __syncthreads().  Returns 2^(E - 61).
+template <int THREADS, class Place>
+__device__ __forceinline__ double build_query_digits(const float* __restrict__ qrow, uint8_t* digits, float* red, Place place) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float amax = 0.f;
+    for (int i = tid; i < 1024; i += THREADS) amax = fmaxf(amax, fabsf(qrow[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, o));
+    if (lane == 0) red[warp] = amax;
+    __syncthreads();
+    amax = red[0];
+#pragma unroll
+    for (int w = 1; w < THREADS / 32; w++) amax = fmaxf(amax, red[w]);
+    int bexp = (__float_as_int(amax) >> 23) & 0xFF;
+    if (bexp == 0) bexp = 1;  // zero / denormal queries: the denormal scale
+    const int E = bexp - 127;
+    const double sc = __hiloint2double((1023 + 61 - E) << 20, 0);  // 2^(61 - E)
+    for (int i = tid; i < 1024; i += THREADS) {
+        long long Q = __double2ll_rn((double)qrow[i] * sc);
+        const uint32_t off = place(i);
+#pragma unroll
+        for (int n = 0; n < P3M_DIGITS; n++) {
+            const long long dgt = (long long)(signed char)(Q & 0xFF);
+            Q = (Q - dgt) >> 8;
+            digits[n * P3M_ROW_STRIDE + off] = (uint8_t)dgt;
+        }
+    }
+    __syncthreads();
+    return __hiloint2double((1023 - 61 + E) << 20, 0);  // 2^(E - 61)
+}
+
 template <int WARPS, int STAGES>
 struct P3mSmem {
     static constexpr size_t RING = (size_t)WARPS * STAGES * P3M_STAGE_BYTES;
@@ -155,7 +194,10 @@ struct P3mSmem {
     static constexpr size_t TOTAL = RING + DIGITS + BARS + 64 + 128;
 };
 
-template <int WARPS, int STAGES>
+// BULK = true: rows arrive as 1 KB bulk copies (UBLKCP) completing on the stage's mbarrier, lane i < 16 starts row i.
+// BULK = false: rows arrive as 16-byte cp.async (LDGSTS) - lane l copies chunks l and 32 + l of every row of the group, one
+// commit group per stage; cp.async.wait_group + __syncwarp() hands the stage to the whole warp.
+template <int WARPS, int STAGES, bool BULK>
 __global__ void __launch_bounds__(WARPS * 32) rescore_int8cos_imma_kernel(const int8_t* __restrict__ rows, const uint64_t* __restrict__ keys,
                                                                           const int64_t* __restrict__ pos, int64_t pos_base, int m,
                                                                           const float* __restrict__ qf, double* __restrict__ score) {
@@ -167,43 +209,13 @@ __global__ void __launch_bounds__(WARPS * 32) rescore_int8cos_imma_kernel(const 
     float* red = (float*)(bars + WARPS * STAGES);                      // [WARPS] max |q| partials
     const int q = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // ---- the query as eight signed base-256 digits of rint(q_i * 2^(61 - E)), E = exponent of max |q| -----------------
-    // |Q_i| < 2^62; exact for every element whose exponent is within 38 of the largest one (below that the dropped bits
-    // are < 2^-61 of max |q| - far under float64 accumulation error).  Digits are in [-128, 127]: Q = sum_n l_n 256^n.
-    float amax = 0.f;
-    for (int i = tid; i < 1024; i += WARPS * 32) amax = fmaxf(amax, fabsf(qf[(size_t)q * 1024 + i]));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(FULL, amax, o));
-    if (lane == 0) red[warp] = amax;
-    if (tid < WARPS * STAGES) mbar_init_((uint32_t)__cvta_generic_to_shared(&bars[tid]), 1);
-    __syncthreads();
-    amax = red[0];
-#pragma unroll
-    for (int w = 1; w < WARPS; w++) amax = fmaxf(amax, red[w]);
-    int bexp = (__float_as_int(amax) >> 23) & 0xFF;
-    if (bexp == 0) bexp = 1;  // zero / denormal queries: the denormal scale
-    const int E = bexp - 127;
-    const double sc = __hiloint2double((1023 + 61 - E) << 20, 0);        // 2^(61 - E)
-    const double unscale = __hiloint2double((1023 - 61 + E) << 20, 0);   // 2^(E - 61)
-    for (int c = tid; c < 256; c += WARPS * 32) {  // four consecutive elements -> one 32-bit store per digit plane
-        const float4 f = *reinterpret_cast<const float4*>(qf + (size_t)q * 1024 + 4 * c);
-        long long Q[4] = {__double2ll_rn((double)f.x * sc), __double2ll_rn((double)f.y * sc), __double2ll_rn((double)f.z * sc),
-                          __double2ll_rn((double)f.w * sc)};
-#pragma unroll
-        for (int n = 0; n < P3M_DIGITS; n++) {
-            uint32_t word = 0;
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const long long dgt = (long long)(signed char)(Q[e] & 0xFF);
-                Q[e] = (Q[e] - dgt) >> 8;
-                word |= ((uint32_t)dgt & 0xFFu) << (8 * e);
-            }
-            *reinterpret_cast<uint32_t*>(digits + n * P3M_ROW_STRIDE + 4 * c) = word;
-        }
+    if (BULK && tid < WARPS * STAGES) mbar_init_((uint32_t)__cvta_generic_to_shared(&bars[tid]), 1);
+    const double unscale = build_query_digits<WARPS * 32>(qf + (size_t)q * 1024, digits, red, [](int i) { return (uint32_t)i; });
+    if (BULK) {
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
 
     const int g = lane >> 2, t = lane & 3;
     const uint32_t ring_w = (uint32_t)__cvta_generic_to_shared(ring) + (uint32_t)(warp * STAGES * P3M_STAGE_BYTES);
@@ -225,12 +237,29 @@ __global__ void __launch_bounds__(WARPS * 32) rescore_int8cos_imma_kernel(const 
             if (i < m) r = cand_row(keys, pos, (size_t)q * m + i, pos_base);
         }
         srow[s] = r;
-        if (it >= mine) return;
-        const unsigned valid = __ballot_sync(FULL, r >= 0);
-        const uint32_t bar = bar_w + (uint32_t)s * 8u;
-        if (lane == 0) mbar_expect_tx_(bar, (uint32_t)__popc(valid) * 1024u);
-        __syncwarp();
-        if (r >= 0) bulk_g2s(ring_w + (uint32_t)(s * P3M_STAGE_BYTES + lane * P3M_ROW_STRIDE), rows + (size_t)r * 1024, 1024u, bar);
+        if (BULK) {
+            if (it >= mine) return;
+            const unsigned valid = __ballot_sync(FULL, r >= 0);
+            const uint32_t bar = bar_w + (uint32_t)s * 8u;
+            if (lane == 0) mbar_expect_tx_(bar, (uint32_t)__popc(valid) * 1024u);
+            __syncwarp();
+            if (r >= 0) bulk_g2s(ring_w + (uint32_t)(s * P3M_STAGE_BYTES + lane * P3M_ROW_STRIDE), rows + (size_t)r * 1024, 1024u, bar);
+        } else {
+            if (it < mine) {
+                const uint32_t dst0 = ring_w + (uint32_t)(s * P3M_STAGE_BYTES + lane * 16);
+#pragma unroll
+                for (int i = 0; i < P3M_GROUP; i++) {
+                    const int64_t ri = __shfl_sync(FULL, r, i);
+                    if (ri >= 0) {
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(rows) + (size_t)ri * 1024 + lane * 16;
+                        const uint32_t dst = dst0 + (uint32_t)(i * P3M_ROW_STRIDE);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512), "l"(src + 512) : "memory");
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");  // one group per stage, even when empty: wait_group counts them
+        }
     };
 #pragma unroll
     for (int s = 0; s < STAGES; s++) issue(s, s);
@@ -240,17 +269,23 @@ __global__ void __launch_bounds__(WARPS * 32) rescore_int8cos_imma_kernel(const 
         for (int s = 0; s < STAGES; s++) {
             const int it = it0 + s;
             if (it >= mine) break;
-            mbar_wait_(bar_w + (uint32_t)s * 8u, (uint32_t)(it0 / STAGES) & 1u);
+            if (BULK) {
+                mbar_wait_(bar_w + (uint32_t)s * 8u, (uint32_t)(it0 / STAGES) & 1u);
+            } else {
+                asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+                __syncwarp();
+            }
             const uint32_t a_addr = ring_w + (uint32_t)(s * P3M_STAGE_BYTES) + a_off;
-            int acc[4] = {0, 0, 0, 0};
+            // two accumulator sets: the 32 MMAs of a group form two dependent chains of 16 instead of one of 32
+            int acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
             int n2a = 0, n2b = 0;
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 const uint4 x = lds128u(a_addr + 64 * j);
                 const uint4 y = lds128u(a_addr + 8 * P3M_ROW_STRIDE + 64 * j);
                 const uint4 b = lds128u(b_addr + 64 * j);
-                mma_s8_16832(acc, x.x, y.x, x.y, y.y, b.x, b.y);
-                mma_s8_16832(acc, x.z, y.z, x.w, y.w, b.z, b.w);
+                mma_s8_16832(acc0, x.x, y.x, x.y, y.y, b.x, b.y);
+                mma_s8_16832(acc1, x.z, y.z, x.w, y.w, b.z, b.w);
                 n2a = __dp4a((int)x.x, (int)x.x, n2a);
                 n2a = __dp4a((int)x.y, (int)x.y, n2a);
                 n2a = __dp4a((int)x.z, (int)x.z, n2a);
@@ -261,10 +296,10 @@ __global__ void __launch_bounds__(WARPS * 32) rescore_int8cos_imma_kernel(const 
                 n2b = __dp4a((int)y.w, (int)y.w, n2b);
             }
             // acc[0], acc[1] = row g, digit columns 2t, 2t + 1; acc[2], acc[3] = row g + 8.  sum_n c_n 256^n: every partial
-            // below is an exact integer in a double (< 2^40 before the power-of-two scale)
+            // below is an exact integer in a double (< 2^41 before the power-of-two scale)
             const double wgt = __hiloint2double((1023 + 16 * t) << 20, 0);  // 256^(2t)
-            double da = (double)((long long)acc[0] + 256ll * (long long)acc[1]) * wgt;
-            double db = (double)((long long)acc[2] + 256ll * (long long)acc[3]) * wgt;
+            double da = (double)(((long long)acc0[0] + (long long)acc1[0]) + 256ll * ((long long)acc0[1] + (long long)acc1[1])) * wgt;
+            double db = (double)(((long long)acc0[2] + (long long)acc1[2]) + 256ll * ((long long)acc0[3] + (long long)acc1[3])) * wgt;
 #pragma unroll
             for (int o = 1; o <= 2; o <<= 1) {
                 da += __shfl_xor_sync(FULL, da, o);
@@ -284,8 +319,106 @@ __global__ void __launch_bounds__(WARPS * 32) rescore_int8cos_imma_kernel(const 
             }
             // the stage is free again: every byte of it that this warp reads has been consumed by the instructions above
             __syncwarp();
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(it + STAGES, s);
+        }
+    }
+    if (!BULK) asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// =====================================================================================================================
+// Phase II on the tensor cores: the same contraction with the candidate's code BITS as the int8 A operand.
+// =====================================================================================================================
+// score = sum_j q_j (2 b_j - 1) = 2 sum_j q_j b_j - sum_j q_j.  Sixteen candidates are the M rows of mma.m16n8k32.s8, their
+// bits become {0, 1} bytes in registers - r_k = (w >> k) & 0x01010101 turns the 32-bit code word w into eight registers of
+// four bytes - and the B operand is, again, the eight base-256 digit planes of the fixed-point query, laid out in shared
+// memory in the order the A fragments walk the dimensions (the K index of a dot product is free).  128 MMAs per lane and
+// group of 16 candidates... = 32 per word pair; no table, no per-candidate reduction, exact integer sums.
+// Lane (g = lane / 4, t = lane % 4) loads 16-byte chunks t and 4 + t of the codes of candidates g and g + 8 (code words
+// 4t .. 4t + 3 and 16 + 4t .. 16 + 4t + 3).  MMA number kk2 = 4 i + kk (i = word of the lane, kk = register pair) takes
+// r_{2kk}, r_{2kk+1} of word i: byte b of r_k is bit 8 b + k of the word = dimension 32 W + 8 b + 7 - k.
+__device__ __forceinline__ uint32_t p2m_place(int dim) {
+    const int W = dim >> 5, b = (dim & 31) >> 3, k = 7 - (dim & 7);
+    const int reg = k & 1, kk = k >> 1;
+    const int t = (W & 15) >> 2, i = (W & 3) + ((W >> 4) << 2);
+    const int kk2 = 4 * i + kk, j = kk2 >> 1, h = kk2 & 1;
+    return (uint32_t)(j * 64 + t * 16 + h * 8 + reg * 4 + b);
+}
+
+constexpr int P2M_WARPS = 4;
+
+__global__ void __launch_bounds__(P2M_WARPS * 32) rescore_binary_imma_kernel(const uint8_t* __restrict__ codes,
+                                                                             const uint64_t* __restrict__ keys,
+                                                                             const int64_t* __restrict__ pos, int64_t pos_base, int m,
+                                                                             const float* __restrict__ qf, double* __restrict__ score) {
+    __shared__ __align__(128) uint8_t digits[P3M_DIGITS * P3M_ROW_STRIDE];
+    __shared__ float red[P2M_WARPS];
+    __shared__ double qsum_s[P2M_WARPS];
+    const int q = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double unscale = build_query_digits<P2M_WARPS * 32>(qf + (size_t)q * 1024, digits, red, [](int i) { return p2m_place(i); });
+    // sum_j q_j in float64 (the -1 part of 2 b - 1)
+    double qs = 0.0;
+    for (int i = tid; i < 1024; i += P2M_WARPS * 32) qs += (double)qf[(size_t)q * 1024 + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qs += __shfl_xor_sync(FULL, qs, o);
+    if (lane == 0) qsum_s[warp] = qs;
+    __syncthreads();
+    double qsum = 0.0;
+#pragma unroll
+    for (int w = 0; w < P2M_WARPS; w++) qsum += qsum_s[w];
+
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t b_addr = (uint32_t)__cvta_generic_to_shared(digits) + (uint32_t)(g * P3M_ROW_STRIDE + 16 * t);
+    const int ngroups = (m + P3M_GROUP - 1) / P3M_GROUP;
+    const int wstride = gridDim.x * P2M_WARPS;
+    for (int grp = blockIdx.x * P2M_WARPS + warp; grp < ngroups; grp += wstride) {
+        // lane i < 16 fetches the position of candidate i of the group
+        int64_t r = -1;
+        if (lane < P3M_GROUP) {
+            const int i = grp * P3M_GROUP + lane;
+            if (i < m) r = cand_row(keys, pos, (size_t)q * m + i, pos_base);
+        }
+        const int64_t ra = __shfl_sync(FULL, r, g), rb = __shfl_sync(FULL, r, g + 8);
+        uint4 xa0 = make_uint4(0, 0, 0, 0), xa1 = xa0, xb0 = xa0, xb1 = xa0;
+        if (ra >= 0) {
+            const uint4* src = reinterpret_cast<const uint4*>(codes + (size_t)ra * 128);
+            xa0 = __ldg(src + t);
+            xa1 = __ldg(src + 4 + t);
+        }
+        if (rb >= 0) {
+            const uint4* src = reinterpret_cast<const uint4*>(codes + (size_t)rb * 128);
+            xb0 = __ldg(src + t);
+            xb1 = __ldg(src + 4 + t);
+        }
+        const uint32_t wa[8] = {xa0.x, xa0.y, xa0.z, xa0.w, xa1.x, xa1.y, xa1.z, xa1.w};
+        const uint32_t wb[8] = {xb0.x, xb0.y, xb0.z, xb0.w, xb1.x, xb1.y, xb1.z, xb1.w};
+        int acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+#pragma unroll
+            for (int kp = 0; kp < 2; kp++) {  // two MMAs (kk = 2 kp, 2 kp + 1) per 16 bytes of digits
+                const uint4 b = lds128u(b_addr + 64 * (2 * i + kp));
+                const int k0 = 4 * kp;
+                mma_s8_16832(acc0, (wa[i] >> k0) & 0x01010101u, (wb[i] >> k0) & 0x01010101u, (wa[i] >> (k0 + 1)) & 0x01010101u,
+                             (wb[i] >> (k0 + 1)) & 0x01010101u, b.x, b.y);
+                mma_s8_16832(acc1, (wa[i] >> (k0 + 2)) & 0x01010101u, (wb[i] >> (k0 + 2)) & 0x01010101u, (wa[i] >> (k0 + 3)) & 0x01010101u,
+                             (wb[i] >> (k0 + 3)) & 0x01010101u, b.z, b.w);
+            }
+        }
+        const double wgt = __hiloint2double((1023 + 16 * t) << 20, 0);  // 256^(2t)
+        double da = (double)(((long long)acc0[0] + (long long)acc1[0]) + 256ll * ((long long)acc0[1] + (long long)acc1[1])) * wgt;
+        double db = (double)(((long long)acc0[2] + (long long)acc1[2]) + 256ll * ((long long)acc0[3] + (long long)acc1[3])) * wgt;
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            da += __shfl_xor_sync(FULL, da, o);
+            db += __shfl_xor_sync(FULL, db, o);
+        }
+        if (t < 2) {
+            const int rr = t == 0 ? g : g + 8;
+            const int i = grp * P3M_GROUP + rr;
+            const int64_t rw = t == 0 ? ra : rb;
+            const double dot = t == 0 ? da : db;
+            if (i < m) score[(size_t)q * m + i] = rw < 0 ? -INFINITY : 2.0 * (dot * unscale) - qsum;
         }
     }
 }
@@ -344,11 +477,11 @@ __global__ void __launch_bounds__(256) rescore_int8cos_synth_kernel(uint64_t see
     }
 }
 
-template <int WARPS, int STAGES>
+template <int WARPS, int STAGES, bool BULK>
 int launch_imma(vrq_ctx* ctx, const int8_t* rows, const uint64_t* keys, const int64_t* pos, int64_t pos_base, int64_t nq, int m,
                 const float* qf, double* score, cudaStream_t st) {
     const size_t smem = P3mSmem<WARPS, STAGES>::TOTAL;
-    auto kern = rescore_int8cos_imma_kernel<WARPS, STAGES>;
+    auto kern = rescore_int8cos_imma_kernel<WARPS, STAGES, BULK>;
     VRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_sm = (int)((ctx->smem_optin ? ctx->smem_optin : 227 * 1024) / (smem + 1024));
     const int ngroups = (m + P3M_GROUP - 1) / P3M_GROUP;
@@ -375,21 +508,40 @@ int vrq_launch_rescore_binary_lut(vrq_ctx* ctx, const uint8_t* codes, const uint
     return 0;
 }
 
+int vrq_launch_rescore_binary_imma(vrq_ctx* ctx, const uint8_t* codes, const uint64_t* keys, const int64_t* pos, int64_t pos_base,
+                                   int64_t nq, int m, const float* qf, double* score, cudaStream_t st) {
+    const int ngroups = (m + P3M_GROUP - 1) / P3M_GROUP;
+    int64_t gx = ((int64_t)ctx->sm_count * 8 + nq - 1) / nq;
+    const int64_t gmax = (ngroups + P2M_WARPS - 1) / P2M_WARPS;
+    if (gx > gmax) gx = gmax;
+    if (gx < 1) gx = 1;
+    rescore_binary_imma_kernel<<<dim3((unsigned)gx, (unsigned)nq), P2M_WARPS * 32, 0, st>>>(codes, keys, pos, pos_base, m, qf, score);
+    vrq_count_launch(ctx);
+    VRQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int vrq_launch_rescore_int8cos_imma(vrq_ctx* ctx, const int8_t* rows, const uint64_t* keys, const int64_t* pos, int64_t pos_base,
                                     int64_t nq, int m, const float* qf, double* score, cudaStream_t st) {
-    // launch shape: VRQ_RESCORE_IMMA_SHAPE = 10 * warps + stages (default 23: two warps x three stages, two blocks per SM)
+    // launch shape: VRQ_RESCORE_IMMA_SHAPE = 100 * bulk + 10 * warps + stages (bulk = 1: 1 KB bulk copies, 0: 16-byte cp.async)
     const char* e = getenv("VRQ_RESCORE_IMMA_SHAPE");
-    const int shape = (e && *e) ? atoi(e) : 23;
+    const int shape = (e && *e) ? atoi(e) : VRQ_RESCORE_IMMA_SHAPE_DEFAULT;
     int r;
+#define VRQ_IMMA_CASE(W, S)                                                                                   \
+    case 100 + 10 * W + S: r = launch_imma<W, S, true>(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st); break; \
+    case 10 * W + S: r = launch_imma<W, S, false>(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st); break;
     switch (shape) {
-        case 43: r = launch_imma<4, 3>(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st); break;
-        case 34: r = launch_imma<3, 4>(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st); break;
-        case 62: r = launch_imma<6, 2>(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st); break;
-        case 24: r = launch_imma<2, 4>(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st); break;
-        case 13: r = launch_imma<1, 3>(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st); break;
-        case 22: r = launch_imma<2, 2>(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st); break;
-        default: r = launch_imma<2, 3>(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st); break;
+        VRQ_IMMA_CASE(2, 3)
+        VRQ_IMMA_CASE(4, 3)
+        VRQ_IMMA_CASE(3, 4)
+        VRQ_IMMA_CASE(4, 2)
+        VRQ_IMMA_CASE(3, 2)
+        VRQ_IMMA_CASE(12, 1)
+        VRQ_IMMA_CASE(8, 1)
+        VRQ_IMMA_CASE(6, 2)
+        default: r = launch_imma<12, 1, false>(ctx, rows, keys, pos, pos_base, nq, m, qf, score, st); break;
     }
+#undef VRQ_IMMA_CASE
     if (r != 0) return r;
     vrq_count_launch(ctx);
     VRQ_CUDA(cudaGetLastError());

@@ -156,7 +156,9 @@ __device__ __forceinline__ int hamming128_csa14(const uint4 (&c)[8], uint32_t qa
 
 // The append is the cold path (a few candidates per million pairs once tau has converged): keep it out of line so
 // the hot loop carries no address arithmetic for it.
-__device__ __noinline__ void append_candidate(int* cnt_s, uint64_t* lists, int q, int cap, int d, unsigned long long pos) {
+__device__ __noinline__ void append_candidate(int* cnt_s, uint64_t* lists, int q, int cap, int d, unsigned long long pos,
+                                              const unsigned long long* key_lo) {
+    if (key_lo && (((unsigned long long)d << VRQ_KEY_POS_BITS) | pos) <= key_lo[q]) return;  // below the chunk's lower bound
     const int slot = atomicAdd(&cnt_s[q], 1);
     if (slot >= cap) __trap();  // cannot happen (overflow check every group_tiles tiles); never write past a list
     lists[(size_t)q * cap + slot] = ((unsigned long long)d << VRQ_KEY_POS_BITS) | pos;
@@ -214,11 +216,16 @@ hamming_scan_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     // query tile -> shared memory; thresholds and counters
-    for (int i = tid; i < p.qtile * p.code_bytes / 4; i += SCAN_THREADS) {
-        const int q = i / (p.code_bytes / 4);
-        uint32_t v = 0;
-        if (q < qt) v = reinterpret_cast<const uint32_t*>(p.queries + (size_t)q0 * p.code_bytes)[i];
-        reinterpret_cast<uint32_t*>(qsm)[i] = v;
+    if ((p.code_bytes & 3) == 0) {
+        for (int i = tid; i < p.qtile * p.code_bytes / 4; i += SCAN_THREADS) {
+            const int q = i / (p.code_bytes / 4);
+            uint32_t v = 0;
+            if (q < qt) v = reinterpret_cast<const uint32_t*>(p.queries + (size_t)q0 * p.code_bytes)[i];
+            reinterpret_cast<uint32_t*>(qsm)[i] = v;
+        }
+    } else {  // d % 32 != 0 (faiss only asks for d % 8 == 0): rows are not word-aligned, everything goes byte by byte
+        for (int i = tid; i < p.qtile * p.code_bytes; i += SCAN_THREADS)
+            qsm[i] = (i / p.code_bytes < qt) ? p.queries[(size_t)q0 * p.code_bytes + i] : (uint8_t)0;
     }
     for (int q = tid; q < p.qtile; q += SCAN_THREADS) {
         tau_s[q] = (q < qt) ? (p.tau0 ? min(p.tau0[q0 + q], TAU_INF) : TAU_INF) : 0;
@@ -228,6 +235,7 @@ hamming_scan_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p) {
     __syncthreads();
 
     uint64_t* my_lists = p.lists + ((size_t)strip * p.nq + q0) * p.cap;
+    const unsigned long long* key_lo_q0 = p.key_lo ? p.key_lo + q0 : nullptr;
 
     if (warp == CONSUMER_WARPS) {
         // ===================== TMA producer warp =====================
@@ -269,7 +277,7 @@ hamming_scan_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p) {
                                    : CSA == 16 ? hamming128_csa(c, qaddr)
                                    : CSA == 14 ? hamming128_csa14(c, qaddr)
                                                : hamming128_popc(c, qaddr));
-                    if (d < lds32(taddr)) append_candidate(cnt_s, my_lists, q, p.cap, d, pos);
+                    if (d < lds32(taddr)) append_candidate(cnt_s, my_lists, q, p.cap, d, pos, key_lo_q0);
                 }
                 }
                 // The stage goes back to the producer only here: ld.shared merely ISSUES the read, and an mbarrier
@@ -280,15 +288,19 @@ hamming_scan_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars[8 + s]));
             } else {
-                const uint32_t* crow = reinterpret_cast<const uint32_t*>(p.codes + (size_t)(valid ? lrow : 0) * p.code_bytes);
+                const uint8_t* crow8 = p.codes + (size_t)(valid ? lrow : 0) * p.code_bytes;
+                const uint32_t* crow = reinterpret_cast<const uint32_t*>(crow8);
+                const bool words_ok = (p.code_bytes & 3) == 0;
                 for (int q = 0; q < qt; q++) {
-                    const uint32_t* qrow = reinterpret_cast<const uint32_t*>(qsm + (size_t)q * p.code_bytes);
+                    const uint8_t* qrow8 = qsm + (size_t)q * p.code_bytes;
+                    const uint32_t* qrow = reinterpret_cast<const uint32_t*>(qrow8);
                     int d = 0;
-                    for (int w = 0; w < w_words; w++) d += __popc(__ldg(crow + w) ^ qrow[w]);
-                    if (d < tau_s[q] && valid) {
-                        const int slot = atomicAdd(&cnt_s[q], 1);
-                        my_lists[(size_t)q * p.cap + slot] = ((unsigned long long)d << VRQ_KEY_POS_BITS) | pos;
+                    if (words_ok) {
+                        for (int w = 0; w < w_words; w++) d += __popc(__ldg(crow + w) ^ qrow[w]);
+                    } else {
+                        for (int b = 0; b < p.code_bytes; b++) d += __popc((uint32_t)(__ldg(crow8 + b) ^ qrow8[b]));
                     }
+                    if (d < tau_s[q] && valid) append_candidate(cnt_s, my_lists, q, p.cap, d, pos, key_lo_q0);
                 }
             }
             // ---- overflow check every group_tiles tiles: no list may exceed cap during the next group ----
@@ -413,6 +425,37 @@ __global__ void verify_counts_kernel(const int* __restrict__ counts, int strips,
     if (total < need) {
         atomicOr(flag, 1);
         tau[q] = 0x7fffffff;
+    }
+}
+
+// List-free sample pass (scan_mma.cu): tau[q] = the k'-th smallest of the distances the epilogue threads kept for query q
+// (strips x 2 threads x 32 values, 0xFFFF = none); "no threshold" when the sample held fewer than k' rows for the query.
+__global__ void __launch_bounds__(128) sample_tau_kernel(const unsigned short* __restrict__ sample, int strips, int nq, int kp, int* __restrict__ tau) {
+    __shared__ int hist[4][1026];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * 4 + warp;
+    for (int i = lane; i < 1026; i += 32) hist[warp][i] = 0;
+    __syncwarp();
+    if (q < nq) {
+        for (int s = 0; s < strips; s++) {
+            const unsigned short* src = sample + ((size_t)s * nq + q) * 64;
+            for (int i = lane; i < 64; i += 32) {
+                const int v = src[i];
+                if (v <= 1024) atomicAdd(&hist[warp][v], 1);
+            }
+        }
+    }
+    __syncwarp();
+    if (q < nq && lane == 0) {
+        int acc = 0, t = 0x7fffffff;
+        for (int d = 0; d <= 1024; d++) {
+            acc += hist[warp][d];
+            if (acc >= kp) {
+                t = d;
+                break;
+            }
+        }
+        tau[q] = t;
     }
 }
 
@@ -610,6 +653,9 @@ static int launch_pass(vrq_ctx* ctx, bool tma, const CUtensorMap& tmap, const CU
     if (pl.mma) {
         sp.qtile = 128;
         sp.group_tiles = pl.mp.group_tiles;
+        sp.seg_cols = pl.mp.seg_cols;
+        sp.seg_full = pl.mp.seg_full;
+        sp.seg_tail = pl.mp.seg_tail;
         if (sp.run_stride == 0) {  // dense scan of [row_begin, row_end)
             sp.run_stride = MMA_TILE_ROWS;
             sp.run_shift = 0;
@@ -624,8 +670,11 @@ static int launch_pass(vrq_ctx* ctx, bool tma, const CUtensorMap& tmap, const CU
 }
 
 // One batch of queries (nq <= 1024): optional prefix pass, main pass, merge.
+// key_lo (nullable, [nq]): only keys strictly greater than key_lo[q] count - the chunk that follows `already` keys returned by
+// earlier calls (vrq_hamming_topk_dev walks a top-k larger than VRQ_PASS_K in chunks).
 static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_bytes, int64_t pos_base,
-                      const uint8_t* q_dev, int nq, int k, uint64_t* keys_out, int32_t* dbg, cudaStream_t st) {
+                      const uint8_t* q_dev, int nq, int k, uint64_t* keys_out, int32_t* dbg, cudaStream_t st,
+                      const unsigned long long* key_lo = nullptr, int64_t already = 0) {
     const bool tma = (code_bytes == CODE_BYTES) && ((uintptr_t)codes % 16 == 0) && n > 0;
     // >= 4 queries per pass go to the tensor cores (scan_mma.cu): measured crossover at 100 M rows (profiles/r01/
     // scan_regime_sweep_final_100M.txt: 4 queries 2.5 ms vs 2.9 ms); fewer are HBM-bound on the integer pipes (scan.cu)
@@ -692,6 +741,7 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
             sp.counts = counts;
             sp.dbg_stride = n;
             sp.one = 1;
+            sp.key_lo = key_lo;
             sp.row_begin = 0;
             sp.row_end = n;
             vrq_timer_scope ts(ctx, VRQ_CAT_SCAN, st);
@@ -703,11 +753,26 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
             sp.compact_limit = kp + 256;  // thresholds start at infinity: tighten them after the first two tiles
             sp.sample_mode = 1;           // only tau[q] matters: distance-only compaction, lists left uncompacted
             s_pl.mp.group_tiles = 2;
+            // the 128-query-tile kernel keeps the k' smallest distances per epilogue thread instead of lists (no flooding, no
+            // compaction: 0.83 -> ~0.1 ms at 100 M rows); the few-queries kernels (lane = database row) keep the list form
+            const bool list_free = !s_pl.mp.few && kp <= 32 && env_int("VRQ_MMA_SAMPLE_LISTS", 0) == 0;
+            if (list_free) {
+                void* so_v;
+                VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_SAMPLE_D, sizeof(unsigned short) * (size_t)s_pl.strips() * nq * 64, &so_v));
+                sp.sample_out = (unsigned short*)so_v;
+            }
             VRQ_TRY(launch_pass(ctx, tma, tmap, tmap_mma, sp, s_pl, st));
             const int sample_list_max = sp.compact_limit + s_pl.mp.group_tiles * MMA_TILE_ROWS;
             sp.compact_limit = 0;
             sp.sample_mode = 0;
-            VRQ_TRY(launch_merge(ctx, lists, counts, s_pl.strips(), nq, cap, kp, (uint64_t*)skeys_v, tau, st, nullptr, sample_list_max));
+            if (list_free) {
+                sample_tau_kernel<<<(nq + 3) / 4, 128, 0, st>>>(sp.sample_out, s_pl.strips(), nq, kp, tau);
+                vrq_count_launch(ctx);
+                VRQ_CUDA(cudaGetLastError());
+                sp.sample_out = nullptr;
+            } else {
+                VRQ_TRY(launch_merge(ctx, lists, counts, s_pl.strips(), nq, cap, kp, (uint64_t*)skeys_v, tau, st, nullptr, sample_list_max));
+            }
             // 2. dense pass with the inclusive threshold d <= T
             sp.k = k;
             sp.run_stride = 0;  // dense
@@ -729,7 +794,8 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
             }
             sp.progress = nullptr;  // the gated fallback pass runs unthrottled (its counters would have to be reset)
             VRQ_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
-            const int need = (int)((int64_t)k < n ? (int64_t)k : n);
+            const int64_t avail = n - already > 0 ? n - already : 0;  // rows not returned by earlier chunks
+            const int need = (int)((int64_t)k < avail ? (int64_t)k : avail);
             verify_counts_kernel<<<(nq + 127) / 128, 128, 0, st>>>(counts, m_pl.strips(), nq, need, flag, tau);
             vrq_count_launch(ctx);
             VRQ_TRY(launch_merge(ctx, lists, counts, m_pl.strips(), nq, cap, k, keys_out, nullptr, st));
@@ -746,7 +812,7 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
     PassPlan main_pl;
     VRQ_TRY(plan_pass(ctx, tma, mma, code_bytes, n, nq, k, &main_pl));
     int64_t m = 0;
-    if (n >= (int64_t)64 * main_pl.tile_rows() * main_pl.strips() && n >= (int64_t)16 * k) {
+    if (key_lo == nullptr && n >= (int64_t)64 * main_pl.tile_rows() * main_pl.strips() && n >= (int64_t)16 * k) {
         m = main_pl.rows_per_strip();  // about one strip's worth of rows
         if (m < 4 * (int64_t)k) m = ((4 * (int64_t)k + main_pl.tile_rows() - 1) / main_pl.tile_rows()) * main_pl.tile_rows();
         if (m > n / 2) m = 0;
@@ -781,6 +847,7 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
     sp.dbg = dbg;
     sp.dbg_stride = n;
     sp.one = 1;
+    sp.key_lo = key_lo;
 
     vrq_timer_scope ts(ctx, VRQ_CAT_SCAN, st);
     int extra = 0;
@@ -813,6 +880,11 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
     return 0;
 }
 
+__global__ void last_keys_kernel(const uint64_t* __restrict__ keys, int64_t nq, int64_t stride, int col, unsigned long long* __restrict__ lo) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) lo[q] = keys[q * stride + col];
+}
+
 int vrq_hamming_topk_dev(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_bytes, int64_t pos_base,
                          const uint8_t* q_dev, int64_t nq, int k, uint64_t* keys_out, cudaStream_t st, int32_t* dbg) {
     if (nq == 0) return 0;
@@ -820,9 +892,9 @@ int vrq_hamming_topk_dev(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code
         vrq_set_error("Hamming top-k supports 1 <= k <= %d (got %d)", VRQ_MAX_K, k);
         return k <= 0 ? VRQ_ERR_ARG : VRQ_ERR_UNSUPPORTED;
     }
-    if (code_bytes % 4 != 0 || code_bytes <= 0) {
-        vrq_set_error("code size must be a positive multiple of 4 bytes (got %d)", code_bytes);
-        return VRQ_ERR_UNSUPPORTED;
+    if (code_bytes <= 0) {
+        vrq_set_error("code size must be positive (got %d)", code_bytes);
+        return VRQ_ERR_ARG;
     }
     if (n >= (1ll << 31)) {
         vrq_set_error("one shard holds at most 2^31 - 1 codes (TMA row coordinate); shard the database across GPUs");
@@ -834,10 +906,38 @@ int vrq_hamming_topk_dev(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code
     }
     VRQ_CUDA(cudaSetDevice(ctx->device));
     const int64_t QB = 1024;
+    if (k <= VRQ_PASS_K) {
+        for (int64_t q0 = 0; q0 < nq; q0 += QB) {
+            const int nb = (int)(nq - q0 < QB ? nq - q0 : QB);
+            VRQ_TRY(topk_batch(ctx, codes, n, code_bytes, pos_base, q_dev + q0 * code_bytes, nb, k, keys_out + q0 * k,
+                               dbg ? dbg + q0 * n : nullptr, st));
+        }
+        return 0;
+    }
+    // k beyond what one pass holds per (strip, query) list: the ranking is produced in chunks of VRQ_PASS_K keys, each chunk
+    // one more exact scan that only accepts keys above the last key of the chunk before it.  Keys are unique, so the
+    // concatenation is exactly the top-k (faiss has no limit on k; CohereEnhancedVectorDB.py:267 with k=1000 asks for 10000).
+    if (dbg) {
+        vrq_set_error("the distance dump supports k <= %d", VRQ_PASS_K);
+        return VRQ_ERR_UNSUPPORTED;
+    }
+    void *chunk_v, *lo_v;
+    VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_CHUNK_KEYS, sizeof(uint64_t) * (size_t)QB * VRQ_PASS_K, &chunk_v));
+    VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_CHUNK_LO, sizeof(uint64_t) * (size_t)QB, &lo_v));
     for (int64_t q0 = 0; q0 < nq; q0 += QB) {
         const int nb = (int)(nq - q0 < QB ? nq - q0 : QB);
-        VRQ_TRY(topk_batch(ctx, codes, n, code_bytes, pos_base, q_dev + q0 * code_bytes, nb, k, keys_out + q0 * k,
-                           dbg ? dbg + q0 * n : nullptr, st));
+        for (int done = 0; done < k; done += VRQ_PASS_K) {
+            const int kk = k - done < VRQ_PASS_K ? k - done : VRQ_PASS_K;
+            VRQ_TRY(topk_batch(ctx, codes, n, code_bytes, pos_base, q_dev + q0 * code_bytes, nb, kk, (uint64_t*)chunk_v, nullptr, st,
+                               done ? (const unsigned long long*)lo_v : nullptr, done));
+            VRQ_CUDA(cudaMemcpy2DAsync(keys_out + q0 * k + done, sizeof(uint64_t) * (size_t)k, chunk_v, sizeof(uint64_t) * (size_t)kk,
+                                       sizeof(uint64_t) * (size_t)kk, (size_t)nb, cudaMemcpyDeviceToDevice, st));
+            if (done + kk < k) {
+                last_keys_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>((const uint64_t*)chunk_v, nb, kk, kk - 1, (unsigned long long*)lo_v);
+                vrq_count_launch(ctx);
+                VRQ_CUDA(cudaGetLastError());
+            }
+        }
     }
     return 0;
 }

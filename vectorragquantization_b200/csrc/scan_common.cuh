@@ -52,6 +52,12 @@ struct ScanParams {
     int64_t total_tiles;
     int32_t* dbg;     // tests only: every (query, row) Hamming distance of the launch, [nq][dbg_stride] (tensor-core kernel)
     int64_t dbg_stride;
+    const unsigned long long* key_lo;  // [nq] or null: only keys STRICTLY GREATER than key_lo[q] are candidates (the next chunk of a
+                                       // top-k larger than one pass can hold: vrq_hamming_topk_dev walks the ranking in chunks)
+    unsigned short* sample_out;  // tensor-core 128-query-tile kernel, sample pass with k <= 32: [strip][nq][2][32] smallest distances
+                                 // seen by each epilogue thread (0xFFFF = none); no lists are written (scan_mma.cu)
+    int seg_cols, seg_full, seg_tail;  // tensor-core pair kernel, 1-D grid of clusters: query-tile pairs, full strips per pair column,
+                                       // clusters that share the tail strip (scan_mma.cu); seg_cols == 0: classic (query tile, strip) grid
     int* progress;    // tensor-core pair kernel, dense pass: [strip][query-tile pair] tile counters (lockstep throttle), or null
     int lock_window;  // a pair's TMA producer stays within this many tiles of the slowest pair of its strip
     int one;          // == 1, opaque to the compiler: multiplier that keeps the popcount accumulation on the FMA pipe (IMAD)
@@ -233,8 +239,10 @@ struct MmaPlan {
     int64_t rows_per_strip;
     size_t smem, smem_limit;
     bool f4;    // packed e2m1 operands (kind::mxf4) instead of int8
+    bool mid;   // 33 .. 96 queries: the swapped-operand kernel with thresholds in shared memory
     bool few;   // <= 64 queries: swapped-operand kernel (database rows = M, expanded straight into tensor memory)
     bool pair;  // CTA pairs (tcgen05 cta_group::2): two query tiles share every tile of database rows
+    int seg_cols, seg_full, seg_tail;  // pair scheduler (see ScanParams); seg_cols == 0: classic grid
 };
 constexpr int MMA_TILE_ROWS = 128;
 int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl);

@@ -53,6 +53,7 @@ constexpr uint32_t TMEM_COLS = 512, TMEM_A_COL = 0, TMEM_D_COL = 256;
 constexpr uint32_t TMEM_SFA_COL = 128, TMEM_SFB_COL = 160, TMEM_SF_COLS = 32;  // F4 only: block scales, all 1.0 (UE8M0 0x7F)
 constexpr int B_STAGES = 8, MAX_RAW_STAGES = 4;
 constexpr int BAR_WARP0 = 2;  // named barriers 2..9: one per epilogue warp (list compaction)
+constexpr int SAMPLE_KEEP = 32;  // largest k' the list-free sample pass supports
 
 // instruction descriptor (bit layout of cute::UMMA::InstrDescriptor): D = s32 (bits 4-5 = 2), A = B = signed 8 bit (bits
 // 7-9, 10-12 = 1), both K-major, N >> 3 in bits 17-22, M >> 4 in bits 24-28
@@ -194,6 +195,7 @@ struct MmaSmem {
     int tau_s[MQ];
     int cnt_s[MQ];
     SelectScratch sc[EPI_WARPS];  // one radix-select scratch per epilogue warp
+    unsigned short sample_d[SAMPLE_KEEP][EPI_THREADS];  // sample pass: the SAMPLE_KEEP smallest distances of each epilogue thread
 };
 
 // CG = 1: one CTA per 128-query tile.  CG = 2 (e2m1 only): a CTA pair shares every tile of database rows - each CTA
@@ -220,14 +222,45 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int q0 = blockIdx.x * MQ;
-    const int qt = min(MQ, p.nq - q0);
-    const int strip = blockIdx.y;
-    // a strip owns tiles_per_strip consecutive tiles of the launch (dense scan: consecutive rows; strided sample: runs of
-    // consecutive tiles spread over the database, see ScanParams)
+    // A CTA (pair) works through one or more SEGMENTS = (query tile, range of tiles, list strip).  Classic 2-D grid
+    // (seg_cols == 0): one segment, blockIdx = (query tile, strip).  Pair scheduler (seg_cols > 0, 1-D grid of clusters):
+    // cluster c < seg_cols * seg_full owns strip c / seg_cols of query-tile pair c % seg_cols - the pairs of one strip walk the
+    // same rows at the same time, so the re-reads hit L2; the remaining seg_tail clusters share the TAIL strip (the rows
+    // after the seg_full full strips), each doing it for seg_cols / seg_tail query-tile pairs one after the other.  With
+    // 148 SMs and 8 query tiles: 72 pairs x 1/18.5 of the rows + 2 pairs x (2 x 1/37): every SM is busy.
     const int tiles_per_strip = (int)(p.rows_per_strip / MROWS);
-    const int64_t tile0 = (int64_t)strip * tiles_per_strip;
-    const int ntiles = (int)max((int64_t)0, min((int64_t)tiles_per_strip, p.total_tiles - tile0));
+    int q0 = 0, qt = 0, strip = 0, ntiles = 0;
+    int64_t tile0 = 0;
+    auto segment = [&](int sgi) -> bool {
+        int col;
+        if (p.seg_cols == 0) {
+            if (sgi > 0) return false;
+            col = blockIdx.x;
+            strip = blockIdx.y;
+            tile0 = (int64_t)strip * tiles_per_strip;
+            ntiles = (int)max((int64_t)0, min((int64_t)tiles_per_strip, p.total_tiles - tile0));
+            q0 = col * MQ;
+        } else {
+            const int c = (int)(blockIdx.x / CG), nfull = p.seg_cols * p.seg_full;
+            if (c < nfull) {
+                if (sgi > 0) return false;
+                col = c % p.seg_cols;
+                strip = c / p.seg_cols;
+                tile0 = (int64_t)strip * tiles_per_strip;
+                ntiles = (int)max((int64_t)0, min((int64_t)tiles_per_strip, p.total_tiles - tile0));
+            } else {
+                const int per = p.seg_cols / p.seg_tail;
+                if (sgi >= per) return false;
+                col = (c - nfull) * per + sgi;
+                strip = p.seg_full;
+                tile0 = (int64_t)p.seg_full * tiles_per_strip;
+                ntiles = (int)max((int64_t)0, p.total_tiles - tile0);
+            }
+            q0 = (col * CG + (int)rank) * MQ;
+        }
+        qt = max(0, min(MQ, p.nq - q0));
+        return true;
+    };
     const int64_t run_mask = ((int64_t)1 << p.run_shift) - 1;
     auto tile_row = [&](int t) -> int64_t {
         const int64_t i = tile0 + t;
@@ -269,6 +302,12 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
     tc_fence_after();
     const uint32_t tmem = sm->tmem_base;
 
+    // running state of the rings across segments (a CTA's tiles are numbered tbase + t over all its segments: stages,
+    // accumulators and barrier phases continue where the previous segment left them)
+    uint32_t prod_s = 0, prod_ph = 0;  // TMA producer: raw ring
+    uint32_t rs = 0, rph = 0;          // expanders: raw ring
+    int tbase = 0;
+  for (int sgi = 0; segment(sgi); sgi++) {
     // ---- the query tile becomes the A operand in tensor memory (lane = query); warps 0-3 write it, every epilogue
     //      thread keeps popc(query) of the query it filters
     int pcq = 0;
@@ -313,7 +352,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
             }
         }
         if (writer) {
-            if constexpr (F4) {
+            if (F4 && sgi == 0) {
                 // every block scale (UE8M0) = 0x7F = 2^0: with one constant the scale-factor layout does not matter
                 uint32_t one[8];
 #pragma unroll
@@ -333,15 +372,16 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
     if (warp == WARP_TMA) {
         // ===================== raw-code producer =====================
         if (lane == 0) {
-            uint32_t s = 0, ph = 0;
+            uint32_t s = prod_s, ph = prod_ph;
             // Lockstep throttle (dense pass, CTA pairs): the pairs of one strip read the same rows, and only the first read
             // of a row comes from HBM as long as the others follow within the L2's reach.  Left alone the pairs drift apart
             // (ncu: DRAM reads 2x the code array); here the leader's producer publishes its tile counter every 16 tiles and
             // does not run more than lock_window tiles ahead of the slowest pair of its strip - which costs nothing, since
             // the launch ends with the slowest pair anyway.
-            const int ncols = (int)(gridDim.x / CG);
-            volatile int* prog = (p.progress && rank == 0 && ncols > 1) ? p.progress + (size_t)strip * ncols : nullptr;
-            const int mycol = (int)(blockIdx.x / CG);
+            const int ncols = p.seg_cols > 0 ? p.seg_cols : (int)(gridDim.x / CG);
+            const bool full_strip = p.seg_cols == 0 || (int)(blockIdx.x / CG) < p.seg_cols * p.seg_full;
+            volatile int* prog = (p.progress && rank == 0 && ncols > 1 && full_strip) ? p.progress + (size_t)strip * ncols : nullptr;
+            const int mycol = p.seg_cols > 0 ? (int)(blockIdx.x / CG) % p.seg_cols : (int)(blockIdx.x / CG);
             for (int t = 0; t < ntiles; t++) {
                 if (prog && (t & 15) == 0) {
                     prog[mycol] = t;
@@ -360,6 +400,8 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                 }
             }
             if (prog) prog[mycol] = 0x7fffffff;
+            prod_s = s;
+            prod_ph = ph;
         }
     } else if (warp >= WARP_MMA && warp < WARP_MMA + MMA_WARPS) {
         // ===================== MMA issuers =====================
@@ -373,13 +415,15 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         // (int8 tiles all share the same 8 stages: a second issuer would wait on a barrier phase two ahead of the completed
         // one, which a parity wait cannot express - so the int8 kind keeps a single issuer.)
         constexpr int ISSUERS = F4 ? MMA_WARPS : 1;
-        for (int t = warp - WARP_MMA; t < ntiles && warp - WARP_MMA < ISSUERS && rank == 0; t += ISSUERS) {
-            const int as = t & 1;
-            const uint32_t grp = (uint32_t)t & (uint32_t)(GROUPS - 1);
-            const uint32_t ph = ((uint32_t)t / (uint32_t)GROUPS) & 1u;
+        for (int t = 0; t < ntiles && warp - WARP_MMA < ISSUERS && rank == 0; t++) {
+            const uint32_t T = (uint32_t)(tbase + t);  // tile number over all segments of this CTA
+            if ((int)(T % (uint32_t)ISSUERS) != warp - WARP_MMA) continue;
+            const int as = (int)(T & 1u);
+            const uint32_t grp = T & (uint32_t)(GROUPS - 1);
+            const uint32_t ph = (T / (uint32_t)GROUPS) & 1u;
             const uint64_t desc_t = desc0 + (uint64_t)(grp * (uint32_t)(KBLOCKS * (STAGE_BYTES_B >> 4)));
             const uint32_t full_t = full0 + grp * (uint32_t)(KBLOCKS * 8), empty_t = empty0 + grp * (uint32_t)(KBLOCKS * 8);
-            mbar_wait(smem_u32(&sm->acc_empty[as]), (((uint32_t)t >> 1) & 1u) ^ 1u);
+            mbar_wait(smem_u32(&sm->acc_empty[as]), ((T >> 1) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem + TMEM_D_COL + (uint32_t)as * MROWS;
 #pragma unroll
@@ -422,10 +466,10 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         // the "stage full" barriers the MMA issuer waits on live in the leader CTA
         const uint32_t full0 = CG == 2 ? mapa_rank(smem_u32(&sm->b_full[0]), 0) : smem_u32(&sm->b_full[0]);
         const uint32_t bmem0 = smem_u32(b_mem) + row_off;
-        uint32_t rs = 0, rph = 0;  // raw ring
         for (int t = 0; t < ntiles; t++) {
-            const uint32_t grp = (uint32_t)t & (uint32_t)(GROUPS - 1);
-            const uint32_t ph = ((uint32_t)t / (uint32_t)GROUPS) & 1u;
+            const uint32_t T = (uint32_t)(tbase + t);
+            const uint32_t grp = T & (uint32_t)(GROUPS - 1);
+            const uint32_t ph = (T / (uint32_t)GROUPS) & 1u;
             const uint32_t stage0 = grp * (uint32_t)KBLOCKS + (uint32_t)par;
             mbar_wait_relaxed(smem_u32(&sm->raw_full[rs]), rph, 64);
             const uint32_t raddr = smem_u32(raw_mem) + rs * (uint32_t)STAGE_BYTES_RAW + row_off;
@@ -488,16 +532,21 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         const int half = warp >> 2;
         const bool qvalid = q < qt;
         uint64_t* my_list = p.lists + ((size_t)strip * p.nq + q0 + (qvalid ? q : 0)) * p.cap;
+        const bool has_lo = p.key_lo != nullptr;
+        const unsigned long long lo_q = (has_lo && qvalid) ? p.key_lo[q0 + q] : 0ull;
         int thr = qvalid ? pcq - sm->tau_s[q] : 0x7fffffff;  // survivor <=> dot > thr <=> hamming < tau
         float thr_f = (float)thr;
+        const bool samp = p.sample_out != nullptr;  // list-free sample pass (thresholds only)
+        int samp_fill = 0, samp_max = 0x7fffffff;
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + TMEM_D_COL + (uint32_t)(half * 64);
         const int limit = p.compact_limit > 0 ? min(p.compact_limit, p.cap - p.group_tiles * MROWS) : p.cap - p.group_tiles * MROWS;
         int until_check = p.group_tiles;
         int64_t cur_row = tile_row(0) + half * 64;
         int in_run = (int)(tile0 & run_mask);
         for (int t = 0; t < ntiles; t++) {
-            const int as = t & 1;
-            mbar_wait(smem_u32(&sm->acc_full[as]), ((uint32_t)t >> 1) & 1u);
+            const uint32_t T = (uint32_t)(tbase + t);
+            const int as = (int)(T & 1u);
+            mbar_wait(smem_u32(&sm->acc_full[as]), (T >> 1) & 1u);
             tc_fence_after();
             const int64_t lrow0 = cur_row;  // first database row of this warp's 64 columns
             const int64_t left = s_end - lrow0;
@@ -562,7 +611,40 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                     for (int j = 1; j < 16; j++) m = max(m, w[j]);
                     any = m > thr;
                 }
-                if (any) {
+                if (any && samp) {
+                    // List-free sample pass: only the k'-th smallest DISTANCE of the sample matters.  Every epilogue thread keeps
+                    // the k' smallest distances it has seen in a private column of shared memory (sample_d[i][thread]); its own
+                    // threshold is the largest of them once the column is full, so after the first tiles almost nothing gets
+                    // here (the chance that row number r of a thread is among its k' best so far is k' / r).
+                    const unsigned long long pos0 = (unsigned long long)(p.pos_base + lrow0 + 16 * g);
+                    const int et = tid;  // epilogue thread 0 .. 255
+#pragma unroll 1
+                    for (int j = 0; j < 16; j++) {
+                        if (j >= nv) break;
+                        const int ham = pcq - dot_of(j);
+                        if (samp_fill == p.k && ham >= samp_max) continue;
+                        if (has_lo && ((((unsigned long long)ham) << VRQ_KEY_POS_BITS) | (pos0 + j)) <= lo_q) continue;
+                        int slot = samp_fill;
+                        if (samp_fill < p.k) {
+                            samp_fill++;
+                        } else {  // replace the current maximum
+                            slot = 0;
+                            int mx = -1;
+                            for (int i = 0; i < p.k; i++) {
+                                const int v_ = sm->sample_d[i][et];
+                                if (v_ > mx) mx = v_, slot = i;
+                            }
+                        }
+                        sm->sample_d[slot][et] = (unsigned short)ham;
+                        if (samp_fill == p.k) {
+                            int mx = 0;
+                            for (int i = 0; i < p.k; i++) mx = max(mx, (int)sm->sample_d[i][et]);
+                            samp_max = mx;
+                            thr = pcq - samp_max;  // survivor <=> hamming < current k'-th smallest of this thread
+                            thr_f = (float)thr;
+                        }
+                    }
+                } else if (any) {
                     // Some column of this lane survives.  bit (15 - j) of mask <=> w[j] > thr: the sign of thr - w[j] is
                     // shifted in with one funnel shift per column (2 instructions per column, no branches).
                     const unsigned long long pos0 = (unsigned long long)(p.pos_base + lrow0 + 16 * g);
@@ -573,7 +655,20 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                         mask = __funnelshift_l(sgn, mask, 1);
                     }
                     if (nv < 16) mask = nv <= 0 ? 0u : (mask & ~(0xFFFFu >> nv));
-                    if (__popc(mask) == 1 && nv >= 16) {
+                    if (has_lo) {
+                        // a later chunk of a large top-k: keys at or below the chunk's lower bound were returned already
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            if ((mask >> (15 - j)) & 1u) {
+                                const unsigned long long key = ((unsigned long long)(pcq - dot_of(j)) << VRQ_KEY_POS_BITS) | (pos0 + j);
+                                if (key > lo_q) {
+                                    const int slot = atomicAdd(&sm->cnt_s[q], 1);
+                                    if (slot >= p.cap) __trap();
+                                    my_list[slot] = key;
+                                }
+                            }
+                        }
+                    } else if (__popc(mask) == 1 && nv >= 16) {
                         // the usual case once tau has converged: the single survivor is the maximum itself
                         const int slot = atomicAdd(&sm->cnt_s[q], 1);
                         if (slot >= p.cap) __trap();  // cannot happen (overflow check every group_tiles tiles); never write past a list
@@ -592,7 +687,7 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                 }
             }
             // ---- overflow check every group_tiles tiles: no list may exceed cap during the next group ----
-            if (--until_check == 0 && t + 1 < ntiles) {
+            if (!samp && --until_check == 0 && t + 1 < ntiles) {
                 until_check = p.group_tiles;
                 group_sync<EPI_THREADS>(BAR_CONSUMERS);  // every append of this group of tiles is in its list
                 if (epi_sync_or(sm->cnt_s[q] > limit)) {
@@ -608,6 +703,10 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                 }
             }
         }
+        if (samp && qvalid) {
+            unsigned short* o_ = p.sample_out + (((size_t)strip * p.nq + q0 + q) * 2 + half) * SAMPLE_KEEP;
+            for (int i = 0; i < SAMPLE_KEEP; i++) o_[i] = i < samp_fill ? sm->sample_d[i][tid] : (unsigned short)0xFFFF;
+        }
         group_sync<EPI_THREADS>(BAR_CONSUMERS);
         // final compaction: every list leaves the kernel with at most k keys (bounds the merge's working set)
         for (int qq = warp; qq < qt && !p.sample_mode; qq += EPI_WARPS) {
@@ -619,10 +718,15 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         group_sync<EPI_THREADS>(BAR_CONSUMERS);
         if (qvalid && half == 0) p.counts[(size_t)strip * p.nq + q0 + q] = sm->cnt_s[q];
     }
-
+    // end of the segment: every role is done with its tiles (the last accumulators were read, so every MMA has completed)
+    // before the next segment rewrites the query operand in tensor memory - in both CTAs of a pair
+    tbase += ntiles;
     tc_fence_before();
     __syncthreads();
     if constexpr (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared memory and TMEM until the very end
+    tc_fence_after();
+  }  // segments
+
     if (warp == WARP_MMA) {
         tc_fence_after();
         if constexpr (CG == 2)
@@ -642,35 +746,44 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
 //     (thread = row = TMEM lane; two 128-column buffers), so the expansion never touches shared memory;
 //   * D = 128 rows x N queries (two buffers); epilogue lane = database row, column = query, thresholds per column.
 // Same lists / counts / thresholds contract as the kernels above, e2m1 kind only.
-constexpr int FEW_MAXQ = 32;
+constexpr int FEW_MAXQ = 32;   // thresholds and a whole tile's accumulator columns in registers
+constexpr int MID_MAXQ = 96;   // 33 .. 96 queries: thresholds in shared memory, accumulator columns read 48 at a time
 constexpr int FEW_WARP_MMA = 4, FEW_WARP_TMA = 5, FEW_WARP_EXP0 = 6, FEW_EXP_WARPS = 8;
 constexpr int FEW_THREADS = (FEW_WARP_EXP0 + FEW_EXP_WARPS) * 32;
 constexpr int FEW_EPI_WARPS = 4, FEW_EPI_THREADS = FEW_EPI_WARPS * 32;
-constexpr uint32_t FEW_A_COL = 0, FEW_D_COL = 256, FEW_SF_COL = 384;  // A: 2 x 128 columns, D: 2 x 64 (32 used), scales: 64
+// tensor memory: A = 2 x 128 columns, D = 2 buffers of 64 (<= 32 queries) or 96 columns, block scales = the last 64 columns
+constexpr uint32_t FEW_A_COL = 0, FEW_D_COL = 256, FEW_SF_COL = 448;
+template <int MAXQ>
+struct FewCfg {
+    static constexpr uint32_t D_STRIDE = MAXQ <= 32 ? 64 : 96;
+};
 constexpr int FEW_MAX_RAW = 8;
 
+template <int MAXQ>
 struct FewSmem {
     unsigned long long raw_full[FEW_MAX_RAW], raw_empty[FEW_MAX_RAW];
     unsigned long long a_full[2], a_empty[2], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
-    int tau_s[FEW_MAXQ];
-    int cnt_s[FEW_MAXQ];
-    int pcq_s[FEW_MAXQ];
-    float thr_s[FEW_MAXQ];
+    int tau_s[MAXQ];
+    int cnt_s[MAXQ];
+    int pcq_s[MAXQ];
+    __align__(16) float thr_s[MAXQ];
     SelectScratch sc[FEW_EPI_WARPS];
 };
 
+template <int MAXQ>
 __global__ void __launch_bounds__(FEW_THREADS, 1)
 hamming_scan_mma_few_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, int raw_stages, int npad) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* raw_mem = base;                                      // [raw_stages][128 rows][128 B], TMA SWIZZLE_128B
     uint8_t* q_mem = raw_mem + (size_t)raw_stages * STAGE_BYTES_RAW;  // [4 K-blocks][npad queries][128 B], same swizzle
-    FewSmem* sm = (FewSmem*)(q_mem + (size_t)4 * FEW_MAXQ * 128);
+    FewSmem<MAXQ>* sm = (FewSmem<MAXQ>*)(q_mem + (size_t)4 * MAXQ * 128);
+    constexpr uint32_t D_STRIDE = FewCfg<MAXQ>::D_STRIDE;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int nq = p.nq;  // <= FEW_MAXQ, one query tile
+    const int nq = p.nq;  // <= MAXQ, one query tile
     const int strip = blockIdx.y;
     const int tiles_per_strip = (int)(p.rows_per_strip / MROWS);
     const int64_t tile0 = (int64_t)strip * tiles_per_strip;
@@ -697,7 +810,7 @@ hamming_scan_mma_few_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (tid < FEW_MAXQ) {
+    if (tid < MAXQ) {
         sm->pcq_s[tid] = 0;
         sm->cnt_s[tid] = 0;
         sm->tau_s[tid] = tid < nq ? (p.tau0 ? min(p.tau0[tid], TAU_INF - 1) + p.tau_bias : TAU_INF) : 0;
@@ -741,7 +854,7 @@ hamming_scan_mma_few_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (tid < FEW_MAXQ) sm->thr_s[tid] = tid < nq ? (float)(sm->pcq_s[tid] - sm->tau_s[tid]) : 3.0e9f;
+    if (tid < MAXQ) sm->thr_s[tid] = tid < nq ? (float)(sm->pcq_s[tid] - sm->tau_s[tid]) : 3.0e9f;
     __syncthreads();
 
     if (warp == FEW_WARP_TMA) {
@@ -768,7 +881,7 @@ hamming_scan_mma_few_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams
             mbar_wait(smem_u32(&sm->acc_empty[ab]), ph ^ 1u);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t d_tmem = tmem + FEW_D_COL + ab * 64, a0 = tmem + FEW_A_COL + ab * 128;
+                const uint32_t d_tmem = tmem + FEW_D_COL + ab * D_STRIDE, a0 = tmem + FEW_A_COL + ab * 128;
 #pragma unroll
                 for (int s = 0; s < 16; s++)
                     umma_f4_ts(d_tmem, a0 + 8 * s, qdesc0 + (uint64_t)((s >> 2) * kb_step + (s & 3) * 2), idesc, tmem + FEW_SF_COL,
@@ -823,13 +936,18 @@ hamming_scan_mma_few_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams
         const int limit = p.compact_limit > 0 ? min(p.compact_limit, p.cap - p.group_tiles * MROWS) : p.cap - p.group_tiles * MROWS;
         uint64_t* const lists0 = p.lists + (size_t)strip * p.nq * p.cap;
         int until_check = p.group_tiles;
-        // the per-query thresholds (survivor <=> dot > popc(q) - tau) live in registers between compactions
-        float thr[FEW_MAXQ / 16][16];
+        // <= 32 queries: the per-query thresholds (survivor <=> dot > popc(q) - tau) live in registers between compactions and
+        // all column groups of a tile are loaded up front.  More queries: thresholds are read from shared memory (one
+        // broadcast LDS.128 per four columns) and the columns are read 48 at a time.
+        constexpr int RCH = MAXQ <= 32 ? MAXQ / 16 : 3;  // 16-column groups held in registers at a time
+        float thr[MAXQ <= 32 ? MAXQ / 16 : 1][16];
         auto load_thr = [&]() {
+            if constexpr (MAXQ <= 32) {
 #pragma unroll
-            for (int ch = 0; ch < FEW_MAXQ / 16; ch++)
+                for (int ch = 0; ch < MAXQ / 16; ch++)
 #pragma unroll
-                for (int j = 0; j < 16; j++) thr[ch][j] = (16 * ch < npad) ? sm->thr_s[16 * ch + j] : 3.0e9f;
+                    for (int j = 0; j < 16; j++) thr[ch][j] = (16 * ch < npad) ? sm->thr_s[16 * ch + j] : 3.0e9f;
+            }
         };
         load_thr();
         for (int t = 0; t < ntiles; t++) {
@@ -838,41 +956,61 @@ hamming_scan_mma_few_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams
             tc_fence_after();
             const int64_t lrow = tile_row(t) + warp * 32 + lane;
             const bool rvalid = lrow < s_end;
-            // all column groups of the tile are loaded up front (<= 32 registers), the accumulator is handed back, then the
-            // groups are examined: max over columns of (dot - threshold of that column) as a tree, not a chain
-            int v[FEW_MAXQ / 16][16];
-            __syncwarp();
 #pragma unroll
-            for (int ch = 0; ch < FEW_MAXQ / 16; ch++)
-                if (16 * ch < npad) tmem_ld16(lane_base + ab * 64 + 16 * ch, v[ch]);
-            tmem_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[ab]));
+            for (int part = 0; part < (MAXQ / 16 + RCH - 1) / RCH; part++) {
+                const int c0 = part * RCH;  // first 16-column group of this part
+                if (16 * c0 >= npad) break;
+                const bool last_part = 16 * (c0 + RCH) >= npad || part == (MAXQ / 16 + RCH - 1) / RCH - 1;
+                int v[RCH][16];
+                __syncwarp();
 #pragma unroll
-            for (int ch = 0; ch < FEW_MAXQ / 16; ch++) {
-                const int cb = 16 * ch;
-                if (cb >= npad) break;
-                float m4[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) m4[j] = __int_as_float(v[ch][j]) - thr[ch][j];
-#pragma unroll
-                for (int j = 4; j < 16; j++) m4[j & 3] = fmaxf(m4[j & 3], __int_as_float(v[ch][j]) - thr[ch][j]);
-                const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-                if (p.dbg && rvalid) {
-                    for (int j = 0; j < 16; j++)
-                        if (cb + j < nq) p.dbg[(size_t)(cb + j) * p.dbg_stride + lrow] = sm->pcq_s[cb + j] - (int)__int_as_float(v[ch][j]);
+                for (int ch = 0; ch < RCH; ch++)
+                    if (16 * (c0 + ch) < npad) tmem_ld16(lane_base + ab * D_STRIDE + 16 * (c0 + ch), v[ch]);
+                tmem_wait_ld();
+                if (last_part) {  // every column of the tile has been read: the accumulator goes back to the issuer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[ab]));
                 }
-                if (mx > 0.0f && rvalid) {
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const float f = __int_as_float(v[ch][j]);
-                        if (f > thr[ch][j]) {
-                            const int q = cb + j;
-                            const int slot = atomicAdd(&sm->cnt_s[q], 1);
-                            if (slot >= p.cap) __trap();
-                            lists0[(size_t)q * p.cap + slot] =
-                                ((unsigned long long)(sm->pcq_s[q] - (int)f) << VRQ_KEY_POS_BITS) | (unsigned long long)(p.pos_base + lrow);
+                for (int ch = 0; ch < RCH; ch++) {
+                    const int cb = 16 * (c0 + ch);
+                    if (cb >= npad) break;
+                    float th[16];
+                    if constexpr (MAXQ <= 32) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) th[j] = thr[c0 + ch][j];
+                    } else {
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; j4++) {
+                            const float4 f = *reinterpret_cast<const float4*>(&sm->thr_s[cb + 4 * j4]);
+                            th[4 * j4] = f.x, th[4 * j4 + 1] = f.y, th[4 * j4 + 2] = f.z, th[4 * j4 + 3] = f.w;
+                        }
+                    }
+                    float m4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) m4[j] = __int_as_float(v[ch][j]) - th[j];
+#pragma unroll
+                    for (int j = 4; j < 16; j++) m4[j & 3] = fmaxf(m4[j & 3], __int_as_float(v[ch][j]) - th[j]);
+                    const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                    if (p.dbg && rvalid) {
+                        for (int j = 0; j < 16; j++)
+                            if (cb + j < nq) p.dbg[(size_t)(cb + j) * p.dbg_stride + lrow] = sm->pcq_s[cb + j] - (int)__int_as_float(v[ch][j]);
+                    }
+                    if (mx > 0.0f && rvalid) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const float f = __int_as_float(v[ch][j]);
+                            if (f > th[j]) {
+                                const int q = cb + j;
+                                const unsigned long long key =
+                                    ((unsigned long long)(sm->pcq_s[q] - (int)f) << VRQ_KEY_POS_BITS) | (unsigned long long)(p.pos_base + lrow);
+                                if (p.key_lo == nullptr || key > p.key_lo[q]) {
+                                    const int slot = atomicAdd(&sm->cnt_s[q], 1);
+                                    if (slot >= p.cap) __trap();
+                                    lists0[(size_t)q * p.cap + slot] = key;
+                                }
+                            }
                         }
                     }
                 }
@@ -924,8 +1062,9 @@ hamming_scan_mma_few_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams
     }
 }
 
-size_t few_smem_bytes(int raw_stages) {
-    return 1024 + (size_t)raw_stages * STAGE_BYTES_RAW + (size_t)4 * FEW_MAXQ * 128 + sizeof(FewSmem) + 16;
+size_t few_smem_bytes(int raw_stages, bool mid) {
+    return 1024 + (size_t)raw_stages * STAGE_BYTES_RAW + (size_t)4 * (mid ? MID_MAXQ : FEW_MAXQ) * 128 +
+           (mid ? sizeof(FewSmem<MID_MAXQ>) : sizeof(FewSmem<FEW_MAXQ>)) + 16;
 }
 
 size_t mma_smem_bytes(int raw_stages, int cap) {
@@ -941,20 +1080,45 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
     pl->qtiles = (nq + MQ - 1) / MQ;
     // <= 64 queries: the swapped-operand kernel (database rows = M), HBM-bound instead of bound by 8 tensor cycles per row
     pl->few = pl->f4 && nq <= FEW_MAXQ && env_int("VRQ_MMA_FEW", 1) != 0;
+    // 33 .. 96 queries: the same kernel with its thresholds in shared memory (VRQ_MMA_MID=0: the 128-query-tile kernel)
+    pl->mid = pl->f4 && !pl->few && nq <= MID_MAXQ && env_int("VRQ_MMA_FEW", 1) != 0 && env_int("VRQ_MMA_MID", 1) != 0;
+    if (pl->mid) pl->few = true;
     // CTA pairs need an even number of query tiles (a pair = two neighbouring tiles); VRQ_MMA_PAIR=0 switches them off
     pl->pair = pl->f4 && pl->qtiles % 2 == 0 && env_int("VRQ_MMA_PAIR", 1) != 0;
     pl->group_tiles = env_int("VRQ_MMA_GROUP_TILES", 8);
     if (pl->group_tiles < 1) pl->group_tiles = 1;
     const int slack = k < 256 ? 256 : (k > 2048 ? 2048 : k);
     pl->cap = k + slack + pl->group_tiles * MROWS;
-    int strips = sms / pl->qtiles;
-    if (strips < 1) strips = 1;
     int64_t tiles = (rows + MROWS - 1) / MROWS;
     if (tiles < 1) tiles = 1;
-    if (strips > tiles) strips = (int)tiles;
-    const int64_t tps = (tiles + strips - 1) / strips;
-    pl->rows_per_strip = tps * MROWS;
-    pl->strips = (int)((tiles + tps - 1) / tps);
+    pl->seg_cols = pl->seg_full = pl->seg_tail = 0;
+    if (pl->pair && !pl->few && env_int("VRQ_MMA_TAIL", 1) != 0) {
+        // pair scheduler: P = sms / 2 clusters, cols query-tile pairs; F full strips per column, the E clusters left over share a
+        // tail strip (E must divide cols: each of them walks cols / E columns one after the other).  Equal work per cluster:
+        // a full strip holds T1 = tiles * cols / (E + F * cols) tiles, the tail strip the rest.
+        const int P = sms / 2, cols = pl->qtiles / 2;
+        int F = P / cols, E = P % cols;
+        while (E > 0 && cols % E != 0) E--;
+        if (F < 1) F = 1, E = 0;
+        int64_t T1 = (tiles * cols + (E + (int64_t)F * cols) - 1) / (E + (int64_t)F * cols);
+        if (T1 < 1) T1 = 1;
+        if (T1 * F >= tiles) {  // nothing left for a tail strip (small inputs)
+            E = 0;
+            F = (int)((tiles + T1 - 1) / T1);
+        }
+        pl->seg_cols = cols;
+        pl->seg_full = F;
+        pl->seg_tail = E;
+        pl->rows_per_strip = T1 * MROWS;
+        pl->strips = F + (E > 0 ? 1 : 0);
+    } else {
+        int strips = sms / pl->qtiles;
+        if (strips < 1) strips = 1;
+        if (strips > tiles) strips = (int)tiles;
+        const int64_t tps = (tiles + strips - 1) / strips;
+        pl->rows_per_strip = tps * MROWS;
+        pl->strips = (int)((tiles + tps - 1) / tps);
+    }
     const size_t limit = ctx->smem_optin ? ctx->smem_optin : 227 * 1024;
     pl->smem_limit = limit;
     pl->raw_stages = env_int("VRQ_MMA_RAW_STAGES", pl->few ? FEW_MAX_RAW : 4);
@@ -972,7 +1136,7 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
 void mma_plan_set_cap(MmaPlan* pl, int cap) {
     pl->cap = cap;
     if (pl->few) {
-        pl->smem = few_smem_bytes(pl->raw_stages);
+        pl->smem = few_smem_bytes(pl->raw_stages, pl->mid);
         return;
     }
     while (pl->raw_stages > 1 && mma_smem_bytes(pl->raw_stages, cap) > pl->smem_limit) pl->raw_stages--;
@@ -987,10 +1151,15 @@ int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const CUtensorMap&
         return VRQ_ERR_UNSUPPORTED;
     }
     dim3 grid(pl.qtiles, pl.strips);
-    if (pl.few) {
+    if (pl.seg_cols > 0) grid = dim3(2 * (pl.seg_cols * pl.seg_full + pl.seg_tail), 1);  // 1-D grid of CTA pairs
+    if (pl.few && pl.mid) {
+        const int npad = ((sp.nq + 15) / 16) * 16;
+        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_few_kernel<MID_MAXQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        hamming_scan_mma_few_kernel<MID_MAXQ><<<grid, FEW_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, npad);
+    } else if (pl.few) {
         const int npad = ((sp.nq + 7) / 8) * 8;
-        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_few_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        hamming_scan_mma_few_kernel<<<grid, FEW_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, npad);
+        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_few_kernel<FEW_MAXQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        hamming_scan_mma_few_kernel<FEW_MAXQ><<<grid, FEW_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, npad);
     } else if (pl.f4 && pl.pair) {
         // CTA pairs: clusters of 2 along x = two neighbouring query tiles of the same strip
         auto kern = hamming_scan_mma_kernel<KIND_F4, 2>;

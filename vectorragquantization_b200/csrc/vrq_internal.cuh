@@ -50,7 +50,7 @@ struct vrq_buf {
 enum { VRQ_WS_STAGE_IN0 = 0, VRQ_WS_STAGE_IN1, VRQ_WS_STAGE_OUT0, VRQ_WS_STAGE_OUT1, VRQ_WS_LISTS, VRQ_WS_COUNTS,
        VRQ_WS_TOPK, VRQ_WS_SEARCH_A, VRQ_WS_SEARCH_B, VRQ_WS_SEARCH_C, VRQ_WS_SEARCH_D, VRQ_WS_SEARCH_E,
        VRQ_WS_QUERY_A, VRQ_WS_QUERY_B, VRQ_WS_OUT_A, VRQ_WS_OUT_B, VRQ_WS_OUT_C, VRQ_WS_OUT_D, VRQ_WS_OUT_E,
-       VRQ_WS_MISC, VRQ_WS_TAU, VRQ_WS_MERGE_A, VRQ_WS_MERGE_B, VRQ_WS_MERGE_CA, VRQ_WS_MERGE_CB, VRQ_WS_SAMPLE_KEYS, VRQ_WS_FLAG, VRQ_WS_PROGRESS, VRQ_WS_SLOTS };
+       VRQ_WS_MISC, VRQ_WS_TAU, VRQ_WS_MERGE_A, VRQ_WS_MERGE_B, VRQ_WS_MERGE_CA, VRQ_WS_MERGE_CB, VRQ_WS_SAMPLE_KEYS, VRQ_WS_FLAG, VRQ_WS_PROGRESS, VRQ_WS_SAMPLE_D, VRQ_WS_CHUNK_KEYS, VRQ_WS_CHUNK_LO, VRQ_WS_M3_SRC, VRQ_WS_M3_R2, VRQ_WS_SLOTS };
 
 struct vrq_ctx {
     int device = 0;
@@ -122,7 +122,8 @@ int vrq_hamming_topk_dev(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code
 #define VRQ_KEY_POS_BITS 40
 #define VRQ_KEY_POS_MASK ((1ull << VRQ_KEY_POS_BITS) - 1ull)
 #define VRQ_KEY_NONE (~0ull)
-#define VRQ_MAX_K 4096
+#define VRQ_MAX_K 16384   // largest k of a Hamming top-k / k * binary_oversample of the fused searches
+#define VRQ_PASS_K 4096  // keys one scan pass keeps per query; larger k are produced in chunks (scan.cu)
 
 // ---- rescore.cu -------------------------------------------------------------------------------------
 int vrq_launch_rescore_binary(vrq_ctx* ctx, const uint8_t* codes, int d, const uint64_t* keys, const int64_t* pos,
@@ -132,6 +133,8 @@ int vrq_launch_rescore_int8cos(vrq_ctx* ctx, const int8_t* rows, int d, const ui
 // rescore_mma.cu (d == 1024): nibble-table Phase II, tensor-core (mma.sync s8) Phase III, Phase III over regenerated rows
 int vrq_launch_rescore_binary_lut(vrq_ctx* ctx, const uint8_t* codes, const uint64_t* keys, const int64_t* pos, int64_t pos_base,
                                   int64_t nq, int m, const float* qf, double* score, cudaStream_t st);
+int vrq_launch_rescore_binary_imma(vrq_ctx* ctx, const uint8_t* codes, const uint64_t* keys, const int64_t* pos, int64_t pos_base,
+                                   int64_t nq, int m, const float* qf, double* score, cudaStream_t st);
 int vrq_launch_rescore_int8cos_imma(vrq_ctx* ctx, const int8_t* rows, const uint64_t* keys, const int64_t* pos, int64_t pos_base,
                                     int64_t nq, int m, const float* qf, double* score, cudaStream_t st);
 int vrq_launch_rescore_int8cos_synth(vrq_ctx* ctx, uint64_t seed, int64_t synth_row0, const uint64_t* keys, const int64_t* pos,
