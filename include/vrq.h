@@ -176,6 +176,15 @@ int vrq_index_search3(vrq_index*, int64_t nq, const float* q_float, const uint8_
 int vrq_index_search2(vrq_index*, int64_t nq, const float* q_float, const uint8_t* q_ubin, int k, int binary_oversample,
                       int64_t* labels, float* score, int32_t* out_count);
 
+/* CohereVectorDBFloat (the float32 recall baseline): faiss.IndexIDMap(faiss.IndexFlatIP(d)) = an index whose payload kind is
+ * VRQ_PAYLOAD_F32 (codes may then be NULL in vrq_index_add_with_ids).  .search (CohereVectorDBFloat.py:156): the k rows with the
+ * largest float32 inner product with each query, descending (ties: lower position first); scores float32[nq,k], labels
+ * int64[nq,k], padded with (-inf, -1).  k <= 4096. */
+int vrq_index_search_ip(vrq_index*, int64_t nq, const float* q_float, int k, float* scores, int64_t* labels);
+/* faiss.write_index / read_index of that index (CohereVectorDBFloat.py:184,58): byte-compatible "IxMp" wrapping "IxFI". */
+int vrq_index_write_float(vrq_index*, const char* path);
+int vrq_index_read_float(vrq_ctx*, const char* path, vrq_index** out);
+
 /* ---------------------------------------------------------------- multi-GPU pieces (device pointers) ----
  * Row-sharded database: every rank runs search3_local on its shard, the host all-gathers the three arrays over
  * NCCL, every rank (or rank 0) runs merge3.  pos_base = global position of this shard's row 0. */
@@ -188,6 +197,26 @@ int vrq_merge3(vrq_ctx*, int world, int64_t nq, int binary_k, int64_t rank_strid
                const int64_t* labels, const double* score_binary, const double* score_cosine, int k, int k2,
                int64_t* out_labels, int32_t* out_hamming, double* out_score_binary, double* out_score_cosine,
                int32_t* out_count);
+
+/* The same exchange inside the library (sharded.cu), for hosts without torch: NCCL is loaded with dlopen at first use
+ * (libnccl.so.2), libvrq.so itself links against libcudart only.
+ *   one process per GPU:  vrq_nccl_unique_id on rank 0 -> ship the 128 bytes -> vrq_nccl_init_rank on every rank ->
+ *                         vrq_ctx_set_nccl -> vrq_index_search3_sharded on every rank (same queries everywhere);
+ *   one process, all GPUs: vrq_nccl_init_all -> vrq_ctx_set_nccl per context -> vrq_search3_sharded_group.
+ * All data pointers are DEVICE pointers on the rank's GPU; work is enqueued on the context's stream.  pos_base = global
+ * position of the shard's row 0, ntotal_global = rows over all shards (binary_k = min(k * oversample, ntotal_global)). */
+int vrq_nccl_unique_id(char* id128);
+int vrq_nccl_init_rank(int device, int world, const char* id128, int rank, void** comm_out);
+int vrq_nccl_init_all(int ndev, const int* devices, void** comms_out);
+int vrq_nccl_destroy(void* comm);
+int vrq_ctx_set_nccl(vrq_ctx*, void* nccl_comm, int rank, int world);
+int vrq_index_search3_sharded(vrq_index*, int64_t nq, const float* q_float, const uint8_t* q_ubin, int k, int binary_oversample,
+                              int int8_oversample, int64_t pos_base, int64_t ntotal_global, int64_t* labels, int32_t* hamming,
+                              double* score_binary, double* score_cosine, int32_t* out_count);
+int vrq_search3_sharded_group(int world, vrq_index* const* ixs, int64_t nq, const float* const* q_float, const uint8_t* const* q_ubin, int k,
+                              int binary_oversample, int int8_oversample, const int64_t* pos_base, int64_t ntotal_global,
+                              int64_t* const* labels, int32_t* const* hamming, double* const* score_binary, double* const* score_cosine,
+                              int32_t* const* out_count);
 
 /* ---------------------------------------------------------------- stand-alone rescoring kernels --- */
 /* Phase II (CohereEnhancedVectorDB.py:283-293): score[q,i] = sum_j qf[q,j] * (2*bit_j(codes[pos[q,i]]) - 1), f64. */

@@ -456,6 +456,34 @@ def read_index_binary_bytes(b: bytes) -> Tuple[int, np.ndarray, np.ndarray]:
     return d, codes, ids
 
 
+def write_index_float_bytes(d: int, x: np.ndarray, ids: np.ndarray) -> bytes:
+    """``faiss.write_index(IndexIDMap(IndexFlatIP(d)))`` (CohereVectorDBFloat.py:184): "IxMp" + "IxFI" headers
+    {d i32, ntotal i64, 1<<20, 1<<20, is_trained u8, metric i32 = 0 (inner product)}, u64 count + float32 rows, u64 count +
+    int64 ids.  Pinned on the header bytes and size of the reference's committed db_cohere_float/index.faiss
+    (tests/golden/float_index_header.json)."""
+    import struct
+    x = np.ascontiguousarray(x, np.float32)
+    n = x.shape[0]
+    hdr = lambda cc: cc + struct.pack("<iqqqBi", d, n, 1 << 20, 1 << 20, 1, 0)  # noqa: E731
+    return (hdr(b"IxMp") + hdr(b"IxFI") + struct.pack("<Q", n * d) + x.tobytes() + struct.pack("<Q", n) +
+            np.ascontiguousarray(ids, np.int64).tobytes())
+
+
+def search_ip(x: np.ndarray, ids: np.ndarray, q: np.ndarray, k: int):
+    """``IndexIDMap(IndexFlatIP).search`` + the reference's descending re-sort (CohereVectorDBFloat.py:156-170): float32 inner
+    products, the k largest per query (ties: lower position first), labels -1 / scores -inf when ntotal < k."""
+    x = np.asarray(x, np.float32)
+    q = np.asarray(q, np.float32).reshape(-1, x.shape[1])
+    scores = q @ x.T
+    out_s = np.full((q.shape[0], k), -np.inf, np.float32)
+    out_l = np.full((q.shape[0], k), -1, np.int64)
+    for i in range(q.shape[0]):
+        order = np.argsort(-scores[i], kind="stable")[:k]
+        out_s[i, :len(order)] = scores[i][order]
+        out_l[i, :len(order)] = np.asarray(ids)[order]
+    return out_s, out_l
+
+
 def config_json(model: str, embedding_dim: int, global_limit: Optional[float] = None) -> str:
     """config.json as written by the reference (VectorDBInt8.py:54-56, VectorDBInt8Global.py:62-69)."""
     cfg = {"version": "1.0", "model": model, "embedding_dim": embedding_dim}

@@ -59,7 +59,8 @@ if what in ("dense", "stream"):
     n = int(os.environ.get("PROF_ROWS", 100_000_000))
     ix = build(n, False)
     kk = 1000
-    for nq in ((1024,) if what == "dense" else (1, 2, 3, 16, 64, 128)):
+    nqs = [int(v) for v in os.environ["PROF_NQS"].split(",")] if os.environ.get("PROF_NQS") else None
+    for nq in (nqs or ((1024,) if what == "dense" else (1, 2, 3, 16, 64, 128))):
         _, qb = queries(nq)
         dist = torch.empty((nq, kk), dtype=torch.int32, device=dev)
         lab = torch.empty((nq, kk), dtype=torch.int64, device=dev)

@@ -175,8 +175,23 @@ def copy_fixture_dbs():
         print("copied", db, sum(os.path.getsize(os.path.join(r, x)) for r, _, fs in os.walk(dst) for x in fs), "bytes")
 
 
+def float_index_header():
+    """Header bytes, size and the first / last stored values of the reference's committed float index (db_cohere_float):
+    pins the oracle's restatement of faiss's IndexIDMap(IndexFlatIP) file layout."""
+    b = open(f"{REF}/db_cohere_float/index.faiss", "rb").read()
+    d, nt = struct.unpack_from("<iq", b, 4)
+    rows = np.frombuffer(b, np.float32, nt * d, 82).reshape(nt, d)
+    ids = np.frombuffer(b, np.int64, nt, 82 + 4 * nt * d + 8)
+    out = {"header_hex": b[:82].hex(), "size": len(b), "d": d, "ntotal": nt, "config_json": open(f"{REF}/db_cohere_float/config.json").read(),
+           "row0_first8": rows[0, :8].tolist(), "rowlast_last8": rows[-1, -8:].tolist(), "ids_first": int(ids[0]), "ids_last": int(ids[-1]),
+           "ids_are_arange": bool(np.array_equal(ids, np.arange(nt))), "sha256": hashlib.sha256(b).hexdigest()}
+    json.dump(out, open(os.path.join(OUT, "float_index_header.json"), "w"), indent=1)
+    print("float index header", out["size"], out["d"], out["ntotal"])
+
+
 def main():
     copy_fixture_dbs()
+    float_index_header()
     rows = {}
     dbs = ["db_int8", "db_int8_global", "db_int4", "db_int4_global", "db_int16", "db_int16_global",
            "db_cohere_int8", "db_cohere_enhanced"]

@@ -321,3 +321,41 @@ def test_remove_and_readd_without_float_rows(tmp_path):
     assert len(db2) == 50 and db2.index.position_of(3) == 49
     db2.remove_document(4)
     assert len(db2) == 49 and "4" not in db2.doc_db
+
+
+def test_cohere_float_class(tmp_path):
+    """CohereVectorDBFloat: float32 rows, brute-force inner-product top-k (faiss IndexIDMap(IndexFlatIP)), index.faiss bytes."""
+    import vectorragquantization_b200 as V
+    from vectorragquantization_b200.embedder import text_row
+    folder = os.path.join(tmp_path, "flt")
+    db = V.CohereVectorDBFloat(folder)
+    db.add_documents(IDS, DOCS, batch_size=64)
+    assert len(db) == len(DOCS)
+    assert open(os.path.join(folder, "config.json")).read() == json.dumps({"model": "embed-english-v3.0", "embedding_dim": 1024})
+    x = np.stack([oc.synth_f32(1, text_row(t), 1)[0] for t in DOCS])
+    assert open(os.path.join(folder, "index.faiss"), "rb").read() == o.write_index_float_bytes(1024, x, np.array(IDS))
+    qf = oc.synth_f32(1, text_row(QUERY), 1)[0]
+    for k in (10, 100, 700):
+        rs, rl = o.search_ip(x, np.array(IDS), qf, k)
+        res = db.search(QUERY, k=k)
+        got_s = np.array([r["score"] for r in res])
+        assert len(res) == min(k, len(DOCS))
+        assert np.all(np.abs(got_s - rs[0][:len(res)]) <= 1e-5 * np.abs(rs[0][:len(res)]) + 1e-7)
+        sep = np.abs(np.diff(rs[0][:len(res)])) > 1e-5  # ranks are only defined where neighbouring scores are apart
+        same = np.array([r["doc_id"] for r in res]) == rl[0][:len(res)]
+        assert np.all(same[:-1][sep] | ~sep[:len(same) - 1]) or np.mean(same) > 0.98
+        assert all(r["doc"] == DOCS[r["doc_id"]] for r in res)
+    # batch of queries incl. more than one pass of 8, and k > ntotal padding
+    Q = np.stack([oc.synth_f32(3, i, 1)[0] for i in range(19)])
+    s, l = db.search_batch(Q, 5)
+    rs, rl = o.search_ip(x, np.array(IDS), Q, 5)
+    assert np.allclose(s, rs, rtol=1e-5, atol=1e-7) and np.mean(l == rl) > 0.98
+    db.remove_document(rl[0][0])
+    assert db.search_batch(Q[:1], 1)[1][0, 0] != rl[0][0]
+    db2 = V.CohereVectorDBFloat(folder)
+    assert len(db2) == len(DOCS) - 1
+    assert [h["doc_id"] for h in db2.search(QUERY, k=10)] == [h["doc_id"] for h in db.search(QUERY, k=10)]
+    small = V.CohereVectorDBFloat(os.path.join(tmp_path, "small"))
+    small.add_documents(IDS[:3], DOCS[:3])
+    assert len(small.search(QUERY, k=10)) == 3
+    assert V.CohereVectorDBFloat(os.path.join(tmp_path, "empty")).search(QUERY) == []

@@ -211,10 +211,11 @@ def test_few_queries_ties_and_sorted_database(V, monkeypatch):
     assert np.array_equal(dist, rd) and np.array_equal(labels, rp)
 
 
-# ---- 33 .. 96 queries per pass: the same swapped-operand kernel with thresholds in shared memory -------------------------
+# ---- 33 .. 96 queries per pass: the same swapped-operand kernel with thresholds in shared memory (opt-in: VRQ_MMA_MID=1) ----
 @pytest.mark.parametrize("n,nq", [(1, 33), (127, 48), (129, 50), (5000, 64), (40000, 96), (300001, 81)])
 def test_mid_queries_distance_matrix_exact(V, monkeypatch, n, nq):
     set_env(monkeypatch, "default")
+    monkeypatch.setenv("VRQ_MMA_MID", "1")
     rng = np.random.default_rng(n * 79 + nq)
     codes = rng.integers(0, 256, (n, 128), dtype=np.uint8)
     q = rng.integers(0, 256, (nq, 128), dtype=np.uint8)
@@ -229,6 +230,7 @@ def test_mid_queries_distance_matrix_exact(V, monkeypatch, n, nq):
 @pytest.mark.parametrize("nq", [33, 64, 96])
 def test_mid_queries_topk_matches_oracle(V, monkeypatch, env, nq):
     set_env(monkeypatch, env)
+    monkeypatch.setenv("VRQ_MMA_MID", "1")
     n = 2_000_000
     codes, _ = oc.synth_codes_int8(61, 0, n, want_int8=False)
     q = o.synth_ubinary_from_f32(oc.synth_f32(62, 0, nq))
@@ -246,6 +248,7 @@ def test_mid_queries_topk_matches_oracle(V, monkeypatch, env, nq):
 
 def test_mid_queries_ties_and_sorted_database(V, monkeypatch):
     set_env(monkeypatch, "default")
+    monkeypatch.setenv("VRQ_MMA_MID", "1")
     rng = np.random.default_rng(44)
     n = 500000
     base = rng.integers(0, 256, (16, 128), dtype=np.uint8)

@@ -255,3 +255,14 @@ def test_live_reference_static_methods():
         assert np.array_equal(M8G._quantize_to_int8(x[r], 0.07), o.quantize_int8_global(x[r], 0.07))
         assert np.array_equal(M16G._quantize_to_int16(x[r], 0.07), o.quantize_int16_global(x[r], 0.07))
         assert np.array_equal(M4._quantize_to_int4(x[r])[0], p4[r])
+
+
+def test_float_index_file_layout_matches_reference_artefact():
+    """KAT: the oracle's IndexIDMap(IndexFlatIP) writer reproduces the header and size of the reference's committed
+    db_cohere_float/index.faiss (1000 x 1024 float32 rows, ids 0..999)."""
+    import json
+    h = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "float_index_header.json")))
+    x = np.zeros((h["ntotal"], h["d"]), np.float32)
+    b = o.write_index_float_bytes(h["d"], x, np.arange(h["ntotal"]))
+    assert b[:82].hex() == h["header_hex"] and len(b) == h["size"] and h["ids_are_arange"]
+    assert h["config_json"] == json.dumps({"model": "embed-english-v3.0", "embedding_dim": 1024})

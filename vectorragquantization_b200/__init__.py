@@ -6,7 +6,7 @@ There is no CPU fallback: without the built library or without a GPU the first k
 """
 from ._lib import Context, VrqError, default_context  # noqa: F401
 from .binary_index import (BinaryIndex, IndexBinaryFlat, IndexBinaryIDMap2, read_index_binary,  # noqa: F401
-                           write_index_binary)
+                           read_index_float, write_index_binary, write_index_float)
 
 __version__ = "0.1.0"
 from .cohere_enhanced import CohereEnhancedVectorDB  # noqa: F401,E402
@@ -14,4 +14,4 @@ from .docstore import DocStore, Rdict  # noqa: F401,E402
 from .embedder import SyntheticCohereEmbedder, SyntheticEmbedder  # noqa: F401,E402
 from .vectordb import (VectorDBInt4, VectorDBInt4Global, VectorDBInt8, VectorDBInt8Global, VectorDBInt16,  # noqa: F401,E402
                        VectorDBInt16Global)
-from .cohere_variants import CohereVectorDBBinary, CohereVectorDBInt8  # noqa: F401,E402
+from .cohere_variants import CohereVectorDBBinary, CohereVectorDBFloat, CohereVectorDBInt8  # noqa: F401,E402

@@ -87,10 +87,20 @@ SIGNATURES = {
     "vrq_index_write_rows": (_i32, [_vp, _i32, _i64, _i64, _vp]),
     "vrq_index_get_payload": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "vrq_index_position_of": (_i64, [_vp, _i64]),
+    "vrq_index_search_ip": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
+    "vrq_index_write_float": (_i32, [_vp, C.c_char_p]),
+    "vrq_index_read_float": (_i32, [_vp, C.c_char_p, C.POINTER(_vp)]),
     "vrq_index_search3": (_i32, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vrq_index_search2": (_i32, [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "vrq_index_search3_local": (_i32, [_vp, _i64, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "vrq_merge3": (_i32, [_vp, _i32, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "vrq_nccl_unique_id": (_i32, [_vp]),
+    "vrq_nccl_init_rank": (_i32, [_i32, _i32, _vp, _i32, C.POINTER(_vp)]),
+    "vrq_nccl_init_all": (_i32, [_i32, _vp, _vp]),
+    "vrq_nccl_destroy": (_i32, [_vp]),
+    "vrq_ctx_set_nccl": (_i32, [_vp, _vp, _i32, _i32]),
+    "vrq_index_search3_sharded": (_i32, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "vrq_search3_sharded_group": (_i32, [_i32, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "vrq_rescore_binary": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp]),
     "vrq_rescore_int8cos": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp]),
     "vrq_synth_f32": (_i32, [_vp, _u64, _i64, _i64, _i32, _i32, _vp]),

@@ -202,6 +202,27 @@ class BinaryIndex:
                                             L.ptr(score), L.ptr(cnt)))
         return labels, score, cnt
 
+    def search_ip(self, q_float, k: int):
+        """``faiss.IndexFlatIP.search`` on the float32 payload rows (CohereVectorDBFloat.py:156): (scores f32[nq,k] descending,
+        labels i64[nq,k]); padded with (-inf, -1)."""
+        qf = np.ascontiguousarray(q_float, np.float32)
+        if qf.ndim == 1:
+            qf = qf[None]
+        if qf.shape[1] != self.d:
+            raise ValueError("q_float must be float32[nq, d]")
+        scores = np.empty((qf.shape[0], k), np.float32)
+        labels = np.empty((qf.shape[0], k), np.int64)
+        L.check(self._lib.vrq_index_search_ip(self._h, qf.shape[0], L.ptr(qf), int(k), L.ptr(scores), L.ptr(labels)))
+        return scores, labels
+
+    def add_float_rows(self, x, ids) -> None:
+        """``IndexIDMap(IndexFlatIP).add_with_ids`` (CohereVectorDBFloat.py:133): float32 rows only, no binary codes."""
+        x = np.ascontiguousarray(x, np.float32)
+        ids = np.ascontiguousarray(ids, np.int64).reshape(-1)
+        if x.ndim != 2 or x.shape != (ids.shape[0], self.d):
+            raise ValueError("x must be float32[n, d] and ids int64[n]")
+        L.check(self._lib.vrq_index_add_with_ids(self._h, x.shape[0], None, L.ptr(ids), L.ptr(x), None))
+
     def search3_local_into(self, q_float_dev, q_ubin_dev, nq: int, binary_k: int, pos_base: int, keys, labels, sbin, scos):
         """Device-pointer, asynchronous: per-shard candidates for the multi-GPU path (sharded.py)."""
         L.check(self._lib.vrq_index_search3_local(self._h, int(nq), L.ptr(q_float_dev), L.ptr(q_ubin_dev), int(binary_k),
@@ -227,6 +248,19 @@ def IndexBinaryIDMap2(inner, **kw) -> BinaryIndex:
 def write_index_binary(index: BinaryIndex, path: str) -> None:
     """``faiss.write_index_binary`` (CohereEnhancedVectorDB.py:346): byte-compatible file."""
     L.check(index._lib.vrq_index_write(index._h, str(path).encode()))
+
+
+def write_index_float(index: BinaryIndex, path: str) -> None:
+    """``faiss.write_index`` of ``IndexIDMap(IndexFlatIP)`` (CohereVectorDBFloat.py:184): byte-compatible "IxMp"/"IxFI" file."""
+    L.check(index._lib.vrq_index_write_float(index._h, str(path).encode()))
+
+
+def read_index_float(path: str, ctx: Optional[L.Context] = None) -> BinaryIndex:
+    """``faiss.read_index`` of that file (CohereVectorDBFloat.py:58)."""
+    ctx = ctx if ctx is not None else L.default_context()
+    h = C.c_void_p()
+    L.check(L.load().vrq_index_read_float(ctx.handle, str(path).encode(), C.byref(h)))
+    return BinaryIndex(0, ctx=ctx, _handle=h)
 
 
 def read_index_binary(path: str, ctx: Optional[L.Context] = None) -> BinaryIndex:

@@ -150,3 +150,140 @@ class CohereVectorDBBinary(_VectorDBBase):
 
     def _result_entry(self, x, payload, aux, ub):
         return {"float": x, "packed_binary": ub}
+
+
+class CohereVectorDBFloat:
+    """``CohereVectorDBFloat`` (CohereVectorDBFloat.py): float32 Cohere embeddings in ``faiss.IndexIDMap(faiss.IndexFlatIP)``,
+    brute-force inner-product search - the recall yardstick the quantised classes are compared with (main.py:289-331).
+    Same constructor, ``add_documents`` / ``search`` / ``remove_document`` / ``save`` / ``len``, ``config.json`` (no
+    "version" key, :48) and ``index.faiss`` bytes as the reference; the rows live in HBM and ``search`` is two kernels
+    (float_ip.cu).  Embeddings come from an injectable ``embedder(texts, input_type, ["float"]) -> {"float": rows}``
+    (default: the synthetic Cohere-like generator; ``embedder="http"`` is the reference's Cohere call)."""
+
+    def __init__(self, folder: str, model: str = "embed-english-v3.0", embedding_dim: int = 1024, rdict_options=None,
+                 embedder: Optional[Callable] = None, ctx=None):
+        import json
+        import os
+
+        from .binary_index import BinaryIndex, read_index_float
+        from .docstore import DocStore
+        self.embedding_dim, self.folder, self.model = embedding_dim, folder, model
+        self.endpoint = os.environ.get("COHERE_EMBED_ENDPOINT")
+        self.api_key = os.environ.get("COHERE_EMBED_KEY")
+        self._ctx = ctx if ctx is not None else L.default_context()
+        if embedder == "http":
+            from .embedder import CohereHttpEmbedder
+            ep = self.endpoint if not self.endpoint or "/v2/embed" in self.endpoint else self.endpoint.rstrip("/") + "/v2/embed"
+            embedder = CohereHttpEmbedder(ep, self.api_key, model)
+        elif embedder is None:
+            from .embedder import SyntheticCohereEmbedder, warn_synthetic
+            warn_synthetic(type(self).__name__, "COHERE_EMBED_ENDPOINT / COHERE_EMBED_KEY")
+            embedder = SyntheticCohereEmbedder(embedding_dim, ctx=self._ctx)
+        self._embedder = embedder
+        config_path = os.path.join(folder, "config.json")
+        if not os.path.exists(config_path):
+            if os.path.exists(folder) and os.listdir(folder):
+                raise Exception(f"Folder {folder} not empty but no config.json found. "
+                                "To create new DB, folder must be empty or have config.json.")
+            os.makedirs(folder, exist_ok=True)
+            self.config = {"model": model, "embedding_dim": embedding_dim}
+            with open(config_path, "w") as f:
+                json.dump(self.config, f)
+        else:
+            with open(config_path, "r") as f:
+                self.config = json.load(f)
+        path = os.path.join(folder, "index.faiss")
+        if os.path.exists(path):
+            self.index = read_index_float(path, ctx=self._ctx)
+            logger.info("Existing float FAISS index loaded.")
+        else:
+            self.index = BinaryIndex(embedding_dim, ctx=self._ctx, payload_kind=L.PAYLOAD_F32)
+            logger.info(f"New float FAISS index created (dim={embedding_dim}).")
+        self.doc_db = DocStore(os.path.join(folder, "docs"), rdict_options)
+        self.doc_db.imported_raw = None
+
+    def _generate_float_embeddings(self, texts: List[str], input_type: str) -> Dict[str, np.ndarray]:
+        """:66-104 - {} on failure; rows of the wrong width are skipped with a warning."""
+        try:
+            rows = self._embedder(list(texts), input_type, ["float"])["float"]
+        except Exception as e:
+            logger.error(f"Float embedding request failed: {e}")
+            return {}
+        out = {}
+        for i, txt in enumerate(texts):
+            emb = np.asarray(rows[i], dtype=np.float32)
+            if emb.ndim > 1:
+                emb = emb[0]
+            if emb.shape[0] != self.embedding_dim:
+                logger.warning(f"Dimension mismatch for text '{txt}': got {emb.shape[0]}, want {self.embedding_dim}")
+                continue
+            out[txt] = emb
+        return out
+
+    def add_documents(self, doc_ids: List[int], docs: List[str], batch_size: int = 64, save: bool = True):
+        if len(doc_ids) != len(docs):
+            raise ValueError("doc_ids and docs must match length.")
+        for doc_id in doc_ids:
+            if str(doc_id) in self.doc_db:
+                self.remove_document(doc_id, save=False)
+        with _Progress(len(docs), "Indexing docs (Float)") as pbar:
+            for start in range(0, len(docs), batch_size):
+                batch_ids, batch_txts = doc_ids[start:start + batch_size], docs[start:start + batch_size]
+                emb_map = self._generate_float_embeddings(batch_txts, input_type="search_document")
+                pairs = [(i, t) for i, t in zip(batch_ids, batch_txts) if t in emb_map]
+                if pairs:
+                    self.index.add_float_rows(np.vstack([emb_map[t] for _, t in pairs]), np.array([i for i, _ in pairs], dtype=np.int64))
+                    self.doc_db.set_many((str(i), {"doc": t}) for i, t in pairs)
+                pbar.update(len(batch_txts))
+        if save:
+            self.save()
+
+    def add_embeddings(self, doc_ids, x: np.ndarray, docs=None, save: bool = False):
+        """Bulk path: precomputed float32 rows [n, D]."""
+        for doc_id in doc_ids:
+            if str(doc_id) in self.doc_db:
+                self.remove_document(doc_id, save=False)
+        self.index.add_float_rows(x, np.asarray(doc_ids, dtype=np.int64))
+        self.doc_db.set_many((str(i), {"doc": docs[j] if docs is not None else ""}) for j, i in enumerate(doc_ids))
+        if save:
+            self.save()
+
+    def search(self, query: str, k: int = 10) -> List[Dict]:
+        """:142-172 - dot-product search; results sorted by score descending."""
+        if self.index.ntotal == 0:
+            logger.warning("No docs in index, add documents first.")
+            return []
+        emb_map = self._generate_float_embeddings([query], input_type="search_query")
+        if not emb_map or query not in emb_map:
+            logger.error("Query embedding generation failed.")
+            return []
+        scores, ids = self.index.search_ip(emb_map[query].reshape(1, -1), k)
+        results = []
+        for dist, did in zip(scores[0], ids[0]):
+            if did == -1:
+                continue
+            results.append({"doc_id": did, "score": float(dist), "doc": self.doc_db.get(str(did), {}).get("doc", "N/A")})
+        results.sort(key=lambda x: x["score"], reverse=True)
+        return results
+
+    def search_batch(self, q_float: np.ndarray, k: int = 10):
+        """(scores f32[nq,k] descending, doc ids i64[nq,k])."""
+        return self.index.search_ip(q_float, k)
+
+    def remove_document(self, doc_id: int, save: bool = True):
+        doc_id_str = str(doc_id)
+        if doc_id_str in self.doc_db:
+            self.index.remove_ids(np.array([doc_id], dtype=np.int64))
+            del self.doc_db[doc_id_str]
+        if save:
+            self.save()
+
+    def save(self):
+        import os
+
+        from .binary_index import write_index_float
+        write_index_float(self.index, os.path.join(self.folder, "index.faiss"))
+        logger.info("Float FAISS index saved to disk.")
+
+    def __len__(self):
+        return self.index.ntotal

@@ -280,6 +280,12 @@ extern "C" int vrq_index_create(vrq_ctx* ctx, int d, vrq_index** out) {
     return 0;
 }
 
+int vrq_index_ctx(vrq_index* ix, vrq_ctx** out) {
+    VRQ_CHECK_ARG(ix != nullptr && out != nullptr, "null argument");
+    *out = ix->ctx;
+    return 0;
+}
+
 extern "C" int vrq_index_free(vrq_index* ix) {
     if (!ix) return 0;
     cudaSetDevice(ix->ctx->device);
@@ -355,7 +361,9 @@ extern "C" int vrq_index_add_with_ids(vrq_index* ix, int64_t n, const uint8_t* c
     }
     if (ix) VRQ_TRY(flush_dead(ix));
     if (n == 0) return 0;
-    VRQ_CHECK_ARG(codes != nullptr && ids != nullptr, "codes / ids are null");
+    VRQ_CHECK_ARG(ids != nullptr, "ids are null");
+    // codes may be NULL only for a float32-payload index that is searched by inner product alone (CohereVectorDBFloat): zero codes
+    VRQ_CHECK_ARG(codes != nullptr || ix->payload_kind == VRQ_PAYLOAD_F32, "codes are null");
     VRQ_CHECK_ARG((ix->payload_row == 0) == (payload == nullptr), "payload must be given exactly when a payload kind is set");
     VRQ_CHECK_ARG((ix->aux_row == 0) == (aux == nullptr), "aux (min,max pairs) must be given exactly for the per-document kinds");
     const void* all[4] = {codes, ids, payload, aux};
@@ -367,7 +375,10 @@ extern "C" int vrq_index_add_with_ids(vrq_index* ix, int64_t n, const uint8_t* c
     if (!ix->ids) VRQ_CUDA(cudaMalloc((void**)&ix->ids, sizeof(int64_t) * (size_t)ix->capacity));
     cudaStream_t st = ix->ctx->stream;
     const cudaMemcpyKind kind = is_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    VRQ_CUDA(cudaMemcpyAsync(ix->codes + (size_t)ix->ntotal * ix->code_bytes, codes, (size_t)n * ix->code_bytes, kind, st));
+    if (codes)
+        VRQ_CUDA(cudaMemcpyAsync(ix->codes + (size_t)ix->ntotal * ix->code_bytes, codes, (size_t)n * ix->code_bytes, kind, st));
+    else
+        VRQ_CUDA(cudaMemsetAsync(ix->codes + (size_t)ix->ntotal * ix->code_bytes, 0, (size_t)n * ix->code_bytes, st));
     VRQ_CUDA(cudaMemcpyAsync(ix->ids + ix->ntotal, ids, sizeof(int64_t) * (size_t)n, kind, st));
     if (payload) VRQ_CUDA(cudaMemcpyAsync(ix->payload + (size_t)ix->ntotal * ix->payload_row, payload, (size_t)n * ix->payload_row, kind, st));
     if (aux) VRQ_CUDA(cudaMemcpyAsync(ix->aux + (size_t)ix->ntotal * ix->aux_row, aux, (size_t)n * ix->aux_row, kind, st));
@@ -899,6 +910,127 @@ extern "C" int vrq_index_read_payload(vrq_index* ix, const char* path) {
     if (r == 0) r = stream_in(ix->ctx, f, ix->aux, ix->aux_row * (size_t)ix->ntotal, pb, path);
     fclose(f);
     return r;
+}
+
+// ---- float32 inner-product index: faiss.IndexIDMap(faiss.IndexFlatIP(d)) of CohereVectorDBFloat.py ----------------------------
+extern "C" int vrq_index_search_ip(vrq_index* ix, int64_t nq, const float* q_float, int k, float* scores, int64_t* labels) {
+    VRQ_CHECK_ARG(ix != nullptr && nq >= 0, "bad argument");
+    VRQ_TRY(flush_dead(ix));
+    if (nq == 0) return 0;
+    VRQ_CHECK_ARG(q_float && scores && labels, "null pointer");
+    if (ix->payload_kind != VRQ_PAYLOAD_F32) {
+        vrq_set_error("search_ip needs an index with the F32 payload (float32 rows)");
+        return VRQ_ERR_STATE;
+    }
+    const void* all[3] = {q_float, scores, labels};
+    bool is_dev;
+    VRQ_TRY(vrq_space_of(all, 3, &is_dev));
+    vrq_ctx* ctx = ix->ctx;
+    VRQ_CUDA(cudaSetDevice(ctx->device));
+    DevIO io{ctx, !is_dev, {}};
+    const void* dq;
+    void *ds, *dl;
+    VRQ_TRY(io.in(q_float, sizeof(float) * (size_t)nq * ix->d, VRQ_WS_QUERY_A, &dq));
+    VRQ_TRY(io.out(scores, sizeof(float) * (size_t)nq * k, VRQ_WS_OUT_A, &ds));
+    VRQ_TRY(io.out(labels, sizeof(int64_t) * (size_t)nq * k, VRQ_WS_OUT_B, &dl));
+    VRQ_TRY(vrq_launch_ip_topk(ctx, (const float*)ix->payload, ix->ntotal, ix->d, (const float*)dq, nq, k, ix->implicit_ids ? nullptr : ix->ids,
+                               ix->id0, (float*)ds, (int64_t*)dl, ctx->stream));
+    return io.finish();
+}
+
+// faiss.write_index / read_index of IndexIDMap(IndexFlatIP) (CohereVectorDBFloat.py:184,58): "IxMp" header, "IxFI" header,
+// u64 count + float32 rows, u64 count + int64 ids; headers = {d i32, ntotal i64, 1 << 20, 1 << 20, is_trained u8, metric i32 = 0}.
+extern "C" int vrq_index_write_float(vrq_index* ix, const char* path) {
+    VRQ_CHECK_ARG(ix != nullptr && path != nullptr, "null argument");
+    VRQ_TRY(flush_dead(ix));
+    if (ix->payload_kind != VRQ_PAYLOAD_F32) {
+        vrq_set_error("write_float needs an index with the F32 payload");
+        return VRQ_ERR_STATE;
+    }
+    VRQ_CUDA(cudaSetDevice(ix->ctx->device));
+    VRQ_TRY(materialise_ids(ix));
+    AtomicFile af;
+    VRQ_TRY(af.open(path));
+    auto hdr = [&](const char* fourcc) -> bool {
+        int32_t d = ix->d, metric = 0;
+        int64_t nt = ix->ntotal, dummy = 1 << 20;
+        uint8_t trained = 1;
+        return af.put(fourcc, 4) && af.put(&d, 4) && af.put(&nt, 8) && af.put(&dummy, 8) && af.put(&dummy, 8) && af.put(&trained, 1) &&
+               af.put(&metric, 4);
+    };
+    const uint64_t nfl = (uint64_t)ix->ntotal * ix->d, nids = (uint64_t)ix->ntotal;
+    if (!hdr("IxMp") || !hdr("IxFI") || !af.put(&nfl, 8)) return af.fail("short write");
+    PinnedBounce pb;
+    VRQ_TRY(stream_out(ix, af, ix->payload, (size_t)nfl * 4, pb));
+    if (!af.put(&nids, 8)) return af.fail("short write");
+    if (nids) VRQ_TRY(stream_out(ix, af, (const uint8_t*)ix->ids, (size_t)nids * 8, pb));
+    return af.commit();
+}
+
+extern "C" int vrq_index_read_float(vrq_ctx* ctx, const char* path, vrq_index** out) {
+    VRQ_CHECK_ARG(ctx != nullptr && path != nullptr && out != nullptr, "null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) {
+        vrq_set_error("cannot open %s", path);
+        return VRQ_ERR_IO;
+    }
+    vrq_index* ix = nullptr;
+    auto fail = [&](const char* why) {
+        fclose(f);
+        if (ix) vrq_index_free(ix);
+        vrq_set_error("%s: %s", path, why);
+        return VRQ_ERR_IO;
+    };
+    struct H {
+        char cc[4];
+        int32_t d;
+        int64_t nt, a, b;
+        uint8_t trained;
+        int32_t metric;
+    };
+    auto rd = [&](H* h) -> bool {
+        return fread(h->cc, 1, 4, f) == 4 && fread(&h->d, 4, 1, f) == 1 && fread(&h->nt, 8, 1, f) == 1 && fread(&h->a, 8, 1, f) == 1 &&
+               fread(&h->b, 8, 1, f) == 1 && fread(&h->trained, 1, 1, f) == 1 && fread(&h->metric, 4, 1, f) == 1;
+    };
+    H h1, h2;
+    if (!rd(&h1) || memcmp(h1.cc, "IxMp", 4) != 0) return fail("not an IndexIDMap file (fourcc IxMp expected)");
+    if (!rd(&h2) || memcmp(h2.cc, "IxFI", 4) != 0) return fail("inner index is not IndexFlatIP (fourcc IxFI expected)");
+    if (h2.d <= 0 || h2.d % 8 != 0 || h2.nt < 0 || h2.metric != 0) return fail("unsupported header (d % 8 == 0 and the inner-product metric are required)");
+    uint64_t nfl = 0;
+    if (fread(&nfl, 8, 1, f) != 1 || nfl != (uint64_t)h2.nt * h2.d) return fail("vector array size mismatch");
+    const int64_t fsz = file_size(f);
+    if (fsz >= 0 && (uint64_t)fsz != 74 + 8 + 4 * nfl + 8 + 8 * (uint64_t)h2.nt) return fail("file size does not match its header");
+    int r = vrq_index_create(ctx, h2.d, &ix);
+    if (r == 0) r = vrq_index_set_payload(ix, VRQ_PAYLOAD_F32, 0.0);
+    if (r != 0) {
+        fclose(f);
+        if (ix) vrq_index_free(ix);
+        return r;
+    }
+    r = cudaSetDevice(ctx->device) == cudaSuccess ? 0 : VRQ_ERR_STATE;
+    if (r == 0 && h2.nt > 0) r = ensure_capacity(ix, h2.nt);
+    if (r == 0 && h2.nt > 0 && cudaMemsetAsync(ix->codes, 0, (size_t)h2.nt * ix->code_bytes, ctx->stream) != cudaSuccess) r = VRQ_ERR_STATE;
+    PinnedBounce pb;
+    if (r == 0) r = stream_in(ctx, f, ix->payload, (size_t)nfl * 4, pb, path);
+    uint64_t nids = 0;
+    if (r == 0 && (fread(&nids, 8, 1, f) != 1 || nids != (uint64_t)h2.nt)) return fail("id map size mismatch");
+    if (r == 0 && h2.nt > 0) {
+        ix->implicit_ids = false;
+        if (cudaMalloc((void**)&ix->ids, sizeof(int64_t) * (size_t)ix->capacity) != cudaSuccess) {
+            cudaGetLastError();
+            vrq_set_error("cudaMalloc of the id map failed");
+            r = VRQ_ERR_NOMEM;
+        }
+        if (r == 0) r = stream_in(ctx, f, (uint8_t*)ix->ids, (size_t)nids * 8, pb, path);
+    }
+    fclose(f);
+    if (r != 0) {
+        vrq_index_free(ix);
+        return r;
+    }
+    ix->ntotal = h2.nt;
+    *out = ix;
+    return 0;
 }
 
 // ---- fused searches ---------------------------------------------------------------------------------------------------

@@ -429,7 +429,8 @@ __global__ void verify_counts_kernel(const int* __restrict__ counts, int strips,
 }
 
 // List-free sample pass (scan_mma.cu): tau[q] = the k'-th smallest of the distances the epilogue threads kept for query q
-// (strips x 2 threads x 32 values, 0xFFFF = none); "no threshold" when the sample held fewer than k' rows for the query.
+// (strips x 2 threads x 4 values, 0xFFFF = none) - the largest one kept when there are fewer than k', "no threshold" when
+// there are none.
 __global__ void __launch_bounds__(128) sample_tau_kernel(const unsigned short* __restrict__ sample, int strips, int nq, int kp, int* __restrict__ tau) {
     __shared__ int hist[4][1026];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -438,9 +439,9 @@ __global__ void __launch_bounds__(128) sample_tau_kernel(const unsigned short* _
     __syncwarp();
     if (q < nq) {
         for (int s = 0; s < strips; s++) {
-            const unsigned short* src = sample + ((size_t)s * nq + q) * 64;
-            for (int i = lane; i < 64; i += 32) {
-                const int v = src[i];
+            const unsigned short* src = sample + ((size_t)s * nq + q) * 8;
+            if (lane < 8) {
+                const int v = src[lane];
                 if (v <= 1024) atomicAdd(&hist[warp][v], 1);
             }
         }
@@ -449,10 +450,10 @@ __global__ void __launch_bounds__(128) sample_tau_kernel(const unsigned short* _
     if (q < nq && lane == 0) {
         int acc = 0, t = 0x7fffffff;
         for (int d = 0; d <= 1024; d++) {
-            acc += hist[warp][d];
-            if (acc >= kp) {
-                t = d;
-                break;
+            if (hist[warp][d]) {
+                acc += hist[warp][d];
+                t = d;  // the largest kept distance so far: the answer when fewer than kp were kept
+                if (acc >= kp) break;
             }
         }
         tau[q] = t;
@@ -755,10 +756,10 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
             s_pl.mp.group_tiles = 2;
             // the 128-query-tile kernel keeps the k' smallest distances per epilogue thread instead of lists (no flooding, no
             // compaction: 0.83 -> ~0.1 ms at 100 M rows); the few-queries kernels (lane = database row) keep the list form
-            const bool list_free = !s_pl.mp.few && kp <= 32 && env_int("VRQ_MMA_SAMPLE_LISTS", 0) == 0;
+            const bool list_free = !s_pl.mp.few && env_int("VRQ_MMA_SAMPLE_LISTS", 0) == 0;
             if (list_free) {
                 void* so_v;
-                VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_SAMPLE_D, sizeof(unsigned short) * (size_t)s_pl.strips() * nq * 64, &so_v));
+                VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_SAMPLE_D, sizeof(unsigned short) * (size_t)s_pl.strips() * nq * 8, &so_v));
                 sp.sample_out = (unsigned short*)so_v;
             }
             VRQ_TRY(launch_pass(ctx, tma, tmap, tmap_mma, sp, s_pl, st));

@@ -54,7 +54,7 @@ struct ScanParams {
     int64_t dbg_stride;
     const unsigned long long* key_lo;  // [nq] or null: only keys STRICTLY GREATER than key_lo[q] are candidates (the next chunk of a
                                        // top-k larger than one pass can hold: vrq_hamming_topk_dev walks the ranking in chunks)
-    unsigned short* sample_out;  // tensor-core 128-query-tile kernel, sample pass with k <= 32: [strip][nq][2][32] smallest distances
+    unsigned short* sample_out;  // tensor-core 128-query-tile kernel, list-free sample pass: [strip][nq][2][4] smallest distances
                                  // seen by each epilogue thread (0xFFFF = none); no lists are written (scan_mma.cu)
     int seg_cols, seg_full, seg_tail;  // tensor-core pair kernel, 1-D grid of clusters: query-tile pairs, full strips per pair column,
                                        // clusters that share the tail strip (scan_mma.cu); seg_cols == 0: classic (query tile, strip) grid

@@ -53,7 +53,7 @@ constexpr uint32_t TMEM_COLS = 512, TMEM_A_COL = 0, TMEM_D_COL = 256;
 constexpr uint32_t TMEM_SFA_COL = 128, TMEM_SFB_COL = 160, TMEM_SF_COLS = 32;  // F4 only: block scales, all 1.0 (UE8M0 0x7F)
 constexpr int B_STAGES = 8, MAX_RAW_STAGES = 4;
 constexpr int BAR_WARP0 = 2;  // named barriers 2..9: one per epilogue warp (list compaction)
-constexpr int SAMPLE_KEEP = 32;  // largest k' the list-free sample pass supports
+constexpr int SAMPLE_KEEP = 4;  // distances each epilogue thread keeps in the list-free sample pass
 
 // instruction descriptor (bit layout of cute::UMMA::InstrDescriptor): D = s32 (bits 4-5 = 2), A = B = signed 8 bit (bits
 // 7-9, 10-12 = 1), both K-major, N >> 3 in bits 17-22, M >> 4 in bits 24-28
@@ -195,13 +195,14 @@ struct MmaSmem {
     int tau_s[MQ];
     int cnt_s[MQ];
     SelectScratch sc[EPI_WARPS];  // one radix-select scratch per epilogue warp
-    unsigned short sample_d[SAMPLE_KEEP][EPI_THREADS];  // sample pass: the SAMPLE_KEEP smallest distances of each epilogue thread
 };
 
 // CG = 1: one CTA per 128-query tile.  CG = 2 (e2m1 only): a CTA pair shares every tile of database rows - each CTA
 // holds its own 128 queries in TMEM, loads and expands HALF of the tile's rows (64), the leader CTA issues
 // tcgen05.mma.cta_group::2 (M = 256, N = 128) which reads both halves; per SM the shared-memory traffic per tile halves.
-template <int KIND, int CG>
+// SAMP = true: the list-free sample pass (thresholds only) - a separate instantiation, so that none of its code sits in the
+// dense pass's epilogue.
+template <int KIND, int CG, bool SAMP>
 __global__ void __launch_bounds__(MMA_KERNEL_THREADS, 1)
 hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, int raw_stages) {
     constexpr bool F4 = KIND == KIND_F4;
@@ -536,8 +537,14 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         const unsigned long long lo_q = (has_lo && qvalid) ? p.key_lo[q0 + q] : 0ull;
         int thr = qvalid ? pcq - sm->tau_s[q] : 0x7fffffff;  // survivor <=> dot > thr <=> hamming < tau
         float thr_f = (float)thr;
-        const bool samp = p.sample_out != nullptr;  // list-free sample pass (thresholds only)
-        int samp_fill = 0, samp_max = 0x7fffffff;
+        constexpr bool samp = SAMP;  // list-free sample pass (thresholds only)
+        int sbest[SAMPLE_KEEP];  // ascending
+#pragma unroll
+        for (int i = 0; i < SAMPLE_KEEP; i++) sbest[i] = 0x7fff;
+        if (samp && qvalid) {
+            thr = pcq - 0x7fff;
+            thr_f = (float)thr;
+        }
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + TMEM_D_COL + (uint32_t)(half * 64);
         const int limit = p.compact_limit > 0 ? min(p.compact_limit, p.cap - p.group_tiles * MROWS) : p.cap - p.group_tiles * MROWS;
         int until_check = p.group_tiles;
@@ -611,38 +618,31 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                     for (int j = 1; j < 16; j++) m = max(m, w[j]);
                     any = m > thr;
                 }
-                if (any && samp) {
-                    // List-free sample pass: only the k'-th smallest DISTANCE of the sample matters.  Every epilogue thread keeps
-                    // the k' smallest distances it has seen in a private column of shared memory (sample_d[i][thread]); its own
-                    // threshold is the largest of them once the column is full, so after the first tiles almost nothing gets
-                    // here (the chance that row number r of a thread is among its k' best so far is k' / r).
-                    const unsigned long long pos0 = (unsigned long long)(p.pos_base + lrow0 + 16 * g);
-                    const int et = tid;  // epilogue thread 0 .. 255
-#pragma unroll 1
-                    for (int j = 0; j < 16; j++) {
-                        if (j >= nv) break;
-                        const int ham = pcq - dot_of(j);
-                        if (samp_fill == p.k && ham >= samp_max) continue;
-                        if (has_lo && ((((unsigned long long)ham) << VRQ_KEY_POS_BITS) | (pos0 + j)) <= lo_q) continue;
-                        int slot = samp_fill;
-                        if (samp_fill < p.k) {
-                            samp_fill++;
-                        } else {  // replace the current maximum
-                            slot = 0;
-                            int mx = -1;
-                            for (int i = 0; i < p.k; i++) {
-                                const int v_ = sm->sample_d[i][et];
-                                if (v_ > mx) mx = v_, slot = i;
+                if (samp) {
+                    // List-free sample pass: only (an upper bound of) the k'-th smallest DISTANCE of the sample matters.  Every
+                    // epilogue thread keeps the SAMPLE_KEEP smallest distances it has seen in registers (a branch-free sorted
+                    // insert, 7 min / max per element); its own threshold is the largest of them, so after the first tiles
+                    // almost no group gets here (the chance that row r of a thread is among its best so far is 4 / r).  The
+                    // k'-th smallest of the union over the threads of a query is >= the k'-th smallest of the whole sample and
+                    // equal to it unless one thread holds more than SAMPLE_KEEP of the k' best - a slightly looser threshold at
+                    // worst, never a wrong result (the dense pass is verified, scan.cu).
+                    if (any) {
+                        const unsigned long long pos0 = (unsigned long long)(p.pos_base + lrow0 + 16 * g);
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            int x = pcq - dot_of(j);
+                            const bool ok = j < nv && !(has_lo && ((((unsigned long long)x) << VRQ_KEY_POS_BITS) | (pos0 + j)) <= lo_q);
+                            x = ok ? x : 0x7fff;
+#pragma unroll
+                            for (int i = 0; i < SAMPLE_KEEP - 1; i++) {
+                                const int lo_ = min(sbest[i], x);
+                                x = max(sbest[i], x);
+                                sbest[i] = lo_;
                             }
+                            sbest[SAMPLE_KEEP - 1] = min(sbest[SAMPLE_KEEP - 1], x);
                         }
-                        sm->sample_d[slot][et] = (unsigned short)ham;
-                        if (samp_fill == p.k) {
-                            int mx = 0;
-                            for (int i = 0; i < p.k; i++) mx = max(mx, (int)sm->sample_d[i][et]);
-                            samp_max = mx;
-                            thr = pcq - samp_max;  // survivor <=> hamming < current k'-th smallest of this thread
-                            thr_f = (float)thr;
-                        }
+                        thr = pcq - sbest[SAMPLE_KEEP - 1];  // survivor <=> hamming < the largest distance this thread keeps
+                        thr_f = (float)thr;
                     }
                 } else if (any) {
                     // Some column of this lane survives.  bit (15 - j) of mask <=> w[j] > thr: the sign of thr - w[j] is
@@ -705,7 +705,8 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
         }
         if (samp && qvalid) {
             unsigned short* o_ = p.sample_out + (((size_t)strip * p.nq + q0 + q) * 2 + half) * SAMPLE_KEEP;
-            for (int i = 0; i < SAMPLE_KEEP; i++) o_[i] = i < samp_fill ? sm->sample_d[i][tid] : (unsigned short)0xFFFF;
+#pragma unroll
+            for (int i = 0; i < SAMPLE_KEEP; i++) o_[i] = sbest[i] >= 0x7fff ? (unsigned short)0xFFFF : (unsigned short)sbest[i];
         }
         group_sync<EPI_THREADS>(BAR_CONSUMERS);
         // final compaction: every list leaves the kernel with at most k keys (bounds the merge's working set)
@@ -773,13 +774,13 @@ struct FewSmem {
 
 template <int MAXQ>
 __global__ void __launch_bounds__(FEW_THREADS, 1)
-hamming_scan_mma_few_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, int raw_stages, int npad) {
+hamming_scan_mma_few_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, int raw_stages, int npad, int dstride_arg, int relax) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* raw_mem = base;                                      // [raw_stages][128 rows][128 B], TMA SWIZZLE_128B
     uint8_t* q_mem = raw_mem + (size_t)raw_stages * STAGE_BYTES_RAW;  // [4 K-blocks][npad queries][128 B], same swizzle
     FewSmem<MAXQ>* sm = (FewSmem<MAXQ>*)(q_mem + (size_t)4 * MAXQ * 128);
-    constexpr uint32_t D_STRIDE = FewCfg<MAXQ>::D_STRIDE;
+    const uint32_t D_STRIDE = dstride_arg > 0 ? (uint32_t)dstride_arg : FewCfg<MAXQ>::D_STRIDE;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -905,7 +906,10 @@ hamming_scan_mma_few_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams
             uint4 c[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) c[j] = lds128(raddr + (((uint32_t)j ^ sw) << 4));
-            mbar_wait(smem_u32(&sm->a_empty[g]), ph ^ 1u);
+            if (relax)
+                mbar_wait_relaxed(smem_u32(&sm->a_empty[g]), ph ^ 1u, 64);
+            else
+                mbar_wait(smem_u32(&sm->a_empty[g]), ph ^ 1u);
             tc_fence_after();
 #pragma unroll
             for (int part = 0; part < 4; part++) {
@@ -1080,8 +1084,10 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
     pl->qtiles = (nq + MQ - 1) / MQ;
     // <= 64 queries: the swapped-operand kernel (database rows = M), HBM-bound instead of bound by 8 tensor cycles per row
     pl->few = pl->f4 && nq <= FEW_MAXQ && env_int("VRQ_MMA_FEW", 1) != 0;
-    // 33 .. 96 queries: the same kernel with its thresholds in shared memory (VRQ_MMA_MID=0: the 128-query-tile kernel)
-    pl->mid = pl->f4 && !pl->few && nq <= MID_MAXQ && env_int("VRQ_MMA_FEW", 1) != 0 && env_int("VRQ_MMA_MID", 1) != 0;
+    // 33 .. 96 queries: the same kernel with its thresholds in shared memory.  OPT-IN (VRQ_MMA_MID=1), a measured negative
+    // result: the time per MMA of the swapped orientation grows like N^2 beyond 32 query columns (100 M codes: 5.3 ms at 48
+    // queries, 8.1 ms at 64, 15.3 ms at 96, against 4.9 ms for the 128-query-tile kernel; profiles/r02/mid_regime.md).
+    pl->mid = pl->f4 && !pl->few && nq <= MID_MAXQ && env_int("VRQ_MMA_FEW", 1) != 0 && env_int("VRQ_MMA_MID", 0) != 0;
     if (pl->mid) pl->few = true;
     // CTA pairs need an even number of query tiles (a pair = two neighbouring tiles); VRQ_MMA_PAIR=0 switches them off
     pl->pair = pl->f4 && pl->qtiles % 2 == 0 && env_int("VRQ_MMA_PAIR", 1) != 0;
@@ -1155,14 +1161,15 @@ int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const CUtensorMap&
     if (pl.few && pl.mid) {
         const int npad = ((sp.nq + 15) / 16) * 16;
         VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_few_kernel<MID_MAXQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        hamming_scan_mma_few_kernel<MID_MAXQ><<<grid, FEW_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, npad);
+        hamming_scan_mma_few_kernel<MID_MAXQ><<<grid, FEW_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, npad, env_int("VRQ_MID_DSTRIDE", 0),
+                                                                              env_int("VRQ_MID_RELAX", 0));
     } else if (pl.few) {
         const int npad = ((sp.nq + 7) / 8) * 8;
         VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_few_kernel<FEW_MAXQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        hamming_scan_mma_few_kernel<FEW_MAXQ><<<grid, FEW_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, npad);
+        hamming_scan_mma_few_kernel<FEW_MAXQ><<<grid, FEW_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, npad, 0, env_int("VRQ_MID_RELAX", 0));
     } else if (pl.f4 && pl.pair) {
         // CTA pairs: clusters of 2 along x = two neighbouring query tiles of the same strip
-        auto kern = hamming_scan_mma_kernel<KIND_F4, 2>;
+        auto kern = sp.sample_out ? hamming_scan_mma_kernel<KIND_F4, 2, true> : hamming_scan_mma_kernel<KIND_F4, 2, false>;
         VRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = grid;
@@ -1178,11 +1185,13 @@ int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const CUtensorMap&
         cfg.numAttrs = 1;
         VRQ_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap64, sp, pl.raw_stages));
     } else if (pl.f4) {
-        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_kernel<KIND_F4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        hamming_scan_mma_kernel<KIND_F4, 1><<<grid, MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages);
+        auto kern = sp.sample_out ? hamming_scan_mma_kernel<KIND_F4, 1, true> : hamming_scan_mma_kernel<KIND_F4, 1, false>;
+        VRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        kern<<<grid, MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages);
     } else {
-        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_kernel<KIND_I8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        hamming_scan_mma_kernel<KIND_I8, 1><<<grid, MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages);
+        auto kern = sp.sample_out ? hamming_scan_mma_kernel<KIND_I8, 1, true> : hamming_scan_mma_kernel<KIND_I8, 1, false>;
+        VRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        kern<<<grid, MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages);
     }
     vrq_count_launch(ctx);
     VRQ_CUDA(cudaGetLastError());

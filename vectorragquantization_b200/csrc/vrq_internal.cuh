@@ -50,7 +50,7 @@ struct vrq_buf {
 enum { VRQ_WS_STAGE_IN0 = 0, VRQ_WS_STAGE_IN1, VRQ_WS_STAGE_OUT0, VRQ_WS_STAGE_OUT1, VRQ_WS_LISTS, VRQ_WS_COUNTS,
        VRQ_WS_TOPK, VRQ_WS_SEARCH_A, VRQ_WS_SEARCH_B, VRQ_WS_SEARCH_C, VRQ_WS_SEARCH_D, VRQ_WS_SEARCH_E,
        VRQ_WS_QUERY_A, VRQ_WS_QUERY_B, VRQ_WS_OUT_A, VRQ_WS_OUT_B, VRQ_WS_OUT_C, VRQ_WS_OUT_D, VRQ_WS_OUT_E,
-       VRQ_WS_MISC, VRQ_WS_TAU, VRQ_WS_MERGE_A, VRQ_WS_MERGE_B, VRQ_WS_MERGE_CA, VRQ_WS_MERGE_CB, VRQ_WS_SAMPLE_KEYS, VRQ_WS_FLAG, VRQ_WS_PROGRESS, VRQ_WS_SAMPLE_D, VRQ_WS_CHUNK_KEYS, VRQ_WS_CHUNK_LO, VRQ_WS_M3_SRC, VRQ_WS_M3_R2, VRQ_WS_SLOTS };
+       VRQ_WS_MISC, VRQ_WS_TAU, VRQ_WS_MERGE_A, VRQ_WS_MERGE_B, VRQ_WS_MERGE_CA, VRQ_WS_MERGE_CB, VRQ_WS_SAMPLE_KEYS, VRQ_WS_FLAG, VRQ_WS_PROGRESS, VRQ_WS_SAMPLE_D, VRQ_WS_CHUNK_KEYS, VRQ_WS_CHUNK_LO, VRQ_WS_M3_SRC, VRQ_WS_M3_R2, VRQ_WS_IP_SCORES, VRQ_WS_SHARD_PACKED, VRQ_WS_SHARD_GATHER, VRQ_WS_SLOTS };
 
 struct vrq_ctx {
     int device = 0;
@@ -62,6 +62,8 @@ struct vrq_ctx {
     cudaEvent_t pipe_ev[2] = {nullptr, nullptr};
     int64_t launches = 0;
     vrq_buf ws[VRQ_WS_SLOTS];
+    void* nccl_comm = nullptr;  // ncclComm_t of this GPU's rank (vrq_ctx_set_nccl), for the sharded searches of sharded.cu
+    int nccl_rank = 0, nccl_world = 1;
     bool timing = false;
     std::vector<vrq_timed> timed;
     std::vector<cudaEvent_t> ev_pool;
@@ -160,6 +162,10 @@ int vrq_launch_select2(vrq_ctx* ctx, int64_t nq, int m, const uint64_t* keys, co
                        int k, int64_t* out_labels, float* out_score, int32_t* out_count, cudaStream_t st);
 int vrq_launch_keys_to_dist_labels(vrq_ctx* ctx, const uint64_t* keys, int64_t count, int64_t pos_base,
                                    const int64_t* id_map, int64_t id0, int32_t* dist, int64_t* labels, cudaStream_t st);
+
+// ---- float_ip.cu: brute-force float32 inner-product top-k (CohereVectorDBFloat) ------------------------------------
+int vrq_launch_ip_topk(vrq_ctx* ctx, const float* rows, int64_t n, int d, const float* q, int64_t nq, int k, const int64_t* id_map,
+                       int64_t id0, float* out_scores, int64_t* out_labels, cudaStream_t st);
 
 // ---- synth.cu ---------------------------------------------------------------------------------------
 int vrq_launch_synth_f32(vrq_ctx* ctx, uint64_t seed, int64_t row0, int64_t nrows, int d, int row_scale, float* out,
