@@ -697,10 +697,15 @@ def hbm_bound_kernels(env, index, qf_d, qb_d, hbm_peak, peak_src, n_local, ms_pe
                                       "ms": s2 * 1e3, "pairs_per_s": nq5 * m5 / s2, "GB/s": nq5 * m5 * 128 / s2 / 1e9,
                                       "variants_ms": bin_ms, "speedup_vs_round1_register_kernel": bin_ms["cuda_core_register_kernel"] / (s2 * 1e3),
                                       "gather_roofline_128B_GBs": 4200.0, "frac": nq5 * m5 * 128 / s2 / 1e9 / 4200.0,
+                                      "traffic": traffic("rescore_binary_cfg5")[0], "traffic_source": traffic("rescore_binary_cfg5")[1],
+                                      "algorithmic_bytes": nq5 * m5 * 128,
                                       "peak_source": "random 128-byte rows stream at 4.0-4.4 TB/s (profiles/microbench/gather_bench_r01.txt)"}
         del pos5, qf5, sc5, sc5b
-    # adversarial step: 64 of the 1024 queries have 32 exact duplicates each inside the first sampled tiles, so their
-    # sampled threshold is 0, the dense pass collects < k candidates for them and the exact fallback pass runs
+    # adversarial steps.  (a) 64 of the 1024 queries have 32 exact duplicates each inside the first sampled tiles.  With round 1's
+    # list-based sample pass their sampled threshold was 0 and the exact fallback pass ran; the list-free sample pass keeps at most
+    # four distances per epilogue thread, so a cluster inside one strip cannot drag the threshold down any more.  (b) thresholds
+    # forced far too tight (k' = 1 of a 100 k-row sample): the verification fails for about half of the queries and the gated
+    # exact fallback - a second dense pass, thresholds of the short queries at infinity - runs.
     try:
         nadv = 64
         qf_a, qb_a = qf_d[1].clone(), qb_d[1].clone()
@@ -712,15 +717,31 @@ def hbm_bound_kernels(env, index, qf_d, qb_d, hbm_peak, peak_src, n_local, ms_pe
         sb = torch.empty((NQ, K), dtype=torch.float64, device=dev)
         sc = torch.empty((NQ, K), dtype=torch.float64, device=dev)
         cnt = torch.empty((NQ,), dtype=torch.int32, device=dev)
-        s_adv = _timed(env, lambda: L.check(lib.vrq_index_search3(index._h, NQ, L.ptr(qf_a), L.ptr(qb_a), K, BO, IO, L.ptr(lab), L.ptr(ham),
-                                                                   L.ptr(sb), L.ptr(sc), L.ptr(cnt))), 3)
+
+        def step(qf_, qb_):
+            return lambda: L.check(lib.vrq_index_search3(index._h, NQ, L.ptr(qf_), L.ptr(qb_), K, BO, IO, L.ptr(lab), L.ptr(ham),
+                                                         L.ptr(sb), L.ptr(sc), L.ptr(cnt)))
+
+        s_adv = _timed(env, step(qf_a, qb_a), 3)
         d_h, _ = index.search(qb_a.cpu().numpy(), K * BO)  # Phase I of the same batch: every duplicate must be found, at distance 0
         ok = bool((d_h[:nadv, :32] == 0).all() and (d_h[:nadv, 32] > 0).all() and (d_h[:, -1] < 1024).all()) and bool((cnt == K).all().item())
         index.write_rows(L.ROWS_CODES, 0, save)
-        out["adversarial"] = {"what": f"{nadv} of the 1024 queries have 32 exact duplicates inside the sampled tiles: sampled threshold 0, "
-                                      "the dense pass comes up short for them, the gated exact fallback pass (a second dense pass) runs",
-                              "ms_per_step": s_adv * 1e3, "normal_ms_per_step": ms_per_step, "ratio": s_adv * 1e3 / ms_per_step,
-                              "results_complete_and_duplicates_found": ok}
+        saved = {k_: os.environ.get(k_) for k_ in ("VRQ_MMA_SAMPLE_K", "VRQ_MMA_SAFETY")}
+        os.environ["VRQ_MMA_SAMPLE_K"], os.environ["VRQ_MMA_SAFETY"] = "1", "1"
+        s_fb = _timed(env, step(qf_d[2], qb_d[2]), 3)
+        ok_fb = bool((cnt == K).all().item())
+        for k_, v in saved.items():
+            if v is None:
+                os.environ.pop(k_, None)
+            else:
+                os.environ[k_] = v
+        out["adversarial"] = {"clustered_duplicates": {"what": f"{nadv} of the 1024 queries have 32 exact duplicates inside the first sampled tiles",
+                                                       "ms_per_step": s_adv * 1e3, "ratio": s_adv * 1e3 / ms_per_step,
+                                                       "results_complete_and_duplicates_found": ok},
+                              "forced_fallback": {"what": "thresholds from k'=1 of a 100k-row sample (VRQ_MMA_SAMPLE_K=1, VRQ_MMA_SAFETY=1): about half of the "
+                                                          "queries come up short in the dense pass, the gated exact fallback pass runs for them",
+                                                  "ms_per_step": s_fb * 1e3, "ratio": s_fb * 1e3 / ms_per_step, "results_complete": ok_fb},
+                              "normal_ms_per_step": ms_per_step}
     except Exception as e:
         out["adversarial"] = {"error": repr(e)}
     return out

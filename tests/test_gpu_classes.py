@@ -341,9 +341,11 @@ def test_cohere_float_class(tmp_path):
         got_s = np.array([r["score"] for r in res])
         assert len(res) == min(k, len(DOCS))
         assert np.all(np.abs(got_s - rs[0][:len(res)]) <= 1e-5 * np.abs(rs[0][:len(res)]) + 1e-7)
-        sep = np.abs(np.diff(rs[0][:len(res)])) > 1e-5  # ranks are only defined where neighbouring scores are apart
+        ref_s = rs[0][:len(res)]
+        gap = np.abs(np.diff(ref_s))
+        apart = np.r_[True, gap > 1e-6] & np.r_[gap > 1e-6, True]  # a rank is only defined where both neighbouring scores differ
         same = np.array([r["doc_id"] for r in res]) == rl[0][:len(res)]
-        assert np.all(same[:-1][sep] | ~sep[:len(same) - 1]) or np.mean(same) > 0.98
+        assert np.all(same[apart]) and np.mean(same) > 0.9
         assert all(r["doc"] == DOCS[r["doc_id"]] for r in res)
     # batch of queries incl. more than one pass of 8, and k > ntotal padding
     Q = np.stack([oc.synth_f32(3, i, 1)[0] for i in range(19)])

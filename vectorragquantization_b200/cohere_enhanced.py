@@ -150,6 +150,16 @@ class CohereEnhancedVectorDB:
         for doc_id in doc_ids:
             if str(doc_id) in self.doc_db:
                 self.remove_document(doc_id, save=False)
+        # one embedder call per batch like the reference (:195-199); the device-resident index is appended to for up to 4096
+        # embedded documents at a time (a 64-row append is pure copy latency) - same order, ids and results
+        pend_ids, pend_i8, pend_ub, pend_docs = [], [], [], []
+
+        def flush():
+            if pend_ids:
+                self.index.add_with_ids(np.concatenate(pend_ub), np.array(pend_ids, dtype=np.int64), payload=np.concatenate(pend_i8))
+                self.doc_db.set_many((str(doc_id), {"doc": doc}) for doc_id, doc in zip(pend_ids, pend_docs))
+                pend_ids.clear(), pend_i8.clear(), pend_ub.clear(), pend_docs.clear()
+
         for start in range(0, len(docs), batch_size):
             batch_ids = doc_ids[start:start + batch_size]
             batch_docs = docs[start:start + batch_size]
@@ -160,11 +170,15 @@ class CohereEnhancedVectorDB:
             try:
                 int8_embs = np.array(emb["int8"], dtype=np.int8)
                 ubinary_embs = np.array(emb["ubinary"], dtype=np.uint8)
+                if int8_embs.shape != (len(batch_ids), self.embedding_dim) or ubinary_embs.shape != (len(batch_ids), self.embedding_dim // 8):
+                    raise ValueError(f"unexpected embedding shapes {int8_embs.shape} / {ubinary_embs.shape}")
             except Exception as e:
                 logger.error("Error processing embeddings: %s", str(e))
                 continue
-            self.index.add_with_ids(ubinary_embs, np.array(batch_ids, dtype=np.int64), payload=int8_embs)
-            self.doc_db.set_many((str(doc_id), {"doc": doc}) for doc_id, doc in zip(batch_ids, batch_docs))
+            pend_ids.extend(batch_ids), pend_i8.append(int8_embs), pend_ub.append(ubinary_embs), pend_docs.extend(batch_docs)
+            if len(pend_ids) >= 4096:
+                flush()
+        flush()
         if save:
             self.save()
 

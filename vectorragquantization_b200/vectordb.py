@@ -61,6 +61,7 @@ class _VectorDBBase:
     _desc = "Indexing docs"
     _has_global_limit = False
     _ge = False  # '>=' mean threshold (CohereVectorDBBinary) instead of '>'
+    _GPU_CHUNK = 4096  # embedded rows per encode + index-append call inside add_documents
 
     def __init__(self, folder: str, model: str = "snowflake-arctic-embed2", embedding_dim: int = 1024, rdict_options=None,
                  embed_url: str = "http://localhost:11434/api/embed", embedder: Optional[Callable] = None, ctx=None):
@@ -198,6 +199,16 @@ class _VectorDBBase:
         for doc_id in doc_ids:
             if str(doc_id) in self.doc_db:
                 self.remove_document(doc_id, save=False)
+        # The embedder is called once per batch of `batch_size` texts, like the reference (:163-165); the GPU work (encode +
+        # append to the device-resident index) is issued for up to _GPU_CHUNK embedded rows at a time: a 64-row call is pure
+        # launch / copy latency.  Order, ids and results are those of per-batch insertion.
+        pend_ids, pend_x, pend_docs = [], [], []
+
+        def flush():
+            if pend_ids:
+                self._add_batch(pend_ids, np.concatenate(pend_x), pend_docs)
+                pend_ids.clear(), pend_x.clear(), pend_docs.clear()
+
         with _Progress(len(docs), self._desc) as pbar:
             for start in range(0, len(docs), batch_size):
                 batch_ids = doc_ids[start:start + batch_size]
@@ -206,8 +217,11 @@ class _VectorDBBase:
                 if x is None:
                     logger.error(f"Embedding generation failed for batch: {batch_docs}")
                     continue
-                self._add_batch(batch_ids, x, batch_docs)
+                pend_ids.extend(batch_ids), pend_x.append(x), pend_docs.extend(batch_docs)
+                if len(pend_ids) >= self._GPU_CHUNK:
+                    flush()
                 pbar.update(len(batch_docs))
+        flush()
         if save:
             self.save()
 
