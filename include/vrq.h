@@ -11,8 +11,10 @@
  * Conventions
  *   - extern "C", plain pointers and sizes, no C++/torch types.
  *   - Every data pointer may be a HOST pointer or a DEVICE pointer (all data pointers of one call in the
- *     same space; the library asks the CUDA runtime which).  Host buffers: the call stages through pinned
- *     memory in chunks, overlapping copies with the kernel, and returns when the outputs are complete.
+ *     same space; the library asks the CUDA runtime which).  Host buffers: the call runs a chunked two-stream pipeline
+ *     (H2D of chunk i+1 and D2H of chunk i-1 around the kernel of chunk i) and returns when the outputs are complete.  The
+ *     copies are issued straight from / to the caller's buffers: they overlap the kernels when those buffers are pinned
+ *     (cudaHostAlloc, torch pin_memory); with pageable memory the runtime stages them itself and the steps serialise.
  *     Device buffers: the call only enqueues work on the context's stream (vrq_ctx_set_stream) and returns.
  *   - Return value: 0 = OK, > 0 = a cudaError_t, < 0 = VRQ_ERR_*.  vrq_last_error() gives the text.
  *   - One vrq_ctx per GPU; a ctx (and the indexes made from it) must not be used from two threads at once.

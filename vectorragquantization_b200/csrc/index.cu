@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <iterator>
+#include <new>
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
@@ -113,7 +114,12 @@ int materialise_ids(vrq_index* ix) {
 
 int load_host_ids(vrq_index* ix) {
     if (ix->host_ids_valid) return 0;
-    ix->host_ids.resize((size_t)ix->ntotal);
+    try {
+        ix->host_ids.resize((size_t)ix->ntotal);
+    } catch (const std::bad_alloc&) {  // never let a C++ exception cross the extern "C" boundary
+        vrq_set_error("out of host memory for %lld ids", (long long)ix->ntotal);
+        return VRQ_ERR_NOMEM;
+    }
     if (ix->implicit_ids) {
         for (int64_t i = 0; i < ix->ntotal; i++) ix->host_ids[(size_t)i] = ix->id0 + i;
     } else if (ix->ntotal > 0) {
@@ -128,9 +134,14 @@ int load_host_ids(vrq_index* ix) {
 int build_rev(vrq_index* ix) {
     if (ix->rev_valid) return 0;
     VRQ_TRY(load_host_ids(ix));
-    ix->rev.clear();
-    ix->rev.reserve((size_t)ix->ntotal * 2);
-    for (int64_t i = 0; i < ix->ntotal; i++) ix->rev[ix->host_ids[(size_t)i]] = i;  // last added wins (IDMap2)
+    try {
+        ix->rev.clear();
+        ix->rev.reserve((size_t)ix->ntotal * 2);
+        for (int64_t i = 0; i < ix->ntotal; i++) ix->rev[ix->host_ids[(size_t)i]] = i;  // last added wins (IDMap2)
+    } catch (const std::bad_alloc&) {
+        vrq_set_error("out of host memory for the id -> position map of %lld ids", (long long)ix->ntotal);
+        return VRQ_ERR_NOMEM;
+    }
     ix->rev_valid = true;
     return 0;
 }

@@ -2,8 +2,9 @@
 
 These are the functions the reference's private static methods turn into (``VectorDBInt8._quantize_to_int8`` etc.,
 see the class modules); they accept a single vector ``[D]`` like the reference or a batch ``[n, D]``.  Arrays live
-in host memory here: the call goes through the C ABI's host-buffer path (chunked H2D -> kernel -> D2H).  Device
-tensors (anything with ``data_ptr()``) are passed through untouched to the device-pointer path via ``*_into``.
+in host memory here: the call goes through the C ABI's host-buffer path (chunked H2D -> kernel -> D2H).  Callers that
+hold device memory (e.g. torch tensors) call the same C entry points with device pointers (``_lib.ptr(tensor)``), which
+only enqueue work on the context's stream - see ``sharded.py`` and ``bench.py``.
 """
 from __future__ import annotations
 
