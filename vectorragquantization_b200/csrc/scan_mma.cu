@@ -171,6 +171,13 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
+// atomicAdd on a shared-memory counter through its 32-bit shared address: ATOMS.  (atomicAdd(&sm->cnt_s[q], ...) on the
+// struct carved out of the dynamic shared-memory block compiles to a GENERIC atomic, ATOM.E.ADD.STRONG.GPU.)
+__device__ __forceinline__ int atoms_add(uint32_t saddr, int v) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(saddr), "r"(v) : "memory");
+    return old;
+}
 // named barrier over the epilogue threads that also ORs a predicate
 __device__ __forceinline__ int epi_sync_or(int pred) {
     int out;
@@ -202,8 +209,12 @@ struct MmaSmem {
 // tcgen05.mma.cta_group::2 (M = 256, N = 128) which reads both halves; per SM the shared-memory traffic per tile halves.
 // SAMP = true: the list-free sample pass (thresholds only) - a separate instantiation, so that none of its code sits in the
 // dense pass's epilogue.
-template <int KIND, int CG, bool SAMP>
-__global__ void __launch_bounds__(MMA_KERNEL_THREADS, 1)
+// VAR = 0: generic epilogue loop at 96 registers (every kind, the sample pass, strided runs, the tests' distance dump).
+// VAR = 4: the dense pass of the CTA-pair kernel.  The epilogue warps run at 128 registers and everyone else at 72
+// (setmaxnreg; the block carries one idle pad warp so that every warpgroup is whole), which lets them load all four
+// accumulator column groups at once and hand the accumulator back before anything is examined; see the lean loop below.
+template <int KIND, int CG, bool SAMP, int VAR = 0>
+__global__ void __launch_bounds__(VAR == 4 ? MMA_KERNEL_THREADS + 32 : MMA_KERNEL_THREADS, 1)
 hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, int raw_stages) {
     constexpr bool F4 = KIND == KIND_F4;
     constexpr int KBLOCKS = KindCfg<KIND>::KBLOCKS;
@@ -308,11 +319,26 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
     uint32_t prod_s = 0, prod_ph = 0;  // TMA producer: raw ring
     uint32_t rs = 0, rph = 0;          // expanders: raw ring
     int tbase = 0;
-  for (int sgi = 0; segment(sgi); sgi++) {
+    // The segment loop is written once per ROLE CLASS (epilogue warps / everyone else) so that VAR = 4 can run the two
+    // classes under different register budgets: ptxas applies a setmaxnreg to the code it dominates.
+    auto seg_begin_sync = [&]() {
+        tc_fence_before();
+        asm volatile("bar.sync 0;" ::: "memory");
+        tc_fence_after();
+    };
+    auto seg_end_sync = [&]() {
+        // end of the segment: every role is done with its tiles (the last accumulators were read, so every MMA has completed)
+        // before the next segment rewrites the query operand in tensor memory - in both CTAs of a pair
+        tc_fence_before();
+        asm volatile("bar.sync 0;" ::: "memory");
+        if constexpr (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared memory and TMEM until the very end
+        tc_fence_after();
+    };
+    auto epilogue_role = [&](const int sgi) {
     // ---- the query tile becomes the A operand in tensor memory (lane = query); warps 0-3 write it, every epilogue
     //      thread keeps popc(query) of the query it filters
     int pcq = 0;
-    if (warp < EPI_WARPS) {
+    {
         const int q = tid & (MQ - 1);
         const bool qvalid = q < qt;
         const bool writer = warp < 4;
@@ -366,10 +392,279 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
             sm->cnt_s[q] = 0;
         }
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
+    seg_begin_sync();
+    {
+        // 8 warps: warp & 3 = TMEM lane quadrant (32 queries), warp >> 2 = which 64 of the tile's 128 columns.  The two
+        // threads that share a query append to the same list through a shared-memory counter.
+        const int q = tid & (MQ - 1);
+        const int half = warp >> 2;
+        const bool qvalid = q < qt;
+        uint64_t* my_list = p.lists + ((size_t)strip * p.nq + q0 + (qvalid ? q : 0)) * p.cap;
+        const bool has_lo = p.key_lo != nullptr;
+        const unsigned long long lo_q = (has_lo && qvalid) ? p.key_lo[q0 + q] : 0ull;
+        int thr = qvalid ? pcq - sm->tau_s[q] : 0x7fffffff;  // survivor <=> dot > thr <=> hamming < tau
+        float thr_f = (float)thr;
+        constexpr bool samp = SAMP;  // list-free sample pass (thresholds only)
+        int sbest[SAMPLE_KEEP];  // ascending
+#pragma unroll
+        for (int i = 0; i < SAMPLE_KEEP; i++) sbest[i] = 0x7fff;
+        if (samp && qvalid) {
+            thr = pcq - 0x7fff;
+            thr_f = (float)thr;
+        }
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + TMEM_D_COL + (uint32_t)(half * 64);
+        const int limit = p.compact_limit > 0 ? min(p.compact_limit, p.cap - p.group_tiles * MROWS) : p.cap - p.group_tiles * MROWS;
+        int until_check = p.group_tiles;
+        auto release_acc = [&](const int as) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (CG == 2)
+                    mbar_arrive_cluster(mapa_rank(smem_u32(&sm->acc_empty[as]), 0));
+                else
+                    mbar_arrive(smem_u32(&sm->acc_empty[as]));
+            }
+        };
+        const uint32_t cnt_addr = smem_u32(&sm->cnt_s[q]);
+        // largest of 16 f32 accumulator columns: a depth-3 tree of 3-input maxima (FMNMX3) instead of a chain of eight
+        auto max16 = [](const int(&w)[16]) -> float {
+            auto f = [&](int j) -> float { return __int_as_float(w[j]); };
+            auto mx3 = [](float x, float y, float z) -> float { return fmaxf(fmaxf(x, y), z); };
+            const float a0 = mx3(f(0), f(1), f(2)), a1 = mx3(f(3), f(4), f(5)), a2 = mx3(f(6), f(7), f(8));
+            const float a3 = mx3(f(9), f(10), f(11)), a4 = mx3(f(12), f(13), f(14));
+            return fmaxf(mx3(a0, a1, a2), mx3(a3, a4, f(15)));
+        };
+        // the survivors of one group of 16 columns go to the (strip, query) list; m = the group's largest dot
+        auto collect = [&](const int(&w)[16], const int g, const int nv, const int64_t lrow0, const int m) {
+            auto dot_of = [&](int j) -> int { return F4 ? (int)__int_as_float(w[j]) : w[j]; };
+            // Some column of this lane survives.  bit (15 - j) of mask <=> w[j] > thr: the sign of thr - w[j] is
+            // shifted in with one funnel shift per column (2 instructions per column, no branches).
+            const unsigned long long pos0 = (unsigned long long)(p.pos_base + lrow0 + 16 * g);
+            uint32_t mask = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint32_t sgn = F4 ? __float_as_uint(thr_f - __int_as_float(w[j])) : (uint32_t)(thr - w[j]);
+                mask = __funnelshift_l(sgn, mask, 1);
+            }
+            if (nv < 16) mask = nv <= 0 ? 0u : (mask & ~(0xFFFFu >> nv));
+            if (has_lo) {
+                // a later chunk of a large top-k: keys at or below the chunk's lower bound were returned already
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    if ((mask >> (15 - j)) & 1u) {
+                        const unsigned long long key = ((unsigned long long)(pcq - dot_of(j)) << VRQ_KEY_POS_BITS) | (pos0 + j);
+                        if (key > lo_q) {
+                            const int slot = atoms_add(cnt_addr, 1);
+                            if (slot >= p.cap) __trap();
+                            my_list[slot] = key;
+                        }
+                    }
+                }
+            } else if (__popc(mask) == 1 && nv >= 16) {
+                // the usual case once tau has converged: the single survivor is the maximum itself
+                const int slot = atoms_add(cnt_addr, 1);
+                if (slot >= p.cap) __trap();  // cannot happen (overflow check every group_tiles tiles); never write past a list
+                my_list[slot] = ((unsigned long long)(pcq - m) << VRQ_KEY_POS_BITS) | (pos0 + (__clz((int)mask) - 16));
+            } else if (mask) {
+                int slot = atoms_add(cnt_addr, __popc(mask));
+                if (slot + __popc(mask) > p.cap) __trap();
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    if ((mask >> (15 - j)) & 1u) {
+                        my_list[slot] = ((unsigned long long)(pcq - dot_of(j)) << VRQ_KEY_POS_BITS) | (pos0 + j);
+                        slot++;
+                    }
+                }
+            }
+        };
+        auto examine = [&](const int(&w)[16], const int g, const int nvalid, const int64_t lrow0) {
+            const int nv = nvalid - 16 * g;  // valid columns in this group (>= 16: all)
+            // F4 accumulates in f32: the dots are integers of magnitude <= 1024, exact in binary32
+            auto dot_of = [&](int j) -> int { return F4 ? (int)__int_as_float(w[j]) : w[j]; };
+            bool any;
+            int m;
+            if constexpr (F4) {
+                float mf;
+                mf = max16(w);
+                any = mf > thr_f;
+                m = (int)mf;
+            } else {
+                m = w[0];
+#pragma unroll
+                for (int j = 1; j < 16; j++) m = max(m, w[j]);
+                any = m > thr;
+            }
+            if (samp) {
+                // List-free sample pass: only (an upper bound of) the k'-th smallest DISTANCE of the sample matters.  Every
+                // epilogue thread keeps the SAMPLE_KEEP smallest distances it has seen in registers (a branch-free sorted
+                // insert, 7 min / max per element); its own threshold is the largest of them, so after the first tiles
+                // almost no group gets here (the chance that row r of a thread is among its best so far is 4 / r).  The
+                // k'-th smallest of the union over the threads of a query is >= the k'-th smallest of the whole sample and
+                // equal to it unless one thread holds more than SAMPLE_KEEP of the k' best - a slightly looser threshold at
+                // worst, never a wrong result (the dense pass is verified, scan.cu).
+                if (any) {
+                    const unsigned long long pos0 = (unsigned long long)(p.pos_base + lrow0 + 16 * g);
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        int x = pcq - dot_of(j);
+                        const bool ok = j < nv && !(has_lo && ((((unsigned long long)x) << VRQ_KEY_POS_BITS) | (pos0 + j)) <= lo_q);
+                        x = ok ? x : 0x7fff;
+#pragma unroll
+                        for (int i = 0; i < SAMPLE_KEEP - 1; i++) {
+                            const int lo_ = min(sbest[i], x);
+                            x = max(sbest[i], x);
+                            sbest[i] = lo_;
+                        }
+                        sbest[SAMPLE_KEEP - 1] = min(sbest[SAMPLE_KEEP - 1], x);
+                    }
+                    thr = pcq - sbest[SAMPLE_KEEP - 1];  // survivor <=> hamming < the largest distance this thread keeps
+                    thr_f = (float)thr;
+                }
+            } else if (any) {
+                collect(w, g, nv, lrow0, m);
+            }
+        };
+        auto overflow_check = [&](const int t) {
+        // ---- overflow check every group_tiles tiles: no list may exceed cap during the next group ----
+        if (!samp && --until_check == 0 && t + 1 < ntiles) {
+            until_check = p.group_tiles;
+            group_sync<EPI_THREADS>(BAR_CONSUMERS);  // every append of this group of tiles is in its list
+            if (epi_sync_or(sm->cnt_s[q] > limit)) {
+                for (int qq = warp; qq < qt; qq += EPI_WARPS) {  // one list per warp, 8 lists at a time
+                    const int n = sm->cnt_s[qq];
+                    if (n > limit)
+                        compact_list_warp(p.lists + ((size_t)strip * p.nq + q0 + qq) * p.cap, n, p.k, &sm->sc[warp], lane, BAR_WARP0 + warp,
+                                          &sm->cnt_s[qq], &sm->tau_s[qq], p.sample_mode ? limit : 0);
+                }
+                group_sync<EPI_THREADS>(BAR_CONSUMERS);
+                if (qvalid) thr = pcq - sm->tau_s[q];
+                thr_f = (float)thr;
+            }
+        }
+        };
+        if constexpr (VAR == 4) {
+            // Lean tile loop of the dense pass (tile t of the segment = rows row_begin + (tile0 + t) * 128 ...).  Measured with
+            // the generic loop below: 151 instructions per tile and warp on the no-survivor path kept the epilogue warps busy
+            // for ~950 of the 1024 cycles a tile's MMAs take, so every survivor made them late for the next accumulator
+            // (tensor pipe 83 % busy; 99.95 % with an epilogue that only loads).  Here: barrier addresses and the number of
+            // full tiles are loop invariants, all four column groups are loaded at once (64 registers - the epilogue warps
+            // run at 128 registers, setmaxnreg), the accumulator goes back before anything is examined, and ONE test on the
+            // maximum of all 64 columns decides whether any group needs a closer look.
+            const int64_t row0 = p.row_begin + tile0 * MROWS + half * 64;  // first row of this warp's columns in tile 0
+            const int64_t left0 = s_end - row0;
+            const int full_tiles = left0 >= 64 ? (int)min((int64_t)ntiles, (left0 - 64) / MROWS + 1) : 0;
+            uint32_t full_bar = smem_u32(&sm->acc_full[0]);
+            uint32_t empty_bar = CG == 2 ? mapa_rank(smem_u32(&sm->acc_empty[0]), 0) : smem_u32(&sm->acc_empty[0]);
+            uint32_t acc0 = lane_base;
+            // opaque to the compiler, or it rematerialises the ~20 instructions of address arithmetic in every tile
+            asm volatile("" : "+r"(full_bar), "+r"(empty_bar), "+r"(acc0));
+            uint32_t T = (uint32_t)tbase;
+            for (int t = 0; t < ntiles; t++, T++) {
+                const uint32_t as = T & 1u;
+                mbar_wait(full_bar + 8u * as, (T >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t acc = acc0 + as * MROWS;
+                int v[4][16];
+                __syncwarp();
+                tmem_ld16(acc, v[0]);
+                tmem_ld16(acc + 16, v[1]);
+                tmem_ld16(acc + 32, v[2]);
+                tmem_ld16(acc + 48, v[3]);
+                tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CG == 2)
+                        mbar_arrive_cluster(empty_bar + 8u * as);
+                    else
+                        mbar_arrive(empty_bar + 8u * as);
+                }
+                float gm[4];
+#pragma unroll
+                for (int g = 0; g < 4; g++) gm[g] = max16(v[g]);
+                if (t >= full_tiles) {
+                    // the last tile(s) of the database: some columns are past its end
+                    const int64_t lrow0 = row0 + (int64_t)t * MROWS;
+                    const int64_t left = s_end - lrow0;
+                    const int nvalid = left >= 64 ? 64 : (int)max(left, (int64_t)0);
+#pragma unroll
+                    for (int g = 0; g < 4; g++) examine(v[g], g, nvalid, lrow0);
+                } else if (fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])) > thr_f) {
+                    const int64_t lrow0 = row0 + (int64_t)t * MROWS;
+#pragma unroll
+                    for (int g = 0; g < 4; g++)
+                        if (gm[g] > thr_f) collect(v[g], g, 16, lrow0, (int)gm[g]);
+                }
+                overflow_check(t);
+            }
+        } else {
+        int64_t cur_row = tile_row(0) + half * 64;
+        int in_run = (int)(tile0 & run_mask);
+        for (int t = 0; t < ntiles; t++) {
+            const uint32_t T = (uint32_t)(tbase + t);
+            const int as = (int)(T & 1u);
+            mbar_wait(smem_u32(&sm->acc_full[as]), (T >> 1) & 1u);
+            tc_fence_after();
+            const int64_t lrow0 = cur_row;  // first database row of this warp's 64 columns
+            const int64_t left = s_end - lrow0;
+            const int nvalid = left >= 64 ? 64 : (int)max(left, (int64_t)0);
+            // advance the tile cursor (dense scan: +128 rows; strided sample: +128 inside a run, a jump at its end)
+            if (++in_run > (int)run_mask) {
+                in_run = 0;
+                cur_row += p.run_stride - run_mask * MROWS;
+            } else {
+                cur_row += MROWS;
+            }
+            const uint32_t acc = lane_base + (uint32_t)as * MROWS;
+            if (p.dbg) {
+                // tests only: every distance of the tile (a second, unpipelined read of the accumulator)
+                for (int g = 0; g < 4; g++) {
+                    int w[16];
+                    __syncwarp();
+                    tmem_ld16(acc + 16 * g, w);
+                    tmem_wait_ld();
+                    if (qvalid)
+                        for (int j = 0; j < 16; j++)
+                            if (16 * g + j < nvalid)
+                                p.dbg[(size_t)(q0 + q) * p.dbg_stride + (lrow0 + 16 * g + j)] = pcq - (F4 ? (int)__int_as_float(w[j]) : w[j]);
+                }
+            }
+            // 64 columns in 4 groups of 16, software-pipelined over two register sets: the tcgen05.ld of group g + 1 is in
+            // flight while group g is examined; the accumulator goes back to the MMA issuer as soon as the last group has landed
+            int v[2][16];
+            __syncwarp();
+            tmem_ld16(acc, v[0]);
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                tmem_wait_ld();
+                if (g < 3)
+                    tmem_ld16(acc + 16 * (g + 1), v[(g + 1) & 1]);
+                else
+                    release_acc(as);
+                examine(v[g & 1], g, nvalid, lrow0);
+            }
+            overflow_check(t);
+        }
+        }
+        if (samp && qvalid) {
+            unsigned short* o_ = p.sample_out + (((size_t)strip * p.nq + q0 + q) * 2 + half) * SAMPLE_KEEP;
+#pragma unroll
+            for (int i = 0; i < SAMPLE_KEEP; i++) o_[i] = sbest[i] >= 0x7fff ? (unsigned short)0xFFFF : (unsigned short)sbest[i];
+        }
+        group_sync<EPI_THREADS>(BAR_CONSUMERS);
+        // final compaction: every list leaves the kernel with at most k keys (bounds the merge's working set)
+        for (int qq = warp; qq < qt && !p.sample_mode; qq += EPI_WARPS) {
+            const int n = sm->cnt_s[qq];
+            if (n > p.k)
+                compact_list_warp(p.lists + ((size_t)strip * p.nq + q0 + qq) * p.cap, n, p.k, &sm->sc[warp], lane, BAR_WARP0 + warp,
+                                  &sm->cnt_s[qq], &sm->tau_s[qq]);
+        }
+        group_sync<EPI_THREADS>(BAR_CONSUMERS);
+        if (qvalid && half == 0) p.counts[(size_t)strip * p.nq + q0 + q] = sm->cnt_s[q];
+    }
+    };
+    auto other_role = [&]() {
+    seg_begin_sync();
     if (warp == WARP_TMA) {
         // ===================== raw-code producer =====================
         if (lane == 0) {
@@ -454,6 +749,8 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                 __syncwarp();
             }
         }
+    } else if (warp >= WARP_EXP0 + EXP_WARPS) {
+        // pad warp (VAR = 4 only): completes the last warpgroup for setmaxnreg, no work
     } else if (warp >= WARP_EXP0) {
         // ===================== expanders: code bits -> one 128-byte K-block row of the B operand =====================
         const int et = tid - WARP_EXP0 * 32;
@@ -525,208 +822,37 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
                 rph ^= 1u;
             }
         }
-    } else {
-        // ===================== epilogue: lane = query, columns = database rows =====================
-        // 8 warps: warp & 3 = TMEM lane quadrant (32 queries), warp >> 2 = which 64 of the tile's 128 columns.  The two
-        // threads that share a query append to the same list through a shared-memory counter.
-        const int q = tid & (MQ - 1);
-        const int half = warp >> 2;
-        const bool qvalid = q < qt;
-        uint64_t* my_list = p.lists + ((size_t)strip * p.nq + q0 + (qvalid ? q : 0)) * p.cap;
-        const bool has_lo = p.key_lo != nullptr;
-        const unsigned long long lo_q = (has_lo && qvalid) ? p.key_lo[q0 + q] : 0ull;
-        int thr = qvalid ? pcq - sm->tau_s[q] : 0x7fffffff;  // survivor <=> dot > thr <=> hamming < tau
-        float thr_f = (float)thr;
-        constexpr bool samp = SAMP;  // list-free sample pass (thresholds only)
-        int sbest[SAMPLE_KEEP];  // ascending
-#pragma unroll
-        for (int i = 0; i < SAMPLE_KEEP; i++) sbest[i] = 0x7fff;
-        if (samp && qvalid) {
-            thr = pcq - 0x7fff;
-            thr_f = (float)thr;
-        }
-        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + TMEM_D_COL + (uint32_t)(half * 64);
-        const int limit = p.compact_limit > 0 ? min(p.compact_limit, p.cap - p.group_tiles * MROWS) : p.cap - p.group_tiles * MROWS;
-        int until_check = p.group_tiles;
-        int64_t cur_row = tile_row(0) + half * 64;
-        int in_run = (int)(tile0 & run_mask);
-        for (int t = 0; t < ntiles; t++) {
-            const uint32_t T = (uint32_t)(tbase + t);
-            const int as = (int)(T & 1u);
-            mbar_wait(smem_u32(&sm->acc_full[as]), (T >> 1) & 1u);
-            tc_fence_after();
-            const int64_t lrow0 = cur_row;  // first database row of this warp's 64 columns
-            const int64_t left = s_end - lrow0;
-            const int nvalid = left >= 64 ? 64 : (int)max(left, (int64_t)0);
-            // advance the tile cursor (dense scan: +128 rows; strided sample: +128 inside a run, a jump at its end)
-            if (++in_run > (int)run_mask) {
-                in_run = 0;
-                cur_row += p.run_stride - run_mask * MROWS;
-            } else {
-                cur_row += MROWS;
-            }
-            const uint32_t acc = lane_base + (uint32_t)as * MROWS;
-            if (p.dbg) {
-                // tests only: every distance of the tile (a second, unpipelined read of the accumulator)
-                for (int g = 0; g < 4; g++) {
-                    int w[16];
-                    __syncwarp();
-                    tmem_ld16(acc + 16 * g, w);
-                    tmem_wait_ld();
-                    if (qvalid)
-                        for (int j = 0; j < 16; j++)
-                            if (16 * g + j < nvalid)
-                                p.dbg[(size_t)(q0 + q) * p.dbg_stride + (lrow0 + 16 * g + j)] = pcq - (F4 ? (int)__int_as_float(w[j]) : w[j]);
-                }
-            }
-            // 64 columns in 4 groups of 16, software-pipelined over two register sets: the tcgen05.ld of group g + 1 is
-            // in flight while group g is examined; the accumulator goes back to the MMA issuer as soon as the last
-            // group has landed.
-            int v[2][16];
-            __syncwarp();
-            tmem_ld16(acc, v[0]);
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-                tmem_wait_ld();
-                if (g < 3) {
-                    tmem_ld16(acc + 16 * (g + 1), v[(g + 1) & 1]);
-                } else {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if constexpr (CG == 2)
-                            mbar_arrive_cluster(mapa_rank(smem_u32(&sm->acc_empty[as]), 0));
-                        else
-                            mbar_arrive(smem_u32(&sm->acc_empty[as]));
-                    }
-                }
-                const int(&w)[16] = v[g & 1];
-                const int nv = nvalid - 16 * g;  // valid columns in this group (>= 16: all)
-                // F4 accumulates in f32: the dots are integers of magnitude <= 1024, exact in binary32
-                auto dot_of = [&](int j) -> int { return F4 ? (int)__int_as_float(w[j]) : w[j]; };
-                bool any;
-                int m;
-                if constexpr (F4) {
-                    float mf = __int_as_float(w[0]);
-#pragma unroll
-                    for (int j = 1; j < 16; j++) mf = fmaxf(mf, __int_as_float(w[j]));
-                    any = mf > thr_f;
-                    m = (int)mf;
-                } else {
-                    m = w[0];
-#pragma unroll
-                    for (int j = 1; j < 16; j++) m = max(m, w[j]);
-                    any = m > thr;
-                }
-                if (samp) {
-                    // List-free sample pass: only (an upper bound of) the k'-th smallest DISTANCE of the sample matters.  Every
-                    // epilogue thread keeps the SAMPLE_KEEP smallest distances it has seen in registers (a branch-free sorted
-                    // insert, 7 min / max per element); its own threshold is the largest of them, so after the first tiles
-                    // almost no group gets here (the chance that row r of a thread is among its best so far is 4 / r).  The
-                    // k'-th smallest of the union over the threads of a query is >= the k'-th smallest of the whole sample and
-                    // equal to it unless one thread holds more than SAMPLE_KEEP of the k' best - a slightly looser threshold at
-                    // worst, never a wrong result (the dense pass is verified, scan.cu).
-                    if (any) {
-                        const unsigned long long pos0 = (unsigned long long)(p.pos_base + lrow0 + 16 * g);
-#pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            int x = pcq - dot_of(j);
-                            const bool ok = j < nv && !(has_lo && ((((unsigned long long)x) << VRQ_KEY_POS_BITS) | (pos0 + j)) <= lo_q);
-                            x = ok ? x : 0x7fff;
-#pragma unroll
-                            for (int i = 0; i < SAMPLE_KEEP - 1; i++) {
-                                const int lo_ = min(sbest[i], x);
-                                x = max(sbest[i], x);
-                                sbest[i] = lo_;
-                            }
-                            sbest[SAMPLE_KEEP - 1] = min(sbest[SAMPLE_KEEP - 1], x);
-                        }
-                        thr = pcq - sbest[SAMPLE_KEEP - 1];  // survivor <=> hamming < the largest distance this thread keeps
-                        thr_f = (float)thr;
-                    }
-                } else if (any) {
-                    // Some column of this lane survives.  bit (15 - j) of mask <=> w[j] > thr: the sign of thr - w[j] is
-                    // shifted in with one funnel shift per column (2 instructions per column, no branches).
-                    const unsigned long long pos0 = (unsigned long long)(p.pos_base + lrow0 + 16 * g);
-                    uint32_t mask = 0;
-#pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const uint32_t sgn = F4 ? __float_as_uint(thr_f - __int_as_float(w[j])) : (uint32_t)(thr - w[j]);
-                        mask = __funnelshift_l(sgn, mask, 1);
-                    }
-                    if (nv < 16) mask = nv <= 0 ? 0u : (mask & ~(0xFFFFu >> nv));
-                    if (has_lo) {
-                        // a later chunk of a large top-k: keys at or below the chunk's lower bound were returned already
-#pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            if ((mask >> (15 - j)) & 1u) {
-                                const unsigned long long key = ((unsigned long long)(pcq - dot_of(j)) << VRQ_KEY_POS_BITS) | (pos0 + j);
-                                if (key > lo_q) {
-                                    const int slot = atomicAdd(&sm->cnt_s[q], 1);
-                                    if (slot >= p.cap) __trap();
-                                    my_list[slot] = key;
-                                }
-                            }
-                        }
-                    } else if (__popc(mask) == 1 && nv >= 16) {
-                        // the usual case once tau has converged: the single survivor is the maximum itself
-                        const int slot = atomicAdd(&sm->cnt_s[q], 1);
-                        if (slot >= p.cap) __trap();  // cannot happen (overflow check every group_tiles tiles); never write past a list
-                        my_list[slot] = ((unsigned long long)(pcq - m) << VRQ_KEY_POS_BITS) | (pos0 + (__clz((int)mask) - 16));
-                    } else if (mask) {
-                        int slot = atomicAdd(&sm->cnt_s[q], __popc(mask));
-                        if (slot + __popc(mask) > p.cap) __trap();
-#pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            if ((mask >> (15 - j)) & 1u) {
-                                my_list[slot] = ((unsigned long long)(pcq - dot_of(j)) << VRQ_KEY_POS_BITS) | (pos0 + j);
-                                slot++;
-                            }
-                        }
-                    }
-                }
-            }
-            // ---- overflow check every group_tiles tiles: no list may exceed cap during the next group ----
-            if (!samp && --until_check == 0 && t + 1 < ntiles) {
-                until_check = p.group_tiles;
-                group_sync<EPI_THREADS>(BAR_CONSUMERS);  // every append of this group of tiles is in its list
-                if (epi_sync_or(sm->cnt_s[q] > limit)) {
-                    for (int qq = warp; qq < qt; qq += EPI_WARPS) {  // one list per warp, 8 lists at a time
-                        const int n = sm->cnt_s[qq];
-                        if (n > limit)
-                            compact_list_warp(p.lists + ((size_t)strip * p.nq + q0 + qq) * p.cap, n, p.k, &sm->sc[warp], lane, BAR_WARP0 + warp,
-                                              &sm->cnt_s[qq], &sm->tau_s[qq], p.sample_mode ? limit : 0);
-                    }
-                    group_sync<EPI_THREADS>(BAR_CONSUMERS);
-                    if (qvalid) thr = pcq - sm->tau_s[q];
-                    thr_f = (float)thr;
-                }
-            }
-        }
-        if (samp && qvalid) {
-            unsigned short* o_ = p.sample_out + (((size_t)strip * p.nq + q0 + q) * 2 + half) * SAMPLE_KEEP;
-#pragma unroll
-            for (int i = 0; i < SAMPLE_KEEP; i++) o_[i] = sbest[i] >= 0x7fff ? (unsigned short)0xFFFF : (unsigned short)sbest[i];
-        }
-        group_sync<EPI_THREADS>(BAR_CONSUMERS);
-        // final compaction: every list leaves the kernel with at most k keys (bounds the merge's working set)
-        for (int qq = warp; qq < qt && !p.sample_mode; qq += EPI_WARPS) {
-            const int n = sm->cnt_s[qq];
-            if (n > p.k)
-                compact_list_warp(p.lists + ((size_t)strip * p.nq + q0 + qq) * p.cap, n, p.k, &sm->sc[warp], lane, BAR_WARP0 + warp,
-                                  &sm->cnt_s[qq], &sm->tau_s[qq]);
-        }
-        group_sync<EPI_THREADS>(BAR_CONSUMERS);
-        if (qvalid && half == 0) p.counts[(size_t)strip * p.nq + q0 + q] = sm->cnt_s[q];
     }
-    // end of the segment: every role is done with its tiles (the last accumulators were read, so every MMA has completed)
-    // before the next segment rewrites the query operand in tensor memory - in both CTAs of a pair
-    tbase += ntiles;
-    tc_fence_before();
-    __syncthreads();
-    if constexpr (CG == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared memory and TMEM until the very end
-    tc_fence_after();
-  }  // segments
+    };
+    if constexpr (VAR == 4) {
+        // The CTA's register pool is what it was launched with: 20 warps x 96.  8 epilogue warps x 128 + 12 others x 72 = 1888
+        // <= 1920 per lane; per scheduler partition 2 x 128 + 3 x 72 = 472 <= 480.  (136 / 80 exceeds the pool: the inc never
+        // returns.)
+        if (warp < EPI_WARPS) {
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+            for (int sgi = 0; segment(sgi); sgi++) {
+                epilogue_role(sgi);
+                tbase += ntiles;
+                seg_end_sync();
+            }
+        } else {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+            for (int sgi = 0; segment(sgi); sgi++) {
+                other_role();
+                tbase += ntiles;
+                seg_end_sync();
+            }
+        }
+    } else {
+        for (int sgi = 0; segment(sgi); sgi++) {
+            if (warp < EPI_WARPS)
+                epilogue_role(sgi);
+            else
+                other_role();
+            tbase += ntiles;
+            seg_end_sync();
+        }
+    }
 
     if (warp == WARP_MMA) {
         tc_fence_after();
@@ -1170,10 +1296,15 @@ int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const CUtensorMap&
     } else if (pl.f4 && pl.pair) {
         // CTA pairs: clusters of 2 along x = two neighbouring query tiles of the same strip
         auto kern = sp.sample_out ? hamming_scan_mma_kernel<KIND_F4, 2, true> : hamming_scan_mma_kernel<KIND_F4, 2, false>;
+        // the lean epilogue loop (VAR 4) is written for the dense scan (runs of one tile) without the tests' distance dump;
+        // VRQ_MMA_VAR=0 keeps the generic loop
+        int var = sp.sample_out ? 0 : env_int("VRQ_MMA_VAR", 4);
+        if (var != 4 || !(sp.run_shift == 0 && sp.run_stride == MROWS && sp.dbg == nullptr)) var = 0;
+        if (var == 4) kern = hamming_scan_mma_kernel<KIND_F4, 2, false, 4>;
         VRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = grid;
-        cfg.blockDim = dim3(MMA_KERNEL_THREADS);
+        cfg.blockDim = dim3(var == 4 ? MMA_KERNEL_THREADS + 32 : MMA_KERNEL_THREADS);
         cfg.dynamicSmemBytes = pl.smem;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
