@@ -1212,12 +1212,12 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
     pl->few = pl->f4 && nq <= FEW_MAXQ && env_int("VRQ_MMA_FEW", 1) != 0;
     // 33 .. 96 queries: the same kernel with its thresholds in shared memory.  OPT-IN (VRQ_MMA_MID=1), a measured negative
     // result: the time per MMA of the swapped orientation grows like N^2 beyond 32 query columns (100 M codes: 5.3 ms at 48
-    // queries, 8.1 ms at 64, 15.3 ms at 96, against 4.9 ms for the 128-query-tile kernel; profiles/r02/mid_regime.md).
+    // queries, 8.1 ms at 64, 15.3 ms at 96, against 4.9 ms for the 128-query-tile kernel).
     pl->mid = pl->f4 && !pl->few && nq <= MID_MAXQ && env_int("VRQ_MMA_FEW", 1) != 0 && env_int("VRQ_MMA_MID", 0) != 0;
     if (pl->mid) pl->few = true;
     // CTA pairs need an even number of query tiles (a pair = two neighbouring tiles); VRQ_MMA_PAIR=0 switches them off
     pl->pair = pl->f4 && pl->qtiles % 2 == 0 && env_int("VRQ_MMA_PAIR", 1) != 0;
-    pl->group_tiles = env_int("VRQ_MMA_GROUP_TILES", 8);
+    pl->group_tiles = env_int("VRQ_MMA_GROUP_TILES", 32);  // tiles between two overflow checks of the lists (measured: 8 -> 32 = +1.3 %)
     if (pl->group_tiles < 1) pl->group_tiles = 1;
     const int slack = k < 256 ? 256 : (k > 2048 ? 2048 : k);
     pl->cap = k + slack + pl->group_tiles * MROWS;
