@@ -16,6 +16,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #define CK(x)                                                                          \
     do {                                                                               \
@@ -94,7 +95,7 @@ template <int CG, int N>
 __global__ void __launch_bounds__(128, 1) mxf4_issue_kernel(int tiles, int pattern, unsigned long long* cycles_out) {
     constexpr int MY_ROWS = N / CG;             // rows of B this CTA holds
     constexpr int KB_BYTES = MY_ROWS * 128;     // one K-block (256 e2m1 elements per row = 128 bytes)
-    constexpr int NACC = N == 128 ? 2 : 1;
+    constexpr int NACC = N <= 128 ? 2 : 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* b_mem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // 4 K-blocks
     __shared__ unsigned long long done_bar[2];
@@ -257,6 +258,16 @@ int main(int argc, char** argv) {
     printf("%s, %d SMs; %d tiles of 16 MMAs per CTA (pair)\n", prop.name, prop.multiProcessorCount, tiles);
     unsigned long long* cyc_dev;
     CK(cudaMalloc(&cyc_dev, sizeof(unsigned long long) * 256));
+    if (argc > 2 && !strcmp(argv[2], "smalln")) {
+        // the swapped-operand kernels (database rows = M = 128, queries = N): does the MMA rate hold at small N?
+        run<1, 16>(prop.multiProcessorCount, tiles, 1, cyc_dev);
+        run<1, 32>(prop.multiProcessorCount, tiles, 1, cyc_dev);
+        run<1, 48>(prop.multiProcessorCount, tiles, 1, cyc_dev);
+        run<1, 64>(prop.multiProcessorCount, tiles, 1, cyc_dev);
+        run<1, 96>(prop.multiProcessorCount, tiles, 1, cyc_dev);
+        run<1, 128>(prop.multiProcessorCount, tiles, 1, cyc_dev);
+        return 0;
+    }
     for (int pattern = 0; pattern < 3; pattern++) {
         run<2, 128>(prop.multiProcessorCount, tiles, pattern, cyc_dev);
         run<2, 256>(prop.multiProcessorCount, tiles, pattern, cyc_dev);

@@ -640,9 +640,9 @@ struct PassPlan {
     }
 };
 
-static int plan_pass(vrq_ctx* ctx, bool tma, bool mma, int code_bytes, int64_t rows, int nq, int k, PassPlan* pl) {
+static int plan_pass(vrq_ctx* ctx, bool tma, bool mma, int code_bytes, int64_t rows, int nq, int k, PassPlan* pl, bool allow_few = true) {
     pl->mma = mma;
-    if (mma) return plan_scan_mma(ctx, rows, nq, k, &pl->mp);
+    if (mma) return plan_scan_mma(ctx, rows, nq, k, &pl->mp, allow_few);
     return plan_scan(ctx, tma, code_bytes, rows, nq, k, &pl->sp);
 }
 
@@ -716,7 +716,9 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
             const int64_t run_stride = (total_tiles / runs) * MMA_TILE_ROWS;  // >= 16 tiles: runs never overlap
             const int64_t actual_tiles = runs * 16;
             PassPlan s_pl, m_pl;
-            VRQ_TRY(plan_pass(ctx, tma, true, code_bytes, actual_tiles * MMA_TILE_ROWS, nq, kp, &s_pl));
+            // the sample pass always runs on the 128-query-tile kernel in its list-free form (a few dozen microseconds); the
+            // swapped-operand kernels would sample through lists that flood until the first compaction (0.2 - 0.5 ms)
+            VRQ_TRY(plan_pass(ctx, tma, true, code_bytes, actual_tiles * MMA_TILE_ROWS, nq, kp, &s_pl, env_int("VRQ_MMA_SAMPLE_FEW", 0) != 0));
             VRQ_TRY(plan_pass(ctx, tma, true, code_bytes, n, nq, k, &m_pl));
             const int cap = s_pl.cap() > m_pl.cap() ? s_pl.cap() : m_pl.cap();
             s_pl.set_cap(tma, code_bytes, cap);

@@ -239,13 +239,14 @@ struct MmaPlan {
     int64_t rows_per_strip;
     size_t smem, smem_limit;
     bool f4;    // packed e2m1 operands (kind::mxf4) instead of int8
-    bool mid;   // 33 .. 96 queries: the swapped-operand kernel with thresholds in shared memory
+    bool mid;   // 33 .. 64 queries on the swapped-operand kernel (wide form only)
+    bool wide;  // the swapped-operand kernel with the bias column (one threshold for all query columns)
     bool few;   // <= 64 queries: swapped-operand kernel (database rows = M, expanded straight into tensor memory)
     bool pair;  // CTA pairs (tcgen05 cta_group::2): two query tiles share every tile of database rows
     int seg_cols, seg_full, seg_tail;  // pair scheduler (see ScanParams); seg_cols == 0: classic grid
 };
 constexpr int MMA_TILE_ROWS = 128;
-int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl);
+int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl, bool allow_few = true);
 void mma_plan_set_cap(MmaPlan* pl, int cap);
 int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const CUtensorMap& tmap64, const ScanParams& sp, const MmaPlan& pl,
                     cudaStream_t st);

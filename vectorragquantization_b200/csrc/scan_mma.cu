@@ -1192,6 +1192,416 @@ hamming_scan_mma_few_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams
     }
 }
 
+// =====================================================================================================================
+// 4 .. 64 queries per pass, second generation of the swapped-operand kernel above ("wide").  Three changes:
+//   * ONE threshold for every query column.  A 17th MMA per tile adds a per-query bias to the accumulator: the A operand of
+//     that MMA is a constant (62 elements 4.0, 2 elements 1.0, written to tensor memory once), its B operand is a fifth
+//     K-block of the query rows in shared memory that encodes bias = -(popc(q) - tau) as a sum of e2m1 products
+//     (4 x {6, 4, 3, 2, 1.5, 1, 0.5} = 24, 16, 12, 8, 6, 4, 2, plus 1 x 1).  The accumulator then holds dot - thr(q): a row has
+//     a survivor <=> the MAXIMUM over its columns is > 0 - a tree of 3-input maxima and one compare per row instead of a
+//     subtract and a maximum per column (which is what made the per-column form slower than linear in N).  Thresholds that
+//     tighten later (compaction) make the bias conservative, never wrong: the exact test is redone on the survivors.
+//   * The expanders split a tile by (row, half of K): all eight warps work on every tile (4 x LDS.128, 64 ALU, 2 x tcgen05.st.x32
+//     per thread) instead of four warps per tile doing twice that.
+//   * The accumulator goes back to the issuer before anything is examined; barrier addresses are loop invariants.
+constexpr int WIDE_MAXQ = 64;
+constexpr uint32_t WIDE_BIAS_COL = 384;  // 8 columns: the constant A operand of the bias MMA
+constexpr int WIDE_BIAS_MAX = 1440;      // 60 x 24: beyond every |dot| <= 1024, i.e. "always" / "never"
+
+// One survivor of the wide kernel goes to its query's list.  NOT inlined: the body (exact re-test against the current
+// threshold, key, slot atomic, store) exists once in the kernel instead of once per accumulator column - unrolled into every
+// column the survivor path was ~40 KB of code that ran out of the instruction cache (ncu: stall_no_inst, ~5600 cycles per
+// visit, which is what made the per-column form of this kernel slower than linear in the number of queries).
+__device__ __noinline__ void wide_append(const float* bias_s, const float* thr_s, const int* pcq_s, int* cnt_s, uint64_t* lists0,
+                                         const unsigned long long* key_lo, int cap, unsigned long long pos, int q, float f) {
+    const float dot = f - bias_s[q];  // exact: integers below 2^24
+    if (dot > thr_s[q]) {             // the CURRENT threshold (the bias may be older)
+        const unsigned long long key = ((unsigned long long)(pcq_s[q] - (int)dot) << VRQ_KEY_POS_BITS) | pos;
+        if (key_lo == nullptr || key > key_lo[q]) {
+            const int slot = atoms_add(smem_u32(&cnt_s[q]), 1);
+            if (slot >= cap) __trap();
+            lists0[(size_t)q * cap + slot] = key;
+        }
+    }
+}
+// element j (runtime) of 16 registers: a tree of selects
+__device__ __forceinline__ int sel16(const int (&w)[16], int j) {
+    int a[8], b[4], c[2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = (j & 1) ? w[2 * i + 1] : w[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+    for (int i = 0; i < 2; i++) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+    return (j & 8) ? c[1] : c[0];
+}
+
+template <int MAXQ>
+struct WideSmem {
+    unsigned long long raw_full[FEW_MAX_RAW], raw_empty[FEW_MAX_RAW];
+    unsigned long long a_full[2], a_empty[2], acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    int tau_s[MAXQ];
+    int cnt_s[MAXQ];
+    int pcq_s[MAXQ];
+    __align__(16) float thr_s[MAXQ];   // current exact threshold of the query: survivor <=> dot > thr_s
+    __align__(16) float bias_s[MAXQ];  // what the bias MMA added to the query's column
+    SelectScratch sc[FEW_EPI_WARPS];
+};
+
+template <int MAXQ>
+__global__ void __launch_bounds__(FEW_THREADS, 1)
+hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, int raw_stages, int npad) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* raw_mem = base;                                          // [raw_stages][128 rows][128 B], TMA SWIZZLE_128B
+    uint8_t* q_mem = raw_mem + (size_t)raw_stages * STAGE_BYTES_RAW;  // [5 K-blocks][npad queries][128 B], same swizzle
+    WideSmem<MAXQ>* sm = (WideSmem<MAXQ>*)(q_mem + (size_t)5 * MAXQ * 128);
+    constexpr uint32_t D_STRIDE = 64;
+    constexpr int NG = MAXQ / 16;  // 16-column groups of the accumulator
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nq = p.nq;  // <= MAXQ, one query tile
+    const int strip = blockIdx.y;
+    const int tiles_per_strip = (int)(p.rows_per_strip / MROWS);
+    const int64_t tile0 = (int64_t)strip * tiles_per_strip;
+    const int ntiles = (int)max((int64_t)0, min((int64_t)tiles_per_strip, p.total_tiles - tile0));
+    const int64_t run_mask = ((int64_t)1 << p.run_shift) - 1;
+    auto tile_row = [&](int t) -> int64_t {
+        const int64_t i = tile0 + t;
+        return p.row_begin + (i >> p.run_shift) * p.run_stride + (i & run_mask) * MROWS;
+    };
+    const int64_t s_end = p.row_end;
+    if (p.guard && *p.guard == 0) return;
+
+    if (tid == 0) {
+        for (int s = 0; s < raw_stages; s++) {
+            mbar_init(smem_u32(&sm->raw_full[s]), 1);
+            mbar_init(smem_u32(&sm->raw_empty[s]), FEW_EXP_WARPS);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(smem_u32(&sm->a_full[s]), FEW_EXP_WARPS);
+            mbar_init(smem_u32(&sm->a_empty[s]), 1);
+            mbar_init(smem_u32(&sm->acc_full[s]), 1);
+            mbar_init(smem_u32(&sm->acc_empty[s]), FEW_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (tid < MAXQ) {
+        sm->pcq_s[tid] = 0;
+        sm->cnt_s[tid] = 0;
+        sm->tau_s[tid] = tid < nq ? (p.tau0 ? min(p.tau0[tid], TAU_INF - 1) + p.tau_bias : TAU_INF) : 0;
+    }
+    if (warp == FEW_WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm->tmem_base;
+
+    // ---- the queries become the B operand in shared memory: row = query, K-block kb = code words 8 kb .. 8 kb + 7, chunk i
+    //      of the 128-byte row = word 8 kb + i as four planes (nibble j of plane t = bit t + 4 j) of +-(1 / plane value)
+    for (int idx = tid; idx < npad * 32; idx += FEW_THREADS) {
+        const int q = idx >> 5, W = idx & 31;
+        const bool qvalid = q < nq;
+        const uint32_t w = qvalid ? __ldg(reinterpret_cast<const uint32_t*>(p.queries + (size_t)q * CODE_BYTES) + W) : 0u;
+        if (qvalid) atomicAdd(&sm->pcq_s[q], __popc(w));
+        uint32_t v[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const uint32_t mag = t == 0 ? 0x44444444u : (t == 1 ? 0x22222222u : 0x11111111u);
+            v[t] = qvalid ? ((mag | 0x88888888u) ^ (((w >> t) & 0x11111111u) << 3)) : 0u;
+        }
+        const int kb = W >> 3, i = W & 7;
+        sts128(smem_u32(q_mem) + (uint32_t)(kb * npad * 128 + q * 128 + ((i ^ (q & 7)) << 4)), v[0], v[1], v[2], v[3]);
+    }
+    if (warp < FEW_EPI_WARPS) {
+        // every block scale (UE8M0) = 0x7F = 2^0; the constant A operand of the bias MMA: K positions 0 .. 61 = 4.0 (0x6),
+        // 62, 63 = 1.0 (0x2)
+        uint32_t one[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) one[t] = 0x7F7F7F7Fu;
+#pragma unroll
+        for (int c = 0; c < 64; c += 8) tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + FEW_SF_COL + c, one);
+        uint32_t ca[8];
+#pragma unroll
+        for (int t = 0; t < 7; t++) ca[t] = 0x66666666u;
+        ca[7] = 0x22666666u;
+        tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + WIDE_BIAS_COL, ca);
+        tmem_wait_st();
+    }
+    __syncthreads();  // pcq_s complete
+    if (tid < npad) {
+        // bias(q) = -(popc(q) - tau(q)) clamped to "always" / "never"; padding columns never survive
+        const int q = tid;
+        const int tau = sm->tau_s[q];
+        int bias = -WIDE_BIAS_MAX;
+        float thr = 3.0e9f;
+        if (q < nq) {
+            const int t = sm->pcq_s[q] - tau;  // survivor <=> dot > t
+            thr = (float)t;
+            bias = tau >= TAU_INF ? WIDE_BIAS_MAX : max(-WIDE_BIAS_MAX, min(WIDE_BIAS_MAX, -t));
+        }
+        sm->thr_s[q] = thr;
+        sm->bias_s[q] = (float)bias;
+        // |bias| = 24 n24 + rem (even, < 24: at most two more products) + odd; nibble p of the 64: products of the constant
+        // operand (4.0 at p < 62, 1.0 at p = 62) with e2m1 codes 7 = 6.0, 6 = 4.0, 5 = 3.0, 4 = 2.0, 3 = 1.5, 2 = 1.0, 1 = 0.5
+        const uint32_t sgn = bias < 0 ? 0x8u : 0x0u;
+        const int mag = bias < 0 ? -bias : bias;
+        const int odd = mag & 1, n24 = (mag - odd) / 24, rem = (mag - odd) % 24;
+        uint32_t c1 = 0, c2 = 0;  // e2m1 codes of the (up to two) products that make up rem
+        switch (rem) {
+            case 2: c1 = 1; break;
+            case 4: c1 = 2; break;
+            case 6: c1 = 3; break;
+            case 8: c1 = 4; break;
+            case 10: c1 = 4, c2 = 1; break;
+            case 12: c1 = 5; break;
+            case 14: c1 = 5, c2 = 1; break;
+            case 16: c1 = 6; break;
+            case 18: c1 = 6, c2 = 1; break;
+            case 20: c1 = 6, c2 = 2; break;
+            case 22: c1 = 6, c2 = 3; break;
+            default: break;
+        }
+        uint32_t wd[8];
+#pragma unroll
+        for (int wi = 0; wi < 8; wi++) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int pos = 8 * wi + j;
+                uint32_t code = 0;
+                if (pos < n24) code = 7;
+                else if (pos == n24) code = c1;
+                else if (pos == n24 + 1) code = c2;
+                if (pos == 62) code = odd ? 2u : 0u;
+                if (pos == 63) code = 0;
+                if (code) code |= sgn;
+                x |= code << (4 * j);
+            }
+            wd[wi] = x;
+        }
+        const uint32_t rowa = smem_u32(q_mem) + (uint32_t)(4 * npad * 128 + q * 128);
+        sts128(rowa + (((uint32_t)0 ^ (uint32_t)(q & 7)) << 4), wd[0], wd[1], wd[2], wd[3]);
+        sts128(rowa + (((uint32_t)1 ^ (uint32_t)(q & 7)) << 4), wd[4], wd[5], wd[6], wd[7]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == FEW_WARP_TMA) {
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (int t = 0; t < ntiles; t++) {
+                mbar_wait_relaxed(smem_u32(&sm->raw_empty[s]), ph ^ 1u, 128);
+                mbar_expect_tx(smem_u32(&sm->raw_full[s]), STAGE_BYTES_RAW);
+                tma_load_2d(smem_u32(raw_mem) + s * (uint32_t)STAGE_BYTES_RAW, &tmap, 0, (int)tile_row(t), smem_u32(&sm->raw_full[s]));
+                if (++s == (uint32_t)raw_stages) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+    } else if (warp == FEW_WARP_MMA) {
+        // ===================== MMA issuer: 16 + 1 MMAs (M = 128 rows, N = npad queries, K = 64) per tile ===================
+        const uint32_t idesc = (1u << 7) | (1u << 10) | ((uint32_t)(npad >> 3) << 17) | (1u << 23) | ((uint32_t)(MQ >> 4) << 24);
+        const uint64_t qdesc0 = umma_desc_sw128(smem_u32(q_mem));
+        const uint32_t kb_step = (uint32_t)(npad * 128) >> 4;
+        uint32_t bar_a_full = smem_u32(&sm->a_full[0]), bar_a_empty = smem_u32(&sm->a_empty[0]);
+        uint32_t bar_acc_full = smem_u32(&sm->acc_full[0]), bar_acc_empty = smem_u32(&sm->acc_empty[0]);
+        asm volatile("" : "+r"(bar_a_full), "+r"(bar_a_empty), "+r"(bar_acc_full), "+r"(bar_acc_empty));
+        for (int t = 0; t < ntiles; t++) {
+            const uint32_t ab = (uint32_t)t & 1u, ph = ((uint32_t)t >> 1) & 1u;
+            mbar_wait(bar_a_full + 8u * ab, ph);
+            mbar_wait(bar_acc_empty + 8u * ab, ph ^ 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d_tmem = tmem + FEW_D_COL + ab * D_STRIDE, a0 = tmem + FEW_A_COL + ab * 128;
+#pragma unroll
+                for (int s = 0; s < 16; s++)
+                    umma_f4_ts(d_tmem, a0 + 8 * s, qdesc0 + (uint64_t)((s >> 2) * kb_step + (s & 3) * 2), idesc, tmem + FEW_SF_COL,
+                               tmem + FEW_SF_COL + 32, s != 0);
+                umma_f4_ts(d_tmem, tmem + WIDE_BIAS_COL, qdesc0 + (uint64_t)(4 * kb_step), idesc, tmem + FEW_SF_COL, tmem + FEW_SF_COL + 32, 1);
+                tc_commit(bar_a_empty + 8u * ab);
+                tc_commit(bar_acc_full + 8u * ab);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= FEW_WARP_EXP0) {
+        // ===================== expanders: thread = (database row = TMEM lane, half of K); all 8 warps on every tile ========
+        const int kh = (warp - FEW_WARP_EXP0) >> 2;  // which 64 code bytes (chunks 4 kh .. 4 kh + 3) -> which 64 columns
+        const int row = (warp & 3) * 32 + lane;      // a warp may only touch the TMEM lane quadrant warp_id % 4
+        const uint32_t sw = (uint32_t)(row & 7);
+        uint32_t a_buf0 = tmem + ((uint32_t)((warp & 3) * 32) << 16) + FEW_A_COL + (uint32_t)kh * 64;
+        uint32_t raw0 = smem_u32(raw_mem) + (uint32_t)row * 128u;
+        uint32_t bar_raw_full = smem_u32(&sm->raw_full[0]), bar_raw_empty = smem_u32(&sm->raw_empty[0]);
+        uint32_t bar_a_full = smem_u32(&sm->a_full[0]), bar_a_empty = smem_u32(&sm->a_empty[0]);
+        asm volatile("" : "+r"(a_buf0), "+r"(raw0), "+r"(bar_raw_full), "+r"(bar_raw_empty), "+r"(bar_a_full), "+r"(bar_a_empty));
+        uint32_t rs = 0, rph = 0;
+        for (int t = 0; t < ntiles; t++) {
+            const uint32_t ab = (uint32_t)t & 1u, ph = ((uint32_t)t >> 1) & 1u;
+            mbar_wait_relaxed(bar_raw_full + 8u * rs, rph, 32);
+            const uint32_t raddr = raw0 + rs * (uint32_t)STAGE_BYTES_RAW;
+            uint4 c[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) c[j] = lds128(raddr + (((uint32_t)(4 * kh + j) ^ sw) << 4));
+            mbar_wait(bar_a_empty + 8u * ab, ph ^ 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int part = 0; part < 2; part++) {
+                // words 8 (2 kh + part) .. + 7 of the code -> columns 64 kh + 32 part .. + 31 (column 4 W + t = plane t of word W)
+                const uint32_t w[8] = {c[2 * part].x, c[2 * part].y, c[2 * part].z, c[2 * part].w,
+                                       c[2 * part + 1].x, c[2 * part + 1].y, c[2 * part + 1].z, c[2 * part + 1].w};
+                uint32_t v[32];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    v[4 * i + 0] = w[i] & 0x11111111u;
+                    v[4 * i + 1] = w[i] & 0x22222222u;
+                    v[4 * i + 2] = w[i] & 0x44444444u;
+                    v[4 * i + 3] = (w[i] >> 1) & 0x44444444u;
+                }
+                tmem_st32(a_buf0 + ab * 128 + 32 * part, v);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar_a_full + 8u * ab);
+                mbar_arrive(bar_raw_empty + 8u * rs);  // every c[j] has been consumed by real instructions
+            }
+            if (++rs == (uint32_t)raw_stages) {
+                rs = 0;
+                rph ^= 1u;
+            }
+        }
+    } else {
+        // ===================== epilogue: lane = database row, column = query ==========================================
+        uint32_t acc0 = tmem + ((uint32_t)(warp * 32) << 16) + FEW_D_COL;
+        uint32_t bar_acc_full = smem_u32(&sm->acc_full[0]), bar_acc_empty = smem_u32(&sm->acc_empty[0]);
+        asm volatile("" : "+r"(acc0), "+r"(bar_acc_full), "+r"(bar_acc_empty));
+        const int limit = p.compact_limit > 0 ? min(p.compact_limit, p.cap - p.group_tiles * MROWS) : p.cap - p.group_tiles * MROWS;
+        uint64_t* const lists0 = p.lists + (size_t)strip * p.nq * p.cap;
+        int until_check = p.group_tiles;
+        const int ng = npad >> 4;  // column groups in use (npad is a multiple of 16)
+        const bool has_dbg = p.dbg != nullptr;
+        auto max16 = [](const int(&w)[16]) -> float {
+            auto f = [&](int j) -> float { return __int_as_float(w[j]); };
+            auto mx3 = [](float x, float y, float z) -> float { return fmaxf(fmaxf(x, y), z); };
+            const float a0 = mx3(f(0), f(1), f(2)), a1 = mx3(f(3), f(4), f(5)), a2 = mx3(f(6), f(7), f(8));
+            const float a3 = mx3(f(9), f(10), f(11)), a4 = mx3(f(12), f(13), f(14));
+            return fmaxf(mx3(a0, a1, a2), mx3(a3, a4, f(15)));
+        };
+        for (int t = 0; t < ntiles; t++) {
+            const uint32_t ab = (uint32_t)t & 1u;
+            mbar_wait(bar_acc_full + 8u * ab, ((uint32_t)t >> 1) & 1u);
+            tc_fence_after();
+            int v[NG][16];
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < NG; g++)
+                if (g < ng) tmem_ld16(acc0 + ab * D_STRIDE + 16 * g, v[g]);
+            tmem_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty + 8u * ab);  // the accumulator goes back before anything is examined
+            float gm[NG];
+            float mx = -3.0e9f;
+#pragma unroll
+            for (int g = 0; g < NG; g++) {
+                gm[g] = g < ng ? max16(v[g]) : -3.0e9f;
+                mx = fmaxf(mx, gm[g]);
+            }
+            if (mx > 0.0f || has_dbg) {
+                const int64_t lrow = tile_row(t) + warp * 32 + lane;
+                if (lrow < s_end) {
+                    if (has_dbg) {
+                        // tests only: every distance of the tile
+#pragma unroll
+                        for (int g = 0; g < NG; g++)
+                            if (g < ng)
+                                for (int j = 0; j < 16; j++) {
+                                    const int q = 16 * g + j;
+                                    if (q < nq) p.dbg[(size_t)q * p.dbg_stride + lrow] = sm->pcq_s[q] - (int)(__int_as_float(sel16(v[g], j)) - sm->bias_s[q]);
+                                }
+                    }
+                    const unsigned long long pos = (unsigned long long)(p.pos_base + lrow);
+#pragma unroll
+                    for (int g = 0; g < NG; g++) {
+                        if (g < ng && gm[g] > 0.0f) {
+                            // bit (15 - j) <=> column 16 g + j is > 0: the sign of 0 - f, one add + one funnel shift per column
+                            uint32_t mask = 0;
+#pragma unroll
+                            for (int j = 0; j < 16; j++) mask = __funnelshift_l(__float_as_uint(0.0f - __int_as_float(v[g][j])), mask, 1);
+                            mask &= 0xFFFFu;
+                            while (mask) {
+                                const int b = 31 - __clz((int)mask);
+                                mask &= ~(1u << b);
+                                const int j = 15 - b;
+                                wide_append(sm->bias_s, sm->thr_s, sm->pcq_s, sm->cnt_s, lists0, p.key_lo, p.cap, pos, 16 * g + j,
+                                            __int_as_float(sel16(v[g], j)));
+                            }
+                        }
+                    }
+                }
+            }
+            if (--until_check == 0 && t + 1 < ntiles) {
+                until_check = p.group_tiles;
+                group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
+                const int over = (tid < nq && sm->cnt_s[tid] > limit) ? 1 : 0;
+                int any;
+                asm volatile(
+                    "{\n"
+                    ".reg .pred p, q;\n"
+                    "setp.ne.s32 q, %1, 0;\n"
+                    "bar.red.or.pred p, %2, %3, q;\n"
+                    "selp.s32 %0, 1, 0, p;\n"
+                    "}\n"
+                    : "=r"(any)
+                    : "r"(over), "n"(BAR_CONSUMERS), "n"(FEW_EPI_THREADS)
+                    : "memory");
+                if (any) {
+                    for (int qq = warp; qq < nq; qq += FEW_EPI_WARPS) {
+                        const int n = sm->cnt_s[qq];
+                        if (n > limit)
+                            compact_list_warp(lists0 + (size_t)qq * p.cap, n, p.k, &sm->sc[warp], lane, BAR_WARP0 + warp, &sm->cnt_s[qq],
+                                              &sm->tau_s[qq], p.sample_mode ? limit : 0);
+                    }
+                    group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
+                    if (tid < nq) sm->thr_s[tid] = (float)(sm->pcq_s[tid] - sm->tau_s[tid]);
+                    group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
+                }
+            }
+        }
+        group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
+        for (int qq = warp; qq < nq && !p.sample_mode; qq += FEW_EPI_WARPS) {
+            const int n = sm->cnt_s[qq];
+            if (n > p.k)
+                compact_list_warp(lists0 + (size_t)qq * p.cap, n, p.k, &sm->sc[warp], lane, BAR_WARP0 + warp, &sm->cnt_s[qq], &sm->tau_s[qq]);
+        }
+        group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
+        if (tid < nq) p.counts[(size_t)strip * p.nq + tid] = sm->cnt_s[tid];
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == FEW_WARP_MMA) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+size_t wide_smem_bytes(int raw_stages, int maxq) {
+    return 1024 + (size_t)raw_stages * STAGE_BYTES_RAW + (size_t)5 * maxq * 128 +
+           (maxq <= 32 ? sizeof(WideSmem<FEW_MAXQ>) : sizeof(WideSmem<WIDE_MAXQ>)) + 16;
+}
+
 size_t few_smem_bytes(int raw_stages, bool mid) {
     return 1024 + (size_t)raw_stages * STAGE_BYTES_RAW + (size_t)4 * (mid ? MID_MAXQ : FEW_MAXQ) * 128 +
            (mid ? sizeof(FewSmem<MID_MAXQ>) : sizeof(FewSmem<FEW_MAXQ>)) + 16;
@@ -1204,16 +1614,17 @@ size_t mma_smem_bytes(int raw_stages, int cap) {
 
 }  // namespace
 
-int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
+int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl, bool allow_few) {
     const int sms = ctx->sm_count;
     pl->f4 = env_int("VRQ_MMA_KIND", 4) != 8;  // 4 (default): packed e2m1 operands, 8: int8 operands
     pl->qtiles = (nq + MQ - 1) / MQ;
     // <= 64 queries: the swapped-operand kernel (database rows = M), HBM-bound instead of bound by 8 tensor cycles per row
-    pl->few = pl->f4 && nq <= FEW_MAXQ && env_int("VRQ_MMA_FEW", 1) != 0;
-    // 33 .. 96 queries: the same kernel with its thresholds in shared memory.  OPT-IN (VRQ_MMA_MID=1), a measured negative
-    // result: the time per MMA of the swapped orientation grows like N^2 beyond 32 query columns (100 M codes: 5.3 ms at 48
-    // queries, 8.1 ms at 64, 15.3 ms at 96, against 4.9 ms for the 128-query-tile kernel).
-    pl->mid = pl->f4 && !pl->few && nq <= MID_MAXQ && env_int("VRQ_MMA_FEW", 1) != 0 && env_int("VRQ_MMA_MID", 0) != 0;
+    pl->few = allow_few && pl->f4 && nq <= FEW_MAXQ && env_int("VRQ_MMA_FEW", 1) != 0;
+    // the second-generation swapped-operand kernel (bias column); VRQ_MMA_WIDE=0 keeps the first one
+    pl->wide = env_int("VRQ_MMA_WIDE", 1) != 0;
+    // 33 .. 64 queries: wide form only (the first-generation kernel with per-column thresholds in shared memory was a
+    // measured negative result there: 100 M codes in 8.1 ms at 64 queries against 4.1 ms for the 128-query-tile kernel)
+    pl->mid = allow_few && pl->f4 && !pl->few && pl->wide && nq <= WIDE_MAXQ && env_int("VRQ_MMA_FEW", 1) != 0 && env_int("VRQ_MMA_MID", 1) != 0;
     if (pl->mid) pl->few = true;
     // CTA pairs need an even number of query tiles (a pair = two neighbouring tiles); VRQ_MMA_PAIR=0 switches them off
     pl->pair = pl->f4 && pl->qtiles % 2 == 0 && env_int("VRQ_MMA_PAIR", 1) != 0;
@@ -1268,7 +1679,7 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl) {
 void mma_plan_set_cap(MmaPlan* pl, int cap) {
     pl->cap = cap;
     if (pl->few) {
-        pl->smem = few_smem_bytes(pl->raw_stages, pl->mid);
+        pl->smem = pl->wide ? wide_smem_bytes(pl->raw_stages, pl->mid ? WIDE_MAXQ : FEW_MAXQ) : few_smem_bytes(pl->raw_stages, false);
         return;
     }
     while (pl->raw_stages > 1 && mma_smem_bytes(pl->raw_stages, cap) > pl->smem_limit) pl->raw_stages--;
@@ -1284,11 +1695,15 @@ int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const CUtensorMap&
     }
     dim3 grid(pl.qtiles, pl.strips);
     if (pl.seg_cols > 0) grid = dim3(2 * (pl.seg_cols * pl.seg_full + pl.seg_tail), 1);  // 1-D grid of CTA pairs
-    if (pl.few && pl.mid) {
+    if (pl.few && pl.wide) {
         const int npad = ((sp.nq + 15) / 16) * 16;
-        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_few_kernel<MID_MAXQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        hamming_scan_mma_few_kernel<MID_MAXQ><<<grid, FEW_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, npad, env_int("VRQ_MID_DSTRIDE", 0),
-                                                                              env_int("VRQ_MID_RELAX", 0));
+        if (pl.mid) {
+            VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_wide_kernel<WIDE_MAXQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+            hamming_scan_mma_wide_kernel<WIDE_MAXQ><<<grid, FEW_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, npad);
+        } else {
+            VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_wide_kernel<FEW_MAXQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+            hamming_scan_mma_wide_kernel<FEW_MAXQ><<<grid, FEW_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, npad);
+        }
     } else if (pl.few) {
         const int npad = ((sp.nq + 7) / 8) * 8;
         VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_few_kernel<FEW_MAXQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
