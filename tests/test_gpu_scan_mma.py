@@ -157,8 +157,8 @@ def test_mma_and_integer_kernels_agree_with_ids(V, monkeypatch):
     assert np.array_equal(a[0][:8], rd) and np.array_equal(a[1][:8], ids[rp])
 
 
-# ---- <= 32 queries per pass: the swapped-operand kernel (database rows = MMA M, expanded straight into tensor memory) ----
-@pytest.mark.parametrize("n,nq", [(1, 6), (127, 8), (129, 7), (5000, 17), (40000, 32), (300001, 24)])
+# ---- <= 32 queries per pass: the swapped-operand kernel (database rows = MMA M, expanded straight into tensor memory, bias column) ----
+@pytest.mark.parametrize("n,nq", [(1, 6), (127, 8), (129, 7), (5000, 17), (40000, 32), (300001, 24), (70000, 3)])
 def test_few_queries_distance_matrix_exact(V, monkeypatch, n, nq):
     set_env(monkeypatch, "default")
     rng = np.random.default_rng(n * 77 + nq)
@@ -172,7 +172,7 @@ def test_few_queries_distance_matrix_exact(V, monkeypatch, n, nq):
 
 
 @pytest.mark.parametrize("env", ["default", "forced_fallback", "no_sampling"])
-@pytest.mark.parametrize("nq", [6, 20, 32])
+@pytest.mark.parametrize("nq", [3, 6, 20, 32])
 def test_few_queries_topk_matches_oracle(V, monkeypatch, env, nq):
     set_env(monkeypatch, env)
     n = 2_000_000
@@ -211,7 +211,8 @@ def test_few_queries_ties_and_sorted_database(V, monkeypatch):
     assert np.array_equal(dist, rd) and np.array_equal(labels, rp)
 
 
-# ---- 33 .. 96 queries per pass: the same swapped-operand kernel with thresholds in shared memory (opt-in: VRQ_MMA_MID=1) ----
+# ---- 33 .. 64 queries per pass: the same swapped-operand kernel with four accumulator column groups (default; 65+ queries
+# in these tests take the 128-query-tile kernel) ----
 @pytest.mark.parametrize("n,nq", [(1, 33), (127, 48), (129, 50), (5000, 64), (40000, 96), (300001, 81)])
 def test_mid_queries_distance_matrix_exact(V, monkeypatch, n, nq):
     set_env(monkeypatch, "default")

@@ -680,7 +680,7 @@ static int topk_batch(vrq_ctx* ctx, const uint8_t* codes, int64_t n, int code_by
     // >= 4 queries per pass go to the tensor cores (scan_mma.cu): measured crossover at 100 M rows (profiles/r01/
     // scan_regime_sweep_final_100M.txt: 4 queries 2.5 ms vs 2.9 ms); fewer are HBM-bound on the integer pipes (scan.cu)
     const int mma_mode = env_int("VRQ_SCAN_MMA", 1);
-    const bool mma = tma && mma_mode != 0 && (nq >= env_int("VRQ_SCAN_MMA_MIN_NQ", 4) || mma_mode == 2) && k + 2048 + 256 <= 8192;
+    const bool mma = tma && mma_mode != 0 && (nq >= env_int("VRQ_SCAN_MMA_MIN_NQ", 3) || mma_mode == 2) && k + 2048 + 256 <= 8192;
     if (dbg && !mma) {
         vrq_set_error("the distance dump is only available on the tensor-core scan path");
         return VRQ_ERR_UNSUPPORTED;

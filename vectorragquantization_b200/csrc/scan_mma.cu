@@ -864,336 +864,25 @@ hamming_scan_mma_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, 
 }
 
 // =====================================================================================================================
-// Few queries per pass (6 .. 32): the operand roles are swapped.  The MMA of the kernel above costs 8 cycles per database
-// row whatever the number of queries, which caps a single 128-query tile at 4.5 TB/s of codes (measured 3.5 TB/s).  Here
-// the DATABASE rows are the M dimension and the queries the N dimension (N = nq rounded up to 8), so one tile costs
-// 8 N cycles of tensor time and the scan goes back to being bound by HBM:
+// Few queries per pass (3 .. 64): the operand roles are swapped.  The MMA of the kernel above costs 8 cycles per database
+// row whatever the number of queries, which caps a single 128-query tile at 4.5 TB/s of codes (measured 3.1 TB/s).  Here
+// the DATABASE rows are the M dimension and the queries the N dimension (N = nq rounded up to 16), so one tile costs
+// 8 N cycles of tensor time:
 //   * B operand = the queries (+-2, +-1, +-0.5 e2m1), expanded once into shared memory (N x 512 bytes);
 //   * A operand = 128 database rows, expanded by the expander threads straight into TENSOR MEMORY with tcgen05.st
 //     (thread = row = TMEM lane; two 128-column buffers), so the expansion never touches shared memory;
-//   * D = 128 rows x N queries (two buffers); epilogue lane = database row, column = query, thresholds per column.
+//   * D = 128 rows x N queries (two buffers); epilogue lane = database row, column = query.
 // Same lists / counts / thresholds contract as the kernels above, e2m1 kind only.
-constexpr int FEW_MAXQ = 32;   // thresholds and a whole tile's accumulator columns in registers
-constexpr int MID_MAXQ = 96;   // 33 .. 96 queries: thresholds in shared memory, accumulator columns read 48 at a time
+constexpr int FEW_MAXQ = 32;   // <= 32 queries: two 16-column groups of the accumulator
 constexpr int FEW_WARP_MMA = 4, FEW_WARP_TMA = 5, FEW_WARP_EXP0 = 6, FEW_EXP_WARPS = 8;
 constexpr int FEW_THREADS = (FEW_WARP_EXP0 + FEW_EXP_WARPS) * 32;
 constexpr int FEW_EPI_WARPS = 4, FEW_EPI_THREADS = FEW_EPI_WARPS * 32;
-// tensor memory: A = 2 x 128 columns, D = 2 buffers of 64 (<= 32 queries) or 96 columns, block scales = the last 64 columns
+// tensor memory: A = 2 x 128 columns, D = 2 buffers of 64 columns, 8 columns of bias operand, block scales = the last 64 columns
 constexpr uint32_t FEW_A_COL = 0, FEW_D_COL = 256, FEW_SF_COL = 448;
-template <int MAXQ>
-struct FewCfg {
-    static constexpr uint32_t D_STRIDE = MAXQ <= 32 ? 64 : 96;
-};
 constexpr int FEW_MAX_RAW = 8;
 
-template <int MAXQ>
-struct FewSmem {
-    unsigned long long raw_full[FEW_MAX_RAW], raw_empty[FEW_MAX_RAW];
-    unsigned long long a_full[2], a_empty[2], acc_full[2], acc_empty[2];
-    uint32_t tmem_base;
-    int tau_s[MAXQ];
-    int cnt_s[MAXQ];
-    int pcq_s[MAXQ];
-    __align__(16) float thr_s[MAXQ];
-    SelectScratch sc[FEW_EPI_WARPS];
-};
-
-template <int MAXQ>
-__global__ void __launch_bounds__(FEW_THREADS, 1)
-hamming_scan_mma_few_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, int raw_stages, int npad, int dstride_arg, int relax) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* raw_mem = base;                                      // [raw_stages][128 rows][128 B], TMA SWIZZLE_128B
-    uint8_t* q_mem = raw_mem + (size_t)raw_stages * STAGE_BYTES_RAW;  // [4 K-blocks][npad queries][128 B], same swizzle
-    FewSmem<MAXQ>* sm = (FewSmem<MAXQ>*)(q_mem + (size_t)4 * MAXQ * 128);
-    const uint32_t D_STRIDE = dstride_arg > 0 ? (uint32_t)dstride_arg : FewCfg<MAXQ>::D_STRIDE;
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int nq = p.nq;  // <= MAXQ, one query tile
-    const int strip = blockIdx.y;
-    const int tiles_per_strip = (int)(p.rows_per_strip / MROWS);
-    const int64_t tile0 = (int64_t)strip * tiles_per_strip;
-    const int ntiles = (int)max((int64_t)0, min((int64_t)tiles_per_strip, p.total_tiles - tile0));
-    const int64_t run_mask = ((int64_t)1 << p.run_shift) - 1;
-    auto tile_row = [&](int t) -> int64_t {
-        const int64_t i = tile0 + t;
-        return p.row_begin + (i >> p.run_shift) * p.run_stride + (i & run_mask) * MROWS;
-    };
-    const int64_t s_end = p.row_end;
-    if (p.guard && *p.guard == 0) return;
-
-    if (tid == 0) {
-        for (int s = 0; s < raw_stages; s++) {
-            mbar_init(smem_u32(&sm->raw_full[s]), 1);
-            mbar_init(smem_u32(&sm->raw_empty[s]), 4);  // the four expander warps of one group
-        }
-        for (int s = 0; s < 2; s++) {
-            mbar_init(smem_u32(&sm->a_full[s]), 4);
-            mbar_init(smem_u32(&sm->a_empty[s]), 1);
-            mbar_init(smem_u32(&sm->acc_full[s]), 1);
-            mbar_init(smem_u32(&sm->acc_empty[s]), FEW_EPI_WARPS);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    if (tid < MAXQ) {
-        sm->pcq_s[tid] = 0;
-        sm->cnt_s[tid] = 0;
-        sm->tau_s[tid] = tid < nq ? (p.tau0 ? min(p.tau0[tid], TAU_INF - 1) + p.tau_bias : TAU_INF) : 0;
-    }
-    if (warp == FEW_WARP_MMA) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "r"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = sm->tmem_base;
-
-    // ---- the queries become the B operand in shared memory: row = query, K-block kb = code words 8 kb .. 8 kb + 7, chunk i
-    //      of the 128-byte row = word 8 kb + i as four planes (nibble j of plane t = bit t + 4 j) of +-(1 / plane value)
-    for (int idx = tid; idx < npad * 32; idx += FEW_THREADS) {
-        const int q = idx >> 5, W = idx & 31;
-        const bool qvalid = q < nq;
-        const uint32_t w = qvalid ? __ldg(reinterpret_cast<const uint32_t*>(p.queries + (size_t)q * CODE_BYTES) + W) : 0u;
-        if (qvalid) atomicAdd(&sm->pcq_s[q], __popc(w));
-        uint32_t v[4];
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const uint32_t mag = t == 0 ? 0x44444444u : (t == 1 ? 0x22222222u : 0x11111111u);
-            v[t] = qvalid ? ((mag | 0x88888888u) ^ (((w >> t) & 0x11111111u) << 3)) : 0u;
-        }
-        const int kb = W >> 3, i = W & 7;
-        sts128(smem_u32(q_mem) + (uint32_t)(kb * npad * 128 + q * 128 + ((i ^ (q & 7)) << 4)), v[0], v[1], v[2], v[3]);
-    }
-    if (warp < FEW_EPI_WARPS) {
-        // every block scale (UE8M0) = 0x7F = 2^0
-        uint32_t one[8];
-#pragma unroll
-        for (int t = 0; t < 8; t++) one[t] = 0x7F7F7F7Fu;
-#pragma unroll
-        for (int c = 0; c < 64; c += 8) tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + FEW_SF_COL + c, one);
-        tmem_wait_st();
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (tid < MAXQ) sm->thr_s[tid] = tid < nq ? (float)(sm->pcq_s[tid] - sm->tau_s[tid]) : 3.0e9f;
-    __syncthreads();
-
-    if (warp == FEW_WARP_TMA) {
-        if (lane == 0) {
-            uint32_t s = 0, ph = 0;
-            for (int t = 0; t < ntiles; t++) {
-                mbar_wait_relaxed(smem_u32(&sm->raw_empty[s]), ph ^ 1u, 128);  // (a tight poll measured 10 % slower at 32 queries)
-                mbar_expect_tx(smem_u32(&sm->raw_full[s]), STAGE_BYTES_RAW);
-                tma_load_2d(smem_u32(raw_mem) + s * (uint32_t)STAGE_BYTES_RAW, &tmap, 0, (int)tile_row(t), smem_u32(&sm->raw_full[s]));
-                if (++s == (uint32_t)raw_stages) {
-                    s = 0;
-                    ph ^= 1u;
-                }
-            }
-        }
-    } else if (warp == FEW_WARP_MMA) {
-        // ===================== MMA issuer: 16 MMAs (M = 128 rows, N = npad queries, K = 64) per tile =====================
-        const uint32_t idesc = (1u << 7) | (1u << 10) | ((uint32_t)(npad >> 3) << 17) | (1u << 23) | ((uint32_t)(MQ >> 4) << 24);
-        const uint64_t qdesc0 = umma_desc_sw128(smem_u32(q_mem));
-        const uint32_t kb_step = (uint32_t)(npad * 128) >> 4;
-        for (int t = 0; t < ntiles; t++) {
-            const uint32_t ab = (uint32_t)t & 1u, ph = ((uint32_t)t >> 1) & 1u;
-            mbar_wait(smem_u32(&sm->a_full[ab]), ph);
-            mbar_wait(smem_u32(&sm->acc_empty[ab]), ph ^ 1u);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t d_tmem = tmem + FEW_D_COL + ab * D_STRIDE, a0 = tmem + FEW_A_COL + ab * 128;
-#pragma unroll
-                for (int s = 0; s < 16; s++)
-                    umma_f4_ts(d_tmem, a0 + 8 * s, qdesc0 + (uint64_t)((s >> 2) * kb_step + (s & 3) * 2), idesc, tmem + FEW_SF_COL,
-                               tmem + FEW_SF_COL + 32, s != 0);
-                tc_commit(smem_u32(&sm->a_empty[ab]));
-                tc_commit(smem_u32(&sm->acc_full[ab]));
-            }
-            __syncwarp();
-        }
-    } else if (warp >= FEW_WARP_EXP0) {
-        // ===================== expanders: thread = database row = TMEM lane; group g writes A buffer g ================
-        const int g = (warp - FEW_WARP_EXP0) >> 2;
-        const int row = (warp & 3) * 32 + lane;  // a warp may only touch the TMEM lane quadrant warp_id % 4
-        const uint32_t sw = (uint32_t)(row & 7);
-        const uint32_t a_buf = tmem + ((uint32_t)((warp & 3) * 32) << 16) + FEW_A_COL + (uint32_t)g * 128;
-        for (int t = g; t < ntiles; t += 2) {
-            const uint32_t rs = (uint32_t)t % (uint32_t)raw_stages, rph = ((uint32_t)t / (uint32_t)raw_stages) & 1u;
-            const uint32_t ph = ((uint32_t)t >> 1) & 1u;
-            mbar_wait_relaxed(smem_u32(&sm->raw_full[rs]), rph, 32);
-            const uint32_t raddr = smem_u32(raw_mem) + rs * (uint32_t)STAGE_BYTES_RAW + (uint32_t)row * 128u;
-            uint4 c[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) c[j] = lds128(raddr + (((uint32_t)j ^ sw) << 4));
-            if (relax)
-                mbar_wait_relaxed(smem_u32(&sm->a_empty[g]), ph ^ 1u, 64);
-            else
-                mbar_wait(smem_u32(&sm->a_empty[g]), ph ^ 1u);
-            tc_fence_after();
-#pragma unroll
-            for (int part = 0; part < 4; part++) {
-                // words 8 part .. 8 part + 7 -> columns 32 part .. 32 part + 31 (column 4 W + t = plane t of word W)
-                const uint32_t w[8] = {c[2 * part].x, c[2 * part].y, c[2 * part].z, c[2 * part].w,
-                                       c[2 * part + 1].x, c[2 * part + 1].y, c[2 * part + 1].z, c[2 * part + 1].w};
-                uint32_t v[32];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    v[4 * i + 0] = w[i] & 0x11111111u;
-                    v[4 * i + 1] = w[i] & 0x22222222u;
-                    v[4 * i + 2] = w[i] & 0x44444444u;
-                    v[4 * i + 3] = (w[i] >> 1) & 0x44444444u;
-                }
-                tmem_st32(a_buf + 32 * part, v);
-            }
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(smem_u32(&sm->a_full[g]));
-                mbar_arrive(smem_u32(&sm->raw_empty[rs]));  // every c[j] has been consumed by real instructions
-            }
-        }
-    } else {
-        // ===================== epilogue: lane = database row, column = query ==========================================
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16) + FEW_D_COL;
-        const int limit = p.compact_limit > 0 ? min(p.compact_limit, p.cap - p.group_tiles * MROWS) : p.cap - p.group_tiles * MROWS;
-        uint64_t* const lists0 = p.lists + (size_t)strip * p.nq * p.cap;
-        int until_check = p.group_tiles;
-        // <= 32 queries: the per-query thresholds (survivor <=> dot > popc(q) - tau) live in registers between compactions and
-        // all column groups of a tile are loaded up front.  More queries: thresholds are read from shared memory (one
-        // broadcast LDS.128 per four columns) and the columns are read 48 at a time.
-        constexpr int RCH = MAXQ <= 32 ? MAXQ / 16 : 3;  // 16-column groups held in registers at a time
-        float thr[MAXQ <= 32 ? MAXQ / 16 : 1][16];
-        auto load_thr = [&]() {
-            if constexpr (MAXQ <= 32) {
-#pragma unroll
-                for (int ch = 0; ch < MAXQ / 16; ch++)
-#pragma unroll
-                    for (int j = 0; j < 16; j++) thr[ch][j] = (16 * ch < npad) ? sm->thr_s[16 * ch + j] : 3.0e9f;
-            }
-        };
-        load_thr();
-        for (int t = 0; t < ntiles; t++) {
-            const uint32_t ab = (uint32_t)t & 1u;
-            mbar_wait(smem_u32(&sm->acc_full[ab]), ((uint32_t)t >> 1) & 1u);
-            tc_fence_after();
-            const int64_t lrow = tile_row(t) + warp * 32 + lane;
-            const bool rvalid = lrow < s_end;
-#pragma unroll
-            for (int part = 0; part < (MAXQ / 16 + RCH - 1) / RCH; part++) {
-                const int c0 = part * RCH;  // first 16-column group of this part
-                if (16 * c0 >= npad) break;
-                const bool last_part = 16 * (c0 + RCH) >= npad || part == (MAXQ / 16 + RCH - 1) / RCH - 1;
-                int v[RCH][16];
-                __syncwarp();
-#pragma unroll
-                for (int ch = 0; ch < RCH; ch++)
-                    if (16 * (c0 + ch) < npad) tmem_ld16(lane_base + ab * D_STRIDE + 16 * (c0 + ch), v[ch]);
-                tmem_wait_ld();
-                if (last_part) {  // every column of the tile has been read: the accumulator goes back to the issuer
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&sm->acc_empty[ab]));
-                }
-#pragma unroll
-                for (int ch = 0; ch < RCH; ch++) {
-                    const int cb = 16 * (c0 + ch);
-                    if (cb >= npad) break;
-                    float th[16];
-                    if constexpr (MAXQ <= 32) {
-#pragma unroll
-                        for (int j = 0; j < 16; j++) th[j] = thr[c0 + ch][j];
-                    } else {
-#pragma unroll
-                        for (int j4 = 0; j4 < 4; j4++) {
-                            const float4 f = *reinterpret_cast<const float4*>(&sm->thr_s[cb + 4 * j4]);
-                            th[4 * j4] = f.x, th[4 * j4 + 1] = f.y, th[4 * j4 + 2] = f.z, th[4 * j4 + 3] = f.w;
-                        }
-                    }
-                    float m4[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) m4[j] = __int_as_float(v[ch][j]) - th[j];
-#pragma unroll
-                    for (int j = 4; j < 16; j++) m4[j & 3] = fmaxf(m4[j & 3], __int_as_float(v[ch][j]) - th[j]);
-                    const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-                    if (p.dbg && rvalid) {
-                        for (int j = 0; j < 16; j++)
-                            if (cb + j < nq) p.dbg[(size_t)(cb + j) * p.dbg_stride + lrow] = sm->pcq_s[cb + j] - (int)__int_as_float(v[ch][j]);
-                    }
-                    if (mx > 0.0f && rvalid) {
-#pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            const float f = __int_as_float(v[ch][j]);
-                            if (f > th[j]) {
-                                const int q = cb + j;
-                                const unsigned long long key =
-                                    ((unsigned long long)(sm->pcq_s[q] - (int)f) << VRQ_KEY_POS_BITS) | (unsigned long long)(p.pos_base + lrow);
-                                if (p.key_lo == nullptr || key > p.key_lo[q]) {
-                                    const int slot = atomicAdd(&sm->cnt_s[q], 1);
-                                    if (slot >= p.cap) __trap();
-                                    lists0[(size_t)q * p.cap + slot] = key;
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            if (--until_check == 0 && t + 1 < ntiles) {
-                until_check = p.group_tiles;
-                group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
-                const int over = (tid < nq && sm->cnt_s[tid] > limit) ? 1 : 0;
-                int any;
-                asm volatile(
-                    "{\n"
-                    ".reg .pred p, q;\n"
-                    "setp.ne.s32 q, %1, 0;\n"
-                    "bar.red.or.pred p, %2, %3, q;\n"
-                    "selp.s32 %0, 1, 0, p;\n"
-                    "}\n"
-                    : "=r"(any)
-                    : "r"(over), "n"(BAR_CONSUMERS), "n"(FEW_EPI_THREADS)
-                    : "memory");
-                if (any) {
-                    for (int qq = warp; qq < nq; qq += FEW_EPI_WARPS) {
-                        const int n = sm->cnt_s[qq];
-                        if (n > limit)
-                            compact_list_warp(lists0 + (size_t)qq * p.cap, n, p.k, &sm->sc[warp], lane, BAR_WARP0 + warp, &sm->cnt_s[qq],
-                                              &sm->tau_s[qq], p.sample_mode ? limit : 0);
-                    }
-                    group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
-                    if (tid < nq) sm->thr_s[tid] = (float)(sm->pcq_s[tid] - sm->tau_s[tid]);
-                    group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
-                    load_thr();
-                }
-            }
-        }
-        group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
-        for (int qq = warp; qq < nq && !p.sample_mode; qq += FEW_EPI_WARPS) {
-            const int n = sm->cnt_s[qq];
-            if (n > p.k)
-                compact_list_warp(lists0 + (size_t)qq * p.cap, n, p.k, &sm->sc[warp], lane, BAR_WARP0 + warp, &sm->cnt_s[qq], &sm->tau_s[qq]);
-        }
-        group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
-        if (tid < nq) p.counts[(size_t)strip * p.nq + tid] = sm->cnt_s[tid];
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == FEW_WARP_MMA) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
-    }
-}
-
-// =====================================================================================================================
-// 4 .. 64 queries per pass, second generation of the swapped-operand kernel above ("wide").  Three changes:
+// What makes it scale to 64 query columns (the first generation, with one threshold per column, was slower than the
+// 128-query-tile kernel beyond 32 queries: 8.1 ms per 100 M codes at 64):
 //   * ONE threshold for every query column.  A 17th MMA per tile adds a per-query bias to the accumulator: the A operand of
 //     that MMA is a constant (62 elements 4.0, 2 elements 1.0, written to tensor memory once), its B operand is a fifth
 //     K-block of the query rows in shared memory that encodes bias = -(popc(q) - tau) as a sum of e2m1 products
@@ -1202,8 +891,9 @@ hamming_scan_mma_few_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams
 //     subtract and a maximum per column (which is what made the per-column form slower than linear in N).  Thresholds that
 //     tighten later (compaction) make the bias conservative, never wrong: the exact test is redone on the survivors.
 //   * The expanders split a tile by (row, half of K): all eight warps work on every tile (4 x LDS.128, 64 ALU, 2 x tcgen05.st.x32
-//     per thread) instead of four warps per tile doing twice that.
+//     per thread).
 //   * The accumulator goes back to the issuer before anything is examined; barrier addresses are loop invariants.
+//   * Survivors go through a mask and ONE out-of-line append (wide_append below).
 constexpr int WIDE_MAXQ = 64;
 constexpr uint32_t WIDE_BIAS_COL = 384;  // 8 columns: the constant A operand of the bias MMA
 constexpr int WIDE_BIAS_MAX = 1440;      // 60 x 24: beyond every |dot| <= 1024, i.e. "always" / "never"
@@ -1602,11 +1292,6 @@ size_t wide_smem_bytes(int raw_stages, int maxq) {
            (maxq <= 32 ? sizeof(WideSmem<FEW_MAXQ>) : sizeof(WideSmem<WIDE_MAXQ>)) + 16;
 }
 
-size_t few_smem_bytes(int raw_stages, bool mid) {
-    return 1024 + (size_t)raw_stages * STAGE_BYTES_RAW + (size_t)4 * (mid ? MID_MAXQ : FEW_MAXQ) * 128 +
-           (mid ? sizeof(FewSmem<MID_MAXQ>) : sizeof(FewSmem<FEW_MAXQ>)) + 16;
-}
-
 size_t mma_smem_bytes(int raw_stages, int cap) {
     (void)cap;  // lists are compacted in place in global memory: no shared-memory copy
     return 1024 + (size_t)raw_stages * STAGE_BYTES_RAW + (size_t)B_STAGES * STAGE_BYTES_B + sizeof(MmaSmem) + 16;
@@ -1618,13 +1303,10 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl, bool a
     const int sms = ctx->sm_count;
     pl->f4 = env_int("VRQ_MMA_KIND", 4) != 8;  // 4 (default): packed e2m1 operands, 8: int8 operands
     pl->qtiles = (nq + MQ - 1) / MQ;
-    // <= 64 queries: the swapped-operand kernel (database rows = M), HBM-bound instead of bound by 8 tensor cycles per row
+    // <= 32 queries: the swapped-operand kernel (database rows = M) instead of 8 tensor cycles per row whatever the batch
     pl->few = allow_few && pl->f4 && nq <= FEW_MAXQ && env_int("VRQ_MMA_FEW", 1) != 0;
-    // the second-generation swapped-operand kernel (bias column); VRQ_MMA_WIDE=0 keeps the first one
-    pl->wide = env_int("VRQ_MMA_WIDE", 1) != 0;
-    // 33 .. 64 queries: wide form only (the first-generation kernel with per-column thresholds in shared memory was a
-    // measured negative result there: 100 M codes in 8.1 ms at 64 queries against 4.1 ms for the 128-query-tile kernel)
-    pl->mid = allow_few && pl->f4 && !pl->few && pl->wide && nq <= WIDE_MAXQ && env_int("VRQ_MMA_FEW", 1) != 0 && env_int("VRQ_MMA_MID", 1) != 0;
+    // 33 .. 64 queries: the same kernel with four column groups (VRQ_MMA_MID=0: the 128-query-tile kernel)
+    pl->mid = allow_few && pl->f4 && !pl->few && nq <= WIDE_MAXQ && env_int("VRQ_MMA_FEW", 1) != 0 && env_int("VRQ_MMA_MID", 1) != 0;
     if (pl->mid) pl->few = true;
     // CTA pairs need an even number of query tiles (a pair = two neighbouring tiles); VRQ_MMA_PAIR=0 switches them off
     pl->pair = pl->f4 && pl->qtiles % 2 == 0 && env_int("VRQ_MMA_PAIR", 1) != 0;
@@ -1679,7 +1361,7 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl, bool a
 void mma_plan_set_cap(MmaPlan* pl, int cap) {
     pl->cap = cap;
     if (pl->few) {
-        pl->smem = pl->wide ? wide_smem_bytes(pl->raw_stages, pl->mid ? WIDE_MAXQ : FEW_MAXQ) : few_smem_bytes(pl->raw_stages, false);
+        pl->smem = wide_smem_bytes(pl->raw_stages, pl->mid ? WIDE_MAXQ : FEW_MAXQ);
         return;
     }
     while (pl->raw_stages > 1 && mma_smem_bytes(pl->raw_stages, cap) > pl->smem_limit) pl->raw_stages--;
@@ -1695,7 +1377,7 @@ int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const CUtensorMap&
     }
     dim3 grid(pl.qtiles, pl.strips);
     if (pl.seg_cols > 0) grid = dim3(2 * (pl.seg_cols * pl.seg_full + pl.seg_tail), 1);  // 1-D grid of CTA pairs
-    if (pl.few && pl.wide) {
+    if (pl.few) {
         const int npad = ((sp.nq + 15) / 16) * 16;
         if (pl.mid) {
             VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_wide_kernel<WIDE_MAXQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
@@ -1704,10 +1386,6 @@ int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const CUtensorMap&
             VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_wide_kernel<FEW_MAXQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
             hamming_scan_mma_wide_kernel<FEW_MAXQ><<<grid, FEW_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, npad);
         }
-    } else if (pl.few) {
-        const int npad = ((sp.nq + 7) / 8) * 8;
-        VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_few_kernel<FEW_MAXQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        hamming_scan_mma_few_kernel<FEW_MAXQ><<<grid, FEW_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, npad, 0, env_int("VRQ_MID_RELAX", 0));
     } else if (pl.f4 && pl.pair) {
         // CTA pairs: clusters of 2 along x = two neighbouring query tiles of the same strip
         auto kern = sp.sample_out ? hamming_scan_mma_kernel<KIND_F4, 2, true> : hamming_scan_mma_kernel<KIND_F4, 2, false>;
