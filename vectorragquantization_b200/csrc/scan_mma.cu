@@ -1410,8 +1410,11 @@ int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const CUtensorMap&
         VRQ_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap64, sp, pl.raw_stages));
     } else if (pl.f4) {
         auto kern = sp.sample_out ? hamming_scan_mma_kernel<KIND_F4, 1, true> : hamming_scan_mma_kernel<KIND_F4, 1, false>;
+        int var = sp.sample_out ? 0 : env_int("VRQ_MMA_VAR", 4);  // the lean dense-pass epilogue, as for the CTA pairs
+        if (var != 4 || !(sp.run_shift == 0 && sp.run_stride == MROWS && sp.dbg == nullptr)) var = 0;
+        if (var == 4) kern = hamming_scan_mma_kernel<KIND_F4, 1, false, 4>;
         VRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        kern<<<grid, MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages);
+        kern<<<grid, var == 4 ? MMA_KERNEL_THREADS + 32 : MMA_KERNEL_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages);
     } else {
         auto kern = sp.sample_out ? hamming_scan_mma_kernel<KIND_I8, 1, true> : hamming_scan_mma_kernel<KIND_I8, 1, false>;
         VRQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
