@@ -576,7 +576,8 @@ def headline_roofline(args, clocks, n_local, scan_ms, scan_n, dense_ms, dense_n,
     tr, tr_src = traffic("scan_dense_100M_1024q") if (f4 and pair and n_local == N_PER_GPU) else (None, None)
     return {
         "kernel": f"hamming_scan_mma_kernel<{'e2m1' if f4 else 'int8'}>, dense pass: {kind}; M=128 queries resident in TMEM x N=128 "
-                  "codes expanded from bits in shared memory, K=1024; 1024-query batch",
+                  "codes expanded from bits in shared memory, K=1024; 1024-query batch; epilogue warps at 128 registers (setmaxnreg): "
+                  "the accumulator goes back to the issuer before it is examined",
         "bound": "tensor", "unit": "TFLOP/s", "ops": "multiply-add of a query bit and a code bit = 2 ops",
         "achieved": achieved, "peak": peak, "frac": achieved / peak,
         "peak_source": (f"MEASURED: bare {mkey} issue loop of profiles/microbench/mxf4_peak.cu on this pool's B200 "
@@ -592,7 +593,7 @@ def headline_roofline(args, clocks, n_local, scan_ms, scan_n, dense_ms, dense_n,
                 "frac": n_local * 128 * 8 / dense_s / 1e9 / hbm_peak, "peak_source": peak_src,
                 "note": "requested bytes = 128 B per code per 128-query tile (8 tiles per 1024-query batch; the re-reads are served by "
                         "L2 when the CTA pairs of a strip stay in lockstep); not the binding resource for a query batch"},
-        "integer_pipe_kernel": {"note": "scan.cu (XOR + carry-save POPC) handles <= 3 queries per pass and VRQ_SCAN_MMA=0; "
+        "integer_pipe_kernel": {"note": "scan.cu (XOR + carry-save POPC) handles <= 2 queries per pass and VRQ_SCAN_MMA=0; "
                                         "its 1024-query rate measured in round 1 was 216 Gpair/s (profiles/r01)",
                                 "alu_peak_Gpair_s": alu_peak / 1e9},
         "scan_ms_per_step": scan_ms / args.steps, "rescore_ms_per_step": resc_ms / args.steps,
@@ -626,9 +627,9 @@ def hbm_bound_kernels(env, index, qf_d, qb_d, hbm_peak, peak_src, n_local, ms_pe
         q = qb_d[0][:nq].contiguous()
         s = _timed(env, lambda: L.check(lib.vrq_index_search(index._h, nq, L.ptr(q), kk, L.ptr(dist_d), L.ptr(lab_d))), 5)
         gbs = n_local * 128 / s / 1e9
-        kern = ("hamming_scan_kernel<true> (XOR + POPC)" if nq < 4 else
-                ("hamming_scan_mma_few_kernel (tcgen05, database rows = M expanded into TMEM) incl. its sample pass" if nq <= 32 else
-                 "hamming_scan_mma_kernel, one 128-query tile per CTA, incl. its sample pass"))
+        kern = ("hamming_scan_kernel<true> (XOR + POPC)" if nq < 3 else
+                ("hamming_scan_mma_wide_kernel (tcgen05, database rows = M expanded into TMEM, queries = N, bias column) incl. the "
+                 "sample pass" if nq <= 64 else "hamming_scan_mma_kernel, one 128-query tile per CTA, incl. the sample pass"))
         tr, tr_src = traffic(f"scan_stream_nq{nq}")
         out[f"roofline_scan_stream_nq{nq}"] = {"kernel": f"{kern} + merge, {nq} query/pass, top-{kk}", "bound": "hbm",
                                                 "unit": "GB/s", "achieved": gbs, "peak": hbm_peak, "frac": gbs / hbm_peak,
