@@ -30,7 +30,7 @@ def V():
 
 def set_env(monkeypatch, name):
     for k in ("VRQ_MMA_SAMPLE_K", "VRQ_MMA_SAFETY", "VRQ_SCAN_MMA", "VRQ_MMA_RAW_STAGES", "VRQ_MMA_KIND", "VRQ_MMA_PAIR",
-              "VRQ_MMA_GROUP_TILES", "VRQ_MMA_FEW", "VRQ_MMA_MID", "VRQ_MMA_TAIL", "VRQ_MMA_LOCKSTEP"):
+              "VRQ_MMA_GROUP_TILES", "VRQ_MMA_FEW", "VRQ_MMA_MID", "VRQ_MMA_TAIL", "VRQ_MMA_LOCKSTEP", "VRQ_MMA_W128", "VRQ_MMA_VAR"):
         monkeypatch.delenv(k, raising=False)
     for k, v in ENVS[name].items():
         monkeypatch.setenv(k, v)
@@ -211,12 +211,13 @@ def test_few_queries_ties_and_sorted_database(V, monkeypatch):
     assert np.array_equal(dist, rd) and np.array_equal(labels, rp)
 
 
-# ---- 33 .. 64 queries per pass: the same swapped-operand kernel with four accumulator column groups (default; 65+ queries
-# in these tests take the 128-query-tile kernel) ----
+# ---- 33 .. 96 queries per pass: the same swapped-operand kernel with four accumulator column groups (33 .. 64) or, 65 .. 96,
+# with one A buffer handed over per K half and eight epilogue warps; VRQ_MMA_W128=128 extends the latter to 128 queries ----
 @pytest.mark.parametrize("n,nq", [(1, 33), (127, 48), (129, 50), (5000, 64), (40000, 96), (300001, 81)])
 def test_mid_queries_distance_matrix_exact(V, monkeypatch, n, nq):
     set_env(monkeypatch, "default")
     monkeypatch.setenv("VRQ_MMA_MID", "1")
+    monkeypatch.setenv("VRQ_MMA_W128", "128")
     rng = np.random.default_rng(n * 79 + nq)
     codes = rng.integers(0, 256, (n, 128), dtype=np.uint8)
     q = rng.integers(0, 256, (nq, 128), dtype=np.uint8)
@@ -228,10 +229,11 @@ def test_mid_queries_distance_matrix_exact(V, monkeypatch, n, nq):
 
 
 @pytest.mark.parametrize("env", ["default", "forced_fallback", "no_sampling"])
-@pytest.mark.parametrize("nq", [33, 64, 96])
+@pytest.mark.parametrize("nq", [33, 64, 96, 128])
 def test_mid_queries_topk_matches_oracle(V, monkeypatch, env, nq):
     set_env(monkeypatch, env)
     monkeypatch.setenv("VRQ_MMA_MID", "1")
+    monkeypatch.setenv("VRQ_MMA_W128", "128")
     n = 2_000_000
     codes, _ = oc.synth_codes_int8(61, 0, n, want_int8=False)
     q = o.synth_ubinary_from_f32(oc.synth_f32(62, 0, nq))
@@ -243,6 +245,7 @@ def test_mid_queries_topk_matches_oracle(V, monkeypatch, env, nq):
         rd, rp = oc.hamming_topk(codes, q, k)
         assert np.array_equal(dist, rd) and np.array_equal(labels, rp)
     monkeypatch.setenv("VRQ_MMA_MID", "0")  # the 128-query-tile kernel on the same batch
+    monkeypatch.setenv("VRQ_MMA_W128", "0")
     d2, l2 = ix.search(q, 1000)
     assert np.array_equal(d2, rd) and np.array_equal(l2, rp)
 

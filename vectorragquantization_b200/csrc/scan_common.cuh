@@ -240,7 +240,8 @@ struct MmaPlan {
     size_t smem, smem_limit;
     bool f4;    // packed e2m1 operands (kind::mxf4) instead of int8
     bool mid;   // 33 .. 64 queries on the swapped-operand kernel (four accumulator column groups instead of two)
-    bool few;   // <= 64 queries: swapped-operand kernel (database rows = M, expanded straight into tensor memory, bias column)
+    bool w128;  // 65 .. 128 queries on the swapped-operand kernel (one A buffer handed over per K half, 8 column groups)
+    bool few;   // <= 128 queries: swapped-operand kernel (database rows = M, expanded straight into tensor memory, bias column)
     bool pair;  // CTA pairs (tcgen05 cta_group::2): two query tiles share every tile of database rows
     int seg_cols, seg_full, seg_tail;  // pair scheduler (see ScanParams); seg_cols == 0: classic grid
 };

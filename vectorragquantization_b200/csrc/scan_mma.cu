@@ -894,7 +894,7 @@ constexpr int FEW_MAX_RAW = 8;
 //     per thread).
 //   * The accumulator goes back to the issuer before anything is examined; barrier addresses are loop invariants.
 //   * Survivors go through a mask and ONE out-of-line append (wide_append below).
-constexpr int WIDE_MAXQ = 64;
+constexpr int WIDE_MAXQ = 64, WIDE128_MAXQ = 128;
 constexpr uint32_t WIDE_BIAS_COL = 384;  // 8 columns: the constant A operand of the bias MMA
 constexpr int WIDE_BIAS_MAX = 1440;      // 60 x 24: beyond every |dot| <= 1024, i.e. "always" / "never"
 
@@ -929,26 +929,48 @@ __device__ __forceinline__ int sel16(const int (&w)[16], int j) {
 template <int MAXQ>
 struct WideSmem {
     unsigned long long raw_full[FEW_MAX_RAW], raw_empty[FEW_MAX_RAW];
-    unsigned long long a_full[2], a_empty[2], acc_full[2], acc_empty[2];
+    unsigned long long a_full[4], a_empty[4], acc_full[2], acc_empty[2];  // a_*: per A buffer (2 used) or per K quarter (HALVES)
     uint32_t tmem_base;
     int tau_s[MAXQ];
     int cnt_s[MAXQ];
     int pcq_s[MAXQ];
     __align__(16) float thr_s[MAXQ];   // current exact threshold of the query: survivor <=> dot > thr_s
     __align__(16) float bias_s[MAXQ];  // what the bias MMA added to the query's column
-    SelectScratch sc[FEW_EPI_WARPS];
+    SelectScratch sc[8];  // one per epilogue warp (4 or 8)
 };
 
+// MAXQ = 32 / 64: two A buffers of 128 columns, handed over whole; 4 epilogue warps (one per TMEM lane quadrant).
+// MAXQ = 128: tensor memory has room for ONE A buffer next to two 128-column accumulators, so it is handed over per K HALF
+// (64 columns): one half is refilled while the MMAs of the other run.  8 epilogue warps: warps w and w + 4 share a lane
+// quadrant and split the query columns (64 each, as many as an epilogue warp of the 128-query-tile kernel examines) - with 4
+// warps holding 128 columns each (184 registers via setmaxnreg) the epilogue was the bound (128 queries: 5.0 ms per 100 M
+// codes).  4 expander warps (one per lane quadrant, whole rows) keep the block at 14 warps = 4 per scheduler partition;
+// with 8 (18 warps, 96 registers) everything was slower.  Per K quarter instead of per half: the same within 3 %.
 template <int MAXQ>
-__global__ void __launch_bounds__(FEW_THREADS, 1)
+struct WideCfg {
+    static constexpr int EPIW = MAXQ > 64 ? 8 : 4;  // epilogue warps
+    static constexpr int WARP_MMA = EPIW, WARP_TMA = EPIW + 1, WARP_EXP0 = EPIW + 2;
+    static constexpr int EXPW = MAXQ > 64 ? 4 : 8;   // expander warps (MAXQ = 128: one per lane quadrant, whole rows)
+    static constexpr int THREADS = (WARP_EXP0 + EXPW) * 32;  // 14 warps either way: at most 4 per scheduler partition, 144 registers
+    static constexpr int PARTS = 2;                  // MAXQ = 128: hand-overs of the single A buffer per tile (K halves)
+};
+template <int MAXQ>
+__global__ void __launch_bounds__(WideCfg<MAXQ>::THREADS, 1)
 hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParams p, int raw_stages, int npad) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* raw_mem = base;                                          // [raw_stages][128 rows][128 B], TMA SWIZZLE_128B
     uint8_t* q_mem = raw_mem + (size_t)raw_stages * STAGE_BYTES_RAW;  // [5 K-blocks][npad queries][128 B], same swizzle
     WideSmem<MAXQ>* sm = (WideSmem<MAXQ>*)(q_mem + (size_t)5 * MAXQ * 128);
-    constexpr uint32_t D_STRIDE = 64;
+    constexpr bool HALVES = MAXQ > 64;
+    constexpr int EPIW = WideCfg<MAXQ>::EPIW, EPI_THREADS_ = EPIW * 32;
+    constexpr int W_MMA = WideCfg<MAXQ>::WARP_MMA, W_TMA = WideCfg<MAXQ>::WARP_TMA, W_EXP0 = WideCfg<MAXQ>::WARP_EXP0;
+    constexpr int NGW = (MAXQ / 16) / (EPIW / 4);  // 16-column groups per epilogue warp
+    constexpr uint32_t D_COL = HALVES ? 128 : FEW_D_COL, D_STRIDE = HALVES ? 128 : 64, A_STRIDE = HALVES ? 0 : 128;
     constexpr int NG = MAXQ / 16;  // 16-column groups of the accumulator
+    // barrier a_full / a_empty [i]: i = A buffer (tile parity), or with HALVES i = K half; their phase flips every second tile
+    // resp. every tile
+    auto a_phase = [](uint32_t t) -> uint32_t { return HALVES ? (t & 1u) : ((t >> 1) & 1u); };
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -968,13 +990,15 @@ hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParam
     if (tid == 0) {
         for (int s = 0; s < raw_stages; s++) {
             mbar_init(smem_u32(&sm->raw_full[s]), 1);
-            mbar_init(smem_u32(&sm->raw_empty[s]), FEW_EXP_WARPS);
+            mbar_init(smem_u32(&sm->raw_empty[s]), WideCfg<MAXQ>::EXPW);
+        }
+        for (int s = 0; s < 4; s++) {
+            mbar_init(smem_u32(&sm->a_full[s]), WideCfg<MAXQ>::EXPW);  // every expander warp contributes to every hand-over
+            mbar_init(smem_u32(&sm->a_empty[s]), 1);
         }
         for (int s = 0; s < 2; s++) {
-            mbar_init(smem_u32(&sm->a_full[s]), FEW_EXP_WARPS);
-            mbar_init(smem_u32(&sm->a_empty[s]), 1);
             mbar_init(smem_u32(&sm->acc_full[s]), 1);
-            mbar_init(smem_u32(&sm->acc_empty[s]), FEW_EPI_WARPS);
+            mbar_init(smem_u32(&sm->acc_empty[s]), EPIW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -984,7 +1008,7 @@ hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParam
         sm->cnt_s[tid] = 0;
         sm->tau_s[tid] = tid < nq ? (p.tau0 ? min(p.tau0[tid], TAU_INF - 1) + p.tau_bias : TAU_INF) : 0;
     }
-    if (warp == FEW_WARP_MMA) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "r"(TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -996,7 +1020,7 @@ hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParam
 
     // ---- the queries become the B operand in shared memory: row = query, K-block kb = code words 8 kb .. 8 kb + 7, chunk i
     //      of the 128-byte row = word 8 kb + i as four planes (nibble j of plane t = bit t + 4 j) of +-(1 / plane value)
-    for (int idx = tid; idx < npad * 32; idx += FEW_THREADS) {
+    for (int idx = tid; idx < npad * 32; idx += WideCfg<MAXQ>::THREADS) {
         const int q = idx >> 5, W = idx & 31;
         const bool qvalid = q < nq;
         const uint32_t w = qvalid ? __ldg(reinterpret_cast<const uint32_t*>(p.queries + (size_t)q * CODE_BYTES) + W) : 0u;
@@ -1010,7 +1034,7 @@ hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParam
         const int kb = W >> 3, i = W & 7;
         sts128(smem_u32(q_mem) + (uint32_t)(kb * npad * 128 + q * 128 + ((i ^ (q & 7)) << 4)), v[0], v[1], v[2], v[3]);
     }
-    if (warp < FEW_EPI_WARPS) {
+    if (warp < 4) {
         // every block scale (UE8M0) = 0x7F = 2^0; the constant A operand of the bias MMA: K positions 0 .. 61 = 4.0 (0x6),
         // 62, 63 = 1.0 (0x2)
         uint32_t one[8];
@@ -1086,7 +1110,7 @@ hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParam
     __syncthreads();
     tc_fence_after();
 
-    if (warp == FEW_WARP_TMA) {
+    if (warp == W_TMA) {
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
             for (int t = 0; t < ntiles; t++) {
@@ -1099,7 +1123,7 @@ hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParam
                 }
             }
         }
-    } else if (warp == FEW_WARP_MMA) {
+    } else if (warp == W_MMA) {
         // ===================== MMA issuer: 16 + 1 MMAs (M = 128 rows, N = npad queries, K = 64) per tile ===================
         const uint32_t idesc = (1u << 7) | (1u << 10) | ((uint32_t)(npad >> 3) << 17) | (1u << 23) | ((uint32_t)(MQ >> 4) << 24);
         const uint64_t qdesc0 = umma_desc_sw128(smem_u32(q_mem));
@@ -1108,64 +1132,123 @@ hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParam
         uint32_t bar_acc_full = smem_u32(&sm->acc_full[0]), bar_acc_empty = smem_u32(&sm->acc_empty[0]);
         asm volatile("" : "+r"(bar_a_full), "+r"(bar_a_empty), "+r"(bar_acc_full), "+r"(bar_acc_empty));
         for (int t = 0; t < ntiles; t++) {
-            const uint32_t ab = (uint32_t)t & 1u, ph = ((uint32_t)t >> 1) & 1u;
-            mbar_wait(bar_a_full + 8u * ab, ph);
+            const uint32_t ab = (uint32_t)t & 1u, ph = ((uint32_t)t >> 1) & 1u, aph = a_phase((uint32_t)t);
+            const uint32_t d_tmem = tmem + D_COL + ab * D_STRIDE, a0 = tmem + FEW_A_COL + ab * A_STRIDE;
             mbar_wait(bar_acc_empty + 8u * ab, ph ^ 1u);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t d_tmem = tmem + FEW_D_COL + ab * D_STRIDE, a0 = tmem + FEW_A_COL + ab * 128;
+            if constexpr (!HALVES) {
+                mbar_wait(bar_a_full + 8u * ab, aph);  // the tile is in tensor memory
+                tc_fence_after();
+                if (elect_one()) {
 #pragma unroll
-                for (int s = 0; s < 16; s++)
-                    umma_f4_ts(d_tmem, a0 + 8 * s, qdesc0 + (uint64_t)((s >> 2) * kb_step + (s & 3) * 2), idesc, tmem + FEW_SF_COL,
-                               tmem + FEW_SF_COL + 32, s != 0);
-                umma_f4_ts(d_tmem, tmem + WIDE_BIAS_COL, qdesc0 + (uint64_t)(4 * kb_step), idesc, tmem + FEW_SF_COL, tmem + FEW_SF_COL + 32, 1);
-                tc_commit(bar_a_empty + 8u * ab);
-                tc_commit(bar_acc_full + 8u * ab);
+                    for (int s = 0; s < 16; s++)
+                        umma_f4_ts(d_tmem, a0 + 8 * s, qdesc0 + (uint64_t)((s >> 2) * kb_step + (s & 3) * 2), idesc, tmem + FEW_SF_COL,
+                                   tmem + FEW_SF_COL + 32, s != 0);
+                    umma_f4_ts(d_tmem, tmem + WIDE_BIAS_COL, qdesc0 + (uint64_t)(4 * kb_step), idesc, tmem + FEW_SF_COL, tmem + FEW_SF_COL + 32, 1);
+                    tc_commit(bar_a_empty + 8u * ab);
+                    tc_commit(bar_acc_full + 8u * ab);
+                }
+                __syncwarp();
+            } else {
+                constexpr int PARTS = WideCfg<MAXQ>::PARTS, SPP = 16 / PARTS;  // MMAs per piece
+#pragma unroll
+                for (int part = 0; part < PARTS; part++) {
+                    mbar_wait(bar_a_full + 8u * part, aph);  // piece `part` of the tile's A operand is in tensor memory
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int s = SPP * part; s < SPP * part + SPP; s++)
+                            umma_f4_ts(d_tmem, a0 + 8 * s, qdesc0 + (uint64_t)((s >> 2) * kb_step + (s & 3) * 2), idesc, tmem + FEW_SF_COL,
+                                       tmem + FEW_SF_COL + 32, s != 0);
+                        if (part == PARTS - 1)
+                            umma_f4_ts(d_tmem, tmem + WIDE_BIAS_COL, qdesc0 + (uint64_t)(4 * kb_step), idesc, tmem + FEW_SF_COL, tmem + FEW_SF_COL + 32,
+                                       1);
+                        tc_commit(bar_a_empty + 8u * part);
+                        if (part == PARTS - 1) tc_commit(bar_acc_full + 8u * ab);
+                    }
+                    __syncwarp();
+                }
             }
-            __syncwarp();
         }
-    } else if (warp >= FEW_WARP_EXP0) {
+    } else if (warp >= W_EXP0) {
         // ===================== expanders: thread = (database row = TMEM lane, half of K); all 8 warps on every tile ========
-        const int kh = (warp - FEW_WARP_EXP0) >> 2;  // which 64 code bytes (chunks 4 kh .. 4 kh + 3) -> which 64 columns
+        const int kh = (warp - W_EXP0) >> 2;  // which 64 code bytes (chunks 4 kh .. 4 kh + 3) -> which 64 columns
         const int row = (warp & 3) * 32 + lane;      // a warp may only touch the TMEM lane quadrant warp_id % 4
         const uint32_t sw = (uint32_t)(row & 7);
         uint32_t a_buf0 = tmem + ((uint32_t)((warp & 3) * 32) << 16) + FEW_A_COL + (uint32_t)kh * 64;
+        uint32_t a_quad0 = tmem + ((uint32_t)((warp & 3) * 32) << 16) + FEW_A_COL;
+        asm volatile("" : "+r"(a_quad0));
         uint32_t raw0 = smem_u32(raw_mem) + (uint32_t)row * 128u;
         uint32_t bar_raw_full = smem_u32(&sm->raw_full[0]), bar_raw_empty = smem_u32(&sm->raw_empty[0]);
         uint32_t bar_a_full = smem_u32(&sm->a_full[0]), bar_a_empty = smem_u32(&sm->a_empty[0]);
         asm volatile("" : "+r"(a_buf0), "+r"(raw0), "+r"(bar_raw_full), "+r"(bar_raw_empty), "+r"(bar_a_full), "+r"(bar_a_empty));
         uint32_t rs = 0, rph = 0;
         for (int t = 0; t < ntiles; t++) {
-            const uint32_t ab = (uint32_t)t & 1u, ph = ((uint32_t)t >> 1) & 1u;
+            const uint32_t ab = (uint32_t)t & 1u, aph = a_phase((uint32_t)t);
             mbar_wait_relaxed(bar_raw_full + 8u * rs, rph, 32);
             const uint32_t raddr = raw0 + rs * (uint32_t)STAGE_BYTES_RAW;
-            uint4 c[4];
+            if constexpr (HALVES) {
+                // one expander warp per lane quadrant: the whole 128-byte row, handed over in PARTS pieces of 128 / PARTS columns;
+                // the planes of piece i + 1 are computed while the tcgen05.st of piece i are in flight
+                constexpr int PARTS = WideCfg<MAXQ>::PARTS, QPP = 4 / PARTS;  // 32-column quarters per piece
+                uint4 c[8];
 #pragma unroll
-            for (int j = 0; j < 4; j++) c[j] = lds128(raddr + (((uint32_t)(4 * kh + j) ^ sw) << 4));
-            mbar_wait(bar_a_empty + 8u * ab, ph ^ 1u);
-            tc_fence_after();
+                for (int j = 0; j < 8; j++) c[j] = lds128(raddr + (((uint32_t)j ^ sw) << 4));
+                uint32_t v[2][QPP][32];
+                auto planes = [&](const int quarter, uint32_t(&o)[32]) {
+                    const uint32_t w[8] = {c[2 * quarter].x, c[2 * quarter].y, c[2 * quarter].z, c[2 * quarter].w,
+                                           c[2 * quarter + 1].x, c[2 * quarter + 1].y, c[2 * quarter + 1].z, c[2 * quarter + 1].w};
 #pragma unroll
-            for (int part = 0; part < 2; part++) {
-                // words 8 (2 kh + part) .. + 7 of the code -> columns 64 kh + 32 part .. + 31 (column 4 W + t = plane t of word W)
-                const uint32_t w[8] = {c[2 * part].x, c[2 * part].y, c[2 * part].z, c[2 * part].w,
-                                       c[2 * part + 1].x, c[2 * part + 1].y, c[2 * part + 1].z, c[2 * part + 1].w};
-                uint32_t v[32];
+                    for (int i = 0; i < 8; i++) {
+                        o[4 * i + 0] = w[i] & 0x11111111u;
+                        o[4 * i + 1] = w[i] & 0x22222222u;
+                        o[4 * i + 2] = w[i] & 0x44444444u;
+                        o[4 * i + 3] = (w[i] >> 1) & 0x44444444u;
+                    }
+                };
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    v[4 * i + 0] = w[i] & 0x11111111u;
-                    v[4 * i + 1] = w[i] & 0x22222222u;
-                    v[4 * i + 2] = w[i] & 0x44444444u;
-                    v[4 * i + 3] = (w[i] >> 1) & 0x44444444u;
+                for (int qq = 0; qq < QPP; qq++) planes(qq, v[0][qq]);
+#pragma unroll
+                for (int part = 0; part < PARTS; part++) {
+                    mbar_wait(bar_a_empty + 8u * part, aph ^ 1u);
+                    tc_fence_after();
+#pragma unroll
+                    for (int qq = 0; qq < QPP; qq++) tmem_st32(a_quad0 + 32 * (part * QPP + qq), v[part & 1][qq]);
+                    if (part + 1 < PARTS) {
+#pragma unroll
+                        for (int qq = 0; qq < QPP; qq++) planes((part + 1) * QPP + qq, v[(part + 1) & 1][qq]);
+                    }
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_a_full + 8u * part);
                 }
-                tmem_st32(a_buf0 + ab * 128 + 32 * part, v);
+            } else {
+                uint4 c[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) c[j] = lds128(raddr + (((uint32_t)(4 * kh + j) ^ sw) << 4));
+                mbar_wait(bar_a_empty + 8u * ab, aph ^ 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int part = 0; part < 2; part++) {
+                    // words 8 (2 kh + part) .. + 7 of the code -> columns 64 kh + 32 part .. + 31 (column 4 W + t = plane t of word W)
+                    const uint32_t w[8] = {c[2 * part].x, c[2 * part].y, c[2 * part].z, c[2 * part].w,
+                                           c[2 * part + 1].x, c[2 * part + 1].y, c[2 * part + 1].z, c[2 * part + 1].w};
+                    uint32_t v[32];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        v[4 * i + 0] = w[i] & 0x11111111u;
+                        v[4 * i + 1] = w[i] & 0x22222222u;
+                        v[4 * i + 2] = w[i] & 0x44444444u;
+                        v[4 * i + 3] = (w[i] >> 1) & 0x44444444u;
+                    }
+                    tmem_st32(a_buf0 + ab * A_STRIDE + 32 * part, v);
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_a_full + 8u * ab);
             }
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(bar_a_full + 8u * ab);
-                mbar_arrive(bar_raw_empty + 8u * rs);  // every c[j] has been consumed by real instructions
-            }
+            if (lane == 0) mbar_arrive(bar_raw_empty + 8u * rs);  // every c[j] has been consumed by real instructions
             if (++rs == (uint32_t)raw_stages) {
                 rs = 0;
                 rph ^= 1u;
@@ -1173,7 +1256,9 @@ hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParam
         }
     } else {
         // ===================== epilogue: lane = database row, column = query ==========================================
-        uint32_t acc0 = tmem + ((uint32_t)(warp * 32) << 16) + FEW_D_COL;
+        // warp & 3 = TMEM lane quadrant (32 database rows); warp >> 2 (MAXQ = 128 only) = which half of the query columns
+        const int quad = warp & 3, g0 = (warp >> 2) * NGW;  // first 16-column group of this warp
+        uint32_t acc0 = tmem + ((uint32_t)(quad * 32) << 16) + D_COL + 16u * (uint32_t)g0;
         uint32_t bar_acc_full = smem_u32(&sm->acc_full[0]), bar_acc_empty = smem_u32(&sm->acc_empty[0]);
         asm volatile("" : "+r"(acc0), "+r"(bar_acc_full), "+r"(bar_acc_empty));
         const int limit = p.compact_limit > 0 ? min(p.compact_limit, p.cap - p.group_tiles * MROWS) : p.cap - p.group_tiles * MROWS;
@@ -1192,39 +1277,39 @@ hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParam
             const uint32_t ab = (uint32_t)t & 1u;
             mbar_wait(bar_acc_full + 8u * ab, ((uint32_t)t >> 1) & 1u);
             tc_fence_after();
-            int v[NG][16];
+            int v[NGW][16];
             __syncwarp();
 #pragma unroll
-            for (int g = 0; g < NG; g++)
-                if (g < ng) tmem_ld16(acc0 + ab * D_STRIDE + 16 * g, v[g]);
+            for (int g = 0; g < NGW; g++)
+                if (g0 + g < ng) tmem_ld16(acc0 + ab * D_STRIDE + 16 * g, v[g]);
             tmem_wait_ld();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acc_empty + 8u * ab);  // the accumulator goes back before anything is examined
-            float gm[NG];
+            float gm[NGW];
             float mx = -3.0e9f;
 #pragma unroll
-            for (int g = 0; g < NG; g++) {
-                gm[g] = g < ng ? max16(v[g]) : -3.0e9f;
+            for (int g = 0; g < NGW; g++) {
+                gm[g] = g0 + g < ng ? max16(v[g]) : -3.0e9f;
                 mx = fmaxf(mx, gm[g]);
             }
             if (mx > 0.0f || has_dbg) {
-                const int64_t lrow = tile_row(t) + warp * 32 + lane;
+                const int64_t lrow = tile_row(t) + quad * 32 + lane;
                 if (lrow < s_end) {
                     if (has_dbg) {
                         // tests only: every distance of the tile
 #pragma unroll
-                        for (int g = 0; g < NG; g++)
-                            if (g < ng)
+                        for (int g = 0; g < NGW; g++)
+                            if (g0 + g < ng)
                                 for (int j = 0; j < 16; j++) {
-                                    const int q = 16 * g + j;
+                                    const int q = 16 * (g0 + g) + j;
                                     if (q < nq) p.dbg[(size_t)q * p.dbg_stride + lrow] = sm->pcq_s[q] - (int)(__int_as_float(sel16(v[g], j)) - sm->bias_s[q]);
                                 }
                     }
                     const unsigned long long pos = (unsigned long long)(p.pos_base + lrow);
 #pragma unroll
-                    for (int g = 0; g < NG; g++) {
-                        if (g < ng && gm[g] > 0.0f) {
+                    for (int g = 0; g < NGW; g++) {
+                        if (g0 + g < ng && gm[g] > 0.0f) {
                             // bit (15 - j) <=> column 16 g + j is > 0: the sign of 0 - f, one add + one funnel shift per column
                             uint32_t mask = 0;
 #pragma unroll
@@ -1234,7 +1319,7 @@ hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParam
                                 const int b = 31 - __clz((int)mask);
                                 mask &= ~(1u << b);
                                 const int j = 15 - b;
-                                wide_append(sm->bias_s, sm->thr_s, sm->pcq_s, sm->cnt_s, lists0, p.key_lo, p.cap, pos, 16 * g + j,
+                                wide_append(sm->bias_s, sm->thr_s, sm->pcq_s, sm->cnt_s, lists0, p.key_lo, p.cap, pos, 16 * (g0 + g) + j,
                                             __int_as_float(sel16(v[g], j)));
                             }
                         }
@@ -1243,7 +1328,7 @@ hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParam
             }
             if (--until_check == 0 && t + 1 < ntiles) {
                 until_check = p.group_tiles;
-                group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
+                group_sync<EPI_THREADS_>(BAR_CONSUMERS);
                 const int over = (tid < nq && sm->cnt_s[tid] > limit) ? 1 : 0;
                 int any;
                 asm volatile(
@@ -1254,34 +1339,34 @@ hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParam
                     "selp.s32 %0, 1, 0, p;\n"
                     "}\n"
                     : "=r"(any)
-                    : "r"(over), "n"(BAR_CONSUMERS), "n"(FEW_EPI_THREADS)
+                    : "r"(over), "n"(BAR_CONSUMERS), "n"(EPI_THREADS_)
                     : "memory");
                 if (any) {
-                    for (int qq = warp; qq < nq; qq += FEW_EPI_WARPS) {
+                    for (int qq = warp; qq < nq; qq += EPIW) {
                         const int n = sm->cnt_s[qq];
                         if (n > limit)
                             compact_list_warp(lists0 + (size_t)qq * p.cap, n, p.k, &sm->sc[warp], lane, BAR_WARP0 + warp, &sm->cnt_s[qq],
                                               &sm->tau_s[qq], p.sample_mode ? limit : 0);
                     }
-                    group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
+                    group_sync<EPI_THREADS_>(BAR_CONSUMERS);
                     if (tid < nq) sm->thr_s[tid] = (float)(sm->pcq_s[tid] - sm->tau_s[tid]);
-                    group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
+                    group_sync<EPI_THREADS_>(BAR_CONSUMERS);
                 }
             }
         }
-        group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
-        for (int qq = warp; qq < nq && !p.sample_mode; qq += FEW_EPI_WARPS) {
+        group_sync<EPI_THREADS_>(BAR_CONSUMERS);
+        for (int qq = warp; qq < nq && !p.sample_mode; qq += EPIW) {
             const int n = sm->cnt_s[qq];
             if (n > p.k)
                 compact_list_warp(lists0 + (size_t)qq * p.cap, n, p.k, &sm->sc[warp], lane, BAR_WARP0 + warp, &sm->cnt_s[qq], &sm->tau_s[qq]);
         }
-        group_sync<FEW_EPI_THREADS>(BAR_CONSUMERS);
+        group_sync<EPI_THREADS_>(BAR_CONSUMERS);
         if (tid < nq) p.counts[(size_t)strip * p.nq + tid] = sm->cnt_s[tid];
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == FEW_WARP_MMA) {
+    if (warp == W_MMA) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
     }
@@ -1289,7 +1374,7 @@ hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParam
 
 size_t wide_smem_bytes(int raw_stages, int maxq) {
     return 1024 + (size_t)raw_stages * STAGE_BYTES_RAW + (size_t)5 * maxq * 128 +
-           (maxq <= 32 ? sizeof(WideSmem<FEW_MAXQ>) : sizeof(WideSmem<WIDE_MAXQ>)) + 16;
+           (maxq <= 32 ? sizeof(WideSmem<FEW_MAXQ>) : (maxq <= 64 ? sizeof(WideSmem<WIDE_MAXQ>) : sizeof(WideSmem<WIDE128_MAXQ>))) + 16;
 }
 
 size_t mma_smem_bytes(int raw_stages, int cap) {
@@ -1307,7 +1392,11 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl, bool a
     pl->few = allow_few && pl->f4 && nq <= FEW_MAXQ && env_int("VRQ_MMA_FEW", 1) != 0;
     // 33 .. 64 queries: the same kernel with four column groups (VRQ_MMA_MID=0: the 128-query-tile kernel)
     pl->mid = allow_few && pl->f4 && !pl->few && nq <= WIDE_MAXQ && env_int("VRQ_MMA_FEW", 1) != 0 && env_int("VRQ_MMA_MID", 1) != 0;
-    if (pl->mid) pl->few = true;
+    // 65 .. 96 queries: the same kernel with one A buffer handed over per K half, 8 epilogue warps and up to 128 accumulator
+    // columns.  Measured per 100 M codes: 65 queries 3.45 ms (128-query-tile kernel: 3.83), 96: 3.77 (3.98), 112: 4.03 (4.03),
+    // 128: 4.28 (4.08) - so it takes over up to 96 (VRQ_MMA_W128 = upper limit, 0 = off)
+    pl->w128 = allow_few && pl->f4 && !pl->few && !pl->mid && nq <= WIDE128_MAXQ && nq <= env_int("VRQ_MMA_W128", 96) && env_int("VRQ_MMA_FEW", 1) != 0;
+    if (pl->mid || pl->w128) pl->few = true;
     // CTA pairs need an even number of query tiles (a pair = two neighbouring tiles); VRQ_MMA_PAIR=0 switches them off
     pl->pair = pl->f4 && pl->qtiles % 2 == 0 && env_int("VRQ_MMA_PAIR", 1) != 0;
     pl->group_tiles = env_int("VRQ_MMA_GROUP_TILES", 32);  // tiles between two overflow checks of the lists (measured: 8 -> 32 = +1.3 %)
@@ -1361,7 +1450,7 @@ int plan_scan_mma(vrq_ctx* ctx, int64_t rows, int nq, int k, MmaPlan* pl, bool a
 void mma_plan_set_cap(MmaPlan* pl, int cap) {
     pl->cap = cap;
     if (pl->few) {
-        pl->smem = wide_smem_bytes(pl->raw_stages, pl->mid ? WIDE_MAXQ : FEW_MAXQ);
+        pl->smem = wide_smem_bytes(pl->raw_stages, pl->w128 ? WIDE128_MAXQ : (pl->mid ? WIDE_MAXQ : FEW_MAXQ));
         return;
     }
     while (pl->raw_stages > 1 && mma_smem_bytes(pl->raw_stages, cap) > pl->smem_limit) pl->raw_stages--;
@@ -1379,7 +1468,10 @@ int launch_scan_mma(vrq_ctx* ctx, const CUtensorMap& tmap128, const CUtensorMap&
     if (pl.seg_cols > 0) grid = dim3(2 * (pl.seg_cols * pl.seg_full + pl.seg_tail), 1);  // 1-D grid of CTA pairs
     if (pl.few) {
         const int npad = ((sp.nq + 15) / 16) * 16;
-        if (pl.mid) {
+        if (pl.w128) {
+            VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_wide_kernel<WIDE128_MAXQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+            hamming_scan_mma_wide_kernel<WIDE128_MAXQ><<<grid, WideCfg<WIDE128_MAXQ>::THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, npad);
+        } else if (pl.mid) {
             VRQ_CUDA(cudaFuncSetAttribute(hamming_scan_mma_wide_kernel<WIDE_MAXQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
             hamming_scan_mma_wide_kernel<WIDE_MAXQ><<<grid, FEW_THREADS, pl.smem, st>>>(tmap128, sp, pl.raw_stages, npad);
         } else {
