@@ -14,7 +14,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvrq.so")
+LIB_PATH = os.environ.get("VRQ_LIBVRQ") or os.path.join(_HERE, "libvrq.so")  # VRQ_LIBVRQ: A/B runs against another build
 
 ERR_ARG, ERR_UNSUPPORTED, ERR_IO, ERR_STATE, ERR_NOMEM = -1, -2, -3, -4, -5
 

@@ -1134,9 +1134,9 @@ hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParam
         for (int t = 0; t < ntiles; t++) {
             const uint32_t ab = (uint32_t)t & 1u, ph = ((uint32_t)t >> 1) & 1u, aph = a_phase((uint32_t)t);
             const uint32_t d_tmem = tmem + D_COL + ab * D_STRIDE, a0 = tmem + FEW_A_COL + ab * A_STRIDE;
-            mbar_wait(bar_acc_empty + 8u * ab, ph ^ 1u);
             if constexpr (!HALVES) {
                 mbar_wait(bar_a_full + 8u * ab, aph);  // the tile is in tensor memory
+                mbar_wait(bar_acc_empty + 8u * ab, ph ^ 1u);
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
@@ -1149,6 +1149,7 @@ hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParam
                 }
                 __syncwarp();
             } else {
+                mbar_wait(bar_acc_empty + 8u * ab, ph ^ 1u);
                 constexpr int PARTS = WideCfg<MAXQ>::PARTS, SPP = 16 / PARTS;  // MMAs per piece
 #pragma unroll
                 for (int part = 0; part < PARTS; part++) {
@@ -1257,7 +1258,7 @@ hamming_scan_mma_wide_kernel(const __grid_constant__ CUtensorMap tmap, ScanParam
     } else {
         // ===================== epilogue: lane = database row, column = query ==========================================
         // warp & 3 = TMEM lane quadrant (32 database rows); warp >> 2 (MAXQ = 128 only) = which half of the query columns
-        const int quad = warp & 3, g0 = (warp >> 2) * NGW;  // first 16-column group of this warp
+        const int quad = warp & 3, g0 = EPIW == 8 ? (warp >> 2) * NGW : 0;  // first 16-column group of this warp
         uint32_t acc0 = tmem + ((uint32_t)(quad * 32) << 16) + D_COL + 16u * (uint32_t)g0;
         uint32_t bar_acc_full = smem_u32(&sm->acc_full[0]), bar_acc_empty = smem_u32(&sm->acc_empty[0]);
         asm volatile("" : "+r"(acc0), "+r"(bar_acc_full), "+r"(bar_acc_empty));
