@@ -319,7 +319,9 @@ __global__ void __launch_bounds__(256, 2) rescore_int8cos_kernel(const int8_t* _
 // the ring needs no barrier at all: cp.async.wait_group orders a lane's own copies.  Same arithmetic as above.
 constexpr int P3_RING = 8;
 
-// BATCH (opt-in, VRQ_RESCORE_BATCHRED=1; written at the end of round 1, NOT yet run on a GPU): the per-row butterfly
+// BATCH (opt-in, VRQ_RESCORE_BATCHRED=1; held to 1e-13 of the float64 evaluation with the other variants by
+// tests/test_gpu_kernels.py::test_rescore_int8cos_kernel_variants; superseded as the default by the tensor-core kernel of
+// rescore_mma.cu): the per-row butterfly
 // reductions (15 shuffles + 10 adds per row, the top stall of the ncu capture) are replaced by a transpose through shared
 // memory - every lane parks its partial dot / partial norm of row j in red[j & 7][lane]; after 8 rows lane (qd, r) adds
 // the 8 partials of quarter qd of row r (columns visited in the skewed order 8 qd + ((i + r) & 7): conflict-free), two
