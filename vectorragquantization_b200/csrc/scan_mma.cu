@@ -19,11 +19,16 @@
 //     8-stage ring of K-block stages.
 //   * Two issuer warps (one elected lane each; the leader CTA of a pair) issue 4 MMAs per K-block into one of two
 //     128-column TMEM accumulators; tcgen05.commit frees the stage / publishes the accumulator (multicast to both CTAs).
-//   * Eight epilogue warps read the accumulator with software-pipelined tcgen05.ld (lane = query, 16 columns = 16
-//     database rows per load), take the maximum of the 16 dots and compare it with the query's threshold held in a
-//     register; only when a group holds a survivor are the values looked at individually and appended to the
-//     (strip, query) list.  Lists, thresholds and the merge tree are those of scan.cu; overflowing lists are compacted in
-//     place by one warp per list.
+//   * Eight epilogue warps (lane = query, columns = database rows).  In the dense pass they run at 128 registers (setmaxnreg;
+//     everyone else at 72): all four tcgen05.ld.x16 of a tile at once, the accumulator handed back before anything is
+//     examined, then a tree of 3-input maxima and ONE compare of the largest of the 64 dots with the query's threshold; only
+//     a group that holds a survivor is looked at column by column and appended to the (strip, query) list.  The loop is ~70
+//     instructions per tile when nothing survives - measured, the epilogue's instruction stream (not tensor memory, not
+//     shared memory) was what kept the tensor pipe at 83 % (now 99.5 % under ncu).  The other instantiations (sample pass,
+//     int8 kind, tests' distance dump) keep a generic loop over two register sets.  Lists, thresholds and the merge tree
+//     are those of scan.cu; overflowing lists are compacted in place by one warp per list.
+// Few queries per pass (3 .. 96) take hamming_scan_mma_wide_kernel further down: operand roles swapped (database rows = M,
+// expanded straight into tensor memory), a bias column that gives all query columns one threshold.
 // Host side (scan.cu: topk_batch): thresholds come from a strided sample pass of this kernel, one dense pass collects the
 // candidates, a verification kernel un-gates an exact fallback pass if a query came up short.  DESIGN.md section 3.2.1.
 #include "scan_common.cuh"
