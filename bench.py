@@ -845,6 +845,9 @@ def cfg1_leg(env):
         allx = np.concatenate([x, qx])
         docs = [f"doc {i}" for i in range(n)]
         with tempfile.TemporaryDirectory() as tmp:
+            # a throw-away database first: the timed one does not pay the process's first encode launch / allocation
+            V.VectorDBInt8(os.path.join(tmp, "w"), embedder=lambda texts: allx[[table[t] for t in texts]], ctx=env.ctx).add_documents(
+                list(range(256)), docs[:256], batch_size=64, save=False)
             db = V.VectorDBInt8(os.path.join(tmp, "a"), embedder=lambda texts: allx[[table[t] for t in texts]], ctx=env.ctx)
             t0 = time.perf_counter()
             db.add_documents(list(range(n)), docs, batch_size=64, save=False)
@@ -868,7 +871,9 @@ def cfg1_leg(env):
         res.update({"cpu": {"cores": cores, "add_docs_per_s": n / t_add_cpu, "search_queries_per_s": nq / t_search_cpu,
                             "what": "literal per-document NumPy quantise + _to_binary; per query C Hamming scan + per-candidate dequantise/np.dot loop"},
                     "gpu_class_api": {"add_docs_per_s": n / t_add_gpu, "search_queries_per_s": nq / t_search_gpu,
-                                      "what": "VectorDBInt8.add_documents(batch_size=64) + search() one query at a time, host buffers through the C ABI"},
+                                      "what": "VectorDBInt8.add_documents(batch_size=64) + search() one query at a time, host buffers through the C ABI "
+                                              "(document store, duplicate check and index growth included; a 256-document warm-up database "
+                                              "comes first)"},
                     "gpu_bulk_api": {"add_docs_per_s": n / t_bulk_add, "search_queries_per_s": nq / t_bulk_search,
                                      "what": "add_embeddings (one encode call) + search_batch (one call for the 100 queries)"},
                     "codes_and_int8_bit_exact_vs_cpu": codes_equal,
