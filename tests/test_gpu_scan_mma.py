@@ -312,3 +312,24 @@ def test_mma_clustered_rows_partial_fallback(V, monkeypatch, nq):
         dist, labels = ix.search(q, k)
         rd, rp = oc.hamming_topk(codes, q, k)
         assert np.array_equal(dist, rd) and np.array_equal(labels, rp)
+
+
+# ---- the two epilogue loops of the dense pass: lean (128 registers, VRQ_MMA_VAR=4, default) and generic (VRQ_MMA_VAR=0) ----
+@pytest.mark.parametrize("n,nq", [(300001, 256), (1_000_003, 1024), (70000, 128), (250000, 384)])
+def test_lean_and_generic_epilogue_agree(V, monkeypatch, n, nq):
+    """CTA pairs (even numbers of 128-query tiles) and single CTAs (odd), a last tile that is partly past the end of the
+    database, a tail strip shared by two clusters: both loops return the oracle's top-k."""
+    set_env(monkeypatch, "default")
+    codes, _ = oc.synth_codes_int8(71, 0, n, want_int8=False)
+    q = o.synth_ubinary_from_f32(oc.synth_f32(72, 0, nq))
+    q[0] = codes[n - 1]  # an exact hit in the last, partial tile
+    ix = V.BinaryIndex(1024)
+    ix.add_with_ids(codes, np.arange(n))
+    k = 200
+    a = ix.search(q, k)
+    monkeypatch.setenv("VRQ_MMA_VAR", "0")
+    b = ix.search(q, k)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    rd, rp = oc.hamming_topk(codes, q[:12], k)
+    assert np.array_equal(a[0][:12], rd) and np.array_equal(a[1][:12], rp)
+    assert a[1][0, 0] == n - 1 and a[0][0, 0] == 0
