@@ -174,7 +174,9 @@ int vrq_index_search3(vrq_index*, int64_t nq, const float* q_float, const uint8_
                       int int8_oversample, int64_t* labels, int32_t* hamming, double* score_binary, double* score_cosine,
                       int32_t* out_count);
 /* The 2-phase search of the six VectorDB* classes (VectorDBInt8.py:213-242): Hamming top min(k*oversample, ntotal),
- * float32 dot(q, dequantised payload) for every hit, stable sort descending, [:k].  score float32[nq,k]. */
+ * float32 dot(q, dequantised payload) for every hit, stable sort descending, [:k].  score float32[nq,k].
+ * q_ubin may be NULL: the 1-bit code of every query is then computed on the device as the classes do it,
+ * query_bin = _to_binary(query float) = packbits(q > mean(q)) (VectorDBInt8.py:213, :140-146). */
 int vrq_index_search2(vrq_index*, int64_t nq, const float* q_float, const uint8_t* q_ubin, int k, int binary_oversample,
                       int64_t* labels, float* score, int32_t* out_count);
 

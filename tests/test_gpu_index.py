@@ -195,6 +195,11 @@ def test_search2_all_payload_kinds(V):
         ix = V.BinaryIndex(1024, payload_kind=kind, global_limit=lim)
         ix.add_with_ids(ub, ids, payload=payload, aux=aux)
         labels, score, cnt = ix.search2(qf, qb, k, bo)
+        # q_ubin = NULL: the library derives query_bin = _to_binary(query float) on the device (VectorDBInt8.py:213)
+        l0, s0, c0 = ix.search2(qf, None, k, bo)
+        assert np.array_equal(l0, labels) and np.array_equal(s0, score) and np.array_equal(c0, cnt), kind
+        l1, s1, c1 = ix.search2(qf[0], None, k, bo)  # one query per call, as the classes search
+        assert np.array_equal(l1[0], labels[0]) and np.array_equal(s1[0], score[0])
         for qi in range(nq):
             ref = o.search2(ub, ids, deq, qf[qi], qb[qi], k, bo)
             assert cnt[qi] == k

@@ -189,16 +189,18 @@ class BinaryIndex:
 
     def search2(self, q_float, q_ubinary, k: int, binary_oversample: int = 10):
         """The VectorDB* 2-phase search (VectorDBInt8.py:213-242) for a batch of queries.
+        ``q_ubinary`` None: the library derives it from ``q_float`` on the device (packbits(q > mean(q))).
         Returns (labels i64[nq,k], score f32[nq,k], count i32[nq])."""
         qf = np.ascontiguousarray(q_float, np.float32)
-        qb = np.ascontiguousarray(q_ubinary, np.uint8)
+        qb = None if q_ubinary is None else np.ascontiguousarray(q_ubinary, np.uint8)
         if qf.ndim == 1:
-            qf, qb = qf[None], qb.reshape(1, -1)
+            qf = qf[None]
+            qb = None if qb is None else qb.reshape(1, -1)
         nq = qf.shape[0]
         labels = np.empty((nq, k), np.int64)
         score = np.empty((nq, k), np.float32)
         cnt = np.empty(nq, np.int32)
-        L.check(self._lib.vrq_index_search2(self._h, nq, L.ptr(qf), L.ptr(qb), int(k), int(binary_oversample), L.ptr(labels),
+        L.check(self._lib.vrq_index_search2(self._h, nq, L.ptr(qf), None if qb is None else L.ptr(qb), int(k), int(binary_oversample), L.ptr(labels),
                                             L.ptr(score), L.ptr(cnt)))
         return labels, score, cnt
 

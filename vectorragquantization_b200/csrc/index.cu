@@ -1127,7 +1127,7 @@ extern "C" int vrq_index_search3(vrq_index* ix, int64_t nq, const float* q_float
 
 extern "C" int vrq_index_search2(vrq_index* ix, int64_t nq, const float* q_float, const uint8_t* q_ubin, int k,
                                  int binary_oversample, int64_t* labels, float* score, int32_t* out_count) {
-    VRQ_CHECK_ARG(ix && q_float && q_ubin && labels && score && out_count, "null argument");
+    VRQ_CHECK_ARG(ix && q_float && labels && score && out_count, "null argument");
     VRQ_TRY(flush_dead(ix));
     VRQ_CHECK_ARG(nq >= 0 && k > 0 && binary_oversample > 0, "bad sizes");
     if (ix->payload_kind == VRQ_PAYLOAD_NONE || ix->payload_kind == VRQ_PAYLOAD_INT8_RAW) {
@@ -1135,7 +1135,7 @@ extern "C" int vrq_index_search2(vrq_index* ix, int64_t nq, const float* q_float
         return VRQ_ERR_STATE;
     }
     if (nq == 0) return 0;
-    const void* all[5] = {q_float, q_ubin, labels, score, out_count};
+    const void* all[5] = {q_float, q_ubin, labels, score, out_count};  // vrq_space_of skips null pointers
     bool is_dev;
     VRQ_TRY(vrq_space_of(all, 5, &is_dev));
     vrq_ctx* ctx = ix->ctx;
@@ -1149,7 +1149,25 @@ extern "C" int vrq_index_search2(vrq_index* ix, int64_t nq, const float* q_float
     const void *dqf, *dqb;
     void *ol, *os, *on;
     VRQ_TRY(io.in(q_float, sizeof(float) * (size_t)nq * ix->d, VRQ_WS_QUERY_A, &dqf));
-    VRQ_TRY(io.in(q_ubin, (size_t)nq * ix->code_bytes, VRQ_WS_QUERY_B, &dqb));
+    if (q_ubin) {
+        VRQ_TRY(io.in(q_ubin, (size_t)nq * ix->code_bytes, VRQ_WS_QUERY_B, &dqb));
+    } else {
+        // query_bin = self._to_binary(query float) (VectorDBInt8.py:213, :140-146) on the device: packbits(q > mean_f32(q)) - one
+        // host round trip less for the one-query-per-call pattern of the classes
+        void* qb_v;
+        VRQ_TRY(vrq_ws_get(ctx, VRQ_WS_QUERY_B, (size_t)nq * ix->code_bytes, &qb_v));
+        vrq_encode_args ea{};
+        ea.x = (const float*)dqf;
+        ea.n = nq;
+        ea.d = ix->d;
+        ea.codec = VRQ_CODEC_NONE;
+        ea.limit_f32 = 1.0f;
+        ea.scale_f32 = 1.0f;
+        ea.ubin = (uint8_t*)qb_v;
+        ea.ge = 0;
+        VRQ_TRY(vrq_launch_encode(ctx, ea, ctx->stream));
+        dqb = qb_v;
+    }
     VRQ_TRY(io.out(labels, 8 * (size_t)nq * k, VRQ_WS_OUT_A, &ol));
     VRQ_TRY(io.out(score, 4 * (size_t)nq * k, VRQ_WS_OUT_B, &os));
     VRQ_TRY(io.out(out_count, 4 * (size_t)nq, VRQ_WS_OUT_E, &on));

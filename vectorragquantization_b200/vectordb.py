@@ -280,7 +280,9 @@ class _VectorDBBase:
     def search_batch(self, q_float: np.ndarray, k: int = 10, binary_oversample: int = 10, compare_float32: bool = False):
         """Batched ``search`` on precomputed query embeddings: (doc_ids i64[nq,k], scores f32[nq,k], count i32[nq])."""
         qf = np.ascontiguousarray(q_float, np.float32)
-        qb = K.to_binary(qf, ge=self._ge, ctx=self._ctx)  # query_bin = self._to_binary(query float)  (VectorDBInt8.py:213)
+        # query_bin = self._to_binary(query float) (VectorDBInt8.py:213): with the `>` threshold the library derives it on the device
+        # inside the search call; the `>=` variant (CohereVectorDBBinary.py:141) goes through its own call
+        qb = K.to_binary(qf, ge=self._ge, ctx=self._ctx) if self._ge else None
         if compare_float32:
             if self._findex is None or self._findex.ntotal != self.index.ntotal:
                 # the reference's float_embeddings dict is RAM-only and gone after a reopen: KeyError (VectorDBInt8.py:232)
