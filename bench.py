@@ -623,13 +623,13 @@ def hbm_bound_kernels(env, index, qf_d, qb_d, hbm_peak, peak_src, n_local, ms_pe
     kk = K * BO
     dist_d = torch.empty((128, kk), dtype=torch.int32, device=dev)
     lab_d = torch.empty((128, kk), dtype=torch.int64, device=dev)
-    for nq in (1, 2, 3, 16, 64, 128):
+    for nq in (1, 2, 3, 16, 64, 96, 128):
         q = qb_d[0][:nq].contiguous()
         s = _timed(env, lambda: L.check(lib.vrq_index_search(index._h, nq, L.ptr(q), kk, L.ptr(dist_d), L.ptr(lab_d))), 5)
         gbs = n_local * 128 / s / 1e9
         kern = ("hamming_scan_kernel<true> (XOR + POPC)" if nq < 3 else
                 ("hamming_scan_mma_wide_kernel (tcgen05, database rows = M expanded into TMEM, queries = N, bias column) incl. the "
-                 "sample pass" if nq <= 64 else "hamming_scan_mma_kernel, one 128-query tile per CTA, incl. the sample pass"))
+                 "sample pass" if nq <= 96 else "hamming_scan_mma_kernel, one 128-query tile per CTA, incl. the sample pass"))
         tr, tr_src = traffic(f"scan_stream_nq{nq}")
         out[f"roofline_scan_stream_nq{nq}"] = {"kernel": f"{kern} + merge, {nq} query/pass, top-{kk}", "bound": "hbm",
                                                 "unit": "GB/s", "achieved": gbs, "peak": hbm_peak, "frac": gbs / hbm_peak,
